@@ -1,0 +1,165 @@
+/* pagraph_b200.h — C-ABI of the B200-native PaGraph hot path (libpagraph_b200.so).
+ *
+ * The reference (zhiqi-0/PaGraph) has no FFI: its boundary is the Python API the trainer calls.
+ * Each entry point below replaces the work behind one reference interface (file:line cited,
+ * relative to the reference tree); pagraph_b200/*.py mirrors those Python interfaces and is the
+ * only caller (ctypes). INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types. Device pointers are CUDA device pointers of
+ *     the device the handle was created on; "host" pointers must be page-locked + mapped
+ *     (pg_host_alloc / pg_host_register) when a kernel reads them.
+ *   - every function returns pg_status (0 = ok); pg_last_error() returns a thread-local message.
+ *   - nothing throws across the ABI; nothing synchronises the device unless stated ("SYNC").
+ *   - the caller owns every output buffer; work is enqueued on the caller's stream
+ *     (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - handles are not thread-safe: one per process/GPU, like the reference's process model
+ *     (examples/profile/pa_gcn.py:157 — mp.spawn, one trainer per GPU).
+ *   - ids are int64 (the reference's width: dgl_id_t / torch.LongTensor).
+ */
+#ifndef PAGRAPH_B200_H_
+#define PAGRAPH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int pg_status;
+enum {
+  PG_OK = 0,
+  PG_ERR_INVALID = 1,   /* bad argument */
+  PG_ERR_CUDA = 2,      /* a CUDA runtime call failed; see pg_last_error() */
+  PG_ERR_OVERFLOW = 3,  /* output capacity too small (reported through meta, see pg_sample) */
+  PG_ERR_NOMEM = 4
+};
+
+typedef struct pg_graph pg_graph;     /* in-CSR adjacency resident in HBM */
+typedef struct pg_sampler pg_sampler; /* sampling workspace bound to one graph */
+typedef struct pg_cache pg_cache;     /* feature-cache lookup state (flag / l2c / nid_map / tables) */
+
+#define PG_MAX_FIELDS 4
+#define PG_MAX_HOPS 8
+
+/* ---------------------------------------------------------------- runtime */
+int pg_version(void);
+const char* pg_last_error(void);
+pg_status pg_device_info(int dev, int* sm_count, size_t* total_mem, size_t* free_mem); /* SYNC */
+
+/* Page-locked, device-mapped host memory: the B200 replacement for the pageable POSIX-shm tensors
+ * DGL's graph store hands out (server/pa_server.py:53-54, PaGraph/storage/storage.py:128). */
+pg_status pg_host_alloc(void** ptr, size_t bytes);
+pg_status pg_host_free(void* ptr);
+pg_status pg_host_register(void* ptr, size_t bytes); /* pin + map an existing mapping (e.g. /dev/shm) */
+pg_status pg_host_unregister(void* ptr);
+
+/* ---------------------------------------------------------------- graph (replaces DGLGraph(adj, readonly=True),
+ * examples/profile/pa_gcn.py:36: the structure the sampler walks). In-CSR: row v lists the sources
+ * of edges u->v in increasing edge-id order; `eids` may be NULL (edge id = CSR position).
+ * Arrays are HOST pointers and are copied to the device. SYNC. */
+pg_status pg_graph_create(const int64_t* indptr, const int64_t* indices, const int64_t* eids,
+                          int64_t num_nodes, int64_t num_edges, int dev, pg_graph** out);
+/* Same, but the arrays already live on device `dev` and are borrowed (caller keeps them alive). */
+pg_status pg_graph_create_device(const int64_t* d_indptr, const int64_t* d_indices, const int64_t* d_eids,
+                                 int64_t num_nodes, int64_t num_edges, int dev, pg_graph** out);
+void pg_graph_destroy(pg_graph* g);
+/* deg[v] = in-degree (row length) if in_edges else out-degree (column count). d_out: device int64[num_nodes]. */
+pg_status pg_graph_degrees(pg_graph* g, int in_edges, int64_t* d_out, void* stream);
+
+/* ---------------------------------------------------------------- sampler (replaces dgl.contrib.sampling.NeighborSampler's
+ * C++ SampleSubgraph + ConstructNodeFlow; call site examples/profile/pa_gcn.py:71-76).
+ * fanouts[h] = expand factor of hop h+1 (index 0 expands the seeds); the reference passes one
+ * scalar for all hops. max_seeds / cap_nodes / cap_edges size the workspace and the outputs. */
+pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, uint64_t seed,
+                            int64_t max_seeds, int64_t cap_nodes, int64_t cap_edges, pg_sampler** out);
+void pg_sampler_destroy(pg_sampler* s);
+
+/* Device output buffers of one NodeFlow (layer 0 = inputs, layer L = seeds). */
+typedef struct {
+  int64_t* node_mapping;  /* [cap_nodes]   parent id of every NodeFlow node, layer by layer          */
+  int64_t* indptr;        /* [cap_nodes+1] CSR over all NodeFlow nodes (layer-0 rows empty)          */
+  int64_t* indices;       /* [cap_edges]   NodeFlow id of each edge's source (previous layer)        */
+  int64_t* edge_mapping;  /* [cap_edges]   parent edge ids                                           */
+  int64_t* meta;          /* [PG_META_LEN] see below                                                 */
+} pg_nodeflow_buffers;
+
+/* meta layout (int64): [0] status (0 ok, PG_ERR_OVERFLOW if a capacity was exceeded — then [1],[2]
+ * hold the capacities that would have sufficed so far), [1] total nodes, [2] total edges,
+ * [3] num_layers, [4 .. 4+num_layers] layer_offsets, then [.. +num_layers-1 +1] flow_offsets. */
+#define PG_META_LEN (4 + (PG_MAX_HOPS + 2) + (PG_MAX_HOPS + 1))
+
+/* Sample one minibatch. d_seeds: device int64[n_seeds] (duplicates allowed; first occurrence kept,
+ * order preserved). (epoch, batch) key the counter-based RNG (oracle/pg_oracle.cpp header).
+ * If h_meta (pinned host, PG_META_LEN int64) is non-NULL the meta block is also copied there on
+ * `stream`; the caller synchronises on the stream/event before reading it. */
+pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int64_t epoch, int64_t batch,
+                    const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream);
+
+/* ---------------------------------------------------------------- feature cache (replaces PaGraph/storage/storage.py) */
+typedef struct {
+  int32_t dim;               /* floats per row                                                       */
+  int64_t host_stride;       /* floats between consecutive rows of the host table                    */
+  const float* host_table;   /* [V_full, dim] pinned+mapped host rows, indexed by FULL-graph id      */
+} pg_field;
+
+/* GraphCacheServer.__init__ (storage.py:23-56). The lookup state is caller-owned DEVICE memory the
+ * handle borrows (the Python attributes gpu_flag / localid2cacheid / nid_map, storage.py:34-51):
+ * d_flag uint8[node_num] (0 = row lives on the host), d_l2c int64[node_num] (local id -> cache row),
+ * d_nid_map int64[node_num] (sub-graph id -> full-graph id). */
+pg_status pg_cache_create(int64_t node_num, uint8_t* d_flag, int64_t* d_l2c, const int64_t* d_nid_map,
+                          int nfields, const pg_field* fields, int dev, pg_cache** out);
+void pg_cache_destroy(pg_cache* c);
+
+/* cache_fix_data (storage.py:135-154): l2c[nids[i]] = i, flag[nids[i]] = 1; d_cache_tables[f] are
+ * caller-allocated [n, dim] device buffers that the handle keeps borrowing afterwards. If
+ * copy_rows != 0 the rows host_table[f][nid_map[nids[i]]] are pulled into d_cache_tables[f][i] by the
+ * GPU (auto_cache, storage.py:94-95,103-104); with copy_rows == 0 the caller has filled them.
+ * d_nids: device int64[n]. */
+pg_status pg_cache_fill(pg_cache* c, const int64_t* d_nids, int64_t n, int is_full,
+                        float* const* d_cache_tables, int copy_rows, void* stream);
+
+/* get_feat_from_server(to_gpu=True) (storage.py:107-132): d_out[f][i] = host_table[f][nid_map[d_nids[i]]]. */
+pg_status pg_cache_fetch_host(pg_cache* c, const int64_t* d_nids, int64_t n, float* const* d_out,
+                              void* stream);
+
+/* fetch_data (storage.py:157-204) for n consecutive NodeFlow nodes (all layers at once):
+ *   d_out[f][j] = flag[t_j] ? cache[f][l2c[t_j]] : host_table[f][nid_map[t_j]],  t_j = d_parent_ids[j].
+ * d_hit_mask (optional, uint8[n]) receives flag[t_j]; d_counts (int64[2], optional) is
+ * INCREMENTED by (tries, misses) — storage.py:219-221. When the cache is full (is_full) this is
+ * fetch_from_cache (storage.py:207-216).
+ * mode: 0 = auto, 1 = plain vector loads for misses, 2 = TMA bulk copies for misses (needs 16-byte
+ * aligned rows). */
+pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out,
+                         uint8_t* d_hit_mask, int64_t* d_counts, int mode, void* stream);
+/* Elapsed ms of the hit and miss kernels of the most recent pg_cache_fetch with timing enabled. SYNC. */
+pg_status pg_cache_set_timing(pg_cache* c, int enabled);
+pg_status pg_cache_last_timing(pg_cache* c, float* ms_split, float* ms_hit, float* ms_miss);
+
+/* ---------------------------------------------------------------- aggregation (replaces nf.block_compute(i, fn.copy_src,
+ * fn.sum|fn.mean, ...), PaGraph/model/gcn_nssc.py:71-74, graphsage_nssc.py:98-106; and, run over
+ * the full graph with mode=PG_AGG_SUM + norm, the server-side --preprocess fold, server/pa_server.py:45-52).
+ *   dst[r] = scale_r * sum_{e in [indptr[r], indptr[r+1])} src[cols[e] - col_base]
+ * scale_r = 1 (SUM), 1/max(deg_r,1) (MEAN); if d_norm != NULL the row is additionally multiplied by
+ * d_norm[r] (NodeUpdate test=True, gcn_nssc.py:16-17). Strides in floats. */
+enum { PG_AGG_SUM = 0, PG_AGG_MEAN = 1 };
+pg_status pg_aggregate_fwd(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base,
+                           const float* d_src, int64_t src_stride, float* d_dst, int64_t dst_stride,
+                           int64_t n_dst, int32_t dim, int mode, const float* d_norm, void* stream);
+/* grad_src[cols[e]-col_base] += scale_r * grad_dst[r]; d_grad_src ([n_src, dim]) is zeroed first. */
+pg_status pg_aggregate_bwd(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base,
+                           const float* d_grad_dst, int64_t gdst_stride, float* d_grad_src,
+                           int64_t gsrc_stride, int64_t n_dst, int64_t n_src, int32_t dim, int mode,
+                           const float* d_norm, void* stream);
+
+/* ---------------------------------------------------------------- measurement helpers */
+/* Pinned H2D copy bandwidth probe (the PCIe roofline denominator). SYNC. */
+pg_status pg_measure_h2d(int dev, size_t bytes, int iters, double* gb_per_s);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+int64_t pg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAGRAPH_B200_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of libpagraph_b200.so (include/pagraph_b200.h). No CPU fallback: if the CUDA
+library is missing or a call fails, this raises."""
+import ctypes
+import os
+
+from . import build as _build
+
+PG_MAX_FIELDS = 4
+PG_MAX_HOPS = 8
+PG_META_LEN = 4 + (PG_MAX_HOPS + 2) + (PG_MAX_HOPS + 1)
+PG_OK, PG_ERR_INVALID, PG_ERR_CUDA, PG_ERR_OVERFLOW, PG_ERR_NOMEM = 0, 1, 2, 3, 4
+PG_AGG_SUM, PG_AGG_MEAN = 0, 1
+
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_vp = ctypes.c_void_p
+
+
+class PGError(RuntimeError):
+    pass
+
+
+class pg_field(ctypes.Structure):
+    _fields_ = [("dim", ctypes.c_int32), ("host_stride", ctypes.c_int64), ("host_table", c_vp)]
+
+
+class pg_nodeflow_buffers(ctypes.Structure):
+    _fields_ = [("node_mapping", c_vp), ("indptr", c_vp), ("indices", c_vp), ("edge_mapping", c_vp),
+                ("meta", c_vp)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/pagraph_b200.h
+SIGNATURES = {
+    "pg_version": (ctypes.c_int, []),
+    "pg_last_error": (ctypes.c_char_p, []),
+    "pg_device_info": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "pg_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t]),
+    "pg_host_free": (ctypes.c_int, [c_vp]),
+    "pg_host_register": (ctypes.c_int, [c_vp, ctypes.c_size_t]),
+    "pg_host_unregister": (ctypes.c_int, [c_vp]),
+    "pg_graph_create": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                       ctypes.POINTER(c_vp)]),
+    "pg_graph_create_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                              ctypes.POINTER(c_vp)]),
+    "pg_graph_destroy": (None, [c_vp]),
+    "pg_graph_degrees": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
+    "pg_sampler_create": (ctypes.c_int, [c_vp, ctypes.c_int, c_i64p, ctypes.c_uint64, ctypes.c_int64,
+                                         ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(c_vp)]),
+    "pg_sampler_destroy": (None, [c_vp]),
+    "pg_sample": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                 ctypes.POINTER(pg_nodeflow_buffers), c_vp, c_vp]),
+    "pg_cache_create": (ctypes.c_int, [ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int,
+                                       ctypes.POINTER(pg_field), ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "pg_cache_destroy": (None, [c_vp]),
+    "pg_cache_fill": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp),
+                                     ctypes.c_int, c_vp]),
+    "pg_cache_fetch_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),
+    "pg_cache_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp, c_vp,
+                                      ctypes.c_int, c_vp]),
+    "pg_cache_set_timing": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "pg_cache_last_timing": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float),
+                                            ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "pg_aggregate_fwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,
+                                        ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
+    "pg_aggregate_bwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,
+                                        ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
+    "pg_measure_h2d": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_double)]),
+    "pg_launch_count": (ctypes.c_int64, []),
+}
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def lib():
+    """Load the CUDA library (building it on first use if nvcc is available). Raises if absent."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc on this box and no prebuilt library: hard error
+                raise PGError("libpagraph_b200.so is missing and could not be built (%s); "
+                              "run `python -m pagraph_b200.build`" % e)
+        L = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(status, what=""):
+    if status != PG_OK:
+        msg = lib().pg_last_error()
+        raise PGError("%s failed (status %d): %s" % (what or "pagraph_b200 call", status,
+                                                     msg.decode() if msg else ""))
+
+
+def ptr(t):
+    """Device/host address of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def launch_count():
+    return int(lib().pg_launch_count())

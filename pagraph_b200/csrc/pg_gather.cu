@@ -1,0 +1,519 @@
+// pg_gather.cu — GPU feature-cache lookup, hit/miss split, HBM-cache gather and host-row fetch.
+//
+// Replaces PaGraph/storage/storage.py (reference): fetch_data :157-204, fetch_from_cache :207-216,
+// cache_fix_data :135-154, get_feat_from_server :107-132. Payload is copied bit-for-bit.
+//
+// B200 design (byte-moving work: HBM-bound for hits, PCIe-bound for misses):
+//   * ONE split kernel classifies every NodeFlow node of every layer (flag lookup, ballot +
+//     block-aggregated atomics) into a hit list (-> cache row) and a miss list (-> full-graph row):
+//     no boolean-mask indexing, no host synchronisation (the reference syncs >= 3x per layer);
+//   * hit rows: one warp per row, 16-byte read-only loads from the HBM cache table, all loads of a
+//     row in flight before the first store, rows written straight into NodeFlow order;
+//   * miss rows: the pinned host table is read directly by the GPU. Each lane of a fetch warp owns a
+//     shared-memory stage + mbarrier and moves one row with TMA bulk copies
+//     (cp.async.bulk global->shared, then shared->global), so a 2400-byte row is two descriptors
+//     instead of 150 vector loads and hundreds of rows are in flight over PCIe;
+//   * the miss kernel runs on an internal high-priority stream concurrently with the hit kernel.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "pg_common.cuh"
+
+namespace {
+
+using pg::kFullMask;
+
+constexpr int kRowWarps = 8;          // warps per CTA of the row-copy kernel
+constexpr int kBulkWarps = 2;         // warps per CTA of the TMA kernel
+constexpr int kSplitThreads = 256;
+
+struct RowsArgs {
+  int nfields;
+  const float* src[PG_MAX_FIELDS];
+  int64_t src_stride[PG_MAX_FIELDS];
+  float* dst[PG_MAX_FIELDS];
+  int64_t dst_stride[PG_MAX_FIELDS];
+  int dim[PG_MAX_FIELDS];
+  int bulk_ok[PG_MAX_FIELDS];         // field may use cp.async.bulk (16-byte aligned rows)
+  int smem_off[PG_MAX_FIELDS];        // byte offset of the field inside a stage
+  int stage_bytes;                    // bytes per stage (bulk fields only)
+  int stages;                         // lanes per warp that own a stage
+  const int64_t* pos;                 // destination row of item i (null: i)
+  const int64_t* row;                 // source row of item i
+  const int64_t* count;               // device-resident item count (null: n)
+  int64_t n;
+};
+
+// ------------------------------------------------------------------ split
+__global__ void __launch_bounds__(kSplitThreads)
+split_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __restrict__ flag,
+             const int64_t* __restrict__ l2c, const int64_t* __restrict__ nid_map, int64_t* hit_pos,
+             int64_t* hit_row, int64_t* miss_pos, int64_t* miss_row, unsigned long long* list_counts,
+             uint8_t* hit_mask, unsigned long long* user_counts) {
+  __shared__ int warp_hits[kSplitThreads / 32], warp_miss[kSplitThreads / 32];
+  __shared__ unsigned long long base_hit, base_miss;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  const int64_t ntiles = (n + kSplitThreads - 1) / kSplitThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t j = tile * kSplitThreads + threadIdx.x;
+    const bool valid = j < n;
+    int64_t t = 0;
+    bool hit = false;
+    if (valid) {
+      t = ids[j];
+      hit = flag[t] != 0;
+      if (hit_mask) hit_mask[j] = hit;
+    }
+    const unsigned hb = __ballot_sync(kFullMask, valid && hit), mb = __ballot_sync(kFullMask, valid && !hit);
+    if (lane == 0) {
+      warp_hits[w] = __popc(hb);
+      warp_miss[w] = __popc(mb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int th = 0, tm = 0;
+      for (int i = 0; i < kSplitThreads / 32; ++i) {
+        const int a = warp_hits[i], b = warp_miss[i];
+        warp_hits[i] = th; warp_miss[i] = tm;
+        th += a; tm += b;
+      }
+      base_hit = th ? atomicAdd(&list_counts[0], (unsigned long long)th) : 0;
+      base_miss = tm ? atomicAdd(&list_counts[1], (unsigned long long)tm) : 0;
+      if (user_counts && tm) atomicAdd(&user_counts[1], (unsigned long long)tm);
+    }
+    __syncthreads();
+    if (valid) {
+      if (hit) {
+        const int64_t o = (int64_t)base_hit + warp_hits[w] + __popc(hb & lt);
+        hit_pos[o] = j;
+        hit_row[o] = l2c[t];
+      } else {
+        const int64_t o = (int64_t)base_miss + warp_miss[w] + __popc(mb & lt);
+        miss_pos[o] = j;
+        miss_row[o] = nid_map[t];
+      }
+    }
+    __syncthreads();
+  }
+  if (user_counts && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&user_counts[0], (unsigned long long)n);
+}
+
+// ------------------------------------------------------------------ row copy with vector loads (hits; generic fallback)
+template <typename V>
+__device__ __forceinline__ void copy_vec(const V* __restrict__ s, V* __restrict__ d, int nvec, int lane) {
+  constexpr int U = 5;  // 600 floats = 150 float4 = 5 per lane: every load issued before the first store
+  for (int c = lane; c < nvec; c += 32 * U) {
+    V v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c + 32 * u < nvec) v[u] = __ldg(s + c + 32 * u);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c + 32 * u < nvec) d[c + 32 * u] = v[u];
+  }
+}
+
+__device__ __forceinline__ void copy_row(const float* src, float* dst, int dim, int lane) {
+  const uintptr_t a = (uintptr_t)src | (uintptr_t)dst;
+  if ((a & 15) == 0 && (dim & 3) == 0) {
+    copy_vec((const float4*)src, (float4*)dst, dim >> 2, lane);
+  } else if ((a & 7) == 0 && (dim & 1) == 0) {
+    copy_vec((const float2*)src, (float2*)dst, dim >> 1, lane);
+  } else {
+    copy_vec(src, dst, dim, lane);
+  }
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) rows_ldg_kernel(RowsArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * kRowWarps;
+  const int64_t n = a.count ? min((int64_t)*a.count, a.n) : a.n;
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const int64_t r = a.row[i], p = a.pos ? a.pos[i] : i;
+#pragma unroll
+    for (int f = 0; f < PG_MAX_FIELDS; ++f) {
+      if (f >= a.nfields) break;
+      copy_row(a.src[f] + r * a.src_stride[f], a.dst[f] + p * a.dst_stride[f], a.dim[f], lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ row copy with TMA bulk copies (misses / cache fill)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst)),
+               "r"(src), "r"(bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kBulkWarps * 32) rows_bulk_kernel(RowsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[kBulkWarps * 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool owner = lane < a.stages;
+  const uint32_t bar = smem_u32(&bars[threadIdx.x]);
+  const uint32_t stage = smem_u32(smem) + (uint32_t)((w * a.stages + (owner ? lane : 0)) * a.stage_bytes);
+  if (owner) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int64_t n = a.count ? min((int64_t)*a.count, a.n) : a.n;
+  const int64_t warp0 = (int64_t)blockIdx.x * kBulkWarps + w, nwarps = (int64_t)gridDim.x * kBulkWarps;
+  uint32_t parity = 0;
+  for (int64_t base = warp0 * a.stages; base < n; base += nwarps * a.stages) {
+    const int64_t i = base + lane;
+    if (owner && i < n) {
+      const int64_t r = a.row[i], p = a.pos ? a.pos[i] : i;
+      mbar_expect_tx(bar, (uint32_t)a.stage_bytes);
+#pragma unroll
+      for (int f = 0; f < PG_MAX_FIELDS; ++f) {
+        if (f >= a.nfields) break;
+        if (a.bulk_ok[f]) bulk_g2s(stage + a.smem_off[f], a.src[f] + r * a.src_stride[f], (uint32_t)a.dim[f] * 4u, bar);
+      }
+      // narrow / unaligned fields (e.g. norm: one float per row) ride along with plain loads
+#pragma unroll
+      for (int f = 0; f < PG_MAX_FIELDS; ++f) {
+        if (f >= a.nfields) break;
+        if (!a.bulk_ok[f]) {
+          const float* s = a.src[f] + r * a.src_stride[f];
+          float* d = a.dst[f] + p * a.dst_stride[f];
+          for (int c = 0; c < a.dim[f]; ++c) d[c] = __ldg(s + c);
+        }
+      }
+      while (!mbar_try_wait(bar, parity)) {
+      }
+      parity ^= 1;
+#pragma unroll
+      for (int f = 0; f < PG_MAX_FIELDS; ++f) {
+        if (f >= a.nfields) break;
+        if (a.bulk_ok[f]) bulk_s2g(a.dst[f] + p * a.dst_stride[f], stage + a.smem_off[f], (uint32_t)a.dim[f] * 4u);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // stage may be overwritten next round
+    }
+    __syncwarp();
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ small index kernels
+__global__ void fill_setup_kernel(const int64_t* __restrict__ nids, int64_t n, const int64_t* __restrict__ nid_map,
+                                  int64_t* l2c, uint8_t* flag, int64_t* row_list) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = nids[i];
+    if (l2c) l2c[v] = i;
+    if (flag) flag[v] = 1;
+    row_list[i] = nid_map[v];
+  }
+}
+
+__global__ void fill_u8_kernel(uint8_t* p, int64_t n, uint8_t v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+// ====================================================================== handle
+struct pg_cache {
+  int dev = 0;
+  int64_t node_num = 0;
+  int nfields = 0;
+  pg_field fields[PG_MAX_FIELDS];
+  const float* host_dev[PG_MAX_FIELDS] = {nullptr};  // device-visible alias of the pinned host tables
+  float* cache_tables[PG_MAX_FIELDS] = {nullptr};
+  int64_t cached_rows = 0;
+  bool is_full = false;
+  uint8_t* flag = nullptr;
+  int64_t* l2c = nullptr;
+  const int64_t* nid_map = nullptr;
+  // workspace
+  int64_t ws_cap = 0;
+  int64_t *hit_pos = nullptr, *hit_row = nullptr, *miss_pos = nullptr, *miss_row = nullptr;
+  unsigned long long* list_counts = nullptr;  // [2] hits, misses
+  cudaStream_t miss_stream = nullptr;
+  cudaEvent_t ev_split = nullptr, ev_miss_done = nullptr;
+  bool timing = false;
+  cudaEvent_t t_begin = nullptr, t_split = nullptr, t_hit = nullptr, t_miss0 = nullptr, t_miss1 = nullptr;
+  bool timed_valid = false, timed_miss = false;
+  int max_smem_optin = 0;
+};
+
+static pg_status ensure_ws(pg_cache* c, int64_t n) {
+  if (n <= c->ws_cap) return PG_OK;
+  const int64_t cap = std::max<int64_t>(n + n / 4, 1 << 16);
+  cudaFree(c->hit_pos); cudaFree(c->hit_row); cudaFree(c->miss_pos); cudaFree(c->miss_row);
+  c->hit_pos = c->hit_row = c->miss_pos = c->miss_row = nullptr;
+  c->ws_cap = 0;
+  const size_t b = (size_t)cap * sizeof(int64_t);
+  if (cudaMalloc(&c->hit_pos, b) != cudaSuccess || cudaMalloc(&c->hit_row, b) != cudaSuccess ||
+      cudaMalloc(&c->miss_pos, b) != cudaSuccess || cudaMalloc(&c->miss_row, b) != cudaSuccess) {
+    cudaGetLastError();
+    pg::set_error("pg_cache: out of device memory for a %lld-row workspace", (long long)cap);
+    return PG_ERR_NOMEM;
+  }
+  c->ws_cap = cap;
+  return PG_OK;
+}
+
+// Launch a row-copy over `n` (or *d_count) items. use_bulk: try the TMA path.
+static pg_status launch_rows(pg_cache* c, const float* const* src, const int64_t* src_stride, float* const* dst,
+                             const int64_t* pos, const int64_t* row, const unsigned long long* d_count, int64_t n,
+                             bool use_bulk, cudaStream_t st) {
+  RowsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nfields = c->nfields;
+  a.pos = pos; a.row = row; a.count = (const int64_t*)d_count; a.n = n;
+  int stage = 0;
+  bool any_bulk = false, wide_unaligned = false;
+  for (int f = 0; f < c->nfields; ++f) {
+    a.src[f] = src[f]; a.src_stride[f] = src_stride[f];
+    a.dst[f] = dst[f]; a.dst_stride[f] = c->fields[f].dim; a.dim[f] = c->fields[f].dim;
+    const bool ok = (a.dim[f] % 4 == 0) && (a.src_stride[f] % 4 == 0) && (((uintptr_t)a.src[f] | (uintptr_t)a.dst[f]) % 16 == 0);
+    a.bulk_ok[f] = ok;
+    a.smem_off[f] = stage;
+    if (ok) { stage += a.dim[f] * 4; any_bulk = true; }
+    else if (a.dim[f] > 16) wide_unaligned = true;
+  }
+  const int sms = pg::sm_count(c->dev);
+  if (use_bulk && any_bulk && !wide_unaligned) {
+    const int budget = std::min(c->max_smem_optin - 1024, env_int("PG_BULK_SMEM", 96 * 1024));
+    int stages = std::min(32, budget / (kBulkWarps * stage));
+    stages = std::min(stages, env_int("PG_BULK_STAGES", 32));
+    if (stages >= 1) {
+      a.stage_bytes = stage;
+      a.stages = stages;
+      const size_t smem = (size_t)kBulkWarps * stages * stage;
+      PG_CUDA(cudaFuncSetAttribute(rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int64_t need = std::max<int64_t>(1, (n + kBulkWarps * stages - 1) / (kBulkWarps * stages));
+      const int grid = (int)std::min<int64_t>(need, (int64_t)sms * env_int("PG_BULK_CTAS_PER_SM", 2));
+      rows_bulk_kernel<<<grid, kBulkWarps * 32, smem, st>>>(a);
+      PG_CHECK_LAUNCH();
+      return PG_OK;
+    }
+  }
+  const int64_t need = std::max<int64_t>(1, (n + kRowWarps - 1) / kRowWarps);
+  const int grid = (int)std::min<int64_t>(need, (int64_t)sms * 8);
+  rows_ldg_kernel<<<grid, kRowWarps * 32, 0, st>>>(a);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+extern "C" {
+
+pg_status pg_cache_create(int64_t node_num, uint8_t* d_flag, int64_t* d_l2c, const int64_t* d_nid_map, int nfields,
+                          const pg_field* fields, int dev, pg_cache** out) {
+  PG_REQUIRE(out && d_flag && d_l2c && d_nid_map && fields && node_num >= 1, "pg_cache_create: bad arguments");
+  PG_REQUIRE(nfields >= 1 && nfields <= PG_MAX_FIELDS, "pg_cache_create: nfields must be in [1, PG_MAX_FIELDS]");
+  pg::DeviceGuard guard(dev);
+  pg_cache* c = new pg_cache;
+  c->dev = dev;
+  c->node_num = node_num;
+  c->nfields = nfields;
+  auto fail = [&](pg_status s) { pg_cache_destroy(c); return s; };
+  for (int f = 0; f < nfields; ++f) {
+    c->fields[f] = fields[f];
+    if (fields[f].dim < 1 || fields[f].host_stride < fields[f].dim || !fields[f].host_table) {
+      pg::set_error("pg_cache_create: field %d has a bad dim/stride/table", f);
+      return fail(PG_ERR_INVALID);
+    }
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, (void*)fields[f].host_table, 0) != cudaSuccess) {
+      cudaGetLastError();
+      pg::set_error("pg_cache_create: host table of field %d is not page-locked+mapped (use pg_host_alloc / pg_host_register)", f);
+      return fail(PG_ERR_INVALID);
+    }
+    c->host_dev[f] = (const float*)dp;
+  }
+  c->flag = d_flag;
+  c->l2c = d_l2c;
+  c->nid_map = d_nid_map;
+  if (cudaMalloc(&c->list_counts, 16) != cudaSuccess) {
+    cudaGetLastError();
+    pg::set_error("pg_cache_create: out of device memory");
+    return fail(PG_ERR_NOMEM);
+  }
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&c->miss_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_split, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_miss_done, cudaEventDisableTiming) != cudaSuccess) {
+    pg::set_error("pg_cache_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(PG_ERR_CUDA);
+  }
+  cudaEventCreate(&c->t_begin); cudaEventCreate(&c->t_split); cudaEventCreate(&c->t_hit);
+  cudaEventCreate(&c->t_miss0); cudaEventCreate(&c->t_miss1);
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  *out = c;
+  return PG_OK;
+}
+
+void pg_cache_destroy(pg_cache* c) {
+  if (!c) return;
+  pg::DeviceGuard guard(c->dev);
+  cudaDeviceSynchronize();
+  cudaFree(c->list_counts);
+  cudaFree(c->hit_pos); cudaFree(c->hit_row); cudaFree(c->miss_pos); cudaFree(c->miss_row);
+  if (c->miss_stream) cudaStreamDestroy(c->miss_stream);
+  for (cudaEvent_t e : {c->ev_split, c->ev_miss_done, c->t_begin, c->t_split, c->t_hit, c->t_miss0, c->t_miss1})
+    if (e) cudaEventDestroy(e);
+  cudaGetLastError();
+  delete c;
+}
+
+pg_status pg_cache_fill(pg_cache* c, const int64_t* d_nids, int64_t n, int is_full, float* const* d_cache_tables,
+                        int copy_rows, void* stream) {
+  PG_REQUIRE(c && d_cache_tables && (d_nids || n == 0) && n >= 0, "pg_cache_fill: bad arguments");
+  pg::DeviceGuard guard(c->dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int f = 0; f < c->nfields; ++f) {
+    PG_REQUIRE(d_cache_tables[f] != nullptr || n == 0, "pg_cache_fill: null cache table");
+    c->cache_tables[f] = d_cache_tables[f];
+  }
+  c->cached_rows = n;
+  c->is_full = is_full != 0;
+  if (n == 0) return PG_OK;
+  pg_status s = ensure_ws(c, n);
+  if (s != PG_OK) return s;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)pg::sm_count(c->dev) * 8);
+  fill_setup_kernel<<<grid, 256, 0, st>>>(d_nids, n, c->nid_map, c->l2c, c->flag, c->miss_row);
+  PG_CHECK_LAUNCH();
+  if (!copy_rows) return PG_OK;
+  int64_t strides[PG_MAX_FIELDS];
+  for (int f = 0; f < c->nfields; ++f) strides[f] = c->fields[f].host_stride;
+  return launch_rows(c, c->host_dev, strides, c->cache_tables, nullptr, c->miss_row, nullptr, n,
+                     env_int("PG_MISS_MODE", 2) == 2, st);
+}
+
+pg_status pg_cache_fetch_host(pg_cache* c, const int64_t* d_nids, int64_t n, float* const* d_out, void* stream) {
+  PG_REQUIRE(c && d_out && (d_nids || n == 0) && n >= 0, "pg_cache_fetch_host: bad arguments");
+  if (n == 0) return PG_OK;
+  pg::DeviceGuard guard(c->dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  pg_status s = ensure_ws(c, n);
+  if (s != PG_OK) return s;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)pg::sm_count(c->dev) * 8);
+  fill_setup_kernel<<<grid, 256, 0, st>>>(d_nids, n, c->nid_map, nullptr, nullptr, c->miss_row);
+  PG_CHECK_LAUNCH();
+  int64_t strides[PG_MAX_FIELDS];
+  for (int f = 0; f < c->nfields; ++f) strides[f] = c->fields[f].host_stride;
+  return launch_rows(c, c->host_dev, strides, d_out, nullptr, c->miss_row, nullptr, n,
+                     env_int("PG_MISS_MODE", 2) == 2, st);
+}
+
+pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out, uint8_t* d_hit_mask,
+                         int64_t* d_counts, int mode, void* stream) {
+  PG_REQUIRE(c && d_out && (d_parent_ids || n == 0) && n >= 0, "pg_cache_fetch: bad arguments");
+  PG_REQUIRE(mode >= 0 && mode <= 2, "pg_cache_fetch: mode must be 0, 1 or 2");
+  if (n == 0) return PG_OK;
+  pg::DeviceGuard guard(c->dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int f = 0; f < c->nfields; ++f) PG_REQUIRE(d_out[f] != nullptr, "pg_cache_fetch: null output table");
+  c->timed_valid = false;
+  int64_t cache_strides[PG_MAX_FIELDS], host_strides[PG_MAX_FIELDS];
+  for (int f = 0; f < c->nfields; ++f) {
+    cache_strides[f] = c->fields[f].dim;
+    host_strides[f] = c->fields[f].host_stride;
+  }
+  const int sms = pg::sm_count(c->dev);
+  if (c->timing) PG_CUDA(cudaEventRecord(c->t_begin, st));
+  if (c->is_full) {
+    // fetch_from_cache (storage.py:207-216): every row is cached in id order, cache row == local id
+    if (d_hit_mask) {
+      fill_u8_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 8), 256, 0, st>>>(d_hit_mask, n, 1);
+      PG_CHECK_LAUNCH();
+    }
+    if (c->timing) PG_CUDA(cudaEventRecord(c->t_split, st));
+    pg_status s = launch_rows(c, c->cache_tables, cache_strides, d_out, nullptr, d_parent_ids, nullptr, n, false, st);
+    if (s != PG_OK) return s;
+    if (c->timing) {
+      PG_CUDA(cudaEventRecord(c->t_hit, st));
+      c->timed_valid = true;
+      c->timed_miss = false;
+    }
+    return PG_OK;
+  }
+  pg_status s = ensure_ws(c, n);
+  if (s != PG_OK) return s;
+  PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
+  const int grid = (int)std::min<int64_t>((n + kSplitThreads - 1) / kSplitThreads, (int64_t)sms * 8);
+  split_kernel<<<grid, kSplitThreads, 0, st>>>(d_parent_ids, n, c->flag, c->l2c, c->nid_map, c->hit_pos, c->hit_row,
+                                               c->miss_pos, c->miss_row, c->list_counts, d_hit_mask,
+                                               (unsigned long long*)d_counts);
+  PG_CHECK_LAUNCH();
+  if (c->timing) PG_CUDA(cudaEventRecord(c->t_split, st));
+  // misses first, on the high-priority side stream, so PCIe is busy while the hit rows stream from HBM
+  if (mode == 0) mode = env_int("PG_MISS_MODE", 2);
+  PG_CUDA(cudaEventRecord(c->ev_split, st));
+  PG_CUDA(cudaStreamWaitEvent(c->miss_stream, c->ev_split, 0));
+  if (c->timing) PG_CUDA(cudaEventRecord(c->t_miss0, c->miss_stream));
+  s = launch_rows(c, c->host_dev, host_strides, d_out, c->miss_pos, c->miss_row, c->list_counts + 1, n, mode == 2,
+                  c->miss_stream);
+  if (s != PG_OK) return s;
+  if (c->timing) PG_CUDA(cudaEventRecord(c->t_miss1, c->miss_stream));
+  PG_CUDA(cudaEventRecord(c->ev_miss_done, c->miss_stream));
+  if (c->cached_rows > 0) {
+    s = launch_rows(c, c->cache_tables, cache_strides, d_out, c->hit_pos, c->hit_row, c->list_counts, n, false, st);
+    if (s != PG_OK) return s;
+  }
+  if (c->timing) {
+    PG_CUDA(cudaEventRecord(c->t_hit, st));
+    c->timed_valid = true;
+    c->timed_miss = true;
+  }
+  PG_CUDA(cudaStreamWaitEvent(st, c->ev_miss_done, 0));
+  return PG_OK;
+}
+
+pg_status pg_cache_set_timing(pg_cache* c, int enabled) {
+  PG_REQUIRE(c, "pg_cache_set_timing: null handle");
+  c->timing = enabled != 0;
+  c->timed_valid = false;
+  return PG_OK;
+}
+
+pg_status pg_cache_last_timing(pg_cache* c, float* ms_split, float* ms_hit, float* ms_miss) {
+  PG_REQUIRE(c && c->timed_valid, "pg_cache_last_timing: no timed fetch recorded");
+  pg::DeviceGuard guard(c->dev);
+  PG_CUDA(cudaEventSynchronize(c->t_hit));
+  float a = 0, b = 0, m = 0;
+  PG_CUDA(cudaEventElapsedTime(&a, c->t_begin, c->t_split));
+  PG_CUDA(cudaEventElapsedTime(&b, c->t_split, c->t_hit));
+  if (c->timed_miss) {
+    PG_CUDA(cudaEventSynchronize(c->t_miss1));
+    PG_CUDA(cudaEventElapsedTime(&m, c->t_miss0, c->t_miss1));
+  }
+  if (ms_split) *ms_split = a;
+  if (ms_hit) *ms_hit = b;
+  if (ms_miss) *ms_miss = m;
+  return PG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// pg_runtime.cu — error state, pinned host memory, device info, PCIe probe.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <unordered_map>
+
+#include "pg_common.cuh"
+
+namespace pg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count(int dev) {
+  static std::mutex mu;
+  static std::unordered_map<int, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  cache[dev] = n;
+  return n;
+}
+
+}  // namespace pg
+
+extern "C" {
+
+int pg_version(void) { return 100; }
+
+const char* pg_last_error(void) { return pg::g_err; }
+
+int64_t pg_launch_count(void) { return pg::g_launches.load(); }
+
+pg_status pg_device_info(int dev, int* sm, size_t* total_mem, size_t* free_mem) {
+  pg::DeviceGuard guard(dev);
+  if (sm) *sm = pg::sm_count(dev);
+  size_t f = 0, t = 0;
+  PG_CUDA(cudaMemGetInfo(&f, &t));
+  if (total_mem) *total_mem = t;
+  if (free_mem) *free_mem = f;
+  return PG_OK;
+}
+
+pg_status pg_host_alloc(void** ptr, size_t bytes) {
+  PG_REQUIRE(ptr != nullptr, "pg_host_alloc: null out pointer");
+  PG_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable));
+  return PG_OK;
+}
+
+pg_status pg_host_free(void* ptr) {
+  if (ptr) PG_CUDA(cudaFreeHost(ptr));
+  return PG_OK;
+}
+
+pg_status pg_host_register(void* ptr, size_t bytes) {
+  PG_REQUIRE(ptr != nullptr && bytes > 0, "pg_host_register: empty range");
+  PG_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  return PG_OK;
+}
+
+pg_status pg_host_unregister(void* ptr) {
+  if (ptr) PG_CUDA(cudaHostUnregister(ptr));
+  return PG_OK;
+}
+
+pg_status pg_measure_h2d(int dev, size_t bytes, int iters, double* gb_per_s) {
+  PG_REQUIRE(gb_per_s != nullptr && bytes > 0 && iters > 0, "pg_measure_h2d: bad arguments");
+  pg::DeviceGuard guard(dev);
+  void *h = nullptr, *d = nullptr;
+  PG_CUDA(cudaHostAlloc(&h, bytes, cudaHostAllocDefault));
+  if (cudaMalloc(&d, bytes) != cudaSuccess) {
+    cudaFreeHost(h);
+    pg::set_error("pg_measure_h2d: cudaMalloc(%zu) failed", bytes);
+    return PG_ERR_NOMEM;
+  }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, 0);  // warm-up
+  float best = 1e30f;
+  for (int i = 0; i < iters; ++i) {
+    cudaEventRecord(a, 0);
+    cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, 0);
+    cudaEventRecord(b, 0);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  cudaFreeHost(h);
+  PG_CUDA(cudaGetLastError());
+  *gb_per_s = (double)bytes / (best * 1e-3) / 1e9;
+  return PG_OK;
+}
+
+}  // extern "C"

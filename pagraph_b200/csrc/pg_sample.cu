@@ -1,0 +1,669 @@
+// pg_sample.cu — k-hop neighbour sampling + NodeFlow construction on the GPU.
+//
+// Replaces dgl==0.4.1 SampleSubgraph / GetUniformSample / ConstructNodeFlow (C++/OpenMP, called from
+// dgl.contrib.sampling.NeighborSampler; reference call site examples/profile/pa_gcn.py:71-76).
+// Semantics follow SURVEY.md Appendix A.3/A.4 and are bit-identical to oracle/pg_oracle.cpp.
+//
+// B200 design (integer, HBM/latency-bound work — no tensor cores):
+//   * the CSR stays resident in HBM; one warp expands one frontier vertex (coalesced take-all rows,
+//     warp-parallel "set until k distinct" draws with match/ballot for the sampled rows);
+//   * per-layer dedup + "sort by parent id" is a V-bit bitmap (fits L2: 1.25 MB at 10 M vertices):
+//     atomicOr marks, a popcount prefix-sum ranks — no sort, no hash table, deterministic;
+//   * every count stays on the device (grids are fixed, kernels read sizes from HBM), so a
+//     minibatch is sampled without a single host synchronisation; sizes go back through `meta`.
+#include <algorithm>
+#include <climits>
+#include <type_traits>
+#include <vector>
+
+#include "pg_common.cuh"
+
+namespace {
+
+using pg::kFullMask;
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kTile = kScanThreads * kScanItems;
+constexpr int kPickWarps = 8;        // warps per CTA in the pick kernel
+constexpr int kSmemPicks = 64;       // accepted-position slots per warp kept in shared memory
+constexpr int64_t kEmptyKey = -1;
+
+// Device-resident counters of one pg_sample call.
+struct Counts {
+  int64_t n_layer[PG_MAX_HOPS + 1];  // sampling order: [0] = seeds
+  int64_t e_hop[PG_MAX_HOPS + 1];    // [h] = edges sampled when expanding layer h-1
+  int64_t overflow;
+};
+
+// ------------------------------------------------------------------ generic two-pass device scan
+// pass1: per-tile sums; the last CTA to finish turns them into exclusive tile prefixes (+ total).
+// pass2: recomputes the values, adds the tile prefix and calls emit(i, exclusive_prefix, value).
+template <class F>
+__global__ void __launch_bounds__(kScanThreads) scan_pass1(F f, int64_t* tile_sums, unsigned* ticket,
+                                                           int64_t* total_out) {
+  __shared__ int64_t sh[kScanThreads / 32 + 1];
+  __shared__ bool is_last;
+  const int64_t n = f.size();
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * kTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) s += f.value(base + k);
+    int64_t total;
+    pg::block_exclusive_scan(s, total, sh);
+    if (threadIdx.x == 0) tile_sums[tile] = total;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int64_t chunk = (ntiles + kScanThreads - 1) / kScanThreads;
+  const int64_t lo = min((int64_t)threadIdx.x * chunk, ntiles), hi = min(lo + chunk, ntiles);
+  int64_t local = 0;
+  for (int64_t i = lo; i < hi; ++i) local += __ldcg(tile_sums + i);
+  int64_t total;
+  int64_t run = pg::block_exclusive_scan(local, total, sh);
+  for (int64_t i = lo; i < hi; ++i) {
+    const int64_t t = __ldcg(tile_sums + i);
+    tile_sums[i] = run;
+    run += t;
+  }
+  if (threadIdx.x == 0) {
+    *total_out = total;
+    *ticket = 0;
+    f.finish(total);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(kScanThreads) scan_pass2(F f, const int64_t* tile_sums) {
+  __shared__ int64_t sh[kScanThreads / 32 + 1];
+  const int64_t n = f.size();
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * kTile + (int64_t)threadIdx.x * kScanItems;
+    int64_t vals[kScanItems];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      vals[k] = (base + k < n) ? f.value(base + k) : 0;
+      s += vals[k];
+    }
+    int64_t total;
+    int64_t excl = pg::block_exclusive_scan(s, total, sh) + tile_sums[tile];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      if (base + k < n) f.emit(base + k, excl, vals[k]);
+      excl += vals[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ seed layer: ordered dedup (first occurrence wins)
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+__global__ void seed_insert_kernel(const int64_t* __restrict__ seeds, int64_t n, int64_t* keys, int* minpos,
+                                   uint64_t mask) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = seeds[i];
+    uint64_t slot = mix64((uint64_t)v) & mask;
+    while (true) {
+      const int64_t old = (int64_t)atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey,
+                                             (unsigned long long)v);
+      if (old == kEmptyKey || old == v) {
+        atomicMin(&minpos[slot], (int)i);
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+}
+
+struct SeedKeep {
+  const int64_t* seeds;
+  int64_t n;
+  const int64_t* keys;
+  const int* minpos;
+  uint64_t mask;
+  int64_t* layer0;
+  __device__ int64_t size() const { return n; }
+  __device__ int64_t value(int64_t i) const {
+    const int64_t v = seeds[i];
+    uint64_t slot = mix64((uint64_t)v) & mask;
+    while (keys[slot] != v) slot = (slot + 1) & mask;
+    return minpos[slot] == (int)i ? 1 : 0;
+  }
+  __device__ void emit(int64_t i, int64_t excl, int64_t val) const {
+    if (val) layer0[excl] = seeds[i];
+  }
+  __device__ void finish(int64_t) const {}
+};
+
+// ------------------------------------------------------------------ per-hop: row counts -> offsets
+struct FrontCount {
+  const int64_t* indptr;
+  const int64_t* front;      // layer h-1
+  const int64_t* n_front;    // device count
+  int64_t cap_front;         // capacity of `front`
+  int64_t fanout;
+  int64_t* row_off;          // [cap_front + 1]
+  __device__ int64_t size() const { return min(*n_front, cap_front); }
+  __device__ int64_t value(int64_t i) const {
+    const int64_t v = front[i];
+    return min(indptr[v + 1] - indptr[v], fanout);
+  }
+  __device__ void emit(int64_t i, int64_t excl, int64_t) const { row_off[i] = excl; }
+  __device__ void finish(int64_t total) const { row_off[size()] = total; }
+};
+
+// ------------------------------------------------------------------ per-hop: pick neighbours (one warp per frontier vertex)
+struct PickArgs {
+  const int64_t* indptr;
+  const int64_t* indices;
+  const int64_t* eids;       // may be null
+  const int64_t* front;
+  const int64_t* n_front;
+  int64_t cap_front;
+  const int64_t* row_off;
+  int64_t fanout;
+  uint32_t hop;
+  uint32_t k0, k1;
+  int64_t* nb_src;           // [cap_edges]
+  int64_t* nb_eid;           // [cap_edges]
+  int64_t cap_edges;
+  uint32_t* bitmap;
+  uint32_t* scratch;         // per-warp accepted lists when m > kSmemPicks
+  int64_t scratch_stride;
+};
+
+__device__ __forceinline__ void emit_edge(const PickArgs& a, int64_t out, int64_t s, int64_t p) {
+  const int64_t u = a.indices[s + p];
+  atomicOr(&a.bitmap[u >> 5], 1u << (u & 31));
+  if (out < a.cap_edges) {
+    a.nb_src[out] = u;
+    a.nb_eid[out] = a.eids ? a.eids[s + p] : s + p;
+  }
+}
+
+__global__ void __launch_bounds__(kPickWarps * 32) pick_kernel(PickArgs a) {
+  __shared__ uint32_t sh_acc[kPickWarps][kSmemPicks];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * kPickWarps + w, nwarps = (int64_t)gridDim.x * kPickWarps;
+  const int64_t n = min(*a.n_front, a.cap_front);
+  const unsigned lt_mask = (1u << lane) - 1;
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const int64_t v = a.front[i];
+    const int64_t s = a.indptr[v], deg = a.indptr[v + 1] - s, k = a.fanout;
+    const int64_t off = a.row_off[i];
+    if (deg <= k) {  // take every in-neighbour, row order
+      for (int64_t p = lane; p < deg; p += 32) emit_edge(a, off + p, s, p);
+      continue;
+    }
+    const bool complement = deg <= 2 * k;
+    const int64_t m = complement ? deg - k : k;
+    uint32_t* acc = (m <= kSmemPicks) ? sh_acc[w] : a.scratch + warp0 * a.scratch_stride;
+    // draws t = 0,1,2,... inserted until m distinct positions (32 draws per round, order preserved)
+    int64_t cnt = 0;
+    for (uint32_t t0 = 0; cnt < m; t0 += 32) {
+      const uint32_t p = (uint32_t)pg::draw_pos(a.k0, a.k1, v, a.hop, t0 + lane, (uint64_t)deg);
+      bool dup = false;
+      for (int64_t j = 0; j < cnt; ++j) dup |= (acc[j] == p);
+      const unsigned peers = __match_any_sync(kFullMask, p);
+      const bool is_new = !dup && ((__ffs(peers) - 1) == lane);
+      const unsigned new_mask = __ballot_sync(kFullMask, is_new);
+      const int64_t slot = cnt + __popc(new_mask & lt_mask);
+      if (is_new && slot < m) acc[slot] = p;
+      cnt = min(m, cnt + (int64_t)__popc(new_mask));
+      __syncwarp();
+    }
+    if (!complement) {
+      // ascending order by rank counting (positions are distinct)
+      for (int64_t j = lane; j < m; j += 32) {
+        const uint32_t p = acc[j];
+        int64_t r = 0;
+        for (int64_t q = 0; q < m; ++q) r += (acc[q] < p);
+        emit_edge(a, off + r, s, (int64_t)p);
+      }
+    } else {
+      // acc holds the excluded positions; keep the complement, ascending
+      int64_t written = 0;
+      for (int64_t base = 0; base < deg; base += 32) {
+        const int64_t p = base + lane;
+        bool keep = p < deg;
+        if (keep)
+          for (int64_t q = 0; q < m; ++q) keep &= (acc[q] != (uint32_t)p);
+        const unsigned km = __ballot_sync(kFullMask, keep);
+        if (keep) emit_edge(a, off + written + __popc(km & lt_mask), s, p);
+        written += __popc(km);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ per-hop: bitmap -> sorted unique layer + ranks
+struct BitCount {
+  const uint32_t* bitmap;
+  int64_t nwords;
+  uint32_t* word_prefix;
+  int64_t* layer;            // [cap]
+  int64_t cap;
+  __device__ int64_t size() const { return nwords; }
+  __device__ int64_t value(int64_t w) const { return __popc(bitmap[w]); }
+  __device__ void emit(int64_t w, int64_t excl, int64_t val) const {
+    word_prefix[w] = (uint32_t)excl;
+    if (!val) return;
+    uint32_t bits = bitmap[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (excl < cap) layer[excl] = w * 32 + b;
+      ++excl;
+    }
+  }
+  __device__ void finish(int64_t) const {}
+};
+
+__global__ void relabel_kernel(int64_t* nb_src, const int64_t* n_edges, int64_t cap_edges,
+                               const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix) {
+  const int64_t n = min(*n_edges, cap_edges);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = nb_src[e];
+    const int64_t w = u >> 5;
+    nb_src[e] = (int64_t)word_prefix[w] + __popc(bitmap[w] & ((1u << (u & 31)) - 1));
+  }
+}
+
+// ------------------------------------------------------------------ assemble the NodeFlow arrays (Appendix A.4)
+struct AssembleArgs {
+  int L;
+  const Counts* counts;
+  const int64_t* layer[PG_MAX_HOPS + 1];
+  const int64_t* nb_src[PG_MAX_HOPS + 1];
+  const int64_t* nb_eid[PG_MAX_HOPS + 1];
+  const int64_t* row_off[PG_MAX_HOPS + 1];
+  int64_t cap_layer[PG_MAX_HOPS + 1];
+  int64_t cap_nodes, cap_edges;
+  pg_nodeflow_buffers out;
+};
+
+__global__ void assemble_kernel(AssembleArgs a) {
+  __shared__ int64_t lay_off[PG_MAX_HOPS + 2], flow_off[PG_MAX_HOPS + 1];
+  __shared__ bool overflow;
+  const int L = a.L;
+  if (threadIdx.x == 0) {
+    bool ovf = false;
+    lay_off[0] = 0;
+    for (int j = 0; j <= L; ++j) {  // NodeFlow layer j = sampling layer L-j
+      const int64_t nl = a.counts->n_layer[L - j];
+      ovf |= nl > a.cap_layer[L - j];
+      lay_off[j + 1] = lay_off[j] + nl;
+    }
+    flow_off[0] = 0;
+    for (int j = 1; j <= L; ++j) flow_off[j] = flow_off[j - 1] + a.counts->e_hop[L - j + 1];
+    ovf |= lay_off[L + 1] > a.cap_nodes || flow_off[L] > a.cap_edges;
+    overflow = ovf;
+    if (blockIdx.x == 0) {
+      int64_t* m = a.out.meta;
+      m[0] = ovf ? PG_ERR_OVERFLOW : PG_OK;
+      m[1] = lay_off[L + 1];
+      m[2] = flow_off[L];
+      m[3] = L + 1;
+      for (int j = 0; j <= L + 1; ++j) m[4 + j] = lay_off[j];
+      for (int j = 0; j <= L; ++j) m[4 + L + 2 + j] = flow_off[j];
+    }
+  }
+  __syncthreads();
+  if (overflow) return;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int j = 0; j <= L; ++j) {
+    const int h = L - j;  // sampling layer
+    const int64_t base = lay_off[j], nl = lay_off[j + 1] - base;
+    const int64_t* lay = a.layer[h];
+    for (int64_t i = tid; i < nl; i += nth) a.out.node_mapping[base + i] = lay[i];
+    if (j == 0) {
+      for (int64_t i = tid; i <= nl; i += nth) a.out.indptr[i] = 0;
+    } else {
+      const int hop = h + 1;  // expansion of sampling layer h produced NodeFlow block j-1
+      const int64_t eb = flow_off[j - 1], ne = flow_off[j] - eb, col_base = lay_off[j - 1];
+      const int64_t* ro = a.row_off[hop];
+      for (int64_t i = tid; i < nl; i += nth) a.out.indptr[base + i + 1] = eb + ro[i + 1];
+      const int64_t* src = a.nb_src[hop];
+      const int64_t* eid = a.nb_eid[hop];
+      for (int64_t e = tid; e < ne; e += nth) {
+        a.out.indices[eb + e] = col_base + src[e];
+        a.out.edge_mapping[eb + e] = eid[e];
+      }
+    }
+  }
+}
+
+__global__ void degree_kernel(const int64_t* __restrict__ indptr, int64_t n, int64_t* out, unsigned long long* max_out) {
+  unsigned long long mx = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t d = indptr[i + 1] - indptr[i];
+    if (out) out[i] = d;
+    mx = max(mx, (unsigned long long)d);
+  }
+  if (max_out) {
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(kFullMask, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_out, mx);
+  }
+}
+
+__global__ void column_count_kernel(const int64_t* __restrict__ indices, int64_t nnz, int64_t* out) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd((unsigned long long*)&out[indices[e]], 1ull);
+}
+
+int grid_for(int64_t items, int per_block, int dev, int waves = 8) {
+  const int64_t need = std::max<int64_t>(1, (items + per_block - 1) / per_block);
+  return (int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev) * waves);
+}
+
+}  // namespace
+
+// ====================================================================== handles
+struct pg_graph {
+  int dev = 0;
+  int64_t num_nodes = 0, num_edges = 0, max_in_degree = 0;
+  const int64_t* indptr = nullptr;
+  const int64_t* indices = nullptr;
+  const int64_t* eids = nullptr;
+  bool owned = false;
+};
+
+struct pg_sampler {
+  pg_graph* g = nullptr;
+  int L = 0;
+  int64_t fanouts[PG_MAX_HOPS] = {0};
+  uint64_t seed = 0;
+  int64_t max_seeds = 0, cap_nodes = 0, cap_edges = 0;
+  int64_t nwords = 0;
+  // workspace (device)
+  uint32_t* bitmap = nullptr;
+  uint32_t* word_prefix = nullptr;
+  int64_t* tile_sums = nullptr;
+  unsigned* ticket = nullptr;
+  Counts* counts = nullptr;
+  int64_t* hash_keys = nullptr;
+  int* hash_minpos = nullptr;
+  uint64_t hash_mask = 0;
+  int64_t* layer[PG_MAX_HOPS + 1] = {nullptr};
+  int64_t cap_layer[PG_MAX_HOPS + 1] = {0};
+  int64_t* nb_src[PG_MAX_HOPS + 1] = {nullptr};
+  int64_t* nb_eid[PG_MAX_HOPS + 1] = {nullptr};
+  int64_t* row_off[PG_MAX_HOPS + 1] = {nullptr};
+  uint32_t* scratch = nullptr;
+  int64_t scratch_stride = 0;
+  int pick_grid = 0;
+  std::vector<void*> allocs;
+};
+
+// Host copy of the minibatch-key derivation (oracle/pg_oracle.cpp minibatch_key).
+static void minibatch_key(uint64_t seed, int64_t epoch, int64_t batch, uint32_t* k0, uint32_t* k1) {
+  const pg::Philox4 r = pg::philox4x32_10((uint32_t)(uint64_t)epoch, (uint32_t)((uint64_t)epoch >> 32),
+                                          (uint32_t)(uint64_t)batch, (uint32_t)((uint64_t)batch >> 32),
+                                          (uint32_t)seed, (uint32_t)(seed >> 32));
+  *k0 = r.c[0];
+  *k1 = r.c[1];
+}
+
+static pg_status graph_finish(pg_graph* g) {
+  unsigned long long* d_max = nullptr;
+  PG_CUDA(cudaMalloc(&d_max, sizeof(*d_max)));
+  PG_CUDA(cudaMemset(d_max, 0, sizeof(*d_max)));
+  if (g->num_nodes > 0) {
+    degree_kernel<<<grid_for(g->num_nodes, 256, g->dev), 256>>>(g->indptr, g->num_nodes, nullptr, d_max);
+    PG_CHECK_LAUNCH();
+  }
+  unsigned long long mx = 0;
+  PG_CUDA(cudaMemcpy(&mx, d_max, sizeof(mx), cudaMemcpyDeviceToHost));
+  cudaFree(d_max);
+  g->max_in_degree = (int64_t)mx;
+  PG_REQUIRE(mx < (1ull << 32), "in-degree >= 2^32 is not supported");
+  return PG_OK;
+}
+
+extern "C" {
+
+pg_status pg_graph_create(const int64_t* indptr, const int64_t* indices, const int64_t* eids, int64_t num_nodes,
+                          int64_t num_edges, int dev, pg_graph** out) {
+  PG_REQUIRE(out && indptr && (indices || num_edges == 0) && num_nodes >= 0 && num_edges >= 0,
+             "pg_graph_create: bad arguments");
+  PG_REQUIRE(indptr[0] == 0 && indptr[num_nodes] == num_edges, "pg_graph_create: indptr does not span [0, num_edges]");
+  pg::DeviceGuard guard(dev);
+  pg_graph* g = new pg_graph;
+  g->dev = dev;
+  g->num_nodes = num_nodes;
+  g->num_edges = num_edges;
+  g->owned = true;
+  int64_t *d_ip = nullptr, *d_ix = nullptr, *d_e = nullptr;
+  const size_t eb = (size_t)std::max<int64_t>(num_edges, 1) * sizeof(int64_t);
+  if (cudaMalloc(&d_ip, (size_t)(num_nodes + 1) * sizeof(int64_t)) != cudaSuccess ||
+      cudaMalloc(&d_ix, eb) != cudaSuccess || (eids && cudaMalloc(&d_e, eb) != cudaSuccess)) {
+    cudaFree(d_ip); cudaFree(d_ix); cudaFree(d_e);
+    delete g;
+    pg::set_error("pg_graph_create: out of device memory (%lld nodes, %lld edges)", (long long)num_nodes,
+                  (long long)num_edges);
+    cudaGetLastError();
+    return PG_ERR_NOMEM;
+  }
+  g->indptr = d_ip; g->indices = d_ix; g->eids = d_e;
+  pg_status st = PG_OK;
+  auto fail = [&](pg_status s) { pg_graph_destroy(g); return s; };
+  if (cudaMemcpy(d_ip, indptr, (size_t)(num_nodes + 1) * sizeof(int64_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+      (num_edges && cudaMemcpy(d_ix, indices, (size_t)num_edges * sizeof(int64_t), cudaMemcpyHostToDevice) != cudaSuccess) ||
+      (num_edges && eids && cudaMemcpy(d_e, eids, (size_t)num_edges * sizeof(int64_t), cudaMemcpyHostToDevice) != cudaSuccess)) {
+    pg::set_error("pg_graph_create: host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(PG_ERR_CUDA);
+  }
+  if ((st = graph_finish(g)) != PG_OK) return fail(st);
+  *out = g;
+  return PG_OK;
+}
+
+pg_status pg_graph_create_device(const int64_t* d_indptr, const int64_t* d_indices, const int64_t* d_eids,
+                                 int64_t num_nodes, int64_t num_edges, int dev, pg_graph** out) {
+  PG_REQUIRE(out && d_indptr && (d_indices || num_edges == 0) && num_nodes >= 0 && num_edges >= 0,
+             "pg_graph_create_device: bad arguments");
+  pg::DeviceGuard guard(dev);
+  pg_graph* g = new pg_graph;
+  g->dev = dev;
+  g->num_nodes = num_nodes;
+  g->num_edges = num_edges;
+  g->indptr = d_indptr; g->indices = d_indices; g->eids = d_eids;
+  g->owned = false;
+  pg_status st = graph_finish(g);
+  if (st != PG_OK) { delete g; return st; }
+  *out = g;
+  return PG_OK;
+}
+
+void pg_graph_destroy(pg_graph* g) {
+  if (!g) return;
+  if (g->owned) {
+    pg::DeviceGuard guard(g->dev);
+    cudaFree((void*)g->indptr);
+    cudaFree((void*)g->indices);
+    cudaFree((void*)g->eids);
+  }
+  delete g;
+}
+
+pg_status pg_graph_degrees(pg_graph* g, int in_edges, int64_t* d_out, void* stream) {
+  PG_REQUIRE(g && d_out, "pg_graph_degrees: bad arguments");
+  pg::DeviceGuard guard(g->dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->num_nodes == 0) return PG_OK;
+  if (in_edges) {
+    degree_kernel<<<grid_for(g->num_nodes, 256, g->dev), 256, 0, st>>>(g->indptr, g->num_nodes, d_out, nullptr);
+    PG_CHECK_LAUNCH();
+  } else {
+    PG_CUDA(cudaMemsetAsync(d_out, 0, (size_t)g->num_nodes * sizeof(int64_t), st));
+    if (g->num_edges) {
+      column_count_kernel<<<grid_for(g->num_edges, 256, g->dev), 256, 0, st>>>(g->indices, g->num_edges, d_out);
+      PG_CHECK_LAUNCH();
+    }
+  }
+  return PG_OK;
+}
+
+pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, uint64_t seed, int64_t max_seeds,
+                            int64_t cap_nodes, int64_t cap_edges, pg_sampler** out) {
+  PG_REQUIRE(g && out && fanouts, "pg_sampler_create: bad arguments");
+  PG_REQUIRE(num_hops >= 1 && num_hops <= PG_MAX_HOPS, "pg_sampler_create: num_hops must be in [1, PG_MAX_HOPS]");
+  PG_REQUIRE(max_seeds >= 1 && max_seeds < INT_MAX && cap_nodes >= max_seeds && cap_edges >= 1,
+             "pg_sampler_create: bad capacities");
+  for (int h = 0; h < num_hops; ++h) PG_REQUIRE(fanouts[h] >= 1, "pg_sampler_create: fanout must be >= 1");
+  pg::DeviceGuard guard(g->dev);
+  pg_sampler* s = new pg_sampler;
+  s->g = g;
+  s->L = num_hops;
+  s->seed = seed;
+  s->max_seeds = max_seeds;
+  s->cap_nodes = cap_nodes;
+  s->cap_edges = cap_edges;
+  s->nwords = (g->num_nodes + 31) / 32;
+  int64_t max_m = 0;
+  for (int h = 0; h < num_hops; ++h) {
+    s->fanouts[h] = fanouts[h];
+    if (fanouts[h] < g->max_in_degree) max_m = std::max(max_m, std::min(fanouts[h], g->max_in_degree - fanouts[h]));
+  }
+  s->pick_grid = pg::sm_count(g->dev) * 8;
+  bool ok = true;
+  auto alloc = [&](auto** p, size_t count) {
+    using T = std::remove_pointer_t<std::remove_pointer_t<decltype(p)>>;
+    if (!ok) return;
+    void* q = nullptr;
+    if (cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) { ok = false; cudaGetLastError(); return; }
+    s->allocs.push_back(q);
+    *p = (T*)q;
+  };
+  alloc(&s->bitmap, (size_t)s->nwords + 1);
+  alloc(&s->word_prefix, (size_t)s->nwords + 1);
+  const int64_t max_items = std::max<int64_t>(std::max(s->nwords, cap_nodes), max_seeds);
+  alloc(&s->tile_sums, (size_t)((max_items + kTile - 1) / kTile + 1));
+  alloc(&s->ticket, 1);
+  alloc(&s->counts, 1);
+  uint64_t tsize = 64;
+  while (tsize < (uint64_t)max_seeds * 2) tsize <<= 1;
+  s->hash_mask = tsize - 1;
+  alloc(&s->hash_keys, tsize);
+  alloc(&s->hash_minpos, tsize);
+  for (int h = 0; h <= num_hops; ++h) {
+    s->cap_layer[h] = (h == 0) ? max_seeds : cap_nodes;
+    alloc(&s->layer[h], (size_t)s->cap_layer[h]);
+    if (h >= 1) {
+      alloc(&s->nb_src[h], (size_t)cap_edges);
+      alloc(&s->nb_eid[h], (size_t)cap_edges);
+      alloc(&s->row_off[h], (size_t)s->cap_layer[h - 1] + 1);
+    }
+  }
+  if (max_m > kSmemPicks) {
+    s->scratch_stride = max_m;
+    alloc(&s->scratch, (size_t)s->pick_grid * kPickWarps * (size_t)max_m);
+  }
+  if (!ok) {
+    pg_sampler_destroy(s);
+    pg::set_error("pg_sampler_create: out of device memory (cap_nodes=%lld cap_edges=%lld)", (long long)cap_nodes,
+                  (long long)cap_edges);
+    return PG_ERR_NOMEM;
+  }
+  PG_CUDA(cudaMemset(s->ticket, 0, sizeof(unsigned)));
+  *out = s;
+  return PG_OK;
+}
+
+void pg_sampler_destroy(pg_sampler* s) {
+  if (!s) return;
+  pg::DeviceGuard guard(s->g->dev);
+  for (void* p : s->allocs) cudaFree(p);
+  delete s;
+}
+
+pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int64_t epoch, int64_t batch,
+                    const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream) {
+  PG_REQUIRE(s && out && out->node_mapping && out->indptr && out->indices && out->edge_mapping && out->meta,
+             "pg_sample: null output buffer");
+  PG_REQUIRE(n_seeds >= 0 && n_seeds <= s->max_seeds, "pg_sample: n_seeds exceeds max_seeds");
+  PG_REQUIRE(d_seeds || n_seeds == 0, "pg_sample: null seeds");
+  pg_graph* g = s->g;
+  pg::DeviceGuard guard(g->dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dev = g->dev;
+  uint32_t k0, k1;
+  minibatch_key(s->seed, epoch, batch, &k0, &k1);
+
+  PG_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(Counts), st));
+  // ---- seed layer
+  if (n_seeds > 0) {
+    PG_CUDA(cudaMemsetAsync(s->hash_keys, 0xFF, (s->hash_mask + 1) * sizeof(int64_t), st));
+    PG_CUDA(cudaMemsetAsync(s->hash_minpos, 0x7F, (s->hash_mask + 1) * sizeof(int), st));
+    seed_insert_kernel<<<grid_for(n_seeds, 256, dev), 256, 0, st>>>(d_seeds, n_seeds, s->hash_keys, s->hash_minpos,
+                                                                    s->hash_mask);
+    PG_CHECK_LAUNCH();
+    SeedKeep f{d_seeds, n_seeds, s->hash_keys, s->hash_minpos, s->hash_mask, s->layer[0]};
+    const int grid = grid_for(n_seeds, kTile, dev);
+    scan_pass1<<<grid, kScanThreads, 0, st>>>(f, s->tile_sums, s->ticket, &s->counts->n_layer[0]);
+    PG_CHECK_LAUNCH();
+    scan_pass2<<<grid, kScanThreads, 0, st>>>(f, s->tile_sums);
+    PG_CHECK_LAUNCH();
+  }
+  // ---- hops
+  for (int h = 1; h <= s->L; ++h) {
+    const int64_t cap_front = s->cap_layer[h - 1];
+    PG_CUDA(cudaMemsetAsync(s->bitmap, 0, (size_t)(s->nwords + 1) * sizeof(uint32_t), st));
+    FrontCount fc{g->indptr, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->fanouts[h - 1], s->row_off[h]};
+    const int grid_f = grid_for(cap_front, kTile, dev);
+    scan_pass1<<<grid_f, kScanThreads, 0, st>>>(fc, s->tile_sums, s->ticket, &s->counts->e_hop[h]);
+    PG_CHECK_LAUNCH();
+    scan_pass2<<<grid_f, kScanThreads, 0, st>>>(fc, s->tile_sums);
+    PG_CHECK_LAUNCH();
+    PickArgs pa{g->indptr, g->indices, g->eids, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->row_off[h],
+                s->fanouts[h - 1], (uint32_t)h, k0, k1, s->nb_src[h], s->nb_eid[h], s->cap_edges, s->bitmap,
+                s->scratch, s->scratch_stride};
+    const int grid_p = (int)std::min<int64_t>(s->pick_grid, std::max<int64_t>(1, (cap_front + kPickWarps - 1) / kPickWarps));
+    pick_kernel<<<grid_p, kPickWarps * 32, 0, st>>>(pa);
+    PG_CHECK_LAUNCH();
+    BitCount bc{s->bitmap, s->nwords, s->word_prefix, s->layer[h], s->cap_layer[h]};
+    const int grid_b = grid_for(s->nwords, kTile, dev);
+    scan_pass1<<<grid_b, kScanThreads, 0, st>>>(bc, s->tile_sums, s->ticket, &s->counts->n_layer[h]);
+    PG_CHECK_LAUNCH();
+    scan_pass2<<<grid_b, kScanThreads, 0, st>>>(bc, s->tile_sums);
+    PG_CHECK_LAUNCH();
+    relabel_kernel<<<grid_for(s->cap_edges, 256, dev), 256, 0, st>>>(s->nb_src[h], &s->counts->e_hop[h], s->cap_edges,
+                                                                     s->bitmap, s->word_prefix);
+    PG_CHECK_LAUNCH();
+  }
+  // ---- assemble
+  AssembleArgs aa;
+  aa.L = s->L;
+  aa.counts = s->counts;
+  for (int h = 0; h <= PG_MAX_HOPS; ++h) {
+    aa.layer[h] = s->layer[h];
+    aa.nb_src[h] = s->nb_src[h];
+    aa.nb_eid[h] = s->nb_eid[h];
+    aa.row_off[h] = s->row_off[h];
+    aa.cap_layer[h] = s->cap_layer[h];
+  }
+  aa.cap_nodes = s->cap_nodes;
+  aa.cap_edges = s->cap_edges;
+  aa.out = *out;
+  assemble_kernel<<<grid_for(s->cap_nodes + s->cap_edges, 256, dev, 4), 256, 0, st>>>(aa);
+  PG_CHECK_LAUNCH();
+  if (h_meta) PG_CUDA(cudaMemcpyAsync(h_meta, out->meta, PG_META_LEN * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  return PG_OK;
+}
+
+}  // extern "C"

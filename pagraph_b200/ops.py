@@ -1,0 +1,55 @@
+"""Autograd wrapper of the CUDA block aggregation (pg_aggregate_fwd / pg_aggregate_bwd)."""
+import torch
+
+from . import _lib
+
+_MODES = {"sum": _lib.PG_AGG_SUM, "mean": _lib.PG_AGG_MEAN}
+
+
+def aggregate_forward(indptr, cols, col_base, src, n_dst, mode, norm=None, out=None):
+    """dst[r] = reduce_{e in row r} src[cols[e] - col_base]; fp32 CUDA only.
+
+    indptr: int64 CUDA tensor with >= n_dst + 1 entries of absolute offsets into `cols`."""
+    if not (src.is_cuda and src.dtype == torch.float32):
+        raise _lib.PGError("aggregate: expected a float32 CUDA tensor (no CPU path)")
+    if src.stride(-1) != 1:
+        src = src.contiguous()
+    dim = src.shape[1]
+    if out is None:
+        out = torch.empty((n_dst, dim), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().pg_aggregate_fwd(_lib.ptr(indptr), _lib.ptr(cols), col_base, _lib.ptr(src),
+                                               src.stride(0), _lib.ptr(out), out.stride(0), n_dst, dim,
+                                               _MODES[mode], _lib.ptr(norm), _lib.stream_ptr()),
+                   "pg_aggregate_fwd")
+    return out
+
+
+def aggregate_backward(indptr, cols, col_base, grad_dst, n_src, mode, norm=None):
+    if grad_dst.stride(-1) != 1:
+        grad_dst = grad_dst.contiguous()
+    n_dst, dim = grad_dst.shape
+    grad_src = torch.empty((n_src, dim), dtype=torch.float32, device=grad_dst.device)
+    with torch.cuda.device(grad_dst.device):
+        _lib.check(_lib.lib().pg_aggregate_bwd(_lib.ptr(indptr), _lib.ptr(cols), col_base, _lib.ptr(grad_dst),
+                                               grad_dst.stride(0), _lib.ptr(grad_src), grad_src.stride(0), n_dst,
+                                               n_src, dim, _MODES[mode], _lib.ptr(norm), _lib.stream_ptr()),
+                   "pg_aggregate_bwd")
+    return grad_src
+
+
+class BlockAggregate(torch.autograd.Function):
+    """copy_src + sum/mean over one NodeFlow block."""
+
+    @staticmethod
+    def forward(ctx, src, indptr, cols, col_base, n_dst, mode):
+        ctx.block = (indptr, cols, col_base, mode, src.shape[0])
+        return aggregate_forward(indptr, cols, col_base, src, n_dst, mode)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        indptr, cols, col_base, mode, n_src = ctx.block
+        grad_src = None
+        if ctx.needs_input_grad[0]:
+            grad_src = aggregate_backward(indptr, cols, col_base, grad_out, n_src, mode)
+        return grad_src, None, None, None, None, None

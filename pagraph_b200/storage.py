@@ -1,0 +1,273 @@
+"""GraphCacheServer — drop-in for PaGraph/storage/storage.py:18-227 on the B200 path.
+
+Same constructor, methods, attributes and error behaviour as the reference class; the work behind
+them is the CUDA library (pg_cache_*): one split kernel + one HBM-cache gather + one TMA fetch of
+missed rows straight from the pinned host table, for all NodeFlow layers in one call, with no host
+synchronisation (the reference: ~10 torch kernels and >= 3 syncs per layer, CPU gather of misses).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .nodeflow import Frame, FrameRef
+
+_REGISTERED = {}   # data_ptr -> nbytes of host tables this process pinned with pg_host_register
+
+
+def _ensure_device_visible(t):
+    """Make a CPU feature table readable by the GPU (page-locked + mapped)."""
+    if t.is_pinned():
+        return
+    key = t.data_ptr()
+    nbytes = t.untyped_storage().nbytes() - (t.data_ptr() - t.untyped_storage().data_ptr())
+    if key in _REGISTERED and _REGISTERED[key] >= nbytes:
+        return
+    _lib.check(_lib.lib().pg_host_register(ctypes.c_void_p(key), nbytes), "pg_host_register")
+    _REGISTERED[key] = nbytes
+
+
+class GraphCacheServer:
+    """
+    Manage graph features: fetch the feature tensors of a NodeFlow from the GPU cache or from the
+    host feature store (reference: PaGraph/storage/storage.py).
+    """
+
+    def __init__(self, graph, node_num, nid_map, gpuid):
+        """
+        graph:    feature store client exposing graph._node_frame._frame[name].data -> CPU tensor
+                  [V, dim] indexed by full-graph id (storage.py:128)
+        node_num: number of nodes of the local (sub-)graph
+        nid_map:  LongTensor[node_num], local id -> full-graph id
+        """
+        self.graph = graph
+        self.gpuid = gpuid
+        self.node_num = node_num
+        dev = torch.device("cuda", gpuid)
+        self._dev = dev
+        self.nid_map = nid_map.clone().detach().to(dev, torch.int64).contiguous()
+        self.nid_map.requires_grad_(False)
+        self.gpu_flag = torch.zeros(self.node_num, dtype=torch.bool, device=dev)
+        self.cached_num = 0
+        self.capability = node_num
+        self.full_cached = False
+        self.dims = {}
+        self.total_dim = 0
+        self.gpu_fix_cache = dict()
+        self.localid2cacheid = torch.zeros(node_num, dtype=torch.int64, device=dev)
+        self.log = False
+        self._counts = torch.zeros(2, dtype=torch.int64, device=dev)   # (tries, misses) on device
+        self._try_base = 0
+        self._miss_base = 0
+        self._handle = None
+        self._field_names = []
+        self._host_tables = {}
+        self.fetch_mode = 0            # 0 auto, 1 plain loads, 2 TMA bulk (pg_cache_fetch `mode`)
+        self.last_hit_mask = None      # bool[N] of the most recent fetch_data when keep_hit_mask
+        self.keep_hit_mask = False
+
+    # ---- logging counters (storage.py:54-56,219-227); kept on the device, read lazily
+    @property
+    def try_num(self):
+        return self._try_base + int(self._counts[0].item())
+
+    @try_num.setter
+    def try_num(self, v):
+        self._try_base = v - int(self._counts[0].item())
+
+    @property
+    def miss_num(self):
+        return self._miss_base + int(self._counts[1].item())
+
+    @miss_num.setter
+    def miss_num(self, v):
+        self._miss_base = v - int(self._counts[1].item())
+
+    def log_miss_rate(self, miss_num, total_num):
+        self._try_base += total_num
+        self._miss_base += miss_num
+
+    def get_miss_rate(self):
+        tries, misses = self.try_num, self.miss_num
+        miss_rate = float(misses) / tries   # ZeroDivisionError when nothing was logged, as the reference
+        self._counts.zero_()
+        self._try_base = 0
+        self._miss_base = 0
+        return miss_rate
+
+    # ---- handle
+    def _table(self, name):
+        return self.graph._node_frame._frame[name].data
+
+    def _make_handle(self, embed_names):
+        if self._handle is not None:
+            _lib.lib().pg_cache_destroy(self._handle)
+            self._handle = None
+        if len(embed_names) > _lib.PG_MAX_FIELDS:
+            raise ValueError("at most %d feature fields are supported" % _lib.PG_MAX_FIELDS)
+        fields = (_lib.pg_field * len(embed_names))()
+        self._host_tables = {}
+        for i, name in enumerate(embed_names):
+            t = self._table(name)
+            if t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+                raise TypeError("feature table %r must be a CPU float32 [V, dim] tensor with unit inner stride" % name)
+            _ensure_device_visible(t)
+            self._host_tables[name] = t
+            fields[i].dim = t.shape[1]
+            fields[i].host_stride = t.stride(0)
+            fields[i].host_table = t.data_ptr()
+        h = ctypes.c_void_p()
+        flag_u8 = self.gpu_flag.view(torch.uint8)
+        _lib.check(_lib.lib().pg_cache_create(self.node_num, _lib.ptr(flag_u8), _lib.ptr(self.localid2cacheid),
+                                              _lib.ptr(self.nid_map), len(embed_names), fields, self.gpuid,
+                                              ctypes.byref(h)), "pg_cache_create")
+        self._handle = h
+        self._field_names = list(embed_names)
+
+    def _out_ptrs(self, tensors):
+        return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    # ---- reference API
+    def init_field(self, embed_names):
+        self._make_handle(embed_names)
+        self.total_dim = 0
+        for name in embed_names:
+            self.dims[name] = self._table(name).size(1)
+            self.total_dim += self.dims[name]
+        print('total dims: {}'.format(self.total_dim))
+
+    def auto_cache(self, dgl_g, embed_names, capability=None):
+        """
+        Cache node features on the GPU (storage.py:70-104): capacity from the free HBM, then the
+        top-`capability` out-degree nodes of the local graph — order (-out_degree, node id).
+        `capability=` (extension) overrides the memory-derived capacity.
+        """
+        if self._field_names != list(embed_names):
+            self._make_handle(embed_names)
+            self.total_dim = sum(self._table(n).size(1) for n in embed_names)
+            for n in embed_names:
+                self.dims[n] = self._table(n).size(1)
+        peak_allocated_mem = torch.cuda.max_memory_allocated(device=self.gpuid)
+        peak_cached_mem = torch.cuda.max_memory_reserved(device=self.gpuid)
+        total_mem = torch.cuda.get_device_properties(self.gpuid).total_memory
+        available = total_mem - peak_allocated_mem - peak_cached_mem - 1024 * 1024 * 1024
+        self.capability = int(available / (self.total_dim * 4)) if capability is None else int(capability)
+        print('Cache Memory: {:.2f}G. Capability: {}'.format(available / 1024 / 1024 / 1024, self.capability))
+        if self.capability >= self.node_num:
+            print('cache the full graph...')
+            nids = torch.arange(self.node_num, device=self._dev)
+            self._fill(nids, is_full=True)
+        else:
+            print('cache the part of graph... caching percentage: {:.4f}'.format(self.capability / self.node_num))
+            out_degrees = dgl_g.out_degrees().to(self._dev)
+            sort_nid = torch.sort(out_degrees, descending=True, stable=True).indices
+            self._fill(sort_nid[:max(self.capability, 0)].contiguous(), is_full=False)
+
+    def _fill(self, nids, is_full):
+        """cache_fix_data with the rows pulled from the pinned host table by the GPU itself."""
+        rows = nids.size(0)
+        tables = [torch.empty((rows, self.dims[n]), dtype=torch.float32, device=self._dev) for n in self._field_names]
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.lib().pg_cache_fill(self._handle, _lib.ptr(nids), rows, int(is_full),
+                                                self._out_ptrs(tables), 1, _lib.stream_ptr()), "pg_cache_fill")
+        for n, t in zip(self._field_names, tables):
+            self.gpu_fix_cache[n] = t
+        self._keep_nids = nids
+        self.cached_num = rows
+        self.full_cached = is_full
+
+    def get_feat_from_server(self, nids, embed_names, to_gpu=False):
+        """
+        Fetch features of local ids `nids` from the host store (storage.py:107-132).
+        to_gpu=False returns CPU tensors (host gather, as the reference); to_gpu=True lets the GPU
+        read the rows directly from pinned host memory.
+        """
+        if to_gpu and list(embed_names) == self._field_names:
+            nids = nids.to(self._dev).contiguous()
+            outs = [torch.empty((nids.numel(), self.dims[n]), dtype=torch.float32, device=self._dev)
+                    for n in embed_names]
+            with torch.cuda.device(self._dev):
+                _lib.check(_lib.lib().pg_cache_fetch_host(self._handle, _lib.ptr(nids), nids.numel(),
+                                                          self._out_ptrs(outs), _lib.stream_ptr()),
+                           "pg_cache_fetch_host")
+            return dict(zip(embed_names, outs))
+        nids_in_full = self.nid_map[nids.to(self._dev)].cpu()
+        frame = {name: self._table(name)[nids_in_full] for name in embed_names}
+        if to_gpu:
+            frame = {k: v.to(self._dev, non_blocking=True) for k, v in frame.items()}
+        return frame
+
+    def cache_fix_data(self, nids, data, is_full=False):
+        """
+        Install caller-provided rows as the GPU cache (storage.py:135-154).
+        nids: local ids (on the GPU); data: {'field name': tensor [len(nids), dim]}
+        """
+        rows = nids.size(0)
+        nids = nids.to(self._dev).contiguous()
+        for name in data:
+            data_rows = data[name].size(0)
+            assert (rows == data_rows)
+            self.dims[name] = data[name].size(1)
+            self.gpu_fix_cache[name] = data[name].to(self._dev, torch.float32).contiguous()
+        if self._handle is None or self._field_names != list(data):
+            self._make_handle(list(data))
+        tables = [self.gpu_fix_cache[n] for n in self._field_names]
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.lib().pg_cache_fill(self._handle, _lib.ptr(nids), rows, int(is_full),
+                                                self._out_ptrs(tables), 0, _lib.stream_ptr()), "pg_cache_fill")
+        self._keep_nids = nids
+        self.cached_num = rows
+        self.full_cached = is_full
+
+    def fetch_data(self, nodeflow):
+        """
+        Fill nodeflow._node_frames[i] for every layer from the GPU cache / host store
+        (storage.py:157-204; fully cached -> fetch_from_cache). One library call for all layers.
+        """
+        if self._handle is None:
+            raise RuntimeError("fetch_data before init_field")
+        offsets = nodeflow._layer_offsets
+        ids = nodeflow._node_mapping.tousertensor()
+        if not ids.is_cuda:
+            ids = ids.to(self._dev)
+        n = offsets[nodeflow.num_layers]
+        outs = [torch.empty((n, self.dims[name]), dtype=torch.float32, device=self._dev)
+                for name in self._field_names]
+        mask = None
+        if self.keep_hit_mask:
+            mask = torch.empty(n, dtype=torch.bool, device=self._dev)
+        counts = self._counts if (self.log and not self.full_cached) else None
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.lib().pg_cache_fetch(self._handle, _lib.ptr(ids), n, self._out_ptrs(outs),
+                                                 None if mask is None else ctypes.c_void_p(mask.data_ptr()),
+                                                 _lib.ptr(counts), self.fetch_mode, _lib.stream_ptr()),
+                       "pg_cache_fetch")
+        self.last_hit_mask = mask
+        for i in range(nodeflow.num_layers):
+            lo, hi = offsets[i], offsets[i + 1]
+            frame = {name: out[lo:hi] for name, out in zip(self._field_names, outs)}
+            nodeflow._node_frames[i] = FrameRef(Frame(frame))
+
+    def fetch_from_cache(self, nodeflow):
+        """Fully-cached fast path (storage.py:207-216)."""
+        if not self.full_cached:
+            raise RuntimeError("fetch_from_cache requires a fully cached graph")
+        self.fetch_data(nodeflow)
+
+    # ---- measurement hooks (not in the reference)
+    def set_timing(self, enabled):
+        _lib.check(_lib.lib().pg_cache_set_timing(self._handle, int(enabled)), "pg_cache_set_timing")
+
+    def last_timing(self):
+        """(split_ms, hit_ms, miss_ms) of the most recent timed fetch_data. Synchronises."""
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        _lib.check(_lib.lib().pg_cache_last_timing(self._handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+                   "pg_cache_last_timing")
+        return a.value, b.value, c.value
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.lib().pg_cache_destroy(self._handle)
+        except Exception:
+            pass
