@@ -133,10 +133,6 @@ pg_status pg_cache_fetch_host(pg_cache* c, const int64_t* d_nids, int64_t n, flo
  * aligned rows). */
 pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out,
                          uint8_t* d_hit_mask, int64_t* d_counts, int mode, void* stream);
-/* Elapsed ms of the hit and miss kernels of the most recent pg_cache_fetch with timing enabled. SYNC. */
-pg_status pg_cache_set_timing(pg_cache* c, int enabled);
-pg_status pg_cache_last_timing(pg_cache* c, float* ms_split, float* ms_hit, float* ms_miss);
-
 /* ---------------------------------------------------------------- aggregation (replaces nf.block_compute(i, fn.copy_src,
  * fn.sum|fn.mean, ...), PaGraph/model/gcn_nssc.py:71-74, graphsage_nssc.py:98-106; and, run over
  * the full graph with mode=PG_AGG_SUM + norm, the server-side --preprocess fold, server/pa_server.py:45-52).
@@ -156,6 +152,20 @@ pg_status pg_aggregate_bwd(const int64_t* d_indptr, const int64_t* d_cols, int64
 /* ---------------------------------------------------------------- measurement helpers */
 /* Pinned H2D copy bandwidth probe (the PCIe roofline denominator). SYNC. */
 pg_status pg_measure_h2d(int dev, size_t bytes, int iters, double* gb_per_s);
+/* Live kernel timing for the roofline numbers: while enabled, every kernel class below brackets its
+ * launches with a CUDA-event pair on the launching stream. pg_timing_drain (SYNC) returns the
+ * records made since the previous drain, in launch order: slots[i] = class, ms[i] = duration. */
+enum {
+  PG_T_SAMPLE = 0,      /* all kernels of one pg_sample call            */
+  PG_T_SPLIT = 1,       /* hit/miss split of one pg_cache_fetch         */
+  PG_T_GATHER_HIT = 2,  /* HBM-cache row gather                         */
+  PG_T_GATHER_MISS = 3, /* pinned-host row fetch (runs on a side stream) */
+  PG_T_AGG_FWD = 4,
+  PG_T_AGG_BWD = 5,
+  PG_T_FUSED = 6        /* fused cache-lookup + aggregation (pg_cache_aggregate) */
+};
+pg_status pg_timing_enable(int enabled);
+pg_status pg_timing_drain(int32_t* slots, float* ms, int64_t cap, int64_t* n_out);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t pg_launch_count(void);
 

@@ -57,15 +57,15 @@ SIGNATURES = {
     "pg_cache_fetch_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),
     "pg_cache_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp, c_vp,
                                       ctypes.c_int, c_vp]),
-    "pg_cache_set_timing": (ctypes.c_int, [c_vp, ctypes.c_int]),
-    "pg_cache_last_timing": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float),
-                                            ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "pg_aggregate_fwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
     "pg_aggregate_bwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
     "pg_measure_h2d": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_double)]),
+    "pg_timing_enable": (ctypes.c_int, [ctypes.c_int]),
+    "pg_timing_drain": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float),
+                                       ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "pg_launch_count": (ctypes.c_int64, []),
 }
 
@@ -112,6 +112,22 @@ def stream_ptr(stream=None):
     import torch
     s = stream if stream is not None else torch.cuda.current_stream()
     return ctypes.c_void_p(s.cuda_stream)
+
+
+T_SAMPLE, T_SPLIT, T_GATHER_HIT, T_GATHER_MISS, T_AGG_FWD, T_AGG_BWD, T_FUSED = range(7)
+
+
+def timing_enable(on):
+    check(lib().pg_timing_enable(int(on)), "pg_timing_enable")
+
+
+def timing_drain(cap=1 << 16):
+    """[(slot, ms)] of every timed launch since the previous drain, in launch order. Synchronises."""
+    slots = (ctypes.c_int32 * cap)()
+    ms = (ctypes.c_float * cap)()
+    n = ctypes.c_int64()
+    check(lib().pg_timing_drain(slots, ms, cap, ctypes.byref(n)), "pg_timing_drain")
+    return [(slots[i], ms[i]) for i in range(n.value)]
 
 
 def launch_count():

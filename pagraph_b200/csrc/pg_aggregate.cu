@@ -194,6 +194,7 @@ pg_status pg_aggregate_fwd(const int64_t* d_indptr, const int64_t* d_cols, int64
   AggArgs a{d_indptr, d_cols, col_base, d_src, src_stride, d_dst, dst_stride, n_dst, dim, mode, d_norm};
   const bool vec4 = (dim % 4 == 0) && (src_stride % 4 == 0) && (dst_stride % 4 == 0) &&
                     (((uintptr_t)d_src | (uintptr_t)d_dst) % 16 == 0);
+  pg::TimedScope timed(PG_T_AGG_FWD, st);
   if (vec4) {
     const int nvec = dim / 4;
     if (nvec <= 8) launch_fwd<8, 1>(a, dev, st);
@@ -220,6 +221,7 @@ pg_status pg_aggregate_bwd(const int64_t* d_indptr, const int64_t* d_cols, int64
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));
   cudaStream_t st = (cudaStream_t)stream;
+  pg::TimedScope timed(PG_T_AGG_BWD, st);
   if (n_src > 0) {
     if (gsrc_stride == dim) {
       PG_CUDA(cudaMemsetAsync(d_grad_src, 0, (size_t)n_src * dim * sizeof(float), st));

@@ -49,6 +49,23 @@ struct DeviceGuard {
 
 int sm_count(int dev);
 
+// Live per-launch timing (pg_timing_* in the header): a TimedScope brackets the launches of one
+// kernel class with a CUDA-event pair on the launching stream when timing is enabled; it costs
+// nothing otherwise.
+bool timing_enabled();
+void timing_begin(int slot, cudaStream_t st, int* token);
+void timing_end(int token, cudaStream_t st);
+struct TimedScope {
+  int token = -1;
+  cudaStream_t st;
+  TimedScope(int slot, cudaStream_t s) : st(s) {
+    if (timing_enabled()) timing_begin(slot, s, &token);
+  }
+  ~TimedScope() {
+    if (token >= 0) timing_end(token, st);
+  }
+};
+
 constexpr unsigned kFullMask = 0xffffffffu;
 
 // ------------------------------------------------------------------ Philox4x32-10 (RNG contract, oracle/pg_oracle.cpp)

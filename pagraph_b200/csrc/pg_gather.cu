@@ -260,9 +260,6 @@ struct pg_cache {
   unsigned long long* list_counts = nullptr;  // [2] hits, misses
   cudaStream_t miss_stream = nullptr;
   cudaEvent_t ev_split = nullptr, ev_miss_done = nullptr;
-  bool timing = false;
-  cudaEvent_t t_begin = nullptr, t_split = nullptr, t_hit = nullptr, t_miss0 = nullptr, t_miss1 = nullptr;
-  bool timed_valid = false, timed_miss = false;
   int max_smem_optin = 0;
 };
 
@@ -368,8 +365,6 @@ pg_status pg_cache_create(int64_t node_num, uint8_t* d_flag, int64_t* d_l2c, con
     pg::set_error("pg_cache_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(PG_ERR_CUDA);
   }
-  cudaEventCreate(&c->t_begin); cudaEventCreate(&c->t_split); cudaEventCreate(&c->t_hit);
-  cudaEventCreate(&c->t_miss0); cudaEventCreate(&c->t_miss1);
   cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   *out = c;
   return PG_OK;
@@ -382,7 +377,7 @@ void pg_cache_destroy(pg_cache* c) {
   cudaFree(c->list_counts);
   cudaFree(c->hit_pos); cudaFree(c->hit_row); cudaFree(c->miss_pos); cudaFree(c->miss_row);
   if (c->miss_stream) cudaStreamDestroy(c->miss_stream);
-  for (cudaEvent_t e : {c->ev_split, c->ev_miss_done, c->t_begin, c->t_split, c->t_hit, c->t_miss0, c->t_miss1})
+  for (cudaEvent_t e : {c->ev_split, c->ev_miss_done})
     if (e) cudaEventDestroy(e);
   cudaGetLastError();
   delete c;
@@ -436,83 +431,49 @@ pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, fl
   pg::DeviceGuard guard(c->dev);
   cudaStream_t st = (cudaStream_t)stream;
   for (int f = 0; f < c->nfields; ++f) PG_REQUIRE(d_out[f] != nullptr, "pg_cache_fetch: null output table");
-  c->timed_valid = false;
   int64_t cache_strides[PG_MAX_FIELDS], host_strides[PG_MAX_FIELDS];
   for (int f = 0; f < c->nfields; ++f) {
     cache_strides[f] = c->fields[f].dim;
     host_strides[f] = c->fields[f].host_stride;
   }
   const int sms = pg::sm_count(c->dev);
-  if (c->timing) PG_CUDA(cudaEventRecord(c->t_begin, st));
   if (c->is_full) {
     // fetch_from_cache (storage.py:207-216): every row is cached in id order, cache row == local id
     if (d_hit_mask) {
       fill_u8_kernel<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 8), 256, 0, st>>>(d_hit_mask, n, 1);
       PG_CHECK_LAUNCH();
     }
-    if (c->timing) PG_CUDA(cudaEventRecord(c->t_split, st));
-    pg_status s = launch_rows(c, c->cache_tables, cache_strides, d_out, nullptr, d_parent_ids, nullptr, n, false, st);
-    if (s != PG_OK) return s;
-    if (c->timing) {
-      PG_CUDA(cudaEventRecord(c->t_hit, st));
-      c->timed_valid = true;
-      c->timed_miss = false;
-    }
-    return PG_OK;
+    pg::TimedScope ts(PG_T_GATHER_HIT, st);
+    return launch_rows(c, c->cache_tables, cache_strides, d_out, nullptr, d_parent_ids, nullptr, n, false, st);
   }
   pg_status s = ensure_ws(c, n);
   if (s != PG_OK) return s;
-  PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
-  const int grid = (int)std::min<int64_t>((n + kSplitThreads - 1) / kSplitThreads, (int64_t)sms * 8);
-  split_kernel<<<grid, kSplitThreads, 0, st>>>(d_parent_ids, n, c->flag, c->l2c, c->nid_map, c->hit_pos, c->hit_row,
-                                               c->miss_pos, c->miss_row, c->list_counts, d_hit_mask,
-                                               (unsigned long long*)d_counts);
-  PG_CHECK_LAUNCH();
-  if (c->timing) PG_CUDA(cudaEventRecord(c->t_split, st));
+  {
+    pg::TimedScope ts(PG_T_SPLIT, st);
+    PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
+    const int grid = (int)std::min<int64_t>((n + kSplitThreads - 1) / kSplitThreads, (int64_t)sms * 8);
+    split_kernel<<<grid, kSplitThreads, 0, st>>>(d_parent_ids, n, c->flag, c->l2c, c->nid_map, c->hit_pos, c->hit_row,
+                                                 c->miss_pos, c->miss_row, c->list_counts, d_hit_mask,
+                                                 (unsigned long long*)d_counts);
+    PG_CHECK_LAUNCH();
+  }
   // misses first, on the high-priority side stream, so PCIe is busy while the hit rows stream from HBM
   if (mode == 0) mode = env_int("PG_MISS_MODE", 2);
   PG_CUDA(cudaEventRecord(c->ev_split, st));
   PG_CUDA(cudaStreamWaitEvent(c->miss_stream, c->ev_split, 0));
-  if (c->timing) PG_CUDA(cudaEventRecord(c->t_miss0, c->miss_stream));
-  s = launch_rows(c, c->host_dev, host_strides, d_out, c->miss_pos, c->miss_row, c->list_counts + 1, n, mode == 2,
-                  c->miss_stream);
+  {
+    pg::TimedScope ts(PG_T_GATHER_MISS, c->miss_stream);
+    s = launch_rows(c, c->host_dev, host_strides, d_out, c->miss_pos, c->miss_row, c->list_counts + 1, n, mode == 2,
+                    c->miss_stream);
+  }
   if (s != PG_OK) return s;
-  if (c->timing) PG_CUDA(cudaEventRecord(c->t_miss1, c->miss_stream));
   PG_CUDA(cudaEventRecord(c->ev_miss_done, c->miss_stream));
   if (c->cached_rows > 0) {
+    pg::TimedScope ts(PG_T_GATHER_HIT, st);
     s = launch_rows(c, c->cache_tables, cache_strides, d_out, c->hit_pos, c->hit_row, c->list_counts, n, false, st);
     if (s != PG_OK) return s;
   }
-  if (c->timing) {
-    PG_CUDA(cudaEventRecord(c->t_hit, st));
-    c->timed_valid = true;
-    c->timed_miss = true;
-  }
   PG_CUDA(cudaStreamWaitEvent(st, c->ev_miss_done, 0));
-  return PG_OK;
-}
-
-pg_status pg_cache_set_timing(pg_cache* c, int enabled) {
-  PG_REQUIRE(c, "pg_cache_set_timing: null handle");
-  c->timing = enabled != 0;
-  c->timed_valid = false;
-  return PG_OK;
-}
-
-pg_status pg_cache_last_timing(pg_cache* c, float* ms_split, float* ms_hit, float* ms_miss) {
-  PG_REQUIRE(c && c->timed_valid, "pg_cache_last_timing: no timed fetch recorded");
-  pg::DeviceGuard guard(c->dev);
-  PG_CUDA(cudaEventSynchronize(c->t_hit));
-  float a = 0, b = 0, m = 0;
-  PG_CUDA(cudaEventElapsedTime(&a, c->t_begin, c->t_split));
-  PG_CUDA(cudaEventElapsedTime(&b, c->t_split, c->t_hit));
-  if (c->timed_miss) {
-    PG_CUDA(cudaEventSynchronize(c->t_miss1));
-    PG_CUDA(cudaEventElapsedTime(&m, c->t_miss0, c->t_miss1));
-  }
-  if (ms_split) *ms_split = a;
-  if (ms_hit) *ms_hit = b;
-  if (ms_miss) *ms_miss = m;
   return PG_OK;
 }
 

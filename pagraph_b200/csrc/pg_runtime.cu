@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <mutex>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "pg_common.cuh"
 
@@ -33,11 +35,70 @@ int sm_count(int dev) {
   return n;
 }
 
+// ------------------------------------------------------------------ live timing
+struct TimingRec {
+  int slot;
+  cudaEvent_t a, b;
+};
+static std::atomic<bool> g_timing{false};
+static std::mutex g_timing_mu;
+static std::vector<TimingRec> g_recs;          // in launch order since the last drain
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_free_events;
+
+bool timing_enabled() { return g_timing.load(std::memory_order_relaxed); }
+
+void timing_begin(int slot, cudaStream_t st, int* token) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  TimingRec r;
+  r.slot = slot;
+  if (!g_free_events.empty()) {
+    r.a = g_free_events.back().first;
+    r.b = g_free_events.back().second;
+    g_free_events.pop_back();
+  } else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+    cudaGetLastError();
+    *token = -1;
+    return;
+  }
+  cudaEventRecord(r.a, st);
+  g_recs.push_back(r);
+  *token = (int)g_recs.size() - 1;
+}
+
+void timing_end(int token, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (token >= 0 && token < (int)g_recs.size()) cudaEventRecord(g_recs[token].b, st);
+}
+
 }  // namespace pg
 
 extern "C" {
 
-int pg_version(void) { return 100; }
+int pg_version(void) { return 101; }
+
+pg_status pg_timing_enable(int enabled) {
+  pg::g_timing.store(enabled != 0);
+  return PG_OK;
+}
+
+pg_status pg_timing_drain(int32_t* slots, float* ms, int64_t cap, int64_t* n_out) {
+  PG_REQUIRE(n_out != nullptr && cap >= 0 && (cap == 0 || (slots && ms)), "pg_timing_drain: bad arguments");
+  std::lock_guard<std::mutex> lk(pg::g_timing_mu);
+  int64_t n = 0;
+  for (const pg::TimingRec& r : pg::g_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && n < cap) {
+      slots[n] = r.slot;
+      ms[n] = t;
+      ++n;
+    }
+    pg::g_free_events.emplace_back(r.a, r.b);
+  }
+  cudaGetLastError();
+  pg::g_recs.clear();
+  *n_out = n;
+  return PG_OK;
+}
 
 const char* pg_last_error(void) { return pg::g_err; }
 

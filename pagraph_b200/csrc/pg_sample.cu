@@ -605,6 +605,7 @@ pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int6
   uint32_t k0, k1;
   minibatch_key(s->seed, epoch, batch, &k0, &k1);
 
+  pg::TimedScope timed(PG_T_SAMPLE, st);
   PG_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(Counts), st));
   // ---- seed layer
   if (n_seeds > 0) {

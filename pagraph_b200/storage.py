@@ -254,17 +254,6 @@ class GraphCacheServer:
             raise RuntimeError("fetch_from_cache requires a fully cached graph")
         self.fetch_data(nodeflow)
 
-    # ---- measurement hooks (not in the reference)
-    def set_timing(self, enabled):
-        _lib.check(_lib.lib().pg_cache_set_timing(self._handle, int(enabled)), "pg_cache_set_timing")
-
-    def last_timing(self):
-        """(split_ms, hit_ms, miss_ms) of the most recent timed fetch_data. Synchronises."""
-        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
-        _lib.check(_lib.lib().pg_cache_last_timing(self._handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
-                   "pg_cache_last_timing")
-        return a.value, b.value, c.value
-
     def __del__(self):
         try:
             if self._handle is not None:

@@ -1,0 +1,45 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+from pagraph_b200 import _lib, build as pg_build
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pagraph_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_builds_and_exports_every_symbol():
+    path = pg_build.build()
+    assert os.path.exists(path)
+    L = ctypes.CDLL(path)
+    for name in _declared_symbols():
+        assert hasattr(L, name), name
+    assert L.pg_version() >= 100
+    lib = _lib.lib()
+    assert lib.pg_last_error() is not None
+
+
+def test_sass_is_sm_100a_with_bulk_copies():
+    """The miss path is TMA bulk copies: the cubin must hold UBLKCP for sm_100a."""
+    import subprocess
+    path = pg_build.build()
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out
+
+
+def test_constants_match_header():
+    text = open(os.path.join(ROOT, "include", "pagraph_b200.h")).read()
+    assert int(re.search(r"#define PG_MAX_FIELDS (\d+)", text).group(1)) == _lib.PG_MAX_FIELDS
+    assert int(re.search(r"#define PG_MAX_HOPS (\d+)", text).group(1)) == _lib.PG_MAX_HOPS
+    assert ctypes.sizeof(_lib.pg_field) == 24
+    assert ctypes.sizeof(_lib.pg_nodeflow_buffers) == 40

@@ -1,0 +1,116 @@
+"""GPU block aggregation (pg_aggregate_fwd/bwd through the C-ABI) vs the float64 oracle.
+Tolerance (BASELINE.json north_star): 1e-5 relative, fp32."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import random_in_csr
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _close(got, want, scale_ref=None):
+    # relative to the magnitude of the row sums (cancellation makes per-element rtol meaningless)
+    denom = np.maximum(np.abs(want), 1e-30) if scale_ref is None else scale_ref
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64)) / denom
+    assert err.max() <= RTOL, err.max()
+
+
+def _nodeflow(V=4000, nnz=80000, seeds=600, fanouts=(25, 10), hub=False):
+    indptr, indices, eids, _ = random_in_csr(V, nnz, seed=6, hub=hub)
+    s = np.random.default_rng(0).choice(V, seeds, replace=False)
+    return oracle.sample(indptr, indices, eids, s, list(fanouts), seed=3)
+
+
+@pytest.mark.parametrize("dim", [600, 64, 32, 128, 16, 4, 13, 602, 1, 2400])
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+def test_forward_matches_oracle(dim, mode):
+    import torch
+    from pagraph_b200 import ops
+    nf = _nodeflow()
+    rng = np.random.default_rng(dim)
+    for i in range(nf.num_blocks):
+        ip, cols, base = nf.block(i)
+        n_src = len(nf.layer_parent_nid(i))
+        x = rng.random((n_src, dim), dtype=np.float32)          # U[0,1) like the reference features
+        want = oracle.aggregate(ip, cols, base, x, mode)
+        got = ops.aggregate_forward(torch.from_numpy(ip).cuda(), torch.from_numpy(cols).cuda(), base,
+                                    torch.from_numpy(x).cuda(), len(ip) - 1, mode)
+        _close(got.cpu().numpy(), want)
+        # signed inputs: error relative to sum |x| over the row (the fp32 accumulation bound)
+        xs = rng.standard_normal((n_src, dim)).astype(np.float32)
+        want = oracle.aggregate(ip, cols, base, xs, mode)
+        bound = oracle.aggregate(ip, cols, base, np.abs(xs), mode)
+        got = ops.aggregate_forward(torch.from_numpy(ip).cuda(), torch.from_numpy(cols).cuda(), base,
+                                    torch.from_numpy(xs).cuda(), len(ip) - 1, mode)
+        _close(got.cpu().numpy(), want, np.maximum(bound.astype(np.float64), 1e-30))
+
+
+@pytest.mark.parametrize("dim", [600, 64, 13])
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+def test_backward_matches_oracle(dim, mode):
+    import torch
+    from pagraph_b200 import ops
+    nf = _nodeflow(hub=True, V=1500, nnz=60000, seeds=300, fanouts=(10, 5))
+    rng = np.random.default_rng(dim + 1)
+    for i in range(nf.num_blocks):
+        ip, cols, base = nf.block(i)
+        n_src, n_dst = len(nf.layer_parent_nid(i)), len(ip) - 1
+        gd = rng.random((n_dst, dim), dtype=np.float32)
+        want = oracle.aggregate_bwd(ip, cols, base, gd, n_src, mode)
+        got = ops.aggregate_backward(torch.from_numpy(ip).cuda(), torch.from_numpy(cols).cuda(), base,
+                                     torch.from_numpy(gd).cuda(), n_src, mode)
+        assert got.shape == (n_src, dim)
+        _close(got.cpu().numpy(), want, np.maximum(np.abs(want.astype(np.float64)), 1e-30))
+
+
+def test_zero_degree_rows_norm_and_strides():
+    import ctypes
+    import torch
+    from pagraph_b200 import _lib
+    indptr = torch.tensor([0, 0, 2, 2, 5], dtype=torch.int64).cuda()
+    cols = torch.tensor([10, 11, 12, 10, 10], dtype=torch.int64).cuda()
+    src_full = torch.arange(3 * 12, dtype=torch.float32).reshape(3, 12).cuda()
+    src = src_full[:, :8]                                             # stride 12, dim 8
+    dst = torch.full((4, 16), -1.0, device="cuda")
+    norm = torch.tensor([2.0, 0.5, 3.0, float("inf")], device="cuda")
+    L = _lib.lib()
+    _lib.check(L.pg_aggregate_fwd(_lib.ptr(indptr), _lib.ptr(cols), 10, _lib.ptr(src), 12, _lib.ptr(dst), 16, 4, 8,
+                                  _lib.PG_AGG_SUM, _lib.ptr(norm), None), "fwd")
+    torch.cuda.synchronize()
+    s = src.cpu().numpy()
+    want = np.stack([np.zeros(8), (s[0] + s[1]) * 0.5, np.zeros(8), (s[2] + s[0] + s[0]) * np.inf])
+    np.testing.assert_array_equal(dst[:, :8].cpu().numpy(), want.astype(np.float32))
+    assert (dst[:, 8:] == -1).all()                                   # padding untouched
+    _lib.check(L.pg_aggregate_fwd(_lib.ptr(indptr), _lib.ptr(cols), 10, _lib.ptr(src), 12, _lib.ptr(dst), 16, 4, 8,
+                                  _lib.PG_AGG_MEAN, None, None), "fwd")
+    want = np.stack([np.zeros(8), (s[0] + s[1]) / 2, np.zeros(8), (s[2] + s[0] + s[0]) / 3])
+    np.testing.assert_allclose(dst[:, :8].cpu().numpy(), want, rtol=1e-6)
+    assert L.pg_aggregate_fwd(_lib.ptr(indptr), _lib.ptr(cols), 10, _lib.ptr(src), 4, _lib.ptr(dst), 16, 4, 8,
+                              _lib.PG_AGG_SUM, None, None) == _lib.PG_ERR_INVALID
+    assert L.pg_aggregate_fwd(_lib.ptr(indptr), _lib.ptr(cols), 10, _lib.ptr(src), 12, _lib.ptr(dst), 16, 4, 8,
+                              7, None, None) == _lib.PG_ERR_INVALID
+    assert ctypes.string_at(L.pg_last_error()) != b""
+
+
+def test_autograd_function_matches_torch_sparse():
+    import torch
+    from pagraph_b200 import ops
+    nf = _nodeflow(V=1000, nnz=20000, seeds=100, fanouts=(6, 4))
+    ip, cols, base = nf.block(1)
+    n_src, n_dst = len(nf.layer_parent_nid(1)), len(ip) - 1
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.random((n_src, 64), dtype=np.float32)).cuda().requires_grad_(True)
+    A = torch.sparse_csr_tensor(torch.from_numpy(ip - ip[0]), torch.from_numpy(cols[ip[0]:ip[-1]] - base),
+                                torch.ones(int(ip[-1] - ip[0]), dtype=torch.float64), size=(n_dst, n_src)).cuda()
+    deg = torch.from_numpy(np.maximum(np.diff(ip), 1)).cuda()[:, None]
+    w = torch.from_numpy(rng.random((n_dst, 64), dtype=np.float32)).cuda()
+    out = ops.BlockAggregate.apply(x, torch.from_numpy(ip).cuda(), torch.from_numpy(cols).cuda(), base, n_dst, "mean")
+    (out * w).sum().backward()
+    x64 = x.detach().double().requires_grad_(True)
+    ref = (A @ x64) / deg
+    (ref * w.double()).sum().backward()
+    torch.testing.assert_close(out.double(), ref, rtol=RTOL, atol=0)
+    torch.testing.assert_close(x.grad.double(), x64.grad, rtol=RTOL, atol=1e-12)
