@@ -1,0 +1,645 @@
+#!/usr/bin/env python
+"""bench.py — minibatches/s and feature-gather GB/s of the PaGraph hot path on B200.
+
+One "step" = one training minibatch of examples/profile/pa_gcn.py:86-97 on BASELINE.json configs[1]
+(R-MAT 10 M vertices / 100 M edges, feat 600, 2-layer GCN, fanout 25/10, batch 6000):
+    sample (pg_sample) -> cache fetch of every NodeFlow layer (pg_cache_fetch) -> labels ->
+    GCN forward (pg_aggregate_fwd x2 + cuBLAS linears) -> loss -> backward (pg_aggregate_bwd) ->
+    gradient all-reduce (N>1) -> Adam step.
+Nothing is skipped or cached between steps; every step samples a new minibatch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]        # our arm (torchrun for N>1)
+    python bench.py --impl reference ...                        # CPU restatement of the reference path
+
+Cache modes ("cache=20 % HBM" is ambiguous, both are measured every run):
+    hbm20   capacity = 20 % of the HBM bytes (= what BASELINE.json says literally); the 24 GB table
+            fits, so auto_cache takes the reference's full_cached branch (storage.py:90-95).  HEADLINE.
+    vtx20   capacity = 20 % of the partition's vertices (the ratio the authors study,
+            examples/opt_cache_hit.py:58): real hit/miss split, misses pulled over PCIe by TMA.
+            Reported under "variants".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+ID_BYTES = 8
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=10)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--vnum", type=int, default=10_000_000)
+    p.add_argument("--nnz", type=int, default=100_000_000)
+    p.add_argument("--feat-size", type=int, default=600)
+    p.add_argument("--n-classes", type=int, default=60)
+    p.add_argument("--n-hidden", type=int, default=32)
+    p.add_argument("--batch-size", type=int, default=6000)
+    p.add_argument("--fanout", default="25,10", help="per hop, index 0 expands the seeds")
+    p.add_argument("--dropout", type=float, default=0.2)
+    p.add_argument("--lr", type=float, default=3e-2)
+    p.add_argument("--modes", default="hbm20,vtx20", help="cache modes to run; the first is the headline")
+    p.add_argument("--cpu-batches", type=int, default=32, help="minibatches of the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--seed", type=int, default=1)
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock / power / throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, dev, period=0.02):
+        super().__init__(daemon=True)
+        self.period, self.samples, self._stop_ev, self.ok = period, [], threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(dev)
+            self.nv = pynvml
+            try:
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch.device(dev).index or 0)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: the clocks object says so instead of inventing numbers
+            self.err = str(e)
+
+    def run(self):
+        nv = self.nv
+        while not self._stop_ev.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), mhz, reasons, watts))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_ev.set()
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        s = [x for x in self.samples if t0 <= x[0] <= t1] or self.samples
+        bits = 0
+        for x in s:
+            bits |= x[2]
+        return {"sm_mhz": float(np.median([x[1] for x in s])) if s else None, "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(v for k, v in self.REASONS.items() if bits & k),
+                "power_w_max": max([x[3] for x in s]) if s else None, "samples": len(s)}
+
+
+def sampling_bytes(lo, bo):
+    """B_S of SURVEY.md §8d for one NodeFlow (layer offsets lo, block offsets bo)."""
+    n = [lo[i + 1] - lo[i] for i in range(len(lo) - 1)]
+    e = [bo[i + 1] - bo[i] for i in range(len(bo) - 1)]
+    b = sum(16 * n[i + 1] + 16 * e[i] for i in range(len(e)))
+    return b + 8 * sum(n) + 16 * sum(e) + 8 * sum(x + 1 for x in n)
+
+
+def agg_bytes(n_src, n_dst, e, d):
+    """B_A of SURVEY.md §8d: every source row read once, every dst row written once, CSR once."""
+    return 4 * d * (n_src + n_dst) + 8 * e + 8 * (n_dst + 1)
+
+
+# ------------------------------------------------------------------------------------ workload
+class Workload:
+    """BASELINE.json configs[1] made concrete: synthetic R-MAT graph, U[0,1) features,
+    norm = 1/in_degree, random labels, 65 % train split, hash partition of the train ids over ranks.
+    At this density the 2-hop in-neighbour closure of any 1/N share of the train vertices is the whole
+    graph, so every rank's partition graph is the full graph and nid_map is the identity."""
+
+    def __init__(self, args, rank, world, dev):
+        from pagraph_b200 import DGLGraph, data
+        from pagraph_b200 import graph_store as gs
+        from pagraph_b200.parallel import hash_split
+        self.args, self.rank, self.world, self.dev = args, rank, world, dev
+        V, Fdim = args.vnum, args.feat_size
+        t0 = time.time()
+        self.indptr, self.indices = data.rmat_in_csr_cuda(V, args.nnz, seed=args.seed, device=dev)
+        self.g = DGLGraph.from_in_csr(self.indptr, self.indices)
+        self.t_graph = time.time() - t0
+        t0 = time.time()
+        name = "bench%d" % os.getpid() if world == 1 else "bench_w%s" % os.environ.get("MASTER_PORT", "0")
+        self.server = None
+        if world == 1:
+            self.store = gs.LocalGraphStore(name=name)
+            feat, norm = self.store.alloc_field("features", V, Fdim), self.store.alloc_field("norm", V, 1)
+        elif rank == 0:
+            self.server = gs.create_graph_store_server(None, name, "shared_mem", world)
+            feat, norm = self.server.alloc_field("features", V, Fdim), self.server.alloc_field("norm", V, 1)
+        if rank == 0:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(2)
+            chunk = 1 << 18
+            for lo in range(0, V, chunk):
+                hi = min(V, lo + chunk)
+                feat[lo:hi].copy_(torch.rand((hi - lo, Fdim), device=dev, generator=gen))
+            deg = (self.indptr[1:] - self.indptr[:-1]).float()
+            norm.copy_((1.0 / deg).unsqueeze(1))          # inf where in-degree is 0 (pa_server.py:43)
+            torch.cuda.synchronize()
+            if self.server is not None:
+                self.server.commit()
+        if world > 1:
+            dist.barrier()
+            self.store = gs.SharedMemoryStoreClient(name, expect_fields=["features", "norm"])
+        self.t_store = time.time() - t0
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(3)
+        self.labels_dev = torch.randint(0, args.n_classes, (V,), device=dev, generator=gen)
+        self.labels_cpu = self.labels_dev.cpu()
+        gen.manual_seed(4)
+        perm = torch.randperm(V, device=dev, generator=gen)
+        train = torch.sort(perm[:int(V * 0.65)]).values.cpu().numpy()
+        self.train_nid = np.sort(hash_split(train, world, seed=5)[rank])
+        self.fanouts = [int(x) for x in args.fanout.split(",")]
+        self.R = 4 * (Fdim + 1)
+
+    def host_graph(self):
+        return self.indptr.cpu().numpy(), self.indices.cpu().numpy()
+
+    def close(self):
+        if self.world > 1:
+            self.store.destroy()
+            dist.barrier()
+            if self.server is not None:
+                self.server.destroy()
+
+
+class Trainer:
+    """The trainer of examples/profile/pa_gcn.py:27-113 on the rebuilt path."""
+
+    def __init__(self, wl, mode, host_inputs):
+        from pagraph_b200.model.gcn_nssc import GCNSampling
+        from pagraph_b200.parallel import FlatGradAllReduce
+        from pagraph_b200.sampling import NeighborSampler
+        from pagraph_b200.storage import GraphCacheServer
+        a = wl.args
+        self.wl, self.mode, self.host_inputs = wl, mode, host_inputs
+        dev = wl.dev
+        V = a.vnum
+        self.cacher = GraphCacheServer(wl.store, V, torch.arange(V, dtype=torch.int64), dev.index)
+        self.cacher.init_field(["features", "norm"])
+        self.cacher.log = True
+        torch.manual_seed(wl.rank)                                            # pa_gcn.py:23
+        self.model = GCNSampling(a.feat_size, a.n_hidden, a.n_classes, 1, F.relu, a.dropout, False).cuda(dev)
+        self.sync = FlatGradAllReduce(self.model)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=a.lr, weight_decay=0)
+        self.loss_fcn = torch.nn.CrossEntropyLoss()
+        self.sampler = NeighborSampler(wl.g, a.batch_size, wl.fanouts, neighbor_type='in', shuffle=True,
+                                       num_workers=16, num_hops=len(wl.fanouts),
+                                       seed_nodes=torch.from_numpy(wl.train_nid), prefetch=True, seed=a.seed,
+                                       device_seeds=not host_inputs)
+        self.label_stage = [torch.empty(a.batch_size, dtype=torch.int64).pin_memory() for _ in range(4)]
+        self.next_batch = 0
+        self.sizes = []          # (layer_offsets, block_offsets) of every timed step
+        self.fetch_events = []
+        # step 1 cold, then fill the cache (pa_gcn.py:99-100)
+        self.run(1, record=False)
+        total = torch.cuda.get_device_properties(dev).total_memory
+        cap = int(0.2 * total / (4 * self.cacher.total_dim)) if mode == "hbm20" else V // 5
+        self.cacher.auto_cache(wl.g, ["features", "norm"], capability=cap)
+        self.cacher.get_miss_rate()
+
+    def run(self, count, record, read_loss=False):
+        """`count` consecutive training steps. Returns the last loss (host float if read_loss)."""
+        wl, dev = self.wl, self.wl.dev
+        loss = None
+        for nf in self.sampler.batches(self.next_batch, count):
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self.cacher.fetch_data(nf)
+            if record:
+                e1.record()
+                self.fetch_events.append((e0, e1))
+                self.sizes.append((nf._layer_offsets, nf._block_offsets))
+            if self.host_inputs:                     # pa_gcn.py:89-91, through a pinned staging buffer
+                batch_nids = nf.layer_parent_nid(-1)
+                self._stage_i = (getattr(self, "_stage_i", 0) + 1) % len(self.label_stage)
+                st = self.label_stage[self._stage_i][:len(batch_nids)]
+                torch.index_select(wl.labels_cpu, 0, batch_nids, out=st)
+                label = st.to(dev, non_blocking=True)
+            else:
+                label = wl.labels_dev[nf.layer_parent_nid_dev(-1)]
+            pred = self.model(nf)
+            loss = self.loss_fcn(pred, label)
+            self.sync.zero_grad()
+            loss.backward()
+            self.sync()
+            self.opt.step()
+            if read_loss:
+                loss = loss.item()                   # D2H read of the step's result
+        self.next_batch += count
+        return loss
+
+
+def timed_region(tr, steps, read_loss, clock, world):
+    """barrier + sync | K steps | sync + barrier; CUDA events on the compute stream, max over ranks."""
+    from pagraph_b200 import _lib
+    tr.sizes, tr.fetch_events = [], []
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tr.cacher.get_miss_rate() if tr.cacher.try_num else None
+    _lib.timing_drain()
+    _lib.timing_enable(True)
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    ev0.record()
+    loss = tr.run(steps, record=True, read_loss=read_loss)
+    ev1.record()
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    _lib.timing_enable(False)
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms, (w1 - w0) * 1e3], device=tr.wl.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms = t.tolist()
+        lt = torch.tensor([launches], device=tr.wl.dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    else:
+        wall_ms = (w1 - w0) * 1e3
+    recs = _lib.timing_drain()
+    tries, misses = tr.cacher.try_num, tr.cacher.miss_num
+    tr.cacher.get_miss_rate() if tries else None
+    return dict(ms=ms, wall_ms=wall_ms, launches=launches, recs=recs, tries=tries, misses=misses,
+                loss=float(loss), clocks=clock.summary(w0, w1) if clock else None,
+                fetch_ms=sum(a.elapsed_time(b) for a, b in tr.fetch_events))
+
+
+def kernel_report(tr, reg, hbm_peak, pcie_peak):
+    """Per-kernel-class live timing (pg_timing_*) against the algorithmic bytes of SURVEY.md §8d."""
+    from pagraph_b200 import _lib
+    wl = tr.wl
+    R, Fdim, H2 = wl.R, wl.args.feat_size, 2 * wl.args.n_hidden
+    by = {}
+    for slot, ms in reg["recs"]:
+        by.setdefault(slot, []).append(ms)
+    steps = len(tr.sizes)
+    N = sum(lo[-1] for lo, _ in tr.sizes)
+    M = reg["misses"]
+    Hh = N - M
+    out = {}
+
+    def add(name, slot_ms, nbytes, peak, peak_name, launches_per_scope=1):
+        if not slot_ms:
+            return
+        t = sum(slot_ms)
+        out[name] = {"launches": len(slot_ms) * launches_per_scope, "avg_ms": t / len(slot_ms),
+                     "alg_bytes_per_launch": nbytes / len(slot_ms), "achieved_gbs": nbytes / t / 1e6,
+                     "peak_gbs": peak, "frac": nbytes / t / 1e6 / peak, "bound": peak_name}
+
+    add("sample(all kernels of one pg_sample)", by.get(_lib.T_SAMPLE), sum(sampling_bytes(lo, bo) for lo, bo in tr.sizes),
+        hbm_peak, "hbm")
+    add("split_kernel", by.get(_lib.T_SPLIT), 9 * N + 16 * N, hbm_peak, "hbm")
+    add("gather_hit(rows_ldg_kernel)", by.get(_lib.T_GATHER_HIT), 2 * R * Hh + ID_BYTES * Hh, hbm_peak, "hbm")
+    add("gather_miss(rows_bulk_kernel)", by.get(_lib.T_GATHER_MISS), R * M, pcie_peak, "pcie")
+    fw = by.get(_lib.T_AGG_FWD, [])
+    if len(fw) == 2 * steps:
+        b0 = sum(agg_bytes(lo[1] - lo[0], lo[2] - lo[1], bo[1] - bo[0], Fdim) for lo, bo in tr.sizes)
+        b1 = sum(agg_bytes(lo[2] - lo[1], lo[3] - lo[2], bo[2] - bo[1], H2) for lo, bo in tr.sizes)
+        add("agg_fwd_block0(D=%d)" % Fdim, fw[0::2], b0, hbm_peak, "hbm")
+        add("agg_fwd_block1(D=%d)" % H2, fw[1::2], b1, hbm_peak, "hbm")
+        add("agg_bwd_block1(D=%d)" % H2, by.get(_lib.T_AGG_BWD), b1, hbm_peak, "hbm")
+    return out, N, M
+
+
+def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
+    """value (device-resident inputs) and e2e (host inputs + loss read back) of one cache mode."""
+    res = {}
+    for host_inputs in (False, True):
+        tr = Trainer(wl, mode, host_inputs)
+        tr.run(args.warmup, record=False, read_loss=host_inputs)
+        clock = None
+        if wl.rank == 0:
+            clock = ClockSampler(wl.dev)
+            if clock.ok:
+                clock.start()
+        prof = os.environ.get("PG_BENCH_CUDA_PROFILER") == "1" and not host_inputs
+        if prof:                                  # ncu --profile-from-start off: capture the timed region only
+            torch.cuda.profiler.start()
+        reg = timed_region(tr, args.steps, host_inputs, clock, world)
+        if prof:
+            torch.cuda.profiler.stop()
+        if clock is not None and clock.ok:
+            clock.stop()
+        kern, N, M = kernel_report(tr, reg, hbm_peak, pcie_peak)
+        steps = args.steps
+        mbps = world * steps / (reg["ms"] * 1e-3)
+        r = dict(minibatches_per_s=mbps, ms_per_step=reg["ms"] / steps, wall_ms_per_step=reg["wall_ms"] / steps,
+                 rows_per_step=N / steps, miss_rows_per_step=M / steps, hit_rate=1.0 - M / max(N, 1),
+                 gather_gbs=wl.R * N / max(reg["fetch_ms"], 1e-9) / 1e6, gather_ms_per_step=reg["fetch_ms"] / steps,
+                 launches=reg["launches"], loss=reg["loss"], clocks=reg["clocks"], kernels=kern,
+                 full_cached=tr.cacher.full_cached, cached_rows=tr.cacher.cached_num,
+                 layer_sizes=[int(np.mean([lo[i + 1] - lo[i] for lo, _ in tr.sizes])) for i in range(3)],
+                 block_edges=[int(np.mean([bo[i + 1] - bo[i] for _, bo in tr.sizes])) for i in range(2)])
+        if host_inputs:
+            b = args.batch_size * ID_BYTES
+            r["h2d_bytes_per_step"] = int(2 * b + wl.R * M / steps)     # seeds + labels + missed rows over PCIe
+            r["d2h_bytes_per_step"] = int(4 + 8 * 23)                   # loss + NodeFlow meta block
+        res["e2e" if host_inputs else "value"] = r
+        del tr
+        torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+class CpuAgg(torch.autograd.Function):
+    """block_compute(copy_src, mean) on the CPU through the oracle (for the CPU arm's model)."""
+
+    @staticmethod
+    def forward(ctx, src, block, threads):
+        import oracle
+        ip, cols, base = block
+        ctx.block, ctx.n_src = block, src.shape[0]
+        return torch.from_numpy(oracle.aggregate(ip, cols, base, src.detach().numpy(), "mean", threads, f32=True))
+
+    @staticmethod
+    def backward(ctx, g):
+        import oracle
+        ip, cols, base = ctx.block
+        return torch.from_numpy(oracle.aggregate_bwd(ip, cols, base, g.contiguous().numpy(), ctx.n_src, "mean")), None, None
+
+
+def cpu_path(args, indptr, indices, tables, seeds, n_batches, threads, first_batch=0):
+    """The reference path restated on the CPU (oracle/): DGL-style sampling (OpenMP over batches, one
+    thread each), storage.py's host gather of every layer's rows for both fields (all rows come from
+    the host table — the reference's miss path, storage.py:117-129 — and no H2D copy is charged),
+    float64 mean aggregation and the GCN forward/backward/Adam on torch-CPU. Returns seconds."""
+    import oracle
+    fan = [int(x) for x in args.fanout.split(",")]
+    V = len(indptr) - 1
+    torch.manual_seed(0)
+    lin1 = torch.nn.Linear(args.feat_size, args.n_hidden)
+    lin2 = torch.nn.Linear(2 * args.n_hidden, args.n_classes)
+    opt = torch.optim.Adam(list(lin1.parameters()) + list(lin2.parameters()), lr=args.lr)
+    labels = torch.randint(0, args.n_classes, (V,))
+    flag = np.zeros(V, np.uint8)
+    ident = np.zeros(1, np.int64)
+    t_total = 0.0
+    done = 0
+    stage = {"sample": 0.0, "gather": 0.0, "aggregate+model": 0.0}
+    while done < n_batches:
+        nb = min(threads, n_batches - done)
+        t0 = time.perf_counter()
+        nfs = oracle.sample_many(indptr, indices, None, seeds, args.batch_size, first_batch + done, nb, fan,
+                                 seed=args.seed, threads=threads)
+        t1 = time.perf_counter()
+        stage["sample"] += t1 - t0
+        for nf in nfs:
+            t1 = time.perf_counter()
+            frames = []
+            for i in range(nf.num_layers):
+                ids = nf.layer_parent_nid(i)
+                fr = {}
+                for name, tab in tables.items():
+                    fr[name] = _cpu_fetch(oracle, ids, flag, ident, tab, threads)
+                frames.append(fr)
+            t2 = time.perf_counter()
+            h = torch.from_numpy(frames[0]["features"])
+            # dropout mask generation is left out of the CPU arm: torch-CPU bernoulli is single-threaded
+            # (0.6 s per minibatch here) and would dominate; leaving it out favours the CPU arm.
+            a0 = CpuAgg.apply(h, nf.block(0), threads)
+            z = lin1(a0)
+            z = torch.cat((z, F.relu(z)), 1)
+            a1 = CpuAgg.apply(z, nf.block(1), threads)
+            pred = lin2(a1)
+            loss = F.cross_entropy(pred, labels[torch.from_numpy(nf.layer_parent_nid(-1))])
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            t3 = time.perf_counter()
+            stage["gather"] += t2 - t1
+            stage["aggregate+model"] += t3 - t2
+        done += nb
+        t_total += time.perf_counter() - t0
+    return t_total, stage
+
+
+def _cpu_fetch(oracle, ids, flag, ident, tab, threads):
+    """storage.py:126-128 host gather of one field with `threads` OpenMP threads (nid_map = identity)."""
+    import ctypes
+    L = oracle.lib()
+    n, dim = len(ids), tab.shape[1]
+    out = np.empty((n, dim), np.float32)
+    i64p, u8p, f32p = (ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_float))
+    ids = np.ascontiguousarray(ids, np.int64)
+    tp = ctypes.cast(ctypes.c_void_p(tab.data_ptr()), f32p)
+    # flag is all-zero => every row is read from host[nid_map[t]]; nid_map is passed as the ids themselves
+    L.pgo_fetch(ids.ctypes.data_as(i64p), ctypes.c_int64(n), flag.ctypes.data_as(u8p),
+                ident.ctypes.data_as(i64p), _identity(len(flag)).ctypes.data_as(i64p), tp, ctypes.c_int64(0), tp,
+                ctypes.c_int64(tab.stride(0)), ctypes.c_int64(dim), out.ctypes.data_as(f32p), None,
+                ctypes.c_int(threads))
+    return out
+
+
+_IDENT = {}
+
+
+def _identity(n):
+    if n not in _IDENT:
+        _IDENT[n] = np.arange(n, dtype=np.int64)
+    return _IDENT[n]
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def workload_name(args):
+    return ("PaRMAT-style R-MAT %d vtx / %d edges, feat=%d, 2-layer GCN (n_hidden %d, %d classes), fanout %s, "
+            "batch %d, hash partition per GPU" % (args.vnum, args.nnz, args.feat_size, args.n_hidden, args.n_classes,
+                                                  args.fanout.replace(",", "/"), args.batch_size))
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def main_reference(args):
+    """`--impl reference`: the reference's CPU path (oracle port; the reference itself is pure Python over
+    dgl==0.4.1, which is not installable here) on this box's host cores. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pagraph_b200 import data
+    threads = host_threads()
+    if torch.cuda.is_available():            # data generation only (setup, untimed) — same graph as our arm
+        dev = torch.device("cuda", 0)
+        ip, ix = data.rmat_in_csr_cuda(args.vnum, args.nnz, seed=args.seed, device=dev)
+        indptr, indices = ip.cpu().numpy(), ix.cpu().numpy()
+        feat = torch.empty((args.vnum, args.feat_size), dtype=torch.float32)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(2)
+        chunk = 1 << 18
+        for lo in range(0, args.vnum, chunk):
+            hi = min(args.vnum, lo + chunk)
+            feat[lo:hi].copy_(torch.rand((hi - lo, args.feat_size), device=dev, generator=gen))
+        norm = (1.0 / (ip[1:] - ip[:-1]).float()).unsqueeze(1).cpu()
+        gen.manual_seed(4)
+        perm = torch.randperm(args.vnum, device=dev, generator=gen)
+        train = torch.sort(perm[:int(args.vnum * 0.65)]).values.cpu().numpy()
+        del ip, ix, perm
+        torch.cuda.empty_cache()
+    else:
+        adj = data.rmat_adj(args.vnum, args.nnz, seed=args.seed).tocsc()
+        indptr, indices = adj.indptr.astype(np.int64), adj.indices.astype(np.int64)
+        feat = torch.rand((args.vnum, args.feat_size))
+        norm = torch.from_numpy(1.0 / np.maximum(np.diff(indptr), 1).astype(np.float32)).unsqueeze(1)
+        train = np.sort(np.random.default_rng(4).permutation(args.vnum)[:int(args.vnum * 0.65)])
+    from pagraph_b200.parallel import hash_split
+    seeds = np.sort(hash_split(train, max(args.gpus, 1), seed=5)[0])
+    torch.manual_seed(0)
+    seeds = np.ascontiguousarray(seeds[torch.randperm(len(seeds)).numpy()])
+    tables = {"features": feat, "norm": norm}
+    torch.set_num_threads(threads)
+    cpu_path(args, indptr, indices, tables, seeds, args.warmup, threads, first_batch=0)
+    t, stage = cpu_path(args, indptr, indices, tables, seeds, args.steps, threads, first_batch=args.warmup)
+    v = args.steps / t
+    line = {"impl": "reference", "metric": "minibatches/sec (sample + cache fetch + GCN train step)", "value": v,
+            "unit": "minibatches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "cache": "none (CPU arm: every row gathered from the host table)"},
+            "cpu_baseline": {"value": v, "unit": "minibatches/s", "cores": threads, "kind": "port",
+                             "sample": "%d full minibatches (sample %d threads over batches; gather+aggregate %d threads)"
+                                       % (args.steps, threads, threads),
+                             "stage_s": stage},
+            "e2e": {"value": v, "unit": "minibatches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback of the product path)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from pagraph_b200 import _lib
+    import ctypes
+    hbm_peak, hbm_src = measured_peaks()
+    bw = ctypes.c_double()
+    _lib.check(_lib.lib().pg_measure_h2d(dev.index, 1 << 30, 5, ctypes.byref(bw)), "pg_measure_h2d")
+    pcie_peak = bw.value
+    t_setup = time.time()
+    wl = Workload(args, rank, world, dev)
+    modes = args.modes.split(",")
+    results = {}
+    for m in modes:
+        results[m] = run_mode(wl, m, args, world, hbm_peak, pcie_peak)
+    t_setup = time.time() - t_setup
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        indptr, indices = wl.host_graph()
+        tables = {"features": wl.store.ndata["features"], "norm": wl.store.ndata["norm"]}
+        torch.manual_seed(0)
+        seeds = np.ascontiguousarray(wl.train_nid[torch.randperm(len(wl.train_nid)).numpy()])
+        torch.set_num_threads(threads)
+        t, stage = cpu_path(args, indptr, indices, tables, seeds, args.cpu_batches, threads)
+        cpu = {"value": args.cpu_batches / t, "unit": "minibatches/s", "cores": threads, "kind": "port",
+               "sample": "%d full minibatches of the same workload (oracle/: DGL-style sampling, %d threads over batches; "
+                         "host gather of all layers' rows + float64 mean aggregation with %d threads; GCN step on torch-CPU)"
+                         % (args.cpu_batches, threads, threads),
+               "stage_s": {k: round(v, 3) for k, v in stage.items()}}
+    wl.close()
+    if rank != 0:
+        return
+    head = results[modes[0]]
+    v, e = head["value"], head["e2e"]
+    # dominant HBM-bound kernel of the headline mode
+    hbm_k = {k: x for k, x in v["kernels"].items() if x["bound"] == "hbm"}
+    top = max(hbm_k, key=lambda k: hbm_k[k]["avg_ms"] * (1 if "sample" not in k else 0))
+    tk = hbm_k[top]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(top.split("(")[0])
+    except Exception:
+        pass
+    line = {
+        "metric": "minibatches/sec (sample + cache fetch + GCN train step) + feature-gather GB/s",
+        "value": v["minibatches_per_s"], "unit": "minibatches/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": v["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "cache_mode": modes[0],
+                   "cache": "hbm20 = capacity 20% of HBM bytes (>= the 24 GB table -> full_cached, headline); "
+                            "vtx20 = top-20%-out-degree vertices cached (under variants)",
+                   "dropout": args.dropout, "optimizer": "Adam lr %g" % args.lr,
+                   "l2": "inputs larger than L2 (24 GB feature table, new random minibatch every step); no flush",
+                   "parallelism": "dp%d (one partition per GPU, flat-bucket NCCL grad all-reduce)" % world},
+        "gather_gbs": v["gather_gbs"], "hit_rate": v["hit_rate"],
+        "e2e": {"value": e["minibatches_per_s"], "unit": "minibatches/s", "h2d_bytes_per_step": e["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": e["d2h_bytes_per_step"], "ms_per_step": e["ms_per_step"],
+                "wall_ms_per_step": e["wall_ms_per_step"], "gather_gbs": e["gather_gbs"]},
+        "gpu_launches": v["launches"],
+        "clocks": v["clocks"],
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": tk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                     "frac": tk["frac"], "traffic": traffic, "peak_source": hbm_src,
+                     "alg_bytes_per_launch": tk["alg_bytes_per_launch"], "avg_ms": tk["avg_ms"]},
+        "pcie": {"peak_gbs_measured_h2d": pcie_peak},
+        "cpu_baseline": cpu,
+        "kernels": v["kernels"],
+        "variants": {m: results[m] for m in modes},
+        "setup_s": round(t_setup, 1),
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)
+    if dist.is_initialized():
+        dist.destroy_process_group()

@@ -136,6 +136,34 @@ def sample_batches(indptr, indices, eids, seeds, batch_size, first_batch, n_batc
     return nodes, edges
 
 
+def _nf_from_handle(h):
+    L = lib()
+    h = ctypes.c_void_p(h)
+    sizes = np.zeros(3, dtype=np.int64)
+    L.pgo_nf_sizes(h, _p(sizes, _i64p))
+    nl, nn, ne = (int(x) for x in sizes)
+    out = [np.zeros(nn, np.int64), np.zeros(nl + 1, np.int64), np.zeros(nn + 1, np.int64),
+           np.zeros(ne, np.int64), np.zeros(ne, np.int64), np.zeros(nl, np.int64)]
+    L.pgo_nf_copy(h, *[_p(a, _i64p) for a in out])
+    L.pgo_nf_free(h)
+    return OracleNodeFlow(*out)
+
+
+def sample_many(indptr, indices, eids, seeds, batch_size, first_batch, n_batches, fanouts, seed=0,
+                epoch=0, threads=1):
+    """`n_batches` consecutive minibatches sampled DGL's way (OpenMP over batches, one thread per
+    batch); returns the OracleNodeFlows. Inputs must be contiguous int64 (no copies are made)."""
+    L = lib()
+    fan = _c64(fanouts)
+    handles = (ctypes.c_void_p * n_batches)()
+    L.pgo_sample_many(_p(indptr, _i64p), _p(indices, _i64p), _p(eids, _i64p),
+                      ctypes.c_int64(len(indptr) - 1), _p(seeds, _i64p), ctypes.c_int64(len(seeds)),
+                      ctypes.c_int64(batch_size), ctypes.c_int64(first_batch), ctypes.c_int64(n_batches),
+                      ctypes.c_int(len(fan)), _p(fan, _i64p), ctypes.c_uint64(seed), ctypes.c_int64(epoch),
+                      ctypes.c_int(threads), handles)
+    return [_nf_from_handle(h) for h in handles]
+
+
 def fetch_c(tnid, flag, l2c, nid_map, cache, host, threads=1):
     """C restatement of storage.py:173-204 for one field (used for timing and large cases)."""
     tnid = _c64(tnid)
@@ -154,13 +182,15 @@ def fetch_c(tnid, flag, l2c, nid_map, cache, host, threads=1):
     return out, mask.astype(bool), int(miss)
 
 
-def aggregate(indptr, cols, col_base, src, mode, threads=1):
-    """float64 copy_src+sum/mean over one block (Appendix A.5). mode: 'sum' | 'mean'."""
+def aggregate(indptr, cols, col_base, src, mode, threads=1, f32=False):
+    """copy_src+sum/mean over one block (Appendix A.5), float64 accumulation (the checker) or, with
+    f32=True, float32 like DGL's CPU kernel (the timing arm). mode: 'sum' | 'mean'."""
     indptr, cols = _c64(indptr), _c64(cols)
     src = np.ascontiguousarray(src, np.float32)
     n_dst, dim = len(indptr) - 1, src.shape[1]
     dst = np.zeros((n_dst, dim), np.float32)
-    lib().pgo_aggregate(_p(indptr, _i64p), _p(cols, _i64p), ctypes.c_int64(col_base), _p(src, _f32p),
+    fn = lib().pgo_aggregate_f32 if f32 else lib().pgo_aggregate
+    fn(_p(indptr, _i64p), _p(cols, _i64p), ctypes.c_int64(col_base), _p(src, _f32p),
                         ctypes.c_int64(n_dst), ctypes.c_int64(dim),
                         ctypes.c_int({"sum": 0, "mean": 1}[mode]), _p(dst, _f32p), ctypes.c_int(threads))
     return dst

@@ -168,6 +168,35 @@ NodeFlow* sample_one(const int64_t* indptr, const int64_t* indices, const int64_
 
 }  // namespace
 
+// dgl block_compute(copy_src, sum|mean) restated: accumulation in edge
+// order, zero-in-degree rows -> 0, mean divides by max(deg,1). mode: 0 = sum, 1 = mean.
+// indptr has n_dst+1 entries (absolute edge offsets), cols[e]-col_base indexes src rows.
+// Acc = double for the parity checker; Acc = float is DGL's own CPU arithmetic (timing arm).
+template <typename Acc>
+static void aggregate_impl(const int64_t* indptr, const int64_t* cols, int64_t col_base, const float* src,
+                           int64_t n_dst, int64_t dim, int mode, float* dst, int threads) {
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads)
+#endif
+  {
+    std::vector<Acc> acc((size_t)dim);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 64)
+#endif
+    for (int64_t r = 0; r < n_dst; ++r) {
+      std::fill(acc.begin(), acc.end(), (Acc)0);
+      const int64_t s = indptr[r], e = indptr[r + 1];
+      for (int64_t j = s; j < e; ++j) {
+        const float* row = src + (cols[j] - col_base) * dim;
+        for (int64_t d = 0; d < dim; ++d) acc[(size_t)d] += (Acc)row[d];
+      }
+      const Acc scale = (mode == 1) ? (Acc)1 / (Acc)std::max<int64_t>(e - s, 1) : (Acc)1;
+      for (int64_t d = 0; d < dim; ++d) dst[r * dim + d] = (float)(acc[(size_t)d] * scale);
+    }
+  }
+  (void)threads;
+}
+
 extern "C" {
 
 void pgo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
@@ -239,6 +268,23 @@ int64_t pgo_sample_batches(const int64_t* indptr, const int64_t* indices, const 
   return total;
 }
 
+// Same parallelism model, but the NodeFlows are kept: handles[b] (pgo_nf_* accessors, pgo_nf_free).
+void pgo_sample_many(const int64_t* indptr, const int64_t* indices, const int64_t* eids, int64_t V,
+                     const int64_t* seeds, int64_t n_seeds, int64_t batch_size, int64_t first_batch,
+                     int64_t n_batches, int num_hops, const int64_t* fanouts, uint64_t seed, int64_t epoch,
+                     int threads, void** handles) {
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+#endif
+  for (int64_t b = 0; b < n_batches; ++b) {
+    const int64_t lo = (first_batch + b) * batch_size;
+    const int64_t n = lo < n_seeds ? std::min(batch_size, n_seeds - lo) : 0;
+    handles[b] = sample_one(indptr, indices, eids, V, seeds + (n ? lo : 0), n, num_hops, fanouts, seed, epoch,
+                            first_batch + b);
+  }
+  (void)threads;
+}
+
 // storage.py:173-204 restated for one field: out[j] = flag[t_j] ? cache[l2c[t_j]] : host[nid_map[t_j]].
 // Returns the number of misses. hit_mask (optional) receives flag[t_j].
 int64_t pgo_fetch(const int64_t* tnid, int64_t n, const uint8_t* flag, const int64_t* l2c,
@@ -260,25 +306,14 @@ int64_t pgo_fetch(const int64_t* tnid, int64_t n, const uint8_t* flag, const int
   return miss;
 }
 
-// dgl block_compute(copy_src, sum|mean) restated: float64 accumulation in
-// edge order, zero-in-degree rows -> 0, mean divides by max(deg,1). mode: 0 = sum, 1 = mean.
-// indptr has n_dst+1 entries (absolute edge offsets), cols[e]-col_base indexes src rows.
 void pgo_aggregate(const int64_t* indptr, const int64_t* cols, int64_t col_base, const float* src,
                    int64_t n_dst, int64_t dim, int mode, float* dst, int threads) {
-#ifdef _OPENMP
-#pragma omp parallel for num_threads(threads) schedule(dynamic, 64)
-#endif
-  for (int64_t r = 0; r < n_dst; ++r) {
-    std::vector<double> acc((size_t)dim, 0.0);
-    const int64_t s = indptr[r], e = indptr[r + 1];
-    for (int64_t j = s; j < e; ++j) {
-      const float* row = src + (cols[j] - col_base) * dim;
-      for (int64_t d = 0; d < dim; ++d) acc[(size_t)d] += (double)row[d];
-    }
-    const double scale = (mode == 1) ? 1.0 / (double)std::max<int64_t>(e - s, 1) : 1.0;
-    for (int64_t d = 0; d < dim; ++d) dst[r * dim + d] = (float)(acc[(size_t)d] * scale);
-  }
-  (void)threads;
+  aggregate_impl<double>(indptr, cols, col_base, src, n_dst, dim, mode, dst, threads);
+}
+
+void pgo_aggregate_f32(const int64_t* indptr, const int64_t* cols, int64_t col_base, const float* src,
+                       int64_t n_dst, int64_t dim, int mode, float* dst, int threads) {
+  aggregate_impl<float>(indptr, cols, col_base, src, n_dst, dim, mode, dst, threads);
 }
 
 // Backward of the above: grad_src[u] += grad_dst[v] * scale(v) over block edges (float64 accumulate).

@@ -119,28 +119,39 @@ class SharedMemoryStoreServer:
         self._node_frame = _NodeFrame()
         self._meta = {"fields": {}, "num_workers": num_workers}
         self._maps = []
+        self._pending = {}
         self.ndata = _NData(self)
         for f in os.listdir(_SHM_DIR):
             if f.startswith("pagraph_%s." % graph_name) and f.endswith(".done"):
                 os.unlink(os.path.join(_SHM_DIR, f))
 
+    def alloc_field(self, name, rows, dim):
+        """Create the shared segment of field `name` and return its [rows, dim] tensor to be filled in
+        place (no staging copy of a 24 GB table); `commit()` then makes it visible to clients."""
+        stride = _padded_stride(dim)
+        path = _seg_path(self.name, name)
+        arr = np.memmap(path, mode="w+", dtype=np.float32, shape=(rows, stride))
+        self._maps.append(arr)
+        t = torch.from_numpy(arr)[:, :dim]
+        self._node_frame._frame[name] = _Column(t)
+        self._pending[name] = {"rows": rows, "dim": dim, "stride": stride}
+        return t
+
+    def commit(self):
+        """Publish the metadata of every allocated field (clients poll for it)."""
+        self._meta["fields"].update(self._pending)
+        self._pending = {}
+        with open(_meta_path(self.name) + ".tmp", "w") as f:
+            json.dump(self._meta, f)
+        os.replace(_meta_path(self.name) + ".tmp", _meta_path(self.name))
+
     def _publish(self, name, value):
         value = torch.as_tensor(value, dtype=torch.float32)
         if value.dim() == 1:
             value = value.unsqueeze(1)
-        rows, dim = value.shape
-        stride = _padded_stride(dim)
-        path = _seg_path(self.name, name)
-        arr = np.memmap(path + ".tmp", mode="w+", dtype=np.float32, shape=(rows, stride))
-        arr[:, :dim] = value.numpy()
-        arr.flush()
-        os.replace(path + ".tmp", path)
-        self._maps.append(arr)
-        self._node_frame._frame[name] = _Column(torch.from_numpy(arr)[:, :dim])
-        self._meta["fields"][name] = {"rows": rows, "dim": dim, "stride": stride}
-        with open(_meta_path(self.name) + ".tmp", "w") as f:
-            json.dump(self._meta, f)
-        os.replace(_meta_path(self.name) + ".tmp", _meta_path(self.name))
+        t = self.alloc_field(name, value.shape[0], value.shape[1])
+        t.copy_(value)
+        self.commit()
 
     def run(self, poll_s=0.5, timeout_s=None):
         """Block until `num_workers` clients have signalled completion (DGL: until all disconnect)."""

@@ -1,0 +1,77 @@
+"""Data-parallel plumbing of the trainer (reference: examples/profile/pa_gcn.py:18-24,65,86-97).
+
+The reference wraps the 23 k-parameter model in DistributedDataParallel; the only cross-GPU traffic
+is the ~92 KB gradient all-reduce. Here that is ONE flat fp32 bucket and ONE all-reduce per step on
+the compute stream (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests): at this size the
+collective is pure latency, so DDP's per-bucket hooks buy nothing. Partitions are self-sufficient
+(PaGraph/partition/utils.py:9-52), so no feature or activation ever crosses GPUs.
+
+Also here: the hash split of train ids (PaGraph/partition/hash.py:25-51) and the per-rank batch
+count equalisation the reference lacks (an uneven count hangs its all-reduce).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class FlatGradAllReduce:
+    """Averages the gradients of `module` across ranks with a single all-reduce of one flat buffer.
+
+    Parameters are re-pointed at views of one flat tensor (and so are their .grad), so the
+    all-reduce needs no pack/unpack kernels. Usage, in place of DDP:
+        sync = FlatGradAllReduce(model); ...; loss.backward(); sync(); optimizer.step()
+    """
+
+    def __init__(self, module, process_group=None):
+        self.group = process_group
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat_param = torch.empty(n, dtype=ref.dtype, device=ref.device)
+        self.flat_grad = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + k].view_as(p)
+                p.grad = self.flat_grad[off:off + k].view_as(p)
+                off += k
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        if self.world > 1:   # same initial weights everywhere (DDP broadcasts rank 0's at construction)
+            dist.broadcast(self.flat_param, src=0, group=process_group)
+
+    def zero_grad(self):
+        """Keeps .grad pointing into the flat bucket (optimizer.zero_grad(set_to_none=True) would not)."""
+        self.flat_grad.zero_()
+
+    def __call__(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat_grad.div_(self.world)
+
+
+def hash_split(train_nids, num_parts, seed=None):
+    """hash.py:25-51: shuffle the train ids, cut them into `num_parts` equal consecutive chunks (the
+    last one takes the remainder). `seed` makes it reproducible (the reference shuffles unseeded)."""
+    ids = np.array(train_nids, dtype=np.int64, copy=True)
+    rng = np.random.default_rng(seed) if seed is not None else np.random
+    rng.shuffle(ids)
+    size = len(ids) // num_parts
+    parts = []
+    for p in range(num_parts):
+        lo = p * size
+        hi = (p + 1) * size if p != num_parts - 1 else len(ids)
+        parts.append(ids[lo:hi])
+    return parts
+
+
+def equalised_num_batches(local_num_batches, process_group=None):
+    """min over ranks of the per-epoch batch count, so that every rank enters the same number of
+    all-reduces (the reference's remote-sampling path pads instead, parallel/dataloader.py:138-143)."""
+    if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
+        return int(local_num_batches)
+    dev = "cuda" if dist.get_backend(process_group) == "nccl" else "cpu"
+    t = torch.tensor([int(local_num_batches)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=process_group)
+    return int(t.item())

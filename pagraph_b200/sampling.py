@@ -24,7 +24,7 @@ _SOFT_CAP = 1 << 28   # start below this many int64 entries per buffer; grow on 
 class NeighborSampler:
     def __init__(self, g, batch_size, expand_factor=None, num_hops=1, neighbor_type='in',
                  transition_prob=None, seed_nodes=None, shuffle=False, num_workers=1, prefetch=False,
-                 add_self_loop=False, seed=0, device=None):
+                 add_self_loop=False, seed=0, device=None, device_seeds=True):
         if not getattr(g, "is_readonly", False):
             raise ValueError("NeighborSampler requires a read-only graph")
         if neighbor_type != 'in':
@@ -58,8 +58,15 @@ class NeighborSampler:
         if shuffle:  # once, at construction (Appendix A.2)
             seed_nodes = seed_nodes[torch.randperm(len(seed_nodes))]
         self._seeds_cpu = seed_nodes.contiguous()
+        # device_seeds=True keeps the whole (shuffled) seed list in HBM; False leaves it in pinned host
+        # memory and copies each minibatch's slice H2D on the sampling stream (what bench.py's e2e times).
+        self._device_seeds = bool(device_seeds)
         with torch.cuda.device(self._dev):
-            self._seeds_dev = self._seeds_cpu.cuda(self._dev)
+            if self._device_seeds:
+                self._seeds_dev = self._seeds_cpu.cuda(self._dev)
+            else:
+                self._seeds_cpu = self._seeds_cpu.pin_memory()
+                self._seeds_dev = None
             self._stream = torch.cuda.Stream(device=self._dev)
         self._num_batches = (len(seed_nodes) + self._batch_size - 1) // self._batch_size
         self._graph_handle = g.handle(self._dev)
@@ -108,7 +115,11 @@ class NeighborSampler:
             self._meta_i = (self._meta_i + 1) % len(self._metas)
             c = _lib.pg_nodeflow_buffers(*[_lib.ptr(bufs[k_]) for k_ in
                                            ("node_mapping", "indptr", "indices", "edge_mapping", "meta")])
-            seeds_ptr = ctypes.c_void_p(self._seeds_dev.data_ptr() + lo * 8)
+            if self._device_seeds:
+                seeds_ptr = ctypes.c_void_p(self._seeds_dev.data_ptr() + lo * 8)
+            else:
+                bufs["seeds"] = self._seeds_cpu[lo:lo + n].to(dev, non_blocking=True)
+                seeds_ptr = _lib.ptr(bufs["seeds"])
             _lib.check(_lib.lib().pg_sample(self._handle, seeds_ptr, n, epoch, k, ctypes.byref(c),
                                             _lib.ptr(h_meta), _lib.stream_ptr(self._stream)), "pg_sample")
             ev = torch.cuda.Event()
@@ -149,17 +160,29 @@ class NeighborSampler:
     def __iter__(self):
         epoch = self._epoch
         self._epoch += 1
+        return self.batches(0, self._num_batches, epoch)
+
+    def batches(self, start, count, epoch=0):
+        """Minibatches [start, start+count) of `epoch`, wrapping around the seed list (batch index
+        modulo the batches per epoch, epoch advanced on every wrap). With prefetch the next
+        minibatches are already being sampled on the side stream while the caller trains on this one;
+        exactly `count` minibatches are sampled."""
         depth = _PREFETCH_DEPTH if self._prefetch else 1
         pending = collections.deque()
-        nxt = 0
-        while nxt < self._num_batches and len(pending) < depth:
-            pending.append(self._issue(epoch, nxt))
+        nxt, end = start, start + count
+        nb = self._num_batches
+
+        def issue(i):
+            return self._issue(epoch + i // nb, i % nb)
+
+        while nxt < end and len(pending) < depth:
+            pending.append(issue(nxt))
             nxt += 1
         while pending:
             job = pending.popleft()
             nf = self._finish(job)
-            if nxt < self._num_batches:
-                pending.append(self._issue(epoch, nxt))
+            if nxt < end:
+                pending.append(issue(nxt))
                 nxt += 1
             yield nf
 
