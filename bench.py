@@ -53,6 +53,11 @@ def parse_args():
     p.add_argument("--dropout", type=float, default=0.2)
     p.add_argument("--lr", type=float, default=3e-2)
     p.add_argument("--modes", default="hbm20,vtx20", help="cache modes to run; the first is the headline")
+    p.add_argument("--path", default="fused", choices=["fused", "eager"],
+                   help="fused: the input layer is aggregated straight from the cache (pg_cache_aggregate, dropout folded "
+                        "in); eager: fetch_data gathers every layer, then torch dropout + pg_aggregate_fwd (the reference's "
+                        "op sequence)")
+    p.add_argument("--gather-batches", type=int, default=50, help="minibatches of the gather-only measurement")
     p.add_argument("--cpu-batches", type=int, default=32, help="minibatches of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--seed", type=int, default=1)
@@ -214,6 +219,7 @@ class Trainer:
         self.cacher = GraphCacheServer(wl.store, V, torch.arange(V, dtype=torch.int64), dev.index)
         self.cacher.init_field(["features", "norm"])
         self.cacher.log = True
+        self.cacher.lazy_input = (a.path == "fused")
         torch.manual_seed(wl.rank)                                            # pa_gcn.py:23
         self.model = GCNSampling(a.feat_size, a.n_hidden, a.n_classes, 1, F.relu, a.dropout, False).cuda(dev)
         self.sync = FlatGradAllReduce(self.model)
@@ -222,7 +228,7 @@ class Trainer:
         self.sampler = NeighborSampler(wl.g, a.batch_size, wl.fanouts, neighbor_type='in', shuffle=True,
                                        num_workers=16, num_hops=len(wl.fanouts),
                                        seed_nodes=torch.from_numpy(wl.train_nid), prefetch=True, seed=a.seed,
-                                       device_seeds=not host_inputs)
+                                       device_seeds=not host_inputs, reuse_buffers=True)
         self.label_stage = [torch.empty(a.batch_size, dtype=torch.int64).pin_memory() for _ in range(4)]
         self.next_batch = 0
         self.sizes = []          # (layer_offsets, block_offsets) of every timed step
@@ -309,7 +315,8 @@ def timed_region(tr, steps, read_loss, clock, world):
 
 
 def kernel_report(tr, reg, hbm_peak, pcie_peak):
-    """Per-kernel-class live timing (pg_timing_*) against the algorithmic bytes of SURVEY.md §8d."""
+    """Per-kernel-class live timing (pg_timing_*: CUDA events on the launching stream, inside the timed region)
+    against the algorithmic bytes of SURVEY.md §8d."""
     from pagraph_b200 import _lib
     wl = tr.wl
     R, Fdim, H2 = wl.R, wl.args.feat_size, 2 * wl.args.n_hidden
@@ -318,31 +325,80 @@ def kernel_report(tr, reg, hbm_peak, pcie_peak):
         by.setdefault(slot, []).append(ms)
     steps = len(tr.sizes)
     N = sum(lo[-1] for lo, _ in tr.sizes)
+    n0 = sum(lo[1] - lo[0] for lo, _ in tr.sizes)
     M = reg["misses"]
-    Hh = N - M
+    fused = _lib.T_FUSED in by
     out = {}
 
-    def add(name, slot_ms, nbytes, peak, peak_name, launches_per_scope=1):
+    def add(name, slot_ms, nbytes, peak, peak_name):
         if not slot_ms:
             return
         t = sum(slot_ms)
-        out[name] = {"launches": len(slot_ms) * launches_per_scope, "avg_ms": t / len(slot_ms),
-                     "alg_bytes_per_launch": nbytes / len(slot_ms), "achieved_gbs": nbytes / t / 1e6,
-                     "peak_gbs": peak, "frac": nbytes / t / 1e6 / peak, "bound": peak_name}
+        out[name] = {"launches": len(slot_ms), "avg_ms": t / len(slot_ms), "alg_bytes_per_launch": nbytes / len(slot_ms),
+                     "achieved_gbs": nbytes / t / 1e6, "peak_gbs": peak, "frac": nbytes / t / 1e6 / peak, "bound": peak_name}
 
     add("sample(all kernels of one pg_sample)", by.get(_lib.T_SAMPLE), sum(sampling_bytes(lo, bo) for lo, bo in tr.sizes),
         hbm_peak, "hbm")
-    add("split_kernel", by.get(_lib.T_SPLIT), 9 * N + 16 * N, hbm_peak, "hbm")
-    add("gather_hit(rows_ldg_kernel)", by.get(_lib.T_GATHER_HIT), 2 * R * Hh + ID_BYTES * Hh, hbm_peak, "hbm")
-    add("gather_miss(rows_bulk_kernel)", by.get(_lib.T_GATHER_MISS), R * M, pcie_peak, "pcie")
+    add("split_kernel/resolve_kernel", by.get(_lib.T_SPLIT), 25 * N, hbm_peak, "hbm")
+    n_hit_rows = (N - n0 if fused else N) - (M * (N - n0) // max(N, 1) if fused else M)   # rows gathered from the HBM cache
+    add("gather_hit(rows_ldg_kernel)", by.get(_lib.T_GATHER_HIT), 2 * R * n_hit_rows + ID_BYTES * n_hit_rows, hbm_peak, "hbm")
+    add("gather_miss(rows_bulk_kernel)", by.get(_lib.T_GATHER_MISS), 4 * Fdim * M, pcie_peak, "pcie")
+    b0 = sum(agg_bytes(lo[1] - lo[0], lo[2] - lo[1], bo[1] - bo[0], Fdim) for lo, bo in tr.sizes)
+    b1 = sum(agg_bytes(lo[2] - lo[1], lo[3] - lo[2], bo[2] - bo[1], H2) for lo, bo in tr.sizes)
     fw = by.get(_lib.T_AGG_FWD, [])
-    if len(fw) == 2 * steps:
-        b0 = sum(agg_bytes(lo[1] - lo[0], lo[2] - lo[1], bo[1] - bo[0], Fdim) for lo, bo in tr.sizes)
-        b1 = sum(agg_bytes(lo[2] - lo[1], lo[3] - lo[2], bo[2] - bo[1], H2) for lo, bo in tr.sizes)
+    if fused:
+        add("cache_aggregate_block0(agg_rows_tma_kernel,D=%d)" % Fdim, by.get(_lib.T_FUSED), b0 + 8 * n0, hbm_peak, "hbm")
+        add("agg_fwd_block1(D=%d)" % H2, fw, b1, hbm_peak, "hbm")
+    elif len(fw) == 2 * steps:
         add("agg_fwd_block0(D=%d)" % Fdim, fw[0::2], b0, hbm_peak, "hbm")
         add("agg_fwd_block1(D=%d)" % H2, fw[1::2], b1, hbm_peak, "hbm")
-        add("agg_bwd_block1(D=%d)" % H2, by.get(_lib.T_AGG_BWD), b1, hbm_peak, "hbm")
+    add("agg_bwd_block1(D=%d)" % H2, by.get(_lib.T_AGG_BWD), b1, hbm_peak, "hbm")
     return out, N, M
+
+
+def gather_only(tr, n_batches, hbm_peak, pcie_peak):
+    """Feature-gather GB/s with the hit/miss split: pg_cache_fetch of EVERY NodeFlow layer (what the reference's
+    fetch_data does, storage.py:157-204), on fresh minibatches, no training work in between."""
+    from pagraph_b200 import _lib
+    wl, c = tr.wl, tr.cacher
+    R = wl.R
+    torch.cuda.synchronize()
+    if c.try_num:
+        c.get_miss_rate()
+    _lib.timing_drain()
+    _lib.timing_enable(True)
+    evs, N = [], 0
+    for nf in tr.sampler.batches(tr.next_batch, n_batches):
+        ids = nf._node_mapping.tousertensor()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        c._gather(ids, c._field_names)
+        b.record()
+        evs.append((a, b))
+        N += ids.numel()
+    tr.next_batch += n_batches
+    torch.cuda.synchronize()
+    _lib.timing_enable(False)
+    by = {}
+    for slot, ms in _lib.timing_drain():
+        by.setdefault(slot, []).append(ms)
+    M = c.miss_num if not c.full_cached else 0
+    if c.try_num:
+        c.get_miss_rate()
+    t = sum(a.elapsed_time(b) for a, b in evs)
+    t_hit, t_miss = sum(by.get(_lib.T_GATHER_HIT, [0])), sum(by.get(_lib.T_GATHER_MISS, [0]))
+    H = N - M
+    out = {"batches": n_batches, "rows_per_batch": N / n_batches, "hit_rate": H / max(N, 1),
+           "gather_gbs": R * N / t / 1e6, "ms_per_batch": t / n_batches,
+           "hit": {"kernel": "rows_ldg_kernel", "payload_gbs": R * H / max(t_hit, 1e-9) / 1e6, "avg_ms": t_hit / n_batches,
+                   "alg_bytes_per_launch": (2 * R * H + ID_BYTES * H) / n_batches,
+                   "achieved_gbs": (2 * R * H + ID_BYTES * H) / max(t_hit, 1e-9) / 1e6, "peak_gbs": hbm_peak,
+                   "frac": (2 * R * H + ID_BYTES * H) / max(t_hit, 1e-9) / 1e6 / hbm_peak, "bound": "hbm"}}
+    if M:
+        out["miss"] = {"kernel": "rows_bulk_kernel", "payload_gbs": R * M / t_miss / 1e6, "avg_ms": t_miss / n_batches,
+                       "alg_bytes_per_launch": R * M / n_batches, "achieved_gbs": R * M / t_miss / 1e6,
+                       "peak_gbs": pcie_peak, "frac": R * M / t_miss / 1e6 / pcie_peak, "bound": "pcie"}
+    return out
 
 
 def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
@@ -365,11 +421,12 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
         if clock is not None and clock.ok:
             clock.stop()
         kern, N, M = kernel_report(tr, reg, hbm_peak, pcie_peak)
+        gather = gather_only(tr, args.gather_batches, hbm_peak, pcie_peak) if not host_inputs else None
         steps = args.steps
         mbps = world * steps / (reg["ms"] * 1e-3)
         r = dict(minibatches_per_s=mbps, ms_per_step=reg["ms"] / steps, wall_ms_per_step=reg["wall_ms"] / steps,
                  rows_per_step=N / steps, miss_rows_per_step=M / steps, hit_rate=1.0 - M / max(N, 1),
-                 gather_gbs=wl.R * N / max(reg["fetch_ms"], 1e-9) / 1e6, gather_ms_per_step=reg["fetch_ms"] / steps,
+                 fetch_ms_per_step=reg["fetch_ms"] / steps, gather=gather,
                  launches=reg["launches"], loss=reg["loss"], clocks=reg["clocks"], kernels=kern,
                  full_cached=tr.cacher.full_cached, cached_rows=tr.cacher.cached_num,
                  layer_sizes=[int(np.mean([lo[i + 1] - lo[i] for lo, _ in tr.sizes])) for i in range(3)],
@@ -598,7 +655,7 @@ def main_ours(args):
     v, e = head["value"], head["e2e"]
     # dominant HBM-bound kernel of the headline mode
     hbm_k = {k: x for k, x in v["kernels"].items() if x["bound"] == "hbm"}
-    top = max(hbm_k, key=lambda k: hbm_k[k]["avg_ms"] * (1 if "sample" not in k else 0))
+    top = max(hbm_k, key=lambda k: hbm_k[k]["avg_ms"] * (1 if "sample" not in k else 0))   # single-kernel classes only
     tk = hbm_k[top]
     traffic = None
     try:
@@ -611,16 +668,17 @@ def main_ours(args):
         "value": v["minibatches_per_s"], "unit": "minibatches/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "cache_mode": modes[0],
+        "config": {"workload": workload_name(args), "cache_mode": modes[0], "path": args.path,
                    "cache": "hbm20 = capacity 20% of HBM bytes (>= the 24 GB table -> full_cached, headline); "
                             "vtx20 = top-20%-out-degree vertices cached (under variants)",
                    "dropout": args.dropout, "optimizer": "Adam lr %g" % args.lr,
                    "l2": "inputs larger than L2 (24 GB feature table, new random minibatch every step); no flush",
                    "parallelism": "dp%d (one partition per GPU, flat-bucket NCCL grad all-reduce)" % world},
-        "gather_gbs": v["gather_gbs"], "hit_rate": v["hit_rate"],
+        "gather_gbs": v["gather"]["gather_gbs"], "hit_rate": v["hit_rate"],
+        "gather": {m: results[m]["value"]["gather"] for m in modes},
         "e2e": {"value": e["minibatches_per_s"], "unit": "minibatches/s", "h2d_bytes_per_step": e["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": e["d2h_bytes_per_step"], "ms_per_step": e["ms_per_step"],
-                "wall_ms_per_step": e["wall_ms_per_step"], "gather_gbs": e["gather_gbs"]},
+                "wall_ms_per_step": e["wall_ms_per_step"]},
         "gpu_launches": v["launches"],
         "clocks": v["clocks"],
         "roofline": {"bound": "hbm", "kernel": top, "achieved": tk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",

@@ -149,6 +149,28 @@ pg_status pg_aggregate_bwd(const int64_t* d_indptr, const int64_t* d_cols, int64
                            int64_t gsrc_stride, int64_t n_dst, int64_t n_src, int32_t dim, int mode,
                            const float* d_norm, void* stream);
 
+/* ---------------------------------------------------------------- fused cache lookup + aggregation
+ * The GCN / GraphSAGE models consume the input layer's features only through the first block's aggregation
+ * (PaGraph/model/gcn_nssc.py:64-74: activation = features; h = dropout(activation); block_compute(0, copy_src, mean)).
+ * pg_cache_aggregate computes that block straight from the feature cache, without materialising the gathered
+ * [n_src, dim] rows that fetch_data (storage.py:186-200) would write and block_compute would read back:
+ *   dst[r] = scale_r * sum_{e in row r} drop(row(t_e)),   t_e = parent_ids[cols[e] - col_base],
+ *   row(t) = flag[t] ? cache[field][l2c[t]] : host_table[field][nid_map[t]]
+ * (missed rows are first pulled over PCIe into a staging buffer, one TMA bulk copy per row). drop() is inverted
+ * dropout with probability dropout_p, mask keyed by (dropout_seed + *d_step, source node, column) so that every
+ * edge of a source node sees the same dropped row, as dropout-then-aggregate does; dropout_p = 0 disables it.
+ * d_norm / mode as pg_aggregate_fwd. Rows [n_dst, zero_rows_to) of d_dst are zero-filled (fixed-shape buffers).
+ * d_counts (optional int64[2]) is incremented by (n_src, misses) like pg_cache_fetch. */
+typedef struct {
+  const int64_t* parent_ids; /* [n_src] parent (local) ids of the block's source layer               */
+  const int64_t* indptr;     /* [n_dst+1] absolute offsets into cols                                  */
+  const int64_t* cols;       /* NodeFlow ids of edge sources; cols[e] - col_base indexes parent_ids   */
+  int64_t col_base, n_src, n_dst;
+} pg_block;
+pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float* d_dst, int64_t dst_stride, int mode,
+                             const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
+                             int64_t zero_rows_to, int64_t* d_counts, void* stream);
+
 /* ---------------------------------------------------------------- measurement helpers */
 /* Pinned H2D copy bandwidth probe (the PCIe roofline denominator). SYNC. */
 pg_status pg_measure_h2d(int dev, size_t bytes, int iters, double* gb_per_s);

@@ -28,6 +28,11 @@ class pg_nodeflow_buffers(ctypes.Structure):
                 ("meta", c_vp)]
 
 
+class pg_block(ctypes.Structure):
+    _fields_ = [("parent_ids", c_vp), ("indptr", c_vp), ("cols", c_vp), ("col_base", ctypes.c_int64),
+                ("n_src", ctypes.c_int64), ("n_dst", ctypes.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/pagraph_b200.h
 SIGNATURES = {
     "pg_version": (ctypes.c_int, []),
@@ -57,6 +62,9 @@ SIGNATURES = {
     "pg_cache_fetch_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),
     "pg_cache_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp, c_vp,
                                       ctypes.c_int, c_vp]),
+    "pg_cache_aggregate": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(pg_block), c_vp, ctypes.c_int64,
+                                          ctypes.c_int, c_vp, ctypes.c_float, ctypes.c_uint64, c_vp, ctypes.c_int64,
+                                          c_vp, c_vp]),
     "pg_aggregate_fwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
     "pg_aggregate_bwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,

@@ -13,6 +13,7 @@
 //   * no degree pass, no atomics, deterministic edge order in the forward;
 //   * backward scatters grad rows with 16-byte vector atomics (red.global.add.v4.f32).
 #include <algorithm>
+#include <cstdlib>
 
 #include "pg_common.cuh"
 
@@ -169,6 +170,232 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(AggBwdArgs a, int 
   }
 }
 
+// ------------------------------------------------------------------ aggregation from row pointers (fused cache lookup)
+// TMA-staged: a warp owns a ring of DEPTH shared-memory buffers of GROUP rows each. For every task
+// (one destination row, <= GROUP of its edges) the lanes read cols -> rowptr, lane 0 arms the buffer's
+// mbarrier with the byte count and each lane pulls its source row with one cp.async.bulk (a 2400-byte
+// row = one descriptor, no registers held while in flight); the warp then sums the staged rows from
+// shared memory (conflict-free 16-byte lanes), applying the dropout mask on the fly, and re-arms the
+// buffer for task t+DEPTH. Bytes in flight per SM = warps * DEPTH * GROUP * row bytes, independent of
+// register pressure; every source row is read from HBM once per edge, every dst row written once.
+constexpr int kRowsMaxWarps = 8;
+constexpr int kRowsMaxDepth = 4;
+constexpr int kRowsMaxGroup = 16;
+
+struct TaskCursor {  // walks (row, edge-chunk) tasks of one warp in order
+  int64_t r, s, e, off;
+  __device__ __forceinline__ void open(const pg::AggRowsArgs& a, int64_t row) {
+    r = row;
+    off = 0;
+    if (r < a.n_dst) {
+      s = a.indptr[r];
+      e = a.indptr[r + 1];
+    } else {
+      s = e = 0;
+    }
+  }
+  __device__ __forceinline__ bool valid(const pg::AggRowsArgs& a) const { return r < a.n_dst; }
+  __device__ __forceinline__ int count(int group) const { return (int)min((int64_t)group, e - s - off); }
+  __device__ __forceinline__ bool last(int group) const { return off + group >= e - s; }
+  __device__ __forceinline__ void next(const pg::AggRowsArgs& a, int group, int64_t stride) {
+    if (last(group)) open(a, r + stride);
+    else off += group;
+  }
+};
+
+__device__ __forceinline__ float4 drop4(float4 v, uint64_t h, uint32_t thr, float scale) {
+  v.x = ((uint32_t)(h & 0xffff) < thr) ? 0.f : v.x * scale;
+  v.y = ((uint32_t)((h >> 16) & 0xffff) < thr) ? 0.f : v.y * scale;
+  v.z = ((uint32_t)((h >> 32) & 0xffff) < thr) ? 0.f : v.z * scale;
+  v.w = ((uint32_t)(h >> 48) < thr) ? 0.f : v.w * scale;
+  return v;
+}
+
+template <int W, int CH, bool DROP>
+__global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a, int group, int depth) {
+  constexpr int kRowsWarps = W;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[kRowsWarps * kRowsMaxDepth];
+  __shared__ int src_idx[kRowsWarps][kRowsMaxDepth][kRowsMaxGroup];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nvec = a.dim >> 2;
+  const uint32_t row_bytes = (uint32_t)a.dim * 4u;
+  const uint32_t warp_smem = pg::smem_u32(smem) + (uint32_t)w * (uint32_t)(depth * group) * row_bytes;
+  if (lane < depth) pg::mbar_init(pg::smem_u32(&bars[w * kRowsMaxDepth + lane]), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int64_t warp0 = (int64_t)blockIdx.x * kRowsWarps + w, nwarps = (int64_t)gridDim.x * kRowsWarps;
+  const uint64_t seed = DROP ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
+
+  auto issue = [&](const TaskCursor& c, int buf) {
+    const int cnt = c.count(group);
+    const uint32_t bar = pg::smem_u32(&bars[w * kRowsMaxDepth + buf]);
+    const float* src = nullptr;
+    if (lane < cnt) {
+      const int64_t j = a.cols[c.s + c.off + lane] - a.col_base;
+      src = a.rowptr[j];
+      src_idx[w][buf][lane] = (int)j;
+    }
+    if (lane == 0) pg::mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
+    __syncwarp();
+    if (lane < cnt) pg::bulk_g2s(warp_smem + (uint32_t)(buf * group + lane) * row_bytes, src, row_bytes, bar);
+  };
+
+  TaskCursor ci, cc;  // issue / consume cursors over the same task sequence
+  ci.open(a, warp0);
+  cc.open(a, warp0);
+  for (int d = 0; d < depth && ci.valid(a); ++d) {
+    issue(ci, d);
+    ci.next(a, group, nwarps);
+  }
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t phase_bits = 0;  // bit b = parity to wait for on buffer b
+  int buf = 0;
+  while (cc.valid(a)) {
+    const int cnt = cc.count(group);
+    const uint32_t bar = pg::smem_u32(&bars[w * kRowsMaxDepth + buf]);
+    while (!pg::mbar_try_wait(bar, (phase_bits >> buf) & 1u)) {
+    }
+    phase_bits ^= 1u << buf;
+    const unsigned char* base = smem + ((size_t)w * depth * group + (size_t)buf * group) * row_bytes;
+    int k = 0;
+    for (; k + 2 <= cnt; k += 2) {  // two staged rows per round: 2*CH independent shared-memory loads in flight
+      const float4* row0 = (const float4*)(base + (size_t)k * row_bytes);
+      const float4* row1 = (const float4*)(base + (size_t)(k + 1) * row_bytes);
+      float4 v0[CH], v1[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int col = c * 32 + lane;
+        if (col < nvec) { v0[c] = row0[col]; v1[c] = row1[col]; }
+      }
+      const uint64_t j0 = DROP ? (uint64_t)src_idx[w][buf][k] : 0ull, j1 = DROP ? (uint64_t)src_idx[w][buf][k + 1] : 0ull;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int col = c * 32 + lane;
+        if (col < nvec) {
+          if (DROP) {
+            v0[c] = drop4(v0[c], pg::drop_hash(seed, j0, (uint32_t)nvec, (uint32_t)col), a.drop_thr, a.keep_scale);
+            v1[c] = drop4(v1[c], pg::drop_hash(seed, j1, (uint32_t)nvec, (uint32_t)col), a.drop_thr, a.keep_scale);
+          }
+          acc[c].x = (acc[c].x + v0[c].x) + v1[c].x; acc[c].y = (acc[c].y + v0[c].y) + v1[c].y;
+          acc[c].z = (acc[c].z + v0[c].z) + v1[c].z; acc[c].w = (acc[c].w + v0[c].w) + v1[c].w;
+        }
+      }
+    }
+    if (k < cnt) {
+      const float4* row = (const float4*)(base + (size_t)k * row_bytes);
+      const uint64_t j = DROP ? (uint64_t)src_idx[w][buf][k] : 0ull;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int col = c * 32 + lane;
+        if (col < nvec) {
+          float4 v = row[col];
+          if (DROP) v = drop4(v, pg::drop_hash(seed, j, (uint32_t)nvec, (uint32_t)col), a.drop_thr, a.keep_scale);
+          acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+        }
+      }
+    }
+    if (cc.last(group)) {  // row complete: scale, write once, reset
+      const float deg = (float)max(cc.e - cc.s, (int64_t)1);
+      const float nrm = a.norm ? a.norm[cc.r] : 1.0f;
+      float4* out = (float4*)(a.dst + cc.r * a.dst_stride);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int col = c * 32 + lane;
+        if (col < nvec) {
+          float4 v = acc[c];
+          if (a.mode == PG_AGG_MEAN) { v.x /= deg; v.y /= deg; v.z /= deg; v.w /= deg; }
+          if (a.norm) { v.x *= nrm; v.y *= nrm; v.z *= nrm; v.w *= nrm; }
+          out[col] = v;
+        }
+        acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cc.next(a, group, nwarps);
+    __syncwarp();  // every lane is done reading this buffer
+    if (ci.valid(a)) {
+      issue(ci, buf);
+      ci.next(a, group, nwarps);
+    }
+    buf = (buf + 1 == depth) ? 0 : buf + 1;
+  }
+  // zero the padding rows of a fixed-shape destination
+  for (int64_t r = a.n_dst + warp0; r < a.zero_rows_to; r += nwarps) {
+    float4* out = (float4*)(a.dst + r * a.dst_stride);
+    for (int col = lane; col < nvec; col += 32) out[col] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// Any width / alignment: one warp per row, scalar columns, plain loads through the row pointers.
+__global__ void __launch_bounds__(kAggThreads) agg_rows_ldg_kernel(pg::AggRowsArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (kAggThreads / 32) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (kAggThreads / 32);
+  const uint32_t groups = (uint32_t)((a.dim + 3) >> 2);
+  const uint64_t seed = a.drop_thr ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
+  for (int64_t r = warp0; r < a.zero_rows_to || r < a.n_dst; r += nwarps) {
+    if (r >= a.n_dst) {
+      for (int col = lane; col < a.dim; col += 32) a.dst[r * a.dst_stride + col] = 0.f;
+      continue;
+    }
+    const int64_t s = a.indptr[r], e = a.indptr[r + 1];
+    const float deg = (float)max(e - s, (int64_t)1);
+    for (int col = lane; col < a.dim; col += 32) {
+      float acc = 0.f;
+      for (int64_t q = s; q < e; ++q) {
+        const int64_t j = a.cols[q] - a.col_base;
+        float v = __ldg(a.rowptr[j] + col);
+        if (a.drop_thr) {
+          const uint64_t h = pg::drop_hash(seed, (uint64_t)j, groups, (uint32_t)(col >> 2));
+          v = ((uint32_t)((h >> (16 * (col & 3))) & 0xffff) < a.drop_thr) ? 0.f : v * a.keep_scale;
+        }
+        acc += v;
+      }
+      if (a.mode == PG_AGG_MEAN) acc /= deg;
+      if (a.norm) acc *= a.norm[r];
+      a.dst[r * a.dst_stride + col] = acc;
+    }
+  }
+}
+
+template <int W, int CH>
+pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, size_t budget, int depth_req) {
+  const size_t row_bytes = (size_t)a.dim * 4;
+  const int slots = (int)(budget / ((size_t)W * row_bytes));
+  if (slots < 2) return PG_ERR_INVALID;  // caller tries fewer warps, then the plain-load kernel
+  int depth = depth_req > 0 ? depth_req : 2;
+  depth = std::max(1, std::min({depth, kRowsMaxDepth, slots}));
+  const int group = std::min(kRowsMaxGroup, slots / depth);
+  const size_t smem = (size_t)W * depth * group * row_bytes;
+  const bool drop = a.drop_thr != 0;
+  auto kern = drop ? agg_rows_tma_kernel<W, CH, true> : agg_rows_tma_kernel<W, CH, false>;
+  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t rows = std::max(a.n_dst, a.zero_rows_to);
+  const int64_t need = std::max<int64_t>(1, (rows + W - 1) / W);
+  const int grid = (int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev));
+  kern<<<grid, W * 32, smem, st>>>(a, group, depth);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+template <int CH>
+pg_status launch_rows_tma(const pg::AggRowsArgs& a, int dev, cudaStream_t st) {
+  static int max_optin = 0;
+  if (!max_optin) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const char* env_b = getenv("PG_AGG_SMEM");
+  const size_t budget = std::min<size_t>((size_t)max_optin - 4096, env_b ? (size_t)atoi(env_b) : 200 * 1024);
+  const char* env_d = getenv("PG_AGG_DEPTH");
+  const char* env_w = getenv("PG_AGG_WARPS");
+  const int depth = env_d ? atoi(env_d) : 0;
+  const int warps = env_w ? atoi(env_w) : 8;
+  pg_status s = PG_ERR_INVALID;
+  if (warps >= 8) s = launch_rows_tma_w<8, CH>(a, dev, st, budget, depth);
+  if (s == PG_ERR_INVALID) s = launch_rows_tma_w<4, CH>(a, dev, st, budget, depth);
+  return s;
+}
+
 template <int LANES, int CH>
 void launch_fwd(const AggArgs& a, int dev, cudaStream_t st) {
   constexpr int rows_per_block = (kAggThreads / 32) * (32 / LANES);
@@ -178,6 +405,29 @@ void launch_fwd(const AggArgs& a, int dev, cudaStream_t st) {
 }
 
 }  // namespace
+
+namespace pg {
+pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st) {
+  const int nvec = a.dim / 4;
+  const bool tma_ok = (a.dim % 4 == 0) && (a.dst_stride % 4 == 0) && ((uintptr_t)a.dst % 16 == 0) && nvec <= 8 * 32 &&
+                      !getenv("PG_AGG_NO_TMA");
+  if (tma_ok) {
+    pg_status s = PG_ERR_INVALID;
+    if (nvec <= 32) s = launch_rows_tma<1>(a, dev, st);
+    else if (nvec <= 64) s = launch_rows_tma<2>(a, dev, st);
+    else if (nvec <= 96) s = launch_rows_tma<3>(a, dev, st);
+    else if (nvec <= 128) s = launch_rows_tma<4>(a, dev, st);
+    else if (nvec <= 160) s = launch_rows_tma<5>(a, dev, st);
+    else s = launch_rows_tma<8>(a, dev, st);
+    if (s != PG_ERR_INVALID) return s;
+  }
+  const int64_t rows = std::max(a.n_dst, a.zero_rows_to);
+  const int64_t need = std::max<int64_t>(1, (rows + kAggThreads / 32 - 1) / (kAggThreads / 32));
+  agg_rows_ldg_kernel<<<(int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev) * 16), kAggThreads, 0, st>>>(a);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+}  // namespace pg
 
 extern "C" {
 

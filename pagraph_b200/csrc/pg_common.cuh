@@ -68,6 +68,37 @@ struct TimedScope {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// ------------------------------------------------------------------ aggregation from per-source row pointers (pg_aggregate.cu)
+// dst[r] = scale_r * sum_{e in [indptr[r], indptr[r+1])} drop(rowptr[cols[e] - col_base][0..dim)), used by the fused
+// cache-lookup + aggregation (pg_cache_aggregate): rowptr[j] points into the HBM cache table or the miss staging buffer.
+struct AggRowsArgs {
+  const int64_t* indptr;
+  const int64_t* cols;
+  int64_t col_base;
+  const float* const* rowptr;  // [n_src] start of every source row (16-byte aligned for the TMA kernel)
+  float* dst;
+  int64_t dst_stride;
+  int64_t n_dst;
+  int64_t zero_rows_to;        // rows [n_dst, zero_rows_to) of dst are zero-filled (padding of fixed-shape buffers)
+  int dim;
+  int mode;
+  const float* norm;
+  uint32_t drop_thr;           // drop a value when its 16-bit hash lane < drop_thr (0 = no dropout)
+  float keep_scale;            // 1 / (1 - p)
+  uint64_t drop_seed;
+  const int64_t* drop_step;    // optional device counter added to the seed (CUDA-graph replays)
+};
+pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st);
+
+// Dropout mask contract (shared with oracle.dropout_mask): one 64-bit hash per (source row j, 4-column group g);
+// its k-th 16-bit lane decides column 4g+k.
+__host__ __device__ __forceinline__ uint64_t drop_hash(uint64_t seed, uint64_t j, uint32_t groups, uint32_t g) {
+  uint64_t x = seed + j * groups + g + 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
 // ------------------------------------------------------------------ Philox4x32-10 (RNG contract, oracle/pg_oracle.cpp)
 struct Philox4 {
   uint32_t c[4];
@@ -101,6 +132,36 @@ __device__ __forceinline__ uint64_t draw_pos(uint32_t k0, uint32_t k1, int64_t v
   const Philox4 r = philox4x32_10((uint32_t)(uint64_t)v, (uint32_t)((uint64_t)v >> 32), hop, t, k0, k1);
   const uint64_t x = (uint64_t)r.c[0] | ((uint64_t)r.c[1] << 32);
   return __umul64hi(x, deg);
+}
+
+// ------------------------------------------------------------------ TMA bulk copy + mbarrier helpers (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst)),
+               "r"(src), "r"(bytes)
+               : "memory");
 }
 
 // ------------------------------------------------------------------ warp / block scans (int64)

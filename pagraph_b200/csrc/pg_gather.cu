@@ -23,6 +23,8 @@
 namespace {
 
 using pg::kFullMask;
+using pg::smem_u32; using pg::mbar_init; using pg::mbar_expect_tx; using pg::mbar_try_wait;
+using pg::bulk_g2s; using pg::bulk_s2g;
 
 constexpr int kRowWarps = 8;          // warps per CTA of the row-copy kernel
 constexpr int kBulkWarps = 2;         // warps per CTA of the TMA kernel
@@ -100,6 +102,54 @@ split_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __restri
   if (user_counts && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&user_counts[0], (unsigned long long)n);
 }
 
+// ------------------------------------------------------------------ resolve (fused path): node -> row pointer
+// rowptr[j] = start of the feature row of NodeFlow node j: inside the HBM cache table when flag[t_j], else inside
+// the miss staging buffer at a freshly allocated slot (the slot's host row goes to miss_row[] for the fetch).
+__global__ void __launch_bounds__(kSplitThreads)
+resolve_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __restrict__ flag,
+               const int64_t* __restrict__ l2c, const int64_t* __restrict__ nid_map, int is_full, const float* cache,
+               int64_t cache_stride, float* stage, int64_t stage_stride, const float** rowptr, int64_t* miss_row,
+               unsigned long long* list_counts, unsigned long long* user_counts) {
+  __shared__ int warp_miss[kSplitThreads / 32];
+  __shared__ unsigned long long base_miss;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  const int64_t ntiles = (n + kSplitThreads - 1) / kSplitThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t j = tile * kSplitThreads + threadIdx.x;
+    const bool valid = j < n;
+    int64_t t = 0;
+    bool hit = true;
+    if (valid) {
+      t = ids[j];
+      hit = is_full || flag[t] != 0;
+      if (hit) rowptr[j] = cache + (is_full ? t : l2c[t]) * cache_stride;
+    }
+    if (is_full) continue;
+    const unsigned mb = __ballot_sync(kFullMask, valid && !hit);
+    if (lane == 0) warp_miss[w] = __popc(mb);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tm = 0;
+      for (int i = 0; i < kSplitThreads / 32; ++i) {
+        const int b = warp_miss[i];
+        warp_miss[i] = tm;
+        tm += b;
+      }
+      base_miss = tm ? atomicAdd(&list_counts[1], (unsigned long long)tm) : 0;
+      if (user_counts && tm) atomicAdd(&user_counts[1], (unsigned long long)tm);
+    }
+    __syncthreads();
+    if (valid && !hit) {
+      const int64_t o = (int64_t)base_miss + warp_miss[w] + __popc(mb & lt);
+      miss_row[o] = nid_map[t];
+      rowptr[j] = stage + o * stage_stride;
+    }
+    __syncthreads();
+  }
+  if (user_counts && !is_full && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&user_counts[0], (unsigned long long)n);
+}
+
 // ------------------------------------------------------------------ row copy with vector loads (hits; generic fallback)
 template <typename V>
 __device__ __forceinline__ void copy_vec(const V* __restrict__ s, V* __restrict__ d, int nvec, int lane) {
@@ -141,35 +191,6 @@ __global__ void __launch_bounds__(kRowWarps * 32) rows_ldg_kernel(RowsArgs a) {
 }
 
 // ------------------------------------------------------------------ row copy with TMA bulk copies (misses / cache fill)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst)),
-               "r"(src), "r"(bytes)
-               : "memory");
-}
-
 __global__ void __launch_bounds__(kBulkWarps * 32) rows_bulk_kernel(RowsArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[kBulkWarps * 32];
@@ -261,6 +282,11 @@ struct pg_cache {
   cudaStream_t miss_stream = nullptr;
   cudaEvent_t ev_split = nullptr, ev_miss_done = nullptr;
   int max_smem_optin = 0;
+  // fused path (pg_cache_aggregate): per-node row pointers + staging rows for misses
+  const float** rowptr = nullptr;
+  int64_t rowptr_cap = 0;
+  float* stage = nullptr;
+  int64_t stage_floats = 0;
 };
 
 static pg_status ensure_ws(pg_cache* c, int64_t n) {
@@ -283,16 +309,18 @@ static pg_status ensure_ws(pg_cache* c, int64_t n) {
 // Launch a row-copy over `n` (or *d_count) items. use_bulk: try the TMA path.
 static pg_status launch_rows(pg_cache* c, const float* const* src, const int64_t* src_stride, float* const* dst,
                              const int64_t* pos, const int64_t* row, const unsigned long long* d_count, int64_t n,
-                             bool use_bulk, cudaStream_t st) {
+                             bool use_bulk, cudaStream_t st, int first_field = 0, int nfields = -1) {
   RowsArgs a;
   memset(&a, 0, sizeof(a));
-  a.nfields = c->nfields;
+  if (nfields < 0) nfields = c->nfields;
+  a.nfields = nfields;
   a.pos = pos; a.row = row; a.count = (const int64_t*)d_count; a.n = n;
   int stage = 0;
   bool any_bulk = false, wide_unaligned = false;
-  for (int f = 0; f < c->nfields; ++f) {
+  for (int f = 0; f < nfields; ++f) {
+    const int dimf = c->fields[first_field + f].dim;
     a.src[f] = src[f]; a.src_stride[f] = src_stride[f];
-    a.dst[f] = dst[f]; a.dst_stride[f] = c->fields[f].dim; a.dim[f] = c->fields[f].dim;
+    a.dst[f] = dst[f]; a.dst_stride[f] = dimf; a.dim[f] = dimf;
     const bool ok = (a.dim[f] % 4 == 0) && (a.src_stride[f] % 4 == 0) && (((uintptr_t)a.src[f] | (uintptr_t)a.dst[f]) % 16 == 0);
     a.bulk_ok[f] = ok;
     a.smem_off[f] = stage;
@@ -376,6 +404,7 @@ void pg_cache_destroy(pg_cache* c) {
   cudaDeviceSynchronize();
   cudaFree(c->list_counts);
   cudaFree(c->hit_pos); cudaFree(c->hit_row); cudaFree(c->miss_pos); cudaFree(c->miss_row);
+  cudaFree((void*)c->rowptr); cudaFree(c->stage);
   if (c->miss_stream) cudaStreamDestroy(c->miss_stream);
   for (cudaEvent_t e : {c->ev_split, c->ev_miss_done})
     if (e) cudaEventDestroy(e);
@@ -475,6 +504,82 @@ pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, fl
   }
   PG_CUDA(cudaStreamWaitEvent(st, c->ev_miss_done, 0));
   return PG_OK;
+}
+
+pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float* d_dst, int64_t dst_stride, int mode,
+                             const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
+                             int64_t zero_rows_to, int64_t* d_counts, void* stream) {
+  PG_REQUIRE(c && blk && d_dst, "pg_cache_aggregate: bad arguments");
+  PG_REQUIRE(field >= 0 && field < c->nfields, "pg_cache_aggregate: no such field");
+  PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_cache_aggregate: mode must be PG_AGG_SUM or PG_AGG_MEAN");
+  PG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pg_cache_aggregate: dropout_p must be in [0, 1)");
+  const int64_t n_src = blk->n_src, n_dst = blk->n_dst;
+  const int dim = c->fields[field].dim;
+  PG_REQUIRE(n_src >= 0 && n_dst >= 0 && dst_stride >= dim, "pg_cache_aggregate: bad sizes");
+  PG_REQUIRE((blk->parent_ids && blk->indptr) || n_dst == 0, "pg_cache_aggregate: null block arrays");
+  if (std::max(n_dst, zero_rows_to) == 0) return PG_OK;
+  pg::DeviceGuard guard(c->dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  // workspaces (grow outside of any stream capture: size them with one eager call first)
+  if (n_src > c->rowptr_cap) {
+    cudaFree((void*)c->rowptr);
+    c->rowptr = nullptr;
+    c->rowptr_cap = 0;
+    const int64_t cap = std::max<int64_t>(n_src + n_src / 4, 1 << 16);
+    if (cudaMalloc((void**)&c->rowptr, (size_t)cap * sizeof(float*)) != cudaSuccess) {
+      cudaGetLastError();
+      pg::set_error("pg_cache_aggregate: out of device memory for %lld row pointers", (long long)cap);
+      return PG_ERR_NOMEM;
+    }
+    c->rowptr_cap = cap;
+  }
+  const bool full = c->is_full;
+  if (!full) {
+    pg_status s = ensure_ws(c, n_src);
+    if (s != PG_OK) return s;
+    const int64_t need = std::max<int64_t>(n_src, 1) * dim;
+    if (need > c->stage_floats) {
+      cudaFree(c->stage);
+      c->stage = nullptr;
+      c->stage_floats = 0;
+      const int64_t cap = need + need / 4;
+      if (cudaMalloc(&c->stage, (size_t)cap * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        pg::set_error("pg_cache_aggregate: out of device memory for a %lld-float miss staging buffer", (long long)cap);
+        return PG_ERR_NOMEM;
+      }
+      c->stage_floats = cap;
+    }
+  }
+  if (n_src > 0) {
+    {
+      pg::TimedScope timed(PG_T_SPLIT, st);
+      if (!full) PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
+      const int grid = (int)std::min<int64_t>((n_src + kSplitThreads - 1) / kSplitThreads, (int64_t)pg::sm_count(c->dev) * 8);
+      resolve_kernel<<<grid, kSplitThreads, 0, st>>>(blk->parent_ids, n_src, c->flag, c->l2c, c->nid_map, full ? 1 : 0,
+                                                    c->cache_tables[field], dim, c->stage, dim, c->rowptr, c->miss_row,
+                                                    c->list_counts, (unsigned long long*)d_counts);
+      PG_CHECK_LAUNCH();
+    }
+    if (!full) {  // missed rows: pinned host table -> staging rows, slot order (TMA bulk copies over PCIe)
+      pg::TimedScope timed(PG_T_GATHER_MISS, st);
+      const float* src[1] = {c->host_dev[field]};
+      const int64_t stride[1] = {c->fields[field].host_stride};
+      float* dst[1] = {c->stage};
+      pg_status s = launch_rows(c, src, stride, dst, nullptr, c->miss_row, c->list_counts + 1, n_src,
+                                env_int("PG_MISS_MODE", 2) == 2, st, field, 1);
+      if (s != PG_OK) return s;
+    }
+  }
+  pg::TimedScope timed(PG_T_FUSED, st);
+  pg::AggRowsArgs a;
+  a.indptr = blk->indptr; a.cols = blk->cols; a.col_base = blk->col_base; a.rowptr = c->rowptr;
+  a.dst = d_dst; a.dst_stride = dst_stride; a.n_dst = n_dst; a.zero_rows_to = zero_rows_to;
+  a.dim = dim; a.mode = mode; a.norm = d_norm;
+  a.drop_thr = (uint32_t)(dropout_p * 65536.0f + 0.5f);
+  a.keep_scale = 1.0f / (1.0f - dropout_p);
+  a.drop_seed = dropout_seed; a.drop_step = d_step;
+  return pg::launch_agg_rows(a, c->dev, st);
 }
 
 }  // extern "C"

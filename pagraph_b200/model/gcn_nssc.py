@@ -40,11 +40,21 @@ def _build_layers(owner, in_feats, n_hidden, n_classes, n_layers, activation, pr
     owner.layers.append(NodeUpdate(2 * n_hidden, n_classes, test=test))
 
 
+def apply_dropout(dropout, h):
+    """dropout(h); rows still living in the feature cache (LazyCacheRows) get the mask folded into the fused
+    aggregation instead of being materialised."""
+    if hasattr(h, "with_dropout"):
+        return h.with_dropout(dropout.p if dropout.training else 0.0)
+    return dropout(h)
+
+
 class _GCNBase(nn.Module):
     _reduce = staticmethod(fn.mean)
 
     def _input_transform(self, nf, dropout):
         h = nf.layers[0].data['features']
+        if hasattr(h, "materialize"):
+            h = h.materialize()
         if dropout is not None:
             h = dropout(h)
         h = self.linear(h)
@@ -64,7 +74,7 @@ class _GCNBase(nn.Module):
         for i, layer in enumerate(self.layers):
             h = nf.layers[i].data.pop('activation')
             if dropout is not None:
-                h = dropout(h)
+                h = apply_dropout(dropout, h)
             nf.layers[i].data['h'] = h
             nf.block_compute(i, fn.copy_src(src='h', out='m'), self._reduce(msg='m', out='h'), layer)
         return nf.layers[-1].data.pop('activation')

@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import function as fn
+from .gcn_nssc import apply_dropout
 
 
 class NodeUpdate(nn.Module):
@@ -53,8 +54,10 @@ class GraphSageSampling(nn.Module):
         reduce_fn = fn.mean if self.aggregator_type == 'mean' else fn.sum
         if self.preprocess:
             for i in range(nf.num_layers):
-                h = self.dropout(nf.layers[i].data.pop('features'))
-                h = self.fc_self(h) + self.fc_neigh(nf.layers[i].data.pop('neigh'))
+                h = nf.layers[i].data.pop('features')
+                h = self.dropout(h.materialize() if hasattr(h, "materialize") else h)
+                neigh = nf.layers[i].data.pop('neigh')
+                h = self.fc_self(h) + self.fc_neigh(neigh.materialize() if hasattr(neigh, "materialize") else neigh)
                 if self.n_layers == 1:
                     h = torch.cat((h, self.activation(h)), dim=1)
                 else:
@@ -66,7 +69,7 @@ class GraphSageSampling(nn.Module):
         # layer `lid` is applied to every remaining block, so each NodeFlow layer keeps a current 'h'
         for lid, layer in enumerate(self.layers):
             for i in range(lid, nf.num_layers - 1):
-                nf.layers[i].data['h'] = self.dropout(nf.layers[i].data.pop('h'))
+                nf.layers[i].data['h'] = apply_dropout(self.dropout, nf.layers[i].data.pop('h'))
                 nf.block_compute(i, fn.copy_src(src='h', out='m'), reduce_fn('m', 'neigh'), layer)
             for i in range(lid + 1, nf.num_layers):
                 nf.layers[i].data['h'] = nf.layers[i].data.pop('activation')

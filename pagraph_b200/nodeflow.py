@@ -219,9 +219,14 @@ class NodeFlow:
                                       "(the only one the reference models use)")
         if reduce_func.msg != message_func.out:
             raise KeyError("reduce reads message field %r but copy_src writes %r" % (reduce_func.msg, message_func.out))
-        indptr, cols, col_base, n_dst, _ = self.block_csr(block_id)
+        indptr, cols, col_base, n_dst, n_src = self.block_csr(block_id)
         h = self._frame_of(block_id)[message_func.src]
-        out = ops.BlockAggregate.apply(h, indptr, cols, col_base, n_dst, reduce_func.mode)
+        if hasattr(h, "materialize"):        # LazyCacheRows (GraphCacheServer.lazy_input): reduce straight from the cache
+            c = h.cacher
+            out = ops.cache_aggregate(c, h.name, h.parent_ids, indptr, cols, col_base, n_src, n_dst, reduce_func.mode,
+                                      dropout_p=h.dropout_p, seed=c.next_dropout_seed() if h.dropout_p > 0 else 0)
+        else:
+            out = ops.BlockAggregate.apply(h, indptr, cols, col_base, n_dst, reduce_func.mode)
         dst_frame = self._frame_of(block_id + 1)
         dst_frame[reduce_func.out] = out
         if apply_node_func is not None:

@@ -53,3 +53,24 @@ class BlockAggregate(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             grad_src = aggregate_backward(indptr, cols, col_base, grad_out, n_src, mode)
         return grad_src, None, None, None, None, None
+
+
+def cache_aggregate(cacher, field, parent_ids, indptr, cols, col_base, n_src, n_dst, mode, norm=None, dropout_p=0.0,
+                    seed=0, step=None, out=None, zero_rows_to=0):
+    """Fused cache lookup + dropout + block aggregation (pg_cache_aggregate): dst rows are reduced straight
+    from the feature cache / host table of `cacher` (a GraphCacheServer), without materialising the
+    gathered source rows. `field` is the field name; `step` an optional int64 CUDA scalar added to the seed."""
+    import ctypes
+    fi = cacher._field_names.index(field)
+    dim = cacher.dims[field]
+    dev = cacher._dev
+    if out is None:
+        out = torch.empty((max(n_dst, zero_rows_to), dim), dtype=torch.float32, device=dev)
+    blk = _lib.pg_block(_lib.ptr(parent_ids), _lib.ptr(indptr), _lib.ptr(cols), col_base, n_src, n_dst)
+    counts = cacher._counts if (cacher.log and not cacher.full_cached) else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pg_cache_aggregate(cacher._handle, fi, ctypes.byref(blk), _lib.ptr(out), out.stride(0),
+                                                 _MODES[mode], _lib.ptr(norm), float(dropout_p), int(seed) & (2 ** 64 - 1),
+                                                 _lib.ptr(step), zero_rows_to, _lib.ptr(counts), _lib.stream_ptr()),
+                   "pg_cache_aggregate")
+    return out

@@ -24,7 +24,7 @@ _SOFT_CAP = 1 << 28   # start below this many int64 entries per buffer; grow on 
 class NeighborSampler:
     def __init__(self, g, batch_size, expand_factor=None, num_hops=1, neighbor_type='in',
                  transition_prob=None, seed_nodes=None, shuffle=False, num_workers=1, prefetch=False,
-                 add_self_loop=False, seed=0, device=None, device_seeds=True):
+                 add_self_loop=False, seed=0, device=None, device_seeds=True, reuse_buffers=False):
         if not getattr(g, "is_readonly", False):
             raise ValueError("NeighborSampler requires a read-only graph")
         if neighbor_type != 'in':
@@ -61,6 +61,12 @@ class NeighborSampler:
         # device_seeds=True keeps the whole (shuffled) seed list in HBM; False leaves it in pinned host
         # memory and copies each minibatch's slice H2D on the sampling stream (what bench.py's e2e times).
         self._device_seeds = bool(device_seeds)
+        # reuse_buffers=True: NodeFlow arrays live in a ring of preallocated buffers (no allocation and no
+        # cross-stream allocator bookkeeping per minibatch). A NodeFlow is then valid until `ring` more minibatches
+        # have been requested — the training loop's use (one NodeFlow alive at a time); keep the default for
+        # callers that hold on to NodeFlows.
+        self._reuse = bool(reuse_buffers)
+        self._ring, self._ring_i = [], 0
         with torch.cuda.device(self._dev):
             if self._device_seeds:
                 self._seeds_dev = self._seeds_cpu.cuda(self._dev)
@@ -100,17 +106,32 @@ class NeighborSampler:
                                                 ctypes.byref(h)), "pg_sampler_create")
         self._handle = h
 
+    def _alloc_bufs(self, dev):
+        return dict(node_mapping=torch.empty(self._cap_nodes, dtype=torch.int64, device=dev),
+                    indptr=torch.empty(self._cap_nodes + 1, dtype=torch.int64, device=dev),
+                    indices=torch.empty(self._cap_edges, dtype=torch.int64, device=dev),
+                    edge_mapping=torch.empty(self._cap_edges, dtype=torch.int64, device=dev),
+                    meta=torch.empty(_lib.PG_META_LEN, dtype=torch.int64, device=dev))
+
     # ---- one minibatch
     def _issue(self, epoch, k):
         lo = k * self._batch_size
         n = min(self._batch_size, len(self._seeds_cpu) - lo)
         dev = "cuda:%d" % self._dev
+        if self._reuse:
+            # the slot being overwritten belonged to a minibatch whose compute is already enqueued on the
+            # caller's stream: order the sampling stream after it
+            ev_free = torch.cuda.Event()
+            ev_free.record(torch.cuda.current_stream(self._dev))
+            self._stream.wait_event(ev_free)
         with torch.cuda.device(self._dev), torch.cuda.stream(self._stream):
-            bufs = dict(node_mapping=torch.empty(self._cap_nodes, dtype=torch.int64, device=dev),
-                        indptr=torch.empty(self._cap_nodes + 1, dtype=torch.int64, device=dev),
-                        indices=torch.empty(self._cap_edges, dtype=torch.int64, device=dev),
-                        edge_mapping=torch.empty(self._cap_edges, dtype=torch.int64, device=dev),
-                        meta=torch.empty(_lib.PG_META_LEN, dtype=torch.int64, device=dev))
+            if self._reuse:
+                if not self._ring:
+                    self._ring = [self._alloc_bufs(dev) for _ in range(_PREFETCH_DEPTH + 2)]
+                bufs = dict(self._ring[self._ring_i])
+                self._ring_i = (self._ring_i + 1) % len(self._ring)
+            else:
+                bufs = self._alloc_bufs(dev)
             h_meta = self._metas[self._meta_i]
             self._meta_i = (self._meta_i + 1) % len(self._metas)
             c = _lib.pg_nodeflow_buffers(*[_lib.ptr(bufs[k_]) for k_ in
@@ -134,6 +155,7 @@ class NeighborSampler:
             self._stream.synchronize()
             self._cap_nodes = max(int(meta[1] * 1.25) + 16, self._cap_nodes * 2)
             self._cap_edges = max(int(meta[2] * 1.25) + 16, self._cap_edges * 2)
+            self._ring, self._ring_i = [], 0
             self._create_handle()
             return self._finish(self._issue(job["epoch"], job["k"]))
         if meta[0] != _lib.PG_OK:
@@ -144,8 +166,9 @@ class NeighborSampler:
         b = job["bufs"]
         cur = torch.cuda.current_stream(self._dev)
         cur.wait_event(job["ev"])
-        for t in b.values():
-            t.record_stream(cur)
+        if not self._reuse:
+            for t in b.values():
+                t.record_stream(cur)
         return NodeFlow(b["node_mapping"], b["indptr"], b["indices"], b["edge_mapping"], layer_offsets,
                         flow_offsets, seeds_cpu=self._seeds_cpu[job["lo"]:job["lo"] + job["n"]], parent=self.g)
 

@@ -27,6 +27,36 @@ def _ensure_device_visible(t):
     _REGISTERED[key] = nbytes
 
 
+class LazyCacheRows:
+    """Stand-in for the not-yet-gathered rows of one field of one NodeFlow layer (`lazy_input`).
+
+    `NodeFlow.block_compute` / the models reduce it straight from the cache with the fused kernel
+    (pg_cache_aggregate); anything else that needs the tensor calls `materialize()` (also triggered by
+    `Frame.__getitem__` through `NodeFlow` layer views), which runs the ordinary gather for that layer.
+    """
+
+    def __init__(self, cacher, name, parent_ids):
+        self.cacher, self.name, self.parent_ids = cacher, name, parent_ids
+        self.shape = (parent_ids.numel(), cacher.dims[name])
+        self.dropout_p = 0.0
+        self._rows = None
+
+    def with_dropout(self, p):
+        """The same rows with (inverted) dropout of probability p folded into the fused aggregation."""
+        if self._rows is not None:
+            return torch.nn.functional.dropout(self._rows, p, True) if p > 0 else self._rows
+        out = LazyCacheRows(self.cacher, self.name, self.parent_ids)
+        out.dropout_p = 1.0 - (1.0 - self.dropout_p) * (1.0 - p)
+        return out
+
+    def materialize(self):
+        if self._rows is None:
+            self._rows = self.cacher._gather(self.parent_ids, [self.name])[0]
+            if self.dropout_p > 0:
+                self._rows = torch.nn.functional.dropout(self._rows, self.dropout_p, True)
+        return self._rows
+
+
 class GraphCacheServer:
     """
     Manage graph features: fetch the feature tensors of a NodeFlow from the GPU cache or from the
@@ -65,6 +95,11 @@ class GraphCacheServer:
         self.fetch_mode = 0            # 0 auto, 1 plain loads, 2 TMA bulk (pg_cache_fetch `mode`)
         self.last_hit_mask = None      # bool[N] of the most recent fetch_data when keep_hit_mask
         self.keep_hit_mask = False
+        # lazy_input (extension): fetch_data leaves the INPUT layer (layer 0) ungathered as LazyCacheRows so
+        # the first block's aggregation can read the cache directly; every other layer is gathered as usual.
+        self.lazy_input = False
+        self._drop_seed = None         # base seed of the fused dropout masks (drawn from torch's RNG on first use)
+        self._drop_calls = 0
 
     # ---- logging counters (storage.py:54-56,219-227); kept on the device, read lazily
     @property
@@ -231,6 +266,30 @@ class GraphCacheServer:
         if not ids.is_cuda:
             ids = ids.to(self._dev)
         n = offsets[nodeflow.num_layers]
+        first = 0
+        if self.lazy_input and nodeflow.num_layers > 1:
+            first = 1
+            layer0 = ids[offsets[0]:offsets[1]]
+            nodeflow._node_frames[0] = FrameRef(Frame({name: LazyCacheRows(self, name, layer0)
+                                                       for name in self._field_names}))
+        lo0 = offsets[first]
+        outs = self._gather(ids[lo0:n], self._field_names)
+        for i in range(first, nodeflow.num_layers):
+            lo, hi = offsets[i] - lo0, offsets[i + 1] - lo0
+            frame = {name: out[lo:hi] for name, out in zip(self._field_names, outs)}
+            nodeflow._node_frames[i] = FrameRef(Frame(frame))
+
+    def next_dropout_seed(self):
+        """A fresh 64-bit seed per fused-dropout call, derived from torch's global RNG state."""
+        if self._drop_seed is None:
+            self._drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._drop_calls += 1
+        return (self._drop_seed + self._drop_calls * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+
+    def _gather(self, ids, names):
+        """rows of `names` (all fields, or a subset -> all fields are gathered and the subset returned) for local
+        ids `ids` (CUDA int64), through pg_cache_fetch."""
+        n = ids.numel()
         outs = [torch.empty((n, self.dims[name]), dtype=torch.float32, device=self._dev)
                 for name in self._field_names]
         mask = None
@@ -243,10 +302,9 @@ class GraphCacheServer:
                                                  _lib.ptr(counts), self.fetch_mode, _lib.stream_ptr()),
                        "pg_cache_fetch")
         self.last_hit_mask = mask
-        for i in range(nodeflow.num_layers):
-            lo, hi = offsets[i], offsets[i + 1]
-            frame = {name: out[lo:hi] for name, out in zip(self._field_names, outs)}
-            nodeflow._node_frames[i] = FrameRef(Frame(frame))
+        if list(names) == self._field_names:
+            return outs
+        return [outs[self._field_names.index(nm)] for nm in names]
 
     def fetch_from_cache(self, nodeflow):
         """Fully-cached fast path (storage.py:207-216)."""
