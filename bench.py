@@ -53,10 +53,12 @@ def parse_args():
     p.add_argument("--dropout", type=float, default=0.2)
     p.add_argument("--lr", type=float, default=3e-2)
     p.add_argument("--modes", default="hbm20,vtx20", help="cache modes to run; the first is the headline")
-    p.add_argument("--path", default="fused", choices=["fused", "eager"],
-                   help="fused: the input layer is aggregated straight from the cache (pg_cache_aggregate, dropout folded "
-                        "in); eager: fetch_data gathers every layer, then torch dropout + pg_aggregate_fwd (the reference's "
-                        "op sequence)")
+    p.add_argument("--path", default="engine", choices=["engine", "fused", "eager"],
+                   help="engine: GCNTrainEngine — two-stream CUDA-graph pipeline over the fused kernels (default); "
+                        "fused: the eager Python loop with the input layer aggregated straight from the cache "
+                        "(pg_cache_aggregate, dropout folded in); eager: fetch_data gathers every layer, then torch dropout + "
+                        "pg_aggregate_fwd (the reference's op sequence)")
+    p.add_argument("--kernel-steps", type=int, default=40, help="steps of the instrumented per-kernel timing pass (engine)")
     p.add_argument("--gather-batches", type=int, default=50, help="minibatches of the gather-only measurement")
     p.add_argument("--cpu-batches", type=int, default=32, help="minibatches of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,8 +225,14 @@ class Trainer:
         torch.manual_seed(wl.rank)                                            # pa_gcn.py:23
         self.model = GCNSampling(a.feat_size, a.n_hidden, a.n_classes, 1, F.relu, a.dropout, False).cuda(dev)
         self.sync = FlatGradAllReduce(self.model)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=a.lr, weight_decay=0)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=a.lr, weight_decay=0, capturable=(a.path == "engine"))
         self.loss_fcn = torch.nn.CrossEntropyLoss()
+        self.engine = None
+        if a.path == "engine":
+            from pagraph_b200.engine import GCNTrainEngine
+            self.engine = GCNTrainEngine(wl.g, self.cacher, self.model, self.opt, wl.train_nid,
+                                         wl.labels_cpu if host_inputs else wl.labels_dev, a.batch_size, wl.fanouts,
+                                         sync=self.sync, seed=a.seed, shuffle=True, host_inputs=host_inputs)
         self.sampler = NeighborSampler(wl.g, a.batch_size, wl.fanouts, neighbor_type='in', shuffle=True,
                                        num_workers=16, num_hops=len(wl.fanouts),
                                        seed_nodes=torch.from_numpy(wl.train_nid), prefetch=True, seed=a.seed,
@@ -244,6 +252,9 @@ class Trainer:
         """`count` consecutive training steps. Returns the last loss (host float if read_loss)."""
         wl, dev = self.wl, self.wl.dev
         loss = None
+        if self.engine is not None:
+            self.engine.size_log = self.sizes if record else None
+            return self.engine.steps(count, read_loss=read_loss)
         for nf in self.sampler.batches(self.next_batch, count):
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,6 +296,7 @@ def timed_region(tr, steps, read_loss, clock, world):
     _lib.timing_drain()
     _lib.timing_enable(True)
     launches0 = _lib.launch_count()
+    eng_launches0 = tr.engine.launches if tr.engine is not None else 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
     ev0.record()
@@ -297,6 +309,8 @@ def timed_region(tr, steps, read_loss, clock, world):
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
+    if tr.engine is not None:
+        launches = tr.engine.launches - eng_launches0
     if world > 1:
         t = torch.tensor([ms, (w1 - w0) * 1e3], device=tr.wl.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,6 +342,8 @@ def kernel_report(tr, reg, hbm_peak, pcie_peak):
     n0 = sum(lo[1] - lo[0] for lo, _ in tr.sizes)
     M = reg["misses"]
     fused = _lib.T_FUSED in by
+    if not by:
+        return {}, N, M
     out = {}
 
     def add(name, slot_ms, nbytes, peak, peak_name):
@@ -420,7 +436,17 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
             torch.cuda.profiler.stop()
         if clock is not None and clock.ok:
             clock.stop()
-        kern, N, M = kernel_report(tr, reg, hbm_peak, pcie_peak)
+        if tr.engine is not None:
+            # per-kernel CUDA-event timing needs host-side launches: same pipeline, same kernels, graphs off
+            steps_total, misses_total, sizes_total = len(tr.sizes), reg["misses"], tr.sizes
+            tr.engine.use_graphs = False
+            kreg = timed_region(tr, min(args.kernel_steps, args.steps), host_inputs, None, world)
+            tr.engine.use_graphs = True
+            kern, _, _ = kernel_report(tr, kreg, hbm_peak, pcie_peak)
+            tr.sizes = sizes_total
+            N, M = sum(lo[-1] for lo, _ in tr.sizes), misses_total
+        else:
+            kern, N, M = kernel_report(tr, reg, hbm_peak, pcie_peak)
         gather = gather_only(tr, args.gather_batches, hbm_peak, pcie_peak) if not host_inputs else None
         steps = args.steps
         mbps = world * steps / (reg["ms"] * 1e-3)
@@ -673,6 +699,11 @@ def main_ours(args):
                             "vtx20 = top-20%-out-degree vertices cached (under variants)",
                    "dropout": args.dropout, "optimizer": "Adam lr %g" % args.lr,
                    "l2": "inputs larger than L2 (24 GB feature table, new random minibatch every step); no flush",
+                   "kernel_timing": ("pg_timing_* CUDA-event pairs on the launching stream; with --path engine the timed region "
+                                     "replays CUDA graphs (no host-side launch to bracket), so the per-kernel numbers come from an "
+                                     "instrumented un-graphed pass of the same pipeline over %d further minibatches"
+                                     % min(args.kernel_steps, args.steps)) if args.path == "engine" else
+                                    "pg_timing_* CUDA-event pairs on the launching stream inside the timed region",
                    "parallelism": "dp%d (one partition per GPU, flat-bucket NCCL grad all-reduce)" % world},
         "gather_gbs": v["gather"]["gather_gbs"], "hit_rate": v["hit_rate"],
         "gather": {m: results[m]["value"]["gather"] for m in modes},

@@ -96,6 +96,11 @@ typedef struct {
  * `stream`; the caller synchronises on the stream/event before reading it. */
 pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int64_t epoch, int64_t batch,
                     const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream);
+/* Same with the minibatch key read from device memory (uint32[2], as produced by pg_minibatch_key): the launch
+ * sequence then depends on nothing but pointers, so one captured CUDA graph samples every minibatch. */
+void pg_minibatch_key(uint64_t seed, int64_t epoch, int64_t batch, uint32_t* key);
+pg_status pg_sample_keyed(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, const uint32_t* d_key,
+                          const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream);
 
 /* ---------------------------------------------------------------- feature cache (replaces PaGraph/storage/storage.py) */
 typedef struct {
@@ -133,6 +138,11 @@ pg_status pg_cache_fetch_host(pg_cache* c, const int64_t* d_nids, int64_t n, flo
  * aligned rows). */
 pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out,
                          uint8_t* d_hit_mask, int64_t* d_counts, int mode, void* stream);
+/* Same for the id range [*d_begin, *d_end) of d_ids_base, the range living on the device (e.g. two entries of a
+ * NodeFlow's meta block): nothing about the minibatch's size is needed on the host, so the call can be captured in a
+ * CUDA graph and replayed. `cap` bounds the row count (output capacity, grid sizing). */
+pg_status pg_cache_fetch_dyn(pg_cache* c, const int64_t* d_ids_base, const int64_t* d_begin, const int64_t* d_end,
+                             int64_t cap, float* const* d_out, int64_t* d_counts, int mode, void* stream);
 /* ---------------------------------------------------------------- aggregation (replaces nf.block_compute(i, fn.copy_src,
  * fn.sum|fn.mean, ...), PaGraph/model/gcn_nssc.py:71-74, graphsage_nssc.py:98-106; and, run over
  * the full graph with mode=PG_AGG_SUM + norm, the server-side --preprocess fold, server/pa_server.py:45-52).
@@ -148,6 +158,14 @@ pg_status pg_aggregate_bwd(const int64_t* d_indptr, const int64_t* d_cols, int64
                            const float* d_grad_dst, int64_t gdst_stride, float* d_grad_src,
                            int64_t gsrc_stride, int64_t n_dst, int64_t n_src, int32_t dim, int mode,
                            const float* d_norm, void* stream);
+/* Device-resident extents (see pg_block.d_layer_offsets): d_indptr_base is the NodeFlow-wide indptr, cap_dst / cap_src
+ * are capacities; rows [n_dst, cap_dst) of d_dst are zero-filled, all cap_src rows of d_grad_src are zeroed first. */
+pg_status pg_aggregate_fwd_dyn(const int64_t* d_indptr_base, const int64_t* d_cols, const int64_t* d_layer_offsets,
+                               const float* d_src, int64_t src_stride, float* d_dst, int64_t dst_stride, int64_t cap_dst,
+                               int32_t dim, int mode, const float* d_norm, void* stream);
+pg_status pg_aggregate_bwd_dyn(const int64_t* d_indptr_base, const int64_t* d_cols, const int64_t* d_layer_offsets,
+                               const float* d_grad_dst, int64_t gdst_stride, float* d_grad_src, int64_t gsrc_stride,
+                               int64_t cap_dst, int64_t cap_src, int32_t dim, int mode, const float* d_norm, void* stream);
 
 /* ---------------------------------------------------------------- fused cache lookup + aggregation
  * The GCN / GraphSAGE models consume the input layer's features only through the first block's aggregation
@@ -166,7 +184,21 @@ typedef struct {
   const int64_t* indptr;     /* [n_dst+1] absolute offsets into cols                                  */
   const int64_t* cols;       /* NodeFlow ids of edge sources; cols[e] - col_base indexes parent_ids   */
   int64_t col_base, n_src, n_dst;
+  /* Optional device-resident extents (CUDA-graph replays, sizes unknown to the host): int64[3] = the NodeFlow layer
+   * offsets of the source layer, the destination layer and the layer after it (&meta[4 + block]). When non-NULL,
+   * parent_ids / indptr are the NodeFlow-wide node_mapping / indptr arrays, col_base is ignored and n_src / n_dst are
+   * capacities (grid sizing, padding); the kernels read the real extents on the device. */
+  const int64_t* d_layer_offsets;
 } pg_block;
+/* The two stages of pg_cache_aggregate, callable separately so that stage 1 (with its PCIe transfer of the missed rows)
+ * can run ahead on another stream while the previous minibatch computes. d_rowptr: caller-owned float*[n_src];
+ * d_stage: caller-owned [stage_rows, dim]. Misses beyond stage_rows are not staged: their row pointer addresses the
+ * pinned host table directly (slower, still correct). */
+pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const float** d_rowptr, float* d_stage,
+                           int64_t stage_rows, int64_t* d_counts, void* stream);
+pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, int32_t dim, float* d_dst,
+                            int64_t dst_stride, int mode, const float* d_norm, float dropout_p, uint64_t dropout_seed,
+                            const int64_t* d_step, int64_t zero_rows_to, void* stream);
 pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float* d_dst, int64_t dst_stride, int mode,
                              const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
                              int64_t zero_rows_to, int64_t* d_counts, void* stream);

@@ -30,7 +30,7 @@ class pg_nodeflow_buffers(ctypes.Structure):
 
 class pg_block(ctypes.Structure):
     _fields_ = [("parent_ids", c_vp), ("indptr", c_vp), ("cols", c_vp), ("col_base", ctypes.c_int64),
-                ("n_src", ctypes.c_int64), ("n_dst", ctypes.c_int64)]
+                ("n_src", ctypes.c_int64), ("n_dst", ctypes.c_int64), ("d_layer_offsets", c_vp)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/pagraph_b200.h
@@ -62,6 +62,19 @@ SIGNATURES = {
     "pg_cache_fetch_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),
     "pg_cache_fetch": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp, c_vp,
                                       ctypes.c_int, c_vp]),
+    "pg_cache_resolve": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(pg_block), c_vp, c_vp, ctypes.c_int64, c_vp,
+                                        c_vp]),
+    "pg_aggregate_rows": (ctypes.c_int, [c_vp, ctypes.POINTER(pg_block), ctypes.c_int32, c_vp, ctypes.c_int64, ctypes.c_int,
+                                         c_vp, ctypes.c_float, ctypes.c_uint64, c_vp, ctypes.c_int64, c_vp]),
+    "pg_cache_fetch_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp,
+                                          ctypes.c_int, c_vp]),
+    "pg_minibatch_key": (None, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint32)]),
+    "pg_sample_keyed": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.POINTER(pg_nodeflow_buffers), c_vp,
+                                       c_vp]),
+    "pg_aggregate_fwd_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
+    "pg_aggregate_bwd_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
     "pg_cache_aggregate": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(pg_block), c_vp, ctypes.c_int64,
                                           ctypes.c_int, c_vp, ctypes.c_float, ctypes.c_uint64, c_vp, ctypes.c_int64,
                                           c_vp, c_vp]),

@@ -33,6 +33,8 @@ struct AggArgs {
   int dim;
   int mode;
   const float* norm;
+  const int64_t* lo;        // optional device-resident extents (pg_common.cuh apply_extents); n_dst is then a capacity
+  int64_t zero_rows_to;     // rows [n_dst, zero_rows_to) are zero-filled
 };
 
 // VEC-wide columns; LANES lanes per row; each lane holds CH column slices per pass.
@@ -43,6 +45,12 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_vec4(AggArgs a) {
   const int64_t warp0 = (int64_t)blockIdx.x * (kAggThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kAggThreads / 32);
   const int nvec = a.dim >> 2;
+  if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
+  for (int64_t r0 = a.n_dst + warp0 * ROWS_PER_WARP; r0 < a.zero_rows_to; r0 += nwarps * ROWS_PER_WARP) {
+    const int64_t r = r0 + grp;
+    if (r < a.zero_rows_to)
+      for (int col = sub; col < nvec; col += LANES) ((float4*)(a.dst + r * a.dst_stride))[col] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int64_t r0 = warp0 * ROWS_PER_WARP; r0 < a.n_dst; r0 += nwarps * ROWS_PER_WARP) {
     const int64_t r = r0 + grp;
     if (r >= a.n_dst) continue;
@@ -110,6 +118,9 @@ __global__ void __launch_bounds__(kAggThreads) agg_fwd_scalar(AggArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (kAggThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kAggThreads / 32);
+  if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
+  for (int64_t r = a.n_dst + warp0; r < a.zero_rows_to; r += nwarps)
+    for (int col = lane; col < a.dim; col += 32) a.dst[r * a.dst_stride + col] = 0.f;
   for (int64_t r = warp0; r < a.n_dst; r += nwarps) {
     const int64_t s = a.indptr[r], e = a.indptr[r + 1];
     const float deg = (float)max(e - s, (int64_t)1);
@@ -135,12 +146,14 @@ struct AggBwdArgs {
   int dim;
   int mode;
   const float* norm;
+  const int64_t* lo;
 };
 
 __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(AggBwdArgs a, int vec4) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (kAggThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kAggThreads / 32);
+  if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
   for (int64_t r = warp0; r < a.n_dst; r += nwarps) {
     const int64_t s = a.indptr[r], e = a.indptr[r + 1];
     if (e == s) continue;
@@ -178,7 +191,6 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(AggBwdArgs a, int 
 // shared memory (conflict-free 16-byte lanes), applying the dropout mask on the fly, and re-arms the
 // buffer for task t+DEPTH. Bytes in flight per SM = warps * DEPTH * GROUP * row bytes, independent of
 // register pressure; every source row is read from HBM once per edge, every dst row written once.
-constexpr int kRowsMaxWarps = 8;
 constexpr int kRowsMaxDepth = 4;
 constexpr int kRowsMaxGroup = 16;
 
@@ -226,6 +238,7 @@ __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a,
   __syncwarp();
   const int64_t warp0 = (int64_t)blockIdx.x * kRowsWarps + w, nwarps = (int64_t)gridDim.x * kRowsWarps;
   const uint64_t seed = DROP ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
+  if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
 
   auto issue = [&](const TaskCursor& c, int buf) {
     const int cnt = c.count(group);
@@ -335,6 +348,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_rows_ldg_kernel(pg::AggRowsAr
   const int64_t nwarps = (int64_t)gridDim.x * (kAggThreads / 32);
   const uint32_t groups = (uint32_t)((a.dim + 3) >> 2);
   const uint64_t seed = a.drop_thr ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
+  if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
   for (int64_t r = warp0; r < a.zero_rows_to || r < a.n_dst; r += nwarps) {
     if (r >= a.n_dst) {
       for (int col = lane; col < a.dim; col += 32) a.dst[r * a.dst_stride + col] = 0.f;
@@ -431,9 +445,28 @@ pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st) {
 
 extern "C" {
 
+static pg_status aggregate_fwd_impl(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base, const float* d_src,
+                                    int64_t src_stride, float* d_dst, int64_t dst_stride, int64_t n_dst, int32_t dim,
+                                    int mode, const float* d_norm, const int64_t* d_lo, int64_t zero_rows_to, void* stream);
+
 pg_status pg_aggregate_fwd(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base, const float* d_src,
                            int64_t src_stride, float* d_dst, int64_t dst_stride, int64_t n_dst, int32_t dim, int mode,
                            const float* d_norm, void* stream) {
+  return aggregate_fwd_impl(d_indptr, d_cols, col_base, d_src, src_stride, d_dst, dst_stride, n_dst, dim, mode, d_norm,
+                            nullptr, 0, stream);
+}
+
+pg_status pg_aggregate_fwd_dyn(const int64_t* d_indptr_base, const int64_t* d_cols, const int64_t* d_layer_offsets,
+                               const float* d_src, int64_t src_stride, float* d_dst, int64_t dst_stride, int64_t cap_dst,
+                               int32_t dim, int mode, const float* d_norm, void* stream) {
+  PG_REQUIRE(d_layer_offsets != nullptr, "pg_aggregate_fwd_dyn: null layer offsets");
+  return aggregate_fwd_impl(d_indptr_base, d_cols, 0, d_src, src_stride, d_dst, dst_stride, cap_dst, dim, mode, d_norm,
+                            d_layer_offsets, cap_dst, stream);
+}
+
+static pg_status aggregate_fwd_impl(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base, const float* d_src,
+                                    int64_t src_stride, float* d_dst, int64_t dst_stride, int64_t n_dst, int32_t dim,
+                                    int mode, const float* d_norm, const int64_t* d_lo, int64_t zero_rows_to, void* stream) {
   PG_REQUIRE(d_indptr && d_dst && n_dst >= 0 && dim >= 1, "pg_aggregate_fwd: bad arguments");
   PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_aggregate_fwd: mode must be PG_AGG_SUM or PG_AGG_MEAN");
   PG_REQUIRE(src_stride >= dim && dst_stride >= dim, "pg_aggregate_fwd: stride smaller than dim");
@@ -441,7 +474,7 @@ pg_status pg_aggregate_fwd(const int64_t* d_indptr, const int64_t* d_cols, int64
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));
   cudaStream_t st = (cudaStream_t)stream;
-  AggArgs a{d_indptr, d_cols, col_base, d_src, src_stride, d_dst, dst_stride, n_dst, dim, mode, d_norm};
+  AggArgs a{d_indptr, d_cols, col_base, d_src, src_stride, d_dst, dst_stride, n_dst, dim, mode, d_norm, d_lo, zero_rows_to};
   const bool vec4 = (dim % 4 == 0) && (src_stride % 4 == 0) && (dst_stride % 4 == 0) &&
                     (((uintptr_t)d_src | (uintptr_t)d_dst) % 16 == 0);
   pg::TimedScope timed(PG_T_AGG_FWD, st);
@@ -462,9 +495,30 @@ pg_status pg_aggregate_fwd(const int64_t* d_indptr, const int64_t* d_cols, int64
   return PG_OK;
 }
 
+static pg_status aggregate_bwd_impl(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base,
+                                    const float* d_grad_dst, int64_t gdst_stride, float* d_grad_src, int64_t gsrc_stride,
+                                    int64_t n_dst, int64_t n_src, int32_t dim, int mode, const float* d_norm,
+                                    const int64_t* d_lo, void* stream);
+
 pg_status pg_aggregate_bwd(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base, const float* d_grad_dst,
                            int64_t gdst_stride, float* d_grad_src, int64_t gsrc_stride, int64_t n_dst, int64_t n_src,
                            int32_t dim, int mode, const float* d_norm, void* stream) {
+  return aggregate_bwd_impl(d_indptr, d_cols, col_base, d_grad_dst, gdst_stride, d_grad_src, gsrc_stride, n_dst, n_src, dim,
+                            mode, d_norm, nullptr, stream);
+}
+
+pg_status pg_aggregate_bwd_dyn(const int64_t* d_indptr_base, const int64_t* d_cols, const int64_t* d_layer_offsets,
+                               const float* d_grad_dst, int64_t gdst_stride, float* d_grad_src, int64_t gsrc_stride,
+                               int64_t cap_dst, int64_t cap_src, int32_t dim, int mode, const float* d_norm, void* stream) {
+  PG_REQUIRE(d_layer_offsets != nullptr, "pg_aggregate_bwd_dyn: null layer offsets");
+  return aggregate_bwd_impl(d_indptr_base, d_cols, 0, d_grad_dst, gdst_stride, d_grad_src, gsrc_stride, cap_dst, cap_src, dim,
+                            mode, d_norm, d_layer_offsets, stream);
+}
+
+static pg_status aggregate_bwd_impl(const int64_t* d_indptr, const int64_t* d_cols, int64_t col_base,
+                                    const float* d_grad_dst, int64_t gdst_stride, float* d_grad_src, int64_t gsrc_stride,
+                                    int64_t n_dst, int64_t n_src, int32_t dim, int mode, const float* d_norm,
+                                    const int64_t* d_lo, void* stream) {
   PG_REQUIRE(d_indptr && d_grad_src && n_dst >= 0 && n_src >= 0 && dim >= 1, "pg_aggregate_bwd: bad arguments");
   PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_aggregate_bwd: mode must be PG_AGG_SUM or PG_AGG_MEAN");
   PG_REQUIRE(gdst_stride >= dim && gsrc_stride >= dim, "pg_aggregate_bwd: stride smaller than dim");
@@ -480,7 +534,7 @@ pg_status pg_aggregate_bwd(const int64_t* d_indptr, const int64_t* d_cols, int64
     }
   }
   if (n_dst == 0 || n_src == 0) return PG_OK;
-  AggBwdArgs a{d_indptr, d_cols, col_base, d_grad_dst, gdst_stride, d_grad_src, gsrc_stride, n_dst, dim, mode, d_norm};
+  AggBwdArgs a{d_indptr, d_cols, col_base, d_grad_dst, gdst_stride, d_grad_src, gsrc_stride, n_dst, dim, mode, d_norm, d_lo};
   const int vec4 = (dim % 4 == 0) && (gdst_stride % 4 == 0) && (gsrc_stride % 4 == 0) &&
                    (((uintptr_t)d_grad_dst | (uintptr_t)d_grad_src) % 16 == 0);
   const int64_t need = std::max<int64_t>(1, (n_dst + kAggThreads / 32 - 1) / (kAggThreads / 32));

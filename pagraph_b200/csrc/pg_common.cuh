@@ -87,7 +87,21 @@ struct AggRowsArgs {
   float keep_scale;            // 1 / (1 - p)
   uint64_t drop_seed;
   const int64_t* drop_step;    // optional device counter added to the seed (CUDA-graph replays)
+  const int64_t* lo;           // optional device-resident extents (see pg_block.d_layer_offsets): indptr/n_dst/col_base
+                               // are then NodeFlow-wide base / capacity / ignored, and the kernel derives the block's
+                               // own from the device (apply_extents)
 };
+
+// Device-resident block extents: lo[0..2] = NodeFlow layer offsets of the block's source layer, its destination layer
+// and the layer after it. Rewrites (indptr, col_base, n_dst) in place; returns the source-layer size.
+__device__ __forceinline__ int64_t apply_extents(const int64_t* lo, const int64_t*& indptr, int64_t& col_base,
+                                                 int64_t& n_dst) {
+  const int64_t l0 = lo[0], l1 = lo[1], l2 = lo[2];
+  indptr += l1;
+  col_base = l0;
+  n_dst = min(n_dst, l2 - l1);
+  return l1 - l0;
+}
 pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st);
 
 // Dropout mask contract (shared with oracle.dropout_mask): one 64-bit hash per (source row j, 4-column group g);

@@ -45,16 +45,31 @@ struct RowsArgs {
   const int64_t* row;                 // source row of item i
   const int64_t* count;               // device-resident item count (null: n)
   int64_t n;
+  const int64_t* dyn_begin;           // optional device-resident range [*dyn_begin, *dyn_end) into `row` (n is then a capacity)
+  const int64_t* dyn_end;
 };
+
+__device__ __forceinline__ int64_t rows_extent(RowsArgs& a) {
+  if (a.dyn_begin) {
+    const int64_t b = *a.dyn_begin;
+    a.row += b;
+    return min(*a.dyn_end - b, a.n);
+  }
+  return a.count ? min((int64_t)*a.count, a.n) : a.n;
+}
 
 // ------------------------------------------------------------------ split
 __global__ void __launch_bounds__(kSplitThreads)
 split_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __restrict__ flag,
              const int64_t* __restrict__ l2c, const int64_t* __restrict__ nid_map, int64_t* hit_pos,
              int64_t* hit_row, int64_t* miss_pos, int64_t* miss_row, unsigned long long* list_counts,
-             uint8_t* hit_mask, unsigned long long* user_counts) {
+             uint8_t* hit_mask, unsigned long long* user_counts, const int64_t* dyn_begin, const int64_t* dyn_end) {
   __shared__ int warp_hits[kSplitThreads / 32], warp_miss[kSplitThreads / 32];
   __shared__ unsigned long long base_hit, base_miss;
+  if (dyn_begin) {  // device-resident range into ids; n is a capacity
+    ids += *dyn_begin;
+    n = min(n, *dyn_end - *dyn_begin);
+  }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   const int64_t ntiles = (n + kSplitThreads - 1) / kSplitThreads;
@@ -108,10 +123,15 @@ split_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __restri
 __global__ void __launch_bounds__(kSplitThreads)
 resolve_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __restrict__ flag,
                const int64_t* __restrict__ l2c, const int64_t* __restrict__ nid_map, int is_full, const float* cache,
-               int64_t cache_stride, float* stage, int64_t stage_stride, const float** rowptr, int64_t* miss_row,
-               unsigned long long* list_counts, unsigned long long* user_counts) {
+               int64_t cache_stride, float* stage, int64_t stage_stride, int64_t stage_rows, const float* host,
+               int64_t host_stride, const float** rowptr, int64_t* miss_row, unsigned long long* list_counts,
+               unsigned long long* user_counts, const int64_t* lo) {
   __shared__ int warp_miss[kSplitThreads / 32];
   __shared__ unsigned long long base_miss;
+  if (lo) {  // device-resident extents: ids is the NodeFlow-wide node_mapping, n a capacity
+    ids += lo[0];
+    n = min(n, lo[1] - lo[0]);
+  }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   const int64_t ntiles = (n + kSplitThreads - 1) / kSplitThreads;
@@ -142,8 +162,13 @@ resolve_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __rest
     __syncthreads();
     if (valid && !hit) {
       const int64_t o = (int64_t)base_miss + warp_miss[w] + __popc(mb & lt);
-      miss_row[o] = nid_map[t];
-      rowptr[j] = stage + o * stage_stride;
+      const int64_t full = nid_map[t];
+      if (o < stage_rows) {
+        miss_row[o] = full;
+        rowptr[j] = stage + o * stage_stride;
+      } else {  // staging buffer exhausted: the consumer reads this row from the pinned host table directly
+        rowptr[j] = host + full * host_stride;
+      }
     }
     __syncthreads();
   }
@@ -179,7 +204,7 @@ __device__ __forceinline__ void copy_row(const float* src, float* dst, int dim, 
 __global__ void __launch_bounds__(kRowWarps * 32) rows_ldg_kernel(RowsArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * kRowWarps;
-  const int64_t n = a.count ? min((int64_t)*a.count, a.n) : a.n;
+  const int64_t n = rows_extent(a);
   for (int64_t i = warp0; i < n; i += nwarps) {
     const int64_t r = a.row[i], p = a.pos ? a.pos[i] : i;
 #pragma unroll
@@ -201,7 +226,7 @@ __global__ void __launch_bounds__(kBulkWarps * 32) rows_bulk_kernel(RowsArgs a) 
   if (owner) mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  const int64_t n = a.count ? min((int64_t)*a.count, a.n) : a.n;
+  const int64_t n = rows_extent(a);
   const int64_t warp0 = (int64_t)blockIdx.x * kBulkWarps + w, nwarps = (int64_t)gridDim.x * kBulkWarps;
   uint32_t parity = 0;
   for (int64_t base = warp0 * a.stages; base < n; base += nwarps * a.stages) {
@@ -309,9 +334,11 @@ static pg_status ensure_ws(pg_cache* c, int64_t n) {
 // Launch a row-copy over `n` (or *d_count) items. use_bulk: try the TMA path.
 static pg_status launch_rows(pg_cache* c, const float* const* src, const int64_t* src_stride, float* const* dst,
                              const int64_t* pos, const int64_t* row, const unsigned long long* d_count, int64_t n,
-                             bool use_bulk, cudaStream_t st, int first_field = 0, int nfields = -1) {
+                             bool use_bulk, cudaStream_t st, int first_field = 0, int nfields = -1,
+                             const int64_t* dyn_begin = nullptr, const int64_t* dyn_end = nullptr) {
   RowsArgs a;
   memset(&a, 0, sizeof(a));
+  a.dyn_begin = dyn_begin; a.dyn_end = dyn_end;
   if (nfields < 0) nfields = c->nfields;
   a.nfields = nfields;
   a.pos = pos; a.row = row; a.count = (const int64_t*)d_count; a.n = n;
@@ -452,8 +479,24 @@ pg_status pg_cache_fetch_host(pg_cache* c, const int64_t* d_nids, int64_t n, flo
                      env_int("PG_MISS_MODE", 2) == 2, st);
 }
 
+static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out,
+                                  uint8_t* d_hit_mask, int64_t* d_counts, int mode, const int64_t* d_begin,
+                                  const int64_t* d_end, void* stream);
+
 pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out, uint8_t* d_hit_mask,
                          int64_t* d_counts, int mode, void* stream) {
+  return cache_fetch_impl(c, d_parent_ids, n, d_out, d_hit_mask, d_counts, mode, nullptr, nullptr, stream);
+}
+
+pg_status pg_cache_fetch_dyn(pg_cache* c, const int64_t* d_ids_base, const int64_t* d_begin, const int64_t* d_end,
+                             int64_t cap, float* const* d_out, int64_t* d_counts, int mode, void* stream) {
+  PG_REQUIRE(d_begin && d_end, "pg_cache_fetch_dyn: null range");
+  return cache_fetch_impl(c, d_ids_base, cap, d_out, nullptr, d_counts, mode, d_begin, d_end, stream);
+}
+
+static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out,
+                                  uint8_t* d_hit_mask, int64_t* d_counts, int mode, const int64_t* d_begin,
+                                  const int64_t* d_end, void* stream) {
   PG_REQUIRE(c && d_out && (d_parent_ids || n == 0) && n >= 0, "pg_cache_fetch: bad arguments");
   PG_REQUIRE(mode >= 0 && mode <= 2, "pg_cache_fetch: mode must be 0, 1 or 2");
   if (n == 0) return PG_OK;
@@ -473,7 +516,8 @@ pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, fl
       PG_CHECK_LAUNCH();
     }
     pg::TimedScope ts(PG_T_GATHER_HIT, st);
-    return launch_rows(c, c->cache_tables, cache_strides, d_out, nullptr, d_parent_ids, nullptr, n, false, st);
+    return launch_rows(c, c->cache_tables, cache_strides, d_out, nullptr, d_parent_ids, nullptr, n, false, st, 0, -1,
+                       d_begin, d_end);
   }
   pg_status s = ensure_ws(c, n);
   if (s != PG_OK) return s;
@@ -483,7 +527,7 @@ pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, fl
     const int grid = (int)std::min<int64_t>((n + kSplitThreads - 1) / kSplitThreads, (int64_t)sms * 8);
     split_kernel<<<grid, kSplitThreads, 0, st>>>(d_parent_ids, n, c->flag, c->l2c, c->nid_map, c->hit_pos, c->hit_row,
                                                  c->miss_pos, c->miss_row, c->list_counts, d_hit_mask,
-                                                 (unsigned long long*)d_counts);
+                                                 (unsigned long long*)d_counts, d_begin, d_end);
     PG_CHECK_LAUNCH();
   }
   // misses first, on the high-priority side stream, so PCIe is busy while the hit rows stream from HBM
@@ -506,21 +550,7 @@ pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, fl
   return PG_OK;
 }
 
-pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float* d_dst, int64_t dst_stride, int mode,
-                             const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
-                             int64_t zero_rows_to, int64_t* d_counts, void* stream) {
-  PG_REQUIRE(c && blk && d_dst, "pg_cache_aggregate: bad arguments");
-  PG_REQUIRE(field >= 0 && field < c->nfields, "pg_cache_aggregate: no such field");
-  PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_cache_aggregate: mode must be PG_AGG_SUM or PG_AGG_MEAN");
-  PG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pg_cache_aggregate: dropout_p must be in [0, 1)");
-  const int64_t n_src = blk->n_src, n_dst = blk->n_dst;
-  const int dim = c->fields[field].dim;
-  PG_REQUIRE(n_src >= 0 && n_dst >= 0 && dst_stride >= dim, "pg_cache_aggregate: bad sizes");
-  PG_REQUIRE((blk->parent_ids && blk->indptr) || n_dst == 0, "pg_cache_aggregate: null block arrays");
-  if (std::max(n_dst, zero_rows_to) == 0) return PG_OK;
-  pg::DeviceGuard guard(c->dev);
-  cudaStream_t st = (cudaStream_t)stream;
-  // workspaces (grow outside of any stream capture: size them with one eager call first)
+static pg_status ensure_fused_ws(pg_cache* c, int64_t n_src, int dim, bool need_stage) {
   if (n_src > c->rowptr_cap) {
     cudaFree((void*)c->rowptr);
     c->rowptr = nullptr;
@@ -533,10 +563,7 @@ pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float*
     }
     c->rowptr_cap = cap;
   }
-  const bool full = c->is_full;
-  if (!full) {
-    pg_status s = ensure_ws(c, n_src);
-    if (s != PG_OK) return s;
+  if (need_stage) {
     const int64_t need = std::max<int64_t>(n_src, 1) * dim;
     if (need > c->stage_floats) {
       cudaFree(c->stage);
@@ -551,35 +578,87 @@ pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float*
       c->stage_floats = cap;
     }
   }
-  if (n_src > 0) {
-    {
-      pg::TimedScope timed(PG_T_SPLIT, st);
-      if (!full) PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
-      const int grid = (int)std::min<int64_t>((n_src + kSplitThreads - 1) / kSplitThreads, (int64_t)pg::sm_count(c->dev) * 8);
-      resolve_kernel<<<grid, kSplitThreads, 0, st>>>(blk->parent_ids, n_src, c->flag, c->l2c, c->nid_map, full ? 1 : 0,
-                                                    c->cache_tables[field], dim, c->stage, dim, c->rowptr, c->miss_row,
-                                                    c->list_counts, (unsigned long long*)d_counts);
-      PG_CHECK_LAUNCH();
-    }
-    if (!full) {  // missed rows: pinned host table -> staging rows, slot order (TMA bulk copies over PCIe)
-      pg::TimedScope timed(PG_T_GATHER_MISS, st);
-      const float* src[1] = {c->host_dev[field]};
-      const int64_t stride[1] = {c->fields[field].host_stride};
-      float* dst[1] = {c->stage};
-      pg_status s = launch_rows(c, src, stride, dst, nullptr, c->miss_row, c->list_counts + 1, n_src,
-                                env_int("PG_MISS_MODE", 2) == 2, st, field, 1);
-      if (s != PG_OK) return s;
-    }
+  return PG_OK;
+}
+
+pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const float** d_rowptr, float* d_stage,
+                           int64_t stage_rows, int64_t* d_counts, void* stream) {
+  PG_REQUIRE(c && blk && d_rowptr, "pg_cache_resolve: bad arguments");
+  PG_REQUIRE(field >= 0 && field < c->nfields, "pg_cache_resolve: no such field");
+  const int64_t n_src = blk->n_src;
+  PG_REQUIRE(n_src >= 0 && (blk->parent_ids || n_src == 0), "pg_cache_resolve: bad block");
+  PG_REQUIRE(c->is_full || stage_rows == 0 || d_stage, "pg_cache_resolve: null staging buffer");
+  if (n_src == 0) return PG_OK;
+  pg::DeviceGuard guard(c->dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int dim = c->fields[field].dim;
+  const bool full = c->is_full;
+  if (!full) {
+    pg_status s = ensure_ws(c, n_src);
+    if (s != PG_OK) return s;
   }
-  pg::TimedScope timed(PG_T_FUSED, st);
+  {
+    pg::TimedScope timed(PG_T_SPLIT, st);
+    if (!full) PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
+    const int grid = (int)std::min<int64_t>((n_src + kSplitThreads - 1) / kSplitThreads, (int64_t)pg::sm_count(c->dev) * 8);
+    resolve_kernel<<<grid, kSplitThreads, 0, st>>>(blk->parent_ids, n_src, c->flag, c->l2c, c->nid_map, full ? 1 : 0,
+                                                  c->cache_tables[field], dim, d_stage, dim, stage_rows, c->host_dev[field],
+                                                  c->fields[field].host_stride, d_rowptr, c->miss_row, c->list_counts,
+                                                  (unsigned long long*)d_counts, blk->d_layer_offsets);
+    PG_CHECK_LAUNCH();
+  }
+  if (!full && stage_rows > 0) {  // missed rows: pinned host table -> staging rows, slot order (TMA bulk copies over PCIe)
+    pg::TimedScope timed(PG_T_GATHER_MISS, st);
+    const float* src[1] = {c->host_dev[field]};
+    const int64_t stride[1] = {c->fields[field].host_stride};
+    float* dst[1] = {d_stage};
+    pg_status s = launch_rows(c, src, stride, dst, nullptr, c->miss_row, c->list_counts + 1, std::min(n_src, stage_rows),
+                              env_int("PG_MISS_MODE", 2) == 2, st, field, 1);
+    if (s != PG_OK) return s;
+  }
+  return PG_OK;
+}
+
+pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, int32_t dim, float* d_dst,
+                            int64_t dst_stride, int mode, const float* d_norm, float dropout_p, uint64_t dropout_seed,
+                            const int64_t* d_step, int64_t zero_rows_to, void* stream) {
+  PG_REQUIRE(d_rowptr && blk && d_dst && dim >= 1, "pg_aggregate_rows: bad arguments");
+  PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_aggregate_rows: mode must be PG_AGG_SUM or PG_AGG_MEAN");
+  PG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pg_aggregate_rows: dropout_p must be in [0, 1)");
+  PG_REQUIRE(blk->n_dst >= 0 && dst_stride >= dim && (blk->indptr || blk->n_dst == 0), "pg_aggregate_rows: bad sizes");
+  if (std::max(blk->n_dst, zero_rows_to) == 0) return PG_OK;
+  int dev = 0;
+  PG_CUDA(cudaGetDevice(&dev));
+  cudaStream_t st = (cudaStream_t)stream;
   pg::AggRowsArgs a;
-  a.indptr = blk->indptr; a.cols = blk->cols; a.col_base = blk->col_base; a.rowptr = c->rowptr;
-  a.dst = d_dst; a.dst_stride = dst_stride; a.n_dst = n_dst; a.zero_rows_to = zero_rows_to;
+  a.indptr = blk->indptr; a.cols = blk->cols; a.col_base = blk->col_base; a.rowptr = d_rowptr;
+  a.dst = d_dst; a.dst_stride = dst_stride; a.n_dst = blk->n_dst; a.zero_rows_to = zero_rows_to;
   a.dim = dim; a.mode = mode; a.norm = d_norm;
   a.drop_thr = (uint32_t)(dropout_p * 65536.0f + 0.5f);
   a.keep_scale = 1.0f / (1.0f - dropout_p);
   a.drop_seed = dropout_seed; a.drop_step = d_step;
-  return pg::launch_agg_rows(a, c->dev, st);
+  a.lo = blk->d_layer_offsets;
+  pg::TimedScope timed(PG_T_FUSED, st);
+  return pg::launch_agg_rows(a, dev, st);
+}
+
+pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float* d_dst, int64_t dst_stride, int mode,
+                             const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
+                             int64_t zero_rows_to, int64_t* d_counts, void* stream) {
+  PG_REQUIRE(c && blk && d_dst, "pg_cache_aggregate: bad arguments");
+  PG_REQUIRE(field >= 0 && field < c->nfields, "pg_cache_aggregate: no such field");
+  PG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pg_cache_aggregate: dropout_p must be in [0, 1)");
+  PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_cache_aggregate: mode must be PG_AGG_SUM or PG_AGG_MEAN");
+  const int dim = c->fields[field].dim;
+  PG_REQUIRE(blk->n_src >= 0 && blk->n_dst >= 0 && dst_stride >= dim, "pg_cache_aggregate: bad sizes");
+  pg::DeviceGuard guard(c->dev);
+  // workspaces grow outside of any stream capture: size them with one eager call first
+  pg_status s = ensure_fused_ws(c, blk->n_src, dim, !c->is_full);
+  if (s != PG_OK) return s;
+  s = pg_cache_resolve(c, field, blk, c->rowptr, c->stage, c->is_full ? 0 : blk->n_src, d_counts, stream);
+  if (s != PG_OK) return s;
+  return pg_aggregate_rows(c->rowptr, blk, dim, d_dst, dst_stride, mode, d_norm, dropout_p, dropout_seed, d_step,
+                           zero_rows_to, stream);
 }
 
 }  // extern "C"

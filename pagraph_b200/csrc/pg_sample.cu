@@ -178,6 +178,7 @@ struct PickArgs {
   int64_t fanout;
   uint32_t hop;
   uint32_t k0, k1;
+  const uint32_t* key_ptr;   // optional device-resident (k0, k1) — CUDA-graph replays re-key without re-capturing
   int64_t* nb_src;           // [cap_edges]
   int64_t* nb_eid;           // [cap_edges]
   int64_t cap_edges;
@@ -201,6 +202,10 @@ __global__ void __launch_bounds__(kPickWarps * 32) pick_kernel(PickArgs a) {
   const int64_t warp0 = (int64_t)blockIdx.x * kPickWarps + w, nwarps = (int64_t)gridDim.x * kPickWarps;
   const int64_t n = min(*a.n_front, a.cap_front);
   const unsigned lt_mask = (1u << lane) - 1;
+  if (a.key_ptr) {
+    a.k0 = a.key_ptr[0];
+    a.k1 = a.key_ptr[1];
+  }
   for (int64_t i = warp0; i < n; i += nwarps) {
     const int64_t v = a.front[i];
     const int64_t s = a.indptr[v], deg = a.indptr[v + 1] - s, k = a.fanout;
@@ -592,8 +597,29 @@ void pg_sampler_destroy(pg_sampler* s) {
   delete s;
 }
 
+static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, uint32_t k0, uint32_t k1,
+                             const uint32_t* d_key, const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream);
+
+void pg_minibatch_key(uint64_t seed, int64_t epoch, int64_t batch, uint32_t* key) {
+  minibatch_key(seed, epoch, batch, &key[0], &key[1]);
+}
+
 pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int64_t epoch, int64_t batch,
                     const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream) {
+  PG_REQUIRE(s != nullptr, "pg_sample: null sampler");
+  uint32_t k0, k1;
+  minibatch_key(s->seed, epoch, batch, &k0, &k1);
+  return sample_impl(s, d_seeds, n_seeds, k0, k1, nullptr, out, h_meta, stream);
+}
+
+pg_status pg_sample_keyed(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, const uint32_t* d_key,
+                          const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream) {
+  PG_REQUIRE(s != nullptr && d_key != nullptr, "pg_sample_keyed: null sampler or key");
+  return sample_impl(s, d_seeds, n_seeds, 0, 0, d_key, out, h_meta, stream);
+}
+
+static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, uint32_t k0, uint32_t k1,
+                             const uint32_t* d_key, const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream) {
   PG_REQUIRE(s && out && out->node_mapping && out->indptr && out->indices && out->edge_mapping && out->meta,
              "pg_sample: null output buffer");
   PG_REQUIRE(n_seeds >= 0 && n_seeds <= s->max_seeds, "pg_sample: n_seeds exceeds max_seeds");
@@ -602,8 +628,6 @@ pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int6
   pg::DeviceGuard guard(g->dev);
   cudaStream_t st = (cudaStream_t)stream;
   const int dev = g->dev;
-  uint32_t k0, k1;
-  minibatch_key(s->seed, epoch, batch, &k0, &k1);
 
   pg::TimedScope timed(PG_T_SAMPLE, st);
   PG_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(Counts), st));
@@ -632,7 +656,7 @@ pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int6
     scan_pass2<<<grid_f, kScanThreads, 0, st>>>(fc, s->tile_sums);
     PG_CHECK_LAUNCH();
     PickArgs pa{g->indptr, g->indices, g->eids, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->row_off[h],
-                s->fanouts[h - 1], (uint32_t)h, k0, k1, s->nb_src[h], s->nb_eid[h], s->cap_edges, s->bitmap,
+                s->fanouts[h - 1], (uint32_t)h, k0, k1, d_key, s->nb_src[h], s->nb_eid[h], s->cap_edges, s->bitmap,
                 s->scratch, s->scratch_stride};
     const int grid_p = (int)std::min<int64_t>(s->pick_grid, std::max<int64_t>(1, (cap_front + kPickWarps - 1) / kPickWarps));
     pick_kernel<<<grid_p, kPickWarps * 32, 0, st>>>(pa);

@@ -1,0 +1,350 @@
+"""GCNTrainEngine — the training loop of examples/profile/pa_gcn.py:86-97 as a two-stream, CUDA-graph pipeline.
+
+The reference loop is `for nf in sampler: cacher.fetch_data(nf); label = ...; pred = model(nf); loss; backward;
+step`. Issued op by op it is launch-bound on a B200 (≈ 40 kernels, ≈ 0.65 ms of GPU work per minibatch at config 2).
+Here the same work is two captured graphs per minibatch, replayed:
+
+  load graph (side stream, one per ring slot)     pg_sample_keyed -> pg_cache_fetch_dyn (layers 1..L frames) ->
+                                                  pg_cache_resolve (row pointers of the input layer + PCIe staging of
+                                                  its missed rows) [-> label gather]
+  compute graph (main stream, per slot x bucket)  pg_aggregate_rows (fused cache lookup + dropout + block-0 aggregation)
+                                                  -> NodeUpdate linears (cuBLAS) -> pg_aggregate_fwd_dyn -> ... -> loss ->
+                                                  backward (pg_aggregate_bwd_dyn) -> gradient all-reduce -> Adam
+
+Nothing about a minibatch's size is needed on the host to launch it: every kernel reads the NodeFlow extents from
+the device (`meta`), the host only picks the padded-shape bucket of the dense layers from the pinned copy of `meta`
+that the load graph leaves behind two minibatches ahead. The PCIe transfer of minibatch k+1's missed rows runs under
+minibatch k's compute. Semantics (what is sampled, fetched, aggregated, and the model math) are those of the eager
+classes in this package; tests/test_gpu_engine.py checks the two paths against each other.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .nodeflow import NodeBatch
+from .ops import _MODES
+
+_RING = 3          # ring slots: load runs up to 2 minibatches ahead of compute
+_BUCKET = 4096     # padded-shape granularity of the dense layers
+
+
+class _BlockAggregateDyn(torch.autograd.Function):
+    """copy_src + mean/sum over NodeFlow block `block` with device-resident extents (fixed-shape buffers)."""
+
+    @staticmethod
+    def forward(ctx, src, indptr, cols, meta, block, cap_dst, mode):
+        ctx.args = (indptr, cols, meta, block, cap_dst, mode, src.shape[0])
+        dim = src.shape[1]
+        out = torch.empty((cap_dst, dim), dtype=torch.float32, device=src.device)
+        lo = ctypes.c_void_p(meta.data_ptr() + 8 * (4 + block))
+        _lib.check(_lib.lib().pg_aggregate_fwd_dyn(_lib.ptr(indptr), _lib.ptr(cols), lo, _lib.ptr(src), src.stride(0),
+                                                   _lib.ptr(out), out.stride(0), cap_dst, dim, _MODES[mode], None,
+                                                   _lib.stream_ptr()), "pg_aggregate_fwd_dyn")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        indptr, cols, meta, block, cap_dst, mode, cap_src = ctx.args
+        grad_out = grad_out.contiguous()
+        dim = grad_out.shape[1]
+        grad_src = torch.empty((cap_src, dim), dtype=torch.float32, device=grad_out.device)
+        lo = ctypes.c_void_p(meta.data_ptr() + 8 * (4 + block))
+        _lib.check(_lib.lib().pg_aggregate_bwd_dyn(_lib.ptr(indptr), _lib.ptr(cols), lo, _lib.ptr(grad_out),
+                                                   grad_out.stride(0), _lib.ptr(grad_src), grad_src.stride(0), cap_dst,
+                                                   cap_src, dim, _MODES[mode], None, _lib.stream_ptr()),
+                   "pg_aggregate_bwd_dyn")
+        return grad_src, None, None, None, None, None, None
+
+
+class _Slot:
+    pass
+
+
+class GCNTrainEngine:
+    def __init__(self, g, cacher, model, optimizer, train_nid, labels, batch_size, fanouts, sync=None, seed=0,
+                 shuffle=True, host_inputs=False, stage_rows=131072, use_graphs=True, loss_fcn=None):
+        """
+        g:          pagraph_b200.DGLGraph of the partition; cacher: GraphCacheServer (init_field done; auto_cache may
+                    come later — graphs are re-captured when the cache state changes)
+        model:      pagraph_b200.model.gcn_nssc.GCNSampling (preprocess=False) on the GPU
+        optimizer:  torch optimizer built with capturable=True when use_graphs (e.g. Adam)
+        train_nid:  int64 seed vertices (local ids); labels: int64 tensor indexed by local id (CUDA, or CPU when
+                    host_inputs — then seeds and labels of every minibatch are copied from pinned host memory)
+        sync:       pagraph_b200.parallel.FlatGradAllReduce or None
+        """
+        if getattr(model, "preprocess", False):
+            raise NotImplementedError("GCNTrainEngine drives the non-preprocess model (input block fused from the cache)")
+        self.g, self.cacher, self.model, self.opt, self.sync = g, cacher, model, optimizer, sync
+        self.dev = cacher._dev
+        self.batch = int(batch_size)
+        self.fanouts = [int(f) for f in fanouts]
+        self.L = len(self.fanouts)
+        if len(model.layers) != self.L:
+            raise ValueError("model has %d blocks but %d hops are sampled" % (len(model.layers), self.L))
+        self.seed = int(seed)
+        self.host_inputs = bool(host_inputs)
+        self.use_graphs = bool(use_graphs)
+        self.loss_fcn = loss_fcn or torch.nn.CrossEntropyLoss()
+        self.field = "features"
+        self.fi = cacher._field_names.index(self.field)
+        self.F = cacher.dims[self.field]
+        seeds = torch.as_tensor(train_nid, dtype=torch.int64).cpu()
+        if shuffle:                                   # once, like NeighborSampler
+            seeds = seeds[torch.randperm(len(seeds))]
+        self.num_batches = (len(seeds) + self.batch - 1) // self.batch
+        self.n_seeds = len(seeds)
+        L = _lib.lib()
+        with torch.cuda.device(self.dev):
+            self.side = torch.cuda.Stream(device=self.dev)
+            if self.host_inputs:
+                self.seeds_host = seeds.pin_memory()
+                self.labels_host = labels.cpu()
+            else:
+                self.seeds_dev = seeds.to(self.dev)
+                self.labels_dev = labels.to(self.dev)
+            # capacities: worst case of the sampler (every frontier vertex contributes `fanout` new vertices)
+            V, E = g.number_of_nodes(), g.number_of_edges()
+            n, self.cap_layer = self.batch, [self.batch]          # sampling order: [0] = seeds
+            cap_edges = 0
+            for f in self.fanouts:
+                e = min(n * min(f, V), E)
+                n = min(e, V)
+                self.cap_layer.append(n)
+                cap_edges += e
+            self.cap_nodes, self.cap_edges = sum(self.cap_layer), max(cap_edges, 1)
+            self.cap_n0 = self.cap_layer[-1]                          # NodeFlow layer 0 = last sampled layer
+            self.cap_rest = sum(self.cap_layer[:-1])                  # NodeFlow layers 1..L
+            self._stage_rows_req = int(stage_rows)
+            self.stage_rows = 0 if cacher.full_cached else int(min(stage_rows, self.cap_n0))
+            h = ctypes.c_void_p()
+            fan = (ctypes.c_int64 * self.L)(*self.fanouts)
+            _lib.check(L.pg_sampler_create(g.handle(self.dev.index), self.L, fan, self.seed, self.batch, self.cap_nodes,
+                                           self.cap_edges, ctypes.byref(h)), "pg_sampler_create")
+            self.sampler = h
+            self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # keys the fused dropout mask
+            self.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self.slots = [self._make_slot() for _ in range(_RING)]
+        self.pool = None
+        self.next_issue = 0          # global minibatch index of the next load to issue
+        self.next_compute = 0
+        self.launches = 0            # kernels launched / replayed by this engine (bench.py's gpu_launches)
+        self.size_log = None         # set to [] to record (layer offsets, block offsets) of every computed minibatch
+        self._cache_state = None
+        self._warm = False
+
+    # ------------------------------------------------------------------ buffers
+    def _make_slot(self):
+        s, dev = _Slot(), self.dev
+        i64 = dict(dtype=torch.int64, device=dev)
+        s.seeds_key = torch.zeros(self.batch + 1, **i64)                   # [seeds..., key(2 x uint32)]
+        s.stage_host = torch.zeros(self.batch + 1, dtype=torch.int64).pin_memory()
+        s.labels = torch.zeros(self.batch, **i64)
+        s.labels_host = torch.zeros(self.batch, dtype=torch.int64).pin_memory()
+        s.nf = dict(node_mapping=torch.zeros(self.cap_nodes, **i64), indptr=torch.zeros(self.cap_nodes + 1, **i64),
+                    indices=torch.zeros(self.cap_edges, **i64), edge_mapping=torch.zeros(self.cap_edges, **i64),
+                    meta=torch.zeros(_lib.PG_META_LEN, **i64))
+        s.h_meta = torch.zeros(_lib.PG_META_LEN, dtype=torch.int64).pin_memory()
+        s.h_meta_np = s.h_meta.numpy()
+        s.rowptr = torch.zeros(self.cap_n0, **i64)
+        s.stage = torch.empty((max(self.stage_rows, 1), self.F), dtype=torch.float32, device=dev)
+        s.rest = [torch.empty((self.cap_rest, self.cacher.dims[n]), dtype=torch.float32, device=dev)
+                  for n in self.cacher._field_names]
+        s.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        s.loaded, s.done = torch.cuda.Event(), torch.cuda.Event()
+        s.load_graph, s.load_kernels = None, 0
+        s.compute_graphs = {}
+        s.n_valid = self.batch
+        return s
+
+    def _meta_ptr(self, s, idx):
+        return ctypes.c_void_p(s.nf["meta"].data_ptr() + 8 * idx)
+
+    # ------------------------------------------------------------------ load stage (side stream)
+    def _load_body(self, s, n_seeds):
+        """sample + fetch layers 1..L + resolve the input layer; everything sized on the device."""
+        L, c = _lib.lib(), self.cacher
+        nfb = _lib.pg_nodeflow_buffers(*[_lib.ptr(s.nf[k]) for k in
+                                         ("node_mapping", "indptr", "indices", "edge_mapping", "meta")])
+        st = _lib.stream_ptr()
+        key = ctypes.c_void_p(s.seeds_key.data_ptr() + 8 * self.batch)
+        _lib.check(L.pg_sample_keyed(self.sampler, _lib.ptr(s.seeds_key), n_seeds, key, ctypes.byref(nfb), _lib.ptr(s.h_meta),
+                                     st), "pg_sample_keyed")
+        if not self.host_inputs:
+            torch.index_select(self.labels_dev, 0, s.seeds_key[:self.batch], out=s.labels)
+        counts = c._counts if (c.log and not c.full_cached) else None
+        outs = (ctypes.c_void_p * len(s.rest))(*[t.data_ptr() for t in s.rest])
+        _lib.check(L.pg_cache_fetch_dyn(c._handle, _lib.ptr(s.nf["node_mapping"]), self._meta_ptr(s, 4 + 1),
+                                        self._meta_ptr(s, 4 + self.L + 1), self.cap_rest, outs, _lib.ptr(counts), 0, st),
+                   "pg_cache_fetch_dyn")
+        blk = _lib.pg_block(_lib.ptr(s.nf["node_mapping"]), _lib.ptr(s.nf["indptr"]), _lib.ptr(s.nf["indices"]), 0,
+                            self.cap_n0, self.cap_layer[-2], self._meta_ptr(s, 4))
+        _lib.check(L.pg_cache_resolve(c._handle, self.fi, ctypes.byref(blk), _lib.ptr(s.rowptr), _lib.ptr(s.stage),
+                                      self.stage_rows, _lib.ptr(counts), st), "pg_cache_resolve")
+
+    def _issue_load(self, k):
+        """Enqueue the load stage of global minibatch k on the side stream."""
+        s = self.slots[k % _RING]
+        epoch, b = divmod(k, self.num_batches)
+        lo = b * self.batch
+        n = min(self.batch, self.n_seeds - lo)
+        key = (ctypes.c_uint32 * 2)()
+        _lib.lib().pg_minibatch_key(self.seed, epoch, b, key)
+        keyword = key[0] | (key[1] << 32)
+        s.n_valid, s.k = n, k
+        self.side.wait_event(s.done)                         # the slot's previous minibatch has been consumed
+        with torch.cuda.stream(self.side):
+            if self.host_inputs:                             # this minibatch's inputs: pinned host -> device
+                s.stage_host[:n] = self.seeds_host[lo:lo + n]
+                s.stage_host[self.batch] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
+                s.seeds_key.copy_(s.stage_host, non_blocking=True)
+                torch.index_select(self.labels_host, 0, self.seeds_host[lo:lo + n], out=s.labels_host[:n])
+                s.labels.copy_(s.labels_host, non_blocking=True)
+            else:
+                s.seeds_key[:n].copy_(self.seeds_dev[lo:lo + n], non_blocking=True)
+                s.stage_host[0] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
+                s.seeds_key[self.batch:].copy_(s.stage_host[:1], non_blocking=True)
+            if self.use_graphs and n == self.batch:
+                if s.load_graph is None:
+                    self._capture_load(s)
+                s.load_graph.replay()
+                self.launches += s.load_kernels
+            else:
+                l0 = _lib.launch_count()
+                self._load_body(s, n)
+                self.launches += _lib.launch_count() - l0
+            s.loaded.record(self.side)
+
+    def _capture_load(self, s):
+        self._load_body(s, self.batch)                       # eager once: sizes every workspace outside the capture
+        self.side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(g, stream=self.side, capture_error_mode="thread_local"):
+            self._load_body(s, self.batch)
+        s.load_graph, s.load_kernels = g, _lib.launch_count() - l0
+
+    # ------------------------------------------------------------------ compute stage (main stream)
+    def _compute_body(self, s, caps, n_valid):
+        """caps[j]: padded row count of NodeFlow layer j (j = 1..L; caps[L] = batch)."""
+        L, m = _lib.lib(), self.model
+        nf = s.nf
+        p = m.dropout.p if (m.dropout is not None and m.training) else 0.0
+        agg = torch.empty((caps[1], self.F), dtype=torch.float32, device=self.dev)
+        blk = _lib.pg_block(_lib.ptr(nf["node_mapping"]), _lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), 0, self.cap_n0,
+                            caps[1], self._meta_ptr(s, 4))
+        _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptr), ctypes.byref(blk), self.F, _lib.ptr(agg), agg.stride(0),
+                                       _MODES["mean"], None, float(p), self.drop_seed, _lib.ptr(self.step_counter), caps[1],
+                                       _lib.stream_ptr()), "pg_aggregate_rows")
+        h = m.layers[0](NodeBatch({"h": agg}))["activation"]
+        for i in range(1, self.L):
+            if m.dropout is not None:
+                h = m.dropout(h)
+            h = _BlockAggregateDyn.apply(h, nf["indptr"], nf["indices"], nf["meta"], i, caps[i + 1], "mean")
+            h = m.layers[i](NodeBatch({"h": h}))["activation"]
+        loss = self.loss_fcn(h[:n_valid], s.labels[:n_valid])
+        if self.sync is not None:
+            self.sync.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=False)
+        loss.backward()
+        if self.sync is not None:
+            self.sync()
+        self.opt.step()
+        self.step_counter.add_(1)
+        s.loss.copy_(loss.detach())
+
+    def _caps_for(self, s):
+        meta = s.h_meta_np
+        lay = [int(meta[4 + j + 1] - meta[4 + j]) for j in range(self.L + 1)]       # NodeFlow layer sizes
+        caps = [0] * (self.L + 1)
+        for j in range(1, self.L):
+            caps[j] = min(-(-max(lay[j], 1) // _BUCKET) * _BUCKET, self.cap_layer[self.L - j])
+        caps[self.L] = self.batch
+        return tuple(caps), lay
+
+    def _capture_compute(self, s, caps):
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+            self._compute_body(s, caps, self.batch)
+        if self.pool is None:
+            self.pool = g.pool()
+        return g, _lib.launch_count() - l0
+
+    # ------------------------------------------------------------------ public loop
+    def _check_cache_state(self):
+        st = (self.cacher.full_cached, self.cacher.cached_num, self.model.training)
+        if st != self._cache_state:                          # auto_cache ran (or train/eval flipped): graphs are stale
+            torch.cuda.synchronize(self.dev)
+            self._cache_state = st
+            new_stage = 0 if self.cacher.full_cached else int(min(self._stage_rows_req, self.cap_n0))
+            for s in self.slots:
+                s.load_graph, s.compute_graphs = None, {}
+                if new_stage != self.stage_rows:
+                    s.stage = torch.empty((max(new_stage, 1), self.F), dtype=torch.float32, device=self.dev)
+            self.stage_rows = new_stage
+            self.pool = None
+
+    def steps(self, count, read_loss=False):
+        """Run `count` training minibatches (continuing from the previous call, wrapping over epochs). Returns the
+        last loss (a CUDA scalar, or a float when read_loss — then every step's loss is read back)."""
+        self._check_cache_state()
+        main = torch.cuda.current_stream(self.dev)
+        end = self.next_compute + count
+        # a previous call may have left loads in flight for minibatches < next_issue
+        while self.next_issue < min(end, self.next_compute + _RING - 1):
+            self._issue_load(self.next_issue)
+            self.next_issue += 1
+        loss = None
+        while self.next_compute < end:
+            k = self.next_compute
+            s = self.slots[k % _RING]
+            s.loaded.synchronize()                           # sampling is >= 1 minibatch ahead: normally no wait
+            if s.h_meta_np[0] != _lib.PG_OK:
+                raise _lib.PGError("sampler reported status %d for minibatch %d" % (int(s.h_meta_np[0]), k))
+            main.wait_event(s.loaded)
+            caps, _ = self._caps_for(s)
+            if self.size_log is not None:
+                self.size_log.append(self.layer_sizes(k % _RING))
+            full = s.n_valid == self.batch
+            if self.use_graphs and full and self._warm:
+                entry = s.compute_graphs.get(caps)
+                if entry is None:
+                    entry = s.compute_graphs[caps] = self._capture_compute(s, caps)
+                entry[0].replay()
+                self.launches += entry[1]
+            else:
+                l0 = _lib.launch_count()
+                self._compute_body(s, caps, s.n_valid)
+                self.launches += _lib.launch_count() - l0
+                self._warm = True                            # optimizer state exists after the first eager step
+            s.done.record(main)
+            self.next_compute += 1
+            if self.next_issue < end:
+                self._issue_load(self.next_issue)
+                self.next_issue += 1
+            loss = s.loss
+            if read_loss:
+                loss = float(s.loss.item())                  # D2H read of the step's result
+        return loss
+
+    def layer_sizes(self, k_slot):
+        """(NodeFlow layer offsets, block offsets) of the minibatch last loaded into ring slot k_slot (host copy)."""
+        m = self.slots[k_slot].h_meta_np
+        L1 = int(m[3])
+        return [int(x) for x in m[4:4 + L1 + 1]], [int(x) for x in m[4 + L1 + 1:4 + L1 + 1 + L1]]
+
+    def close(self):
+        torch.cuda.synchronize(self.dev)
+        for s in self.slots:
+            s.load_graph, s.compute_graphs = None, {}
+        if self.sampler is not None:
+            _lib.lib().pg_sampler_destroy(self.sampler)
+            self.sampler = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,107 @@
+"""GCNTrainEngine (two-stream CUDA-graph pipeline, device-resident sizes) vs the eager public-API loop of
+examples/profile/pa_gcn.py: same minibatches, same model math => same losses and parameters (tolerance only for
+fp32 summation order / atomics in the backward scatter)."""
+import numpy as np
+import pytest
+
+from conftest import random_in_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _world(V=4000, nnz=60000, F=600, classes=7, seed=5):
+    import torch
+    from pagraph_b200 import DGLGraph
+    from pagraph_b200.graph_store import LocalGraphStore
+    rng = np.random.default_rng(seed)
+    indptr, indices, eids, _ = random_in_csr(V, nnz, seed)
+    store = LocalGraphStore(name="engine")
+    store.ndata["features"] = torch.from_numpy(rng.random((V, F), dtype=np.float32))
+    store.ndata["norm"] = torch.from_numpy((1.0 / np.maximum(np.diff(indptr), 1)).astype(np.float32)[:, None])
+    g = DGLGraph.from_in_csr(indptr, indices, eids)
+    labels = torch.from_numpy(rng.integers(0, classes, V))
+    train = rng.choice(V, 1100, replace=False).astype(np.int64)
+    return g, store, labels, train, V, F, classes
+
+
+def _model(F, classes, dropout):
+    import torch
+    from pagraph_b200.model.gcn_nssc import GCNSampling
+    torch.manual_seed(0)
+    return GCNSampling(F, 16, classes, 1, torch.relu, dropout).cuda()
+
+
+def _eager_losses(g, store, labels, train, V, F, classes, cap, batch, fanouts, steps):
+    import torch
+    from pagraph_b200.sampling import NeighborSampler
+    from pagraph_b200.storage import GraphCacheServer
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(["features", "norm"])
+    model = _model(F, classes, 0.0)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-2)
+    sampler = NeighborSampler(g, batch, fanouts, num_hops=len(fanouts), seed_nodes=torch.from_numpy(train), seed=11)
+    lab = labels.cuda()
+    losses = []
+    for k, nf in enumerate(sampler.batches(0, steps)):
+        cs.fetch_data(nf)
+        pred = model(nf)
+        loss = torch.nn.functional.cross_entropy(pred, lab[nf.layer_parent_nid_dev(-1)])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        if k == 0 and cap is not None:
+            cs.auto_cache(g, ["features", "norm"], capability=cap)
+    return losses, [p.detach().cpu().numpy() for p in model.parameters()]
+
+
+@pytest.mark.parametrize("host_inputs", [False, True])
+@pytest.mark.parametrize("use_graphs", [False, True])
+@pytest.mark.parametrize("cap", [None, 900, 10 ** 9])
+def test_engine_matches_eager_loop(cap, use_graphs, host_inputs):
+    import torch
+    from pagraph_b200.engine import GCNTrainEngine
+    from pagraph_b200.storage import GraphCacheServer
+    g, store, labels, train, V, F, classes = _world()
+    batch, fanouts, steps = 256, [6, 4], 7                     # 1100 seeds / 256: minibatch 4 is partial (76 seeds), then wraps
+    want, want_params = _eager_losses(g, store, labels, train, V, F, classes, cap, batch, fanouts, steps)
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(["features", "norm"])
+    cs.log = True
+    model = _model(F, classes, 0.0)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-2, capturable=use_graphs)
+    eng = GCNTrainEngine(g, cs, model, opt, train, labels, batch, fanouts, seed=11, shuffle=False,
+                         host_inputs=host_inputs, use_graphs=use_graphs, stage_rows=300)   # tiny staging: overflow path too
+    got = [eng.steps(1, read_loss=True)]
+    if cap is not None:
+        cs.auto_cache(g, ["features", "norm"], capability=cap)
+    got += [eng.steps(1, read_loss=True) for _ in range(2)]
+    last = eng.steps(steps - 3)                                # pipelined, no read-back
+    got_params = [p.detach().cpu().numpy() for p in model.parameters()]
+    np.testing.assert_allclose(got, want[:3], rtol=2e-4)
+    np.testing.assert_allclose(float(last), want[-1], rtol=2e-4)
+    for a, b in zip(got_params, want_params):
+        np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)   # 7 Adam steps at lr 3e-2 amplify fp32 summation-order noise
+    assert eng.launches > 0
+    if not cs.full_cached:
+        assert cs.try_num > 0 and 0 < cs.miss_num <= cs.try_num
+    eng.close()
+
+
+def test_engine_dropout_trains_and_graph_replays_rekey():
+    """With dropout the fused mask changes every step (device step counter) and the loss goes down."""
+    import torch
+    from pagraph_b200.engine import GCNTrainEngine
+    from pagraph_b200.storage import GraphCacheServer
+    g, store, labels, train, V, F, classes = _world(classes=3)
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(["features", "norm"])
+    cs.auto_cache(g, ["features", "norm"], capability=V)
+    model = _model(F, 3, 0.3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=True)
+    eng = GCNTrainEngine(g, cs, model, opt, train[:1024], labels, 256, [6, 4], seed=3)
+    losses = [eng.steps(1, read_loss=True) for _ in range(24)]
+    assert all(np.isfinite(losses))
+    assert len(set(losses)) == len(losses)
+    assert int(eng.step_counter.item()) == 24
+    eng.close()
