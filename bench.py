@@ -225,7 +225,7 @@ class Trainer:
         torch.manual_seed(wl.rank)                                            # pa_gcn.py:23
         self.model = GCNSampling(a.feat_size, a.n_hidden, a.n_classes, 1, F.relu, a.dropout, False).cuda(dev)
         self.sync = FlatGradAllReduce(self.model)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=a.lr, weight_decay=0, capturable=(a.path == "engine"))
+        self.opt = torch.optim.Adam(self.sync.flat_parameters(), lr=a.lr, weight_decay=0, capturable=(a.path == "engine"))
         self.loss_fcn = torch.nn.CrossEntropyLoss()
         self.engine = None
         if a.path == "engine":

@@ -67,7 +67,7 @@ def trainer(rank, world_size, args, backend='nccl'):
     loss_fcn = torch.nn.CrossEntropyLoss()
     model.cuda(rank)
     sync = FlatGradAllReduce(model)                       # stands where DistributedDataParallel stands
-    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+    optimizer = torch.optim.Adam(sync.flat_parameters(), lr=args.lr, weight_decay=args.weight_decay)
 
     fanout = [int(x) for x in str(args.num_neighbors).split(',')]
     fanout = fanout[0] if len(fanout) == 1 else fanout

@@ -203,6 +203,14 @@ pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float*
                              const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
                              int64_t zero_rows_to, int64_t* d_counts, void* stream);
 
+/* ---------------------------------------------------------------- offline partitioner (host code, host pointers)
+ * The streaming "dg" assignment of PaGraph/partition/dg.py:59-103, same assignments bit for bit (see pg_partition.cu).
+ * indptr / indices: in-neighbour lists (CSC of the row=src, col=dst adjacency). belongs_out: int8[V], partition of every
+ * train vertex, -1 elsewhere. member_out: uint8[P*V], member_out[p*V + v] = 1 iff v is in partition p's vertex set (train
+ * vertices plus their `hops`-hop in-neighbour redundancy). 2 <= P <= 127. */
+pg_status pg_partition_dg(const int64_t* indptr, const int64_t* indices, int64_t V, const int64_t* train,
+                          int64_t n_train, int P, int hops, int8_t* belongs_out, uint8_t* member_out);
+
 /* ---------------------------------------------------------------- measurement helpers */
 /* Pinned H2D copy bandwidth probe (the PCIe roofline denominator). SYNC. */
 pg_status pg_measure_h2d(int dev, size_t bytes, int iters, double* gb_per_s);

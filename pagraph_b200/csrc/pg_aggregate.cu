@@ -216,10 +216,11 @@ struct TaskCursor {  // walks (row, edge-chunk) tasks of one warp in order
 };
 
 __device__ __forceinline__ float4 drop4(float4 v, uint64_t h, uint32_t thr, float scale) {
-  v.x = ((uint32_t)(h & 0xffff) < thr) ? 0.f : v.x * scale;
-  v.y = ((uint32_t)((h >> 16) & 0xffff) < thr) ? 0.f : v.y * scale;
-  v.z = ((uint32_t)((h >> 32) & 0xffff) < thr) ? 0.f : v.z * scale;
-  v.w = ((uint32_t)(h >> 48) < thr) ? 0.f : v.w * scale;
+  const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+  v.x *= ((lo & 0xffffu) < thr) ? 0.f : scale;
+  v.y *= ((lo >> 16) < thr) ? 0.f : scale;
+  v.z *= ((hi & 0xffffu) < thr) ? 0.f : scale;
+  v.w *= ((hi >> 16) < thr) ? 0.f : scale;
   return v;
 }
 
@@ -405,7 +406,8 @@ pg_status launch_rows_tma(const pg::AggRowsArgs& a, int dev, cudaStream_t st) {
   const int depth = env_d ? atoi(env_d) : 0;
   const int warps = env_w ? atoi(env_w) : 8;
   pg_status s = PG_ERR_INVALID;
-  if (warps >= 8) s = launch_rows_tma_w<8, CH>(a, dev, st, budget, depth);
+  if (warps >= 16) s = launch_rows_tma_w<16, CH>(a, dev, st, budget, depth);
+  if (s == PG_ERR_INVALID && warps >= 8) s = launch_rows_tma_w<8, CH>(a, dev, st, budget, depth);
   if (s == PG_ERR_INVALID) s = launch_rows_tma_w<4, CH>(a, dev, st, budget, depth);
   return s;
 }

@@ -41,6 +41,15 @@ class FlatGradAllReduce:
         if self.world > 1:   # same initial weights everywhere (DDP broadcasts rank 0's at construction)
             dist.broadcast(self.flat_param, src=0, group=process_group)
 
+    def flat_parameters(self):
+        """[one nn.Parameter] aliasing every parameter (and its .grad aliasing every gradient): hand it to an
+        elementwise optimizer (SGD / Adam / AdamW) instead of module.parameters() and the update is a single kernel over
+        the flat bucket; the result is identical because those optimizers act elementwise."""
+        if getattr(self, "_flat", None) is None:
+            self._flat = torch.nn.Parameter(self.flat_param, requires_grad=True)
+            self._flat.grad = self.flat_grad
+        return [self._flat]
+
     def zero_grad(self):
         """Keeps .grad pointing into the flat bucket (optimizer.zero_grad(set_to_none=True) would not)."""
         self.flat_grad.zero_()

@@ -11,12 +11,23 @@ What runs:
     mask / copy statement executes as written.
   * PaGraph/partition/dg.py::dg — pure numpy/scipy, unmodified.
 Nothing from /root/reference is copied into the repo; only inputs and outputs are stored.
+
+numpy dispatch: dg.py breaks score ties through `np.argsort(score)[-2:]` (dg.py:31), whose tie order is whatever
+numpy's default sort does. The numpy the reference targets (2019, introsort -> insertion sort below 16 elements) is
+stable for P <= 16; numpy >= 1.25 on an AVX-512 host dispatches to a vectorised sorting network that is not, and then
+the reference's own assignments depend on the CPU it runs on. This script therefore re-executes itself with the SIMD
+sort disabled (NPY_DISABLE_CPU_FEATURES), so that the fixtures hold the era-faithful, CPU-independent behaviour.
 """
 import contextlib
 import importlib.util
 import os
 import sys
 import types
+
+_NO_SIMD = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX2"
+if os.environ.get("NPY_DISABLE_CPU_FEATURES") != _NO_SIMD:
+    os.environ["NPY_DISABLE_CPU_FEATURES"] = _NO_SIMD
+    os.execv(sys.executable, [sys.executable] + sys.argv)
 
 import numpy as np
 import scipy.sparse as spsp
