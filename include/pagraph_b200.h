@@ -203,6 +203,15 @@ pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float*
                              const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
                              int64_t zero_rows_to, int64_t* d_counts, void* stream);
 
+/* ---------------------------------------------------------------- backward of the first NodeUpdate (PaGraph/model/gcn_nssc.py:14-24)
+ * out = concat ? cat(z, relu(z)) : relu(z),  z = x W^T + b, x [n, in_dim] = the aggregated input block (needs no
+ * gradient), W [32, in_dim], out [n, 64 | 32]. Computes grad_weight [32, in_dim] = gz^T x and grad_bias [32] = sum_r gz,
+ * with gz (the gradient of z) recovered from grad_out and out: relu' and the concat split are folded in. Both outputs
+ * are overwritten. One TMA-streamed pass over x. in_dim % 4 == 0, <= 768; out_dim == 32. */
+pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
+                               const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int32_t out_dim, int concat,
+                               float* d_grad_weight, float* d_grad_bias, void* stream);
+
 /* ---------------------------------------------------------------- offline partitioner (host code, host pointers)
  * The streaming "dg" assignment of PaGraph/partition/dg.py:59-103, same assignments bit for bit (see pg_partition.cu).
  * indptr / indices: in-neighbour lists (CSC of the row=src, col=dst adjacency). belongs_out: int8[V], partition of every

@@ -404,7 +404,7 @@ pg_status launch_rows_tma(const pg::AggRowsArgs& a, int dev, cudaStream_t st) {
   const char* env_d = getenv("PG_AGG_DEPTH");
   const char* env_w = getenv("PG_AGG_WARPS");
   const int depth = env_d ? atoi(env_d) : 0;
-  const int warps = env_w ? atoi(env_w) : 8;
+  const int warps = env_w ? atoi(env_w) : 16;
   pg_status s = PG_ERR_INVALID;
   if (warps >= 16) s = launch_rows_tma_w<16, CH>(a, dev, st, budget, depth);
   if (s == PG_ERR_INVALID && warps >= 8) s = launch_rows_tma_w<8, CH>(a, dev, st, budget, depth);

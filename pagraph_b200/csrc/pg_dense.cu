@@ -1,0 +1,145 @@
+// pg_dense.cu — backward of the first NodeUpdate of the GCN / GraphSAGE models, fused around its tall-skinny GEMM.
+//
+// Reference: PaGraph/model/gcn_nssc.py:14-24 (NodeUpdate.forward with concat=True):
+//     h = Linear(h);  h = cat(h, relu(h))
+// applied to the aggregated input block x [n_1, F] (F = 600, n_1 ~ 35 k, out = 32). x needs no gradient (it is an
+// aggregate of constant input features), so the backward is only dW = gz^T x and db = sum gz, with
+// gz = g[:, :32] + g[:, 32:] * (z > 0). In fp32 that is a memory-bound product (85 MB of activations, K = n_1): cuBLAS
+// takes 152 us for the split-K GEMM plus four more kernels (relu', slice-add, bias-grad reduction, split-K reduce).
+// linear_concat_bwd makes one pass over x: tiles of x arrive in shared memory by TMA bulk copies (double-buffered),
+// relu' and the concat split are folded into a per-tile gz, every CTA accumulates a [32, F] partial of dW (and db) in
+// registers and adds it to the result with float atomics.
+// The forward stays on cuBLAS (a plain library GEMM, 42 us); fp32 SIMT here on purpose: TF32 tensor cores would drop
+// below the reference's precision and the op is HBM-bound anyway.
+#include <algorithm>
+
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int kOut = 32;           // output width handled here (n_hidden of the reference default)
+constexpr int kBwdThreads = 256;
+constexpr int kTile = 32;          // rows of x per shared-memory tile
+
+// Thread t owns columns {t, t+256, t+512} x all 32 outputs (96 accumulators). One persistent CTA per SM walks a
+// contiguous range of rows in tiles of kTile.
+__global__ void __launch_bounds__(kBwdThreads, 1) linear_concat_bwd_kernel(const float* __restrict__ x, int64_t x_stride,
+                                                                          const float* __restrict__ g, int64_t g_stride,
+                                                                          const float* __restrict__ y, int64_t y_stride,
+                                                                          int64_t n, int K, int concat, float* dW, float* db) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(16) float gz[kTile][kOut];
+  __shared__ __align__(8) uint64_t bars[2];
+  float* xs = (float*)smem_raw;                       // [2][kTile][K]
+  const int t = threadIdx.x;
+  const uint32_t row_bytes = (uint32_t)K * 4u;
+  if (t == 0) {
+    pg::mbar_init(pg::smem_u32(&bars[0]), 1);
+    pg::mbar_init(pg::smem_u32(&bars[1]), 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(n, r_begin + rows_per_cta);
+  const int ntiles = r_end > r_begin ? (int)((r_end - r_begin + kTile - 1) / kTile) : 0;
+  auto issue = [&](int tile) {                        // warp 0: one bulk copy per row of the tile
+    const int buf = tile & 1;
+    const int64_t r0 = r_begin + (int64_t)tile * kTile;
+    const int rows = (int)min((int64_t)kTile, r_end - r0);
+    const uint32_t bar = pg::smem_u32(&bars[buf]);
+    if (t == 0) pg::mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
+    __syncwarp();
+    if (t < rows) pg::bulk_g2s(pg::smem_u32(xs + ((size_t)buf * kTile + t) * K), x + (r0 + t) * x_stride, row_bytes, bar);
+  };
+  float acc[3][kOut];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int o = 0; o < kOut; ++o) acc[j][o] = 0.f;
+  float dbv = 0.f;
+  if (ntiles > 0 && t < 32) issue(0);
+  uint32_t phase = 0;                                 // bit b: parity to wait for on buffer b
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    const int64_t r0 = r_begin + (int64_t)tile * kTile;
+    const int rows = (int)min((int64_t)kTile, r_end - r0);
+    if (tile + 1 < ntiles && t < 32) issue(tile + 1);  // the other buffer was released by the barrier ending tile-1
+    for (int i = t; i < kTile * kOut; i += kBwdThreads) {
+      const int rr = i / kOut, o = i % kOut;
+      float v = 0.f;
+      if (rr < rows) {
+        const float* grow = g + (r0 + rr) * g_stride;
+        const float* yrow = y + (r0 + rr) * y_stride;
+        v = concat ? grow[o] + (yrow[kOut + o] > 0.f ? grow[kOut + o] : 0.f) : (yrow[o] > 0.f ? grow[o] : 0.f);
+      }
+      gz[rr][o] = v;
+    }
+    __syncthreads();
+    while (!pg::mbar_try_wait(pg::smem_u32(&bars[buf]), (phase >> buf) & 1u)) {
+    }
+    phase ^= 1u << buf;
+    if (t < kOut)
+      for (int rr = 0; rr < rows; ++rr) dbv += gz[rr][t];
+    const float* xt = xs + (size_t)buf * kTile * K;
+#pragma unroll 2
+    for (int rr = 0; rr < rows; ++rr) {
+      float xv[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int c = t + j * kBwdThreads;
+        xv[j] = c < K ? xt[(size_t)rr * K + c] : 0.f;
+      }
+#pragma unroll
+      for (int o4 = 0; o4 < kOut / 4; ++o4) {
+        const float4 gv = *(const float4*)&gz[rr][o4 * 4];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          acc[j][o4 * 4 + 0] += xv[j] * gv.x;
+          acc[j][o4 * 4 + 1] += xv[j] * gv.y;
+          acc[j][o4 * 4 + 2] += xv[j] * gv.z;
+          acc[j][o4 * 4 + 3] += xv[j] * gv.w;
+        }
+      }
+    }
+    __syncthreads();                                  // gz and this x buffer may be overwritten
+  }
+  if (ntiles > 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = t + j * kBwdThreads;
+      if (c < K)
+#pragma unroll
+        for (int o = 0; o < kOut; ++o) atomicAdd(&dW[(size_t)o * K + c], acc[j][o]);
+    }
+    if (t < kOut && db) atomicAdd(&db[t], dbv);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
+                               const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int32_t out_dim, int concat,
+                               float* d_grad_weight, float* d_grad_bias, void* stream) {
+  PG_REQUIRE(d_grad_weight && n >= 0 && ((d_x && d_grad_out && d_out) || n == 0), "pg_linear_concat_bwd: bad arguments");
+  PG_REQUIRE(out_dim == kOut, "pg_linear_concat_bwd: out_dim must be 32");
+  PG_REQUIRE(in_dim >= 4 && in_dim % 4 == 0 && in_dim <= 3 * kBwdThreads && x_stride >= in_dim && x_stride % 4 == 0 &&
+                 (uintptr_t)d_x % 16 == 0,
+             "pg_linear_concat_bwd: in_dim must be a multiple of 4 (<= 768) with 16-byte aligned rows");
+  int dev = 0;
+  PG_CUDA(cudaGetDevice(&dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)kOut * in_dim * sizeof(float), st));
+  if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, kOut * sizeof(float), st));
+  if (n == 0) return PG_OK;
+  const size_t smem = 2 * (size_t)kTile * in_dim * sizeof(float);
+  PG_CUDA(cudaFuncSetAttribute(linear_concat_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (n + kTile - 1) / kTile), (int64_t)pg::sm_count(dev));
+  linear_concat_bwd_kernel<<<grid, kBwdThreads, smem, st>>>(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim,
+                                                            concat, d_grad_weight, d_grad_bias);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+}  // extern "C"

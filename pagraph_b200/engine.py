@@ -96,7 +96,10 @@ class GCNTrainEngine:
         self.n_seeds = len(seeds)
         L = _lib.lib()
         with torch.cuda.device(self.dev):
-            self.side = torch.cuda.Stream(device=self.dev)
+            # the load stage is a chain of small latency-bound kernels: high priority lets them slip in between the
+            # compute stage's full-GPU kernels instead of queueing behind them
+            import os
+            self.side = torch.cuda.Stream(device=self.dev, priority=int(os.environ.get("PG_ENGINE_SIDE_PRIORITY", "-1")))
             if self.host_inputs:
                 self.seeds_host = seeds.pin_memory()
                 self.labels_host = labels.cpu()

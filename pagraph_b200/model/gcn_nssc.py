@@ -20,6 +20,10 @@ class NodeUpdate(nn.Module):
         h = node.data['h']
         if self.test:                       # inference: sum-aggregate then scale by 1/in_degree
             h = h * node.data['norm']
+        if self.concat and self.activation is torch.relu or self.concat and self.activation is torch.nn.functional.relu:
+            from ..ops import LinearConcat   # fused linear + bias + cat(h, relu(h)) when the input carries no gradient
+            if LinearConcat.supported(h, self.linear.weight):
+                return {'activation': LinearConcat.apply(h, self.linear.weight, self.linear.bias, True)}
         h = self.linear(h)
         if self.concat:                     # skip connection
             h = torch.cat((h, self.activation(h)), dim=1)

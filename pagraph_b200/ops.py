@@ -74,3 +74,36 @@ def cache_aggregate(cacher, field, parent_ids, indptr, cols, col_base, n_src, n_
                                                  _lib.ptr(step), zero_rows_to, _lib.ptr(counts), _lib.stream_ptr()),
                    "pg_cache_aggregate")
     return out
+
+
+class LinearConcat(torch.autograd.Function):
+    """cat(z, relu(z)) (concat=True) or relu(z), z = x W^T + b, for an input x that needs no gradient (the aggregated
+    input block). Same math as NodeUpdate.forward (PaGraph/model/gcn_nssc.py:14-24). Forward: the tall-skinny GEMM stays
+    on cuBLAS; backward: pg_linear_concat_bwd — one TMA-streamed pass over x that folds relu', the concat split, dW and
+    db (cuBLAS needs a split-K GEMM plus four elementwise / reduction kernels for the same thing)."""
+
+    @staticmethod
+    def supported(x, weight):
+        return (x.is_cuda and x.dtype == torch.float32 and not x.requires_grad and weight.shape[0] == 32
+                and x.shape[1] % 4 == 0 and x.shape[1] <= 768 and x.stride(1) == 1 and x.stride(0) % 4 == 0)
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, concat):
+        z = torch.nn.functional.linear(x, weight, bias)
+        out = torch.cat((z, torch.relu(z)), dim=1) if concat else torch.relu(z)
+        ctx.save_for_backward(x, out)
+        ctx.concat, ctx.has_bias = concat, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out = ctx.saved_tensors
+        n, K = x.shape
+        grad_out = grad_out.contiguous()
+        gw = torch.empty((32, K), dtype=torch.float32, device=x.device)
+        gb = torch.empty(32, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().pg_linear_concat_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(grad_out), grad_out.stride(0),
+                                                       _lib.ptr(out), out.stride(0), n, K, 32, int(ctx.concat), _lib.ptr(gw),
+                                                       _lib.ptr(gb), _lib.stream_ptr()), "pg_linear_concat_bwd")
+        return None, gw, (gb if ctx.has_bias else None), None

@@ -114,3 +114,30 @@ def test_autograd_function_matches_torch_sparse():
     (ref * w.double()).sum().backward()
     torch.testing.assert_close(out.double(), ref, rtol=RTOL, atol=0)
     torch.testing.assert_close(x.grad.double(), x64.grad, rtol=RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,K", [(1000, 600), (37, 128), (4099, 64), (1, 600), (0, 600)])
+@pytest.mark.parametrize("concat", [True, False])
+def test_linear_concat_matches_torch(n, K, concat):
+    """Fused first NodeUpdate (linear + bias + cat(z, relu(z))) forward and its dW / db against torch autograd."""
+    import torch
+    from pagraph_b200.ops import LinearConcat
+    torch.manual_seed(n + K)
+    x = torch.randn(n, K, device="cuda")
+    lin = torch.nn.Linear(K, 32).cuda()
+    gout = torch.randn(n, 64 if concat else 32, device="cuda")
+    assert LinearConcat.supported(x, lin.weight)
+    out = LinearConcat.apply(x, lin.weight, lin.bias, concat)
+    out.backward(gout)
+    torch.cuda.synchronize()
+    gw, gb = lin.weight.grad.clone(), lin.bias.grad.clone()
+    lin.zero_grad()
+    z = torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double())
+    ref = torch.cat((z, torch.relu(z)), 1) if concat else torch.relu(z)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+    w64 = lin.weight.detach().double().requires_grad_(True)
+    b64 = lin.bias.detach().double().requires_grad_(True)
+    z = torch.nn.functional.linear(x.double(), w64, b64)
+    (torch.cat((z, torch.relu(z)), 1) if concat else torch.relu(z)).backward(gout.double())
+    torch.testing.assert_close(gw.double(), w64.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gb.double(), b64.grad, rtol=1e-4, atol=1e-4)
