@@ -212,6 +212,14 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
                                const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int32_t out_dim, int concat,
                                float* d_grad_weight, float* d_grad_bias, void* stream);
 
+/* Classifier head + loss in one pass (the last NodeUpdate, gcn_nssc.py:48, followed by torch.nn.CrossEntropyLoss,
+ * examples/profile/pa_gcn.py:62,93-94): pred = a W^T + b, loss = mean_r(logsumexp(pred_r) - pred_r[label_r]); also emits
+ * d loss/d a [n, in_dim], d loss/d W [n_classes, in_dim] and d loss/d b [n_classes] (all overwritten). in_dim, n_classes <= 64;
+ * labels in [0, n_classes). */
+pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias,
+                                  const int64_t* d_labels, int64_t n, int32_t in_dim, int32_t n_classes, float* d_loss,
+                                  float* d_grad_a, int64_t ga_stride, float* d_grad_weight, float* d_grad_bias, void* stream);
+
 /* ---------------------------------------------------------------- offline partitioner (host code, host pointers)
  * The streaming "dg" assignment of PaGraph/partition/dg.py:59-103, same assignments bit for bit (see pg_partition.cu).
  * indptr / indices: in-neighbour lists (CSC of the row=src, col=dst adjacency). belongs_out: int8[V], partition of every

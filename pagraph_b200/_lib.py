@@ -84,6 +84,8 @@ SIGNATURES = {
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
     "pg_linear_concat_bwd": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "pg_linear_cross_entropy": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32,
+                                               ctypes.c_int32, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "pg_partition_dg": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                        c_vp, c_vp]),
     "pg_measure_h2d": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int,

@@ -215,16 +215,17 @@ struct TaskCursor {  // walks (row, edge-chunk) tasks of one warp in order
   }
 };
 
-__device__ __forceinline__ float4 drop4(float4 v, uint64_t h, uint32_t thr, float scale) {
+// acc += drop(v): the k-th 16-bit lane of h decides component k. The upper lanes are compared in place
+// (x >> 16 >= thr  <=>  x >= thr << 16), so a float4 costs 2 shifts + 4 compares + 4 predicated FMAs.
+__device__ __forceinline__ void acc_drop4(float4& acc, const float4 v, uint64_t h, uint32_t thr_hi, float scale) {
   const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
-  v.x *= ((lo & 0xffffu) < thr) ? 0.f : scale;
-  v.y *= ((lo >> 16) < thr) ? 0.f : scale;
-  v.z *= ((hi & 0xffffu) < thr) ? 0.f : scale;
-  v.w *= ((hi >> 16) < thr) ? 0.f : scale;
-  return v;
+  if ((lo << 16) >= thr_hi) acc.x = fmaf(v.x, scale, acc.x);
+  if (lo >= thr_hi) acc.y = fmaf(v.y, scale, acc.y);
+  if ((hi << 16) >= thr_hi) acc.z = fmaf(v.z, scale, acc.z);
+  if (hi >= thr_hi) acc.w = fmaf(v.w, scale, acc.w);
 }
 
-template <int W, int CH, bool DROP>
+template <int W, int CH, bool DROP, int ILP>
 __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a, int group, int depth) {
   constexpr int kRowsWarps = W;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -274,40 +275,47 @@ __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a,
     }
     phase_bits ^= 1u << buf;
     const unsigned char* base = smem + ((size_t)w * depth * group + (size_t)buf * group) * row_bytes;
+    const uint32_t thr_hi = a.drop_thr << 16;
     int k = 0;
-    for (; k + 2 <= cnt; k += 2) {  // two staged rows per round: 2*CH independent shared-memory loads in flight
-      const float4* row0 = (const float4*)(base + (size_t)k * row_bytes);
-      const float4* row1 = (const float4*)(base + (size_t)(k + 1) * row_bytes);
-      float4 v0[CH], v1[CH];
+    if (ILP == 2) {
+      for (; k + 2 <= cnt; k += 2) {  // two staged rows per round: 2*CH independent shared-memory loads in flight
+        const float4* row0 = (const float4*)(base + (size_t)k * row_bytes);
+        const float4* row1 = (const float4*)(base + (size_t)(k + 1) * row_bytes);
+        float4 v0[CH], v1[CH];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int col = c * 32 + lane;
-        if (col < nvec) { v0[c] = row0[col]; v1[c] = row1[col]; }
-      }
-      const uint64_t j0 = DROP ? (uint64_t)src_idx[w][buf][k] : 0ull, j1 = DROP ? (uint64_t)src_idx[w][buf][k + 1] : 0ull;
+        for (int c = 0; c < CH; ++c) {
+          const int col = c * 32 + lane;
+          if (col < nvec) { v0[c] = row0[col]; v1[c] = row1[col]; }
+        }
+        const uint64_t j0 = DROP ? (uint64_t)src_idx[w][buf][k] : 0ull, j1 = DROP ? (uint64_t)src_idx[w][buf][k + 1] : 0ull;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int col = c * 32 + lane;
-        if (col < nvec) {
-          if (DROP) {
-            v0[c] = drop4(v0[c], pg::drop_hash(seed, j0, (uint32_t)nvec, (uint32_t)col), a.drop_thr, a.keep_scale);
-            v1[c] = drop4(v1[c], pg::drop_hash(seed, j1, (uint32_t)nvec, (uint32_t)col), a.drop_thr, a.keep_scale);
+        for (int c = 0; c < CH; ++c) {
+          const int col = c * 32 + lane;
+          if (col < nvec) {
+            if (DROP) {
+              acc_drop4(acc[c], v0[c], pg::drop_hash(seed, j0, (uint32_t)nvec, (uint32_t)col), thr_hi, a.keep_scale);
+              acc_drop4(acc[c], v1[c], pg::drop_hash(seed, j1, (uint32_t)nvec, (uint32_t)col), thr_hi, a.keep_scale);
+            } else {
+              acc[c].x = (acc[c].x + v0[c].x) + v1[c].x; acc[c].y = (acc[c].y + v0[c].y) + v1[c].y;
+              acc[c].z = (acc[c].z + v0[c].z) + v1[c].z; acc[c].w = (acc[c].w + v0[c].w) + v1[c].w;
+            }
           }
-          acc[c].x = (acc[c].x + v0[c].x) + v1[c].x; acc[c].y = (acc[c].y + v0[c].y) + v1[c].y;
-          acc[c].z = (acc[c].z + v0[c].z) + v1[c].z; acc[c].w = (acc[c].w + v0[c].w) + v1[c].w;
         }
       }
     }
-    if (k < cnt) {
+    for (; k < cnt; ++k) {
       const float4* row = (const float4*)(base + (size_t)k * row_bytes);
       const uint64_t j = DROP ? (uint64_t)src_idx[w][buf][k] : 0ull;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const int col = c * 32 + lane;
         if (col < nvec) {
-          float4 v = row[col];
-          if (DROP) v = drop4(v, pg::drop_hash(seed, j, (uint32_t)nvec, (uint32_t)col), a.drop_thr, a.keep_scale);
-          acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+          const float4 v = row[col];
+          if (DROP) {
+            acc_drop4(acc[c], v, pg::drop_hash(seed, j, (uint32_t)nvec, (uint32_t)col), thr_hi, a.keep_scale);
+          } else {
+            acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+          }
         }
       }
     }
@@ -385,7 +393,10 @@ pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, 
   const int group = std::min(kRowsMaxGroup, slots / depth);
   const size_t smem = (size_t)W * depth * group * row_bytes;
   const bool drop = a.drop_thr != 0;
-  auto kern = drop ? agg_rows_tma_kernel<W, CH, true> : agg_rows_tma_kernel<W, CH, false>;
+  // 16 warps give enough thread-level parallelism; the 2-row unroll would only cost registers (the kernel must leave
+  // register file for the sampler's CTAs that run next to it on the other stream)
+  constexpr int ILP = W >= 16 ? 1 : 2;
+  auto kern = drop ? agg_rows_tma_kernel<W, CH, true, ILP> : agg_rows_tma_kernel<W, CH, false, ILP>;
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t rows = std::max(a.n_dst, a.zero_rows_to);
   const int64_t need = std::max<int64_t>(1, (rows + W - 1) / W);

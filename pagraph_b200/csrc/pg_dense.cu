@@ -143,3 +143,128 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
 }
 
 }  // extern "C"
+
+// ====================================================================== classifier head + loss, forward and backward
+// Reference: the last NodeUpdate (no activation, gcn_nssc.py:48 / :14-24) followed by torch.nn.CrossEntropyLoss
+// (examples/profile/pa_gcn.py:62,93-94): pred = a W^T + b, loss = mean_r(logsumexp(pred_r) - pred_r[label_r]).
+// On [6000, 64] x [60, 64] that is ~12 library kernels (GEMM, log-softmax, nll, their backwards, split-K reduce, bias
+// reduction) of 4-20 us each — launch latency, not work. linear_ce_kernel does the whole thing in one pass: one warp per
+// row, logits in registers (2 classes per lane), W staged in shared memory in both orientations, and it emits the
+// loss, d loss / d a, d loss / d W and d loss / d b (per-CTA shared-memory reduction, then one atomic per output).
+namespace {
+
+constexpr int kHeadWarps = 8;
+constexpr int kHeadMaxC = 64;   // classes (2 per lane)
+constexpr int kHeadMaxK = 64;   // input width (2 per lane)
+
+__global__ void __launch_bounds__(kHeadWarps * 32) linear_ce_kernel(const float* __restrict__ a, int64_t a_stride,
+                                                                   const float* __restrict__ W, const float* __restrict__ bias,
+                                                                   const int64_t* __restrict__ labels, int64_t n, int K, int C,
+                                                                   float inv_n, float* loss, float* grad_a, int64_t ga_stride,
+                                                                   float* dW, float* db) {
+  extern __shared__ __align__(16) float head_smem[];  // 3 x 16 KB: over the 48 KB static limit, hence dynamic
+  float (*w_kc)[kHeadMaxC] = (float (*)[kHeadMaxC])head_smem;                                  // w_kc[k][c] = W[c][k] (logits: lane = class)
+  float (*w_ck)[kHeadMaxK] = (float (*)[kHeadMaxK])(head_smem + kHeadMaxK * kHeadMaxC);        // w_ck[c][k] = W[c][k] (grad_a: lane = input column)
+  float (*dw_sh)[kHeadMaxK] = (float (*)[kHeadMaxK])(head_smem + 2 * kHeadMaxK * kHeadMaxC);
+  __shared__ float db_sh[kHeadMaxC];
+  __shared__ float loss_sh;
+  for (int i = threadIdx.x; i < kHeadMaxC * kHeadMaxK; i += blockDim.x) {
+    const int c = i / kHeadMaxK, k = i % kHeadMaxK;
+    const float v = (c < C && k < K) ? W[(size_t)c * K + k] : 0.f;
+    w_ck[c][k] = v;
+    w_kc[k][c] = v;
+    dw_sh[c][k] = 0.f;
+  }
+  if (threadIdx.x < kHeadMaxC) db_sh[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) loss_sh = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float b0 = (bias && lane < C) ? bias[lane] : 0.f, b1 = (bias && lane + 32 < C) ? bias[lane + 32] : 0.f;
+  float dwa[kHeadMaxC][2];
+#pragma unroll
+  for (int c = 0; c < kHeadMaxC; ++c) dwa[c][0] = dwa[c][1] = 0.f;
+  float dba0 = 0.f, dba1 = 0.f, loss_acc = 0.f;
+  const int64_t nwarps = (int64_t)gridDim.x * kHeadWarps;
+  for (int64_t r = (int64_t)blockIdx.x * kHeadWarps + w; r < n; r += nwarps) {
+    const float* arow = a + r * a_stride;
+    const float a0 = lane < K ? arow[lane] : 0.f, a1 = lane + 32 < K ? arow[lane + 32] : 0.f;
+    float l0 = b0, l1 = b1;
+#pragma unroll 8
+    for (int k = 0; k < kHeadMaxK; ++k) {
+      const float av = __shfl_sync(pg::kFullMask, k < 32 ? a0 : a1, k & 31);
+      l0 += av * w_kc[k][lane];
+      l1 += av * w_kc[k][lane + 32];
+    }
+    const bool v0 = lane < C, v1 = lane + 32 < C;
+    float m = fmaxf(v0 ? l0 : -INFINITY, v1 ? l1 : -INFINITY);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(pg::kFullMask, m, d));
+    const float e0 = v0 ? expf(l0 - m) : 0.f, e1 = v1 ? expf(l1 - m) : 0.f;
+    float s = e0 + e1;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(pg::kFullMask, s, d);
+    const int y = (int)labels[r];
+    const float ly = __shfl_sync(pg::kFullMask, y < 32 ? l0 : l1, y & 31);
+    loss_acc += (m + logf(s)) - ly;
+    const float inv_s = 1.0f / s;
+    const float g0 = v0 ? (e0 * inv_s - (lane == y ? 1.f : 0.f)) * inv_n : 0.f;
+    const float g1 = v1 ? (e1 * inv_s - (lane + 32 == y ? 1.f : 0.f)) * inv_n : 0.f;
+    dba0 += g0;
+    dba1 += g1;
+    float ga0 = 0.f, ga1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) {
+      const float gc = __shfl_sync(pg::kFullMask, c < 32 ? g0 : g1, c & 31);
+      ga0 += gc * w_ck[c][lane];
+      ga1 += gc * w_ck[c][lane + 32];
+      dwa[c][0] += gc * a0;
+      dwa[c][1] += gc * a1;
+    }
+    float* grow = grad_a + r * ga_stride;
+    if (lane < K) grow[lane] = ga0;
+    if (lane + 32 < K) grow[lane + 32] = ga1;
+  }
+  // CTA reduction in shared memory, then one global atomic per output
+#pragma unroll
+  for (int c = 0; c < kHeadMaxC; ++c) {
+    atomicAdd(&dw_sh[c][lane], dwa[c][0]);
+    atomicAdd(&dw_sh[c][lane + 32], dwa[c][1]);
+  }
+  atomicAdd(&db_sh[lane], dba0);
+  atomicAdd(&db_sh[lane + 32], dba1);
+  if (lane == 0) atomicAdd(&loss_sh, loss_acc);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
+    const int c = i / K, k = i % K;
+    atomicAdd(&dW[i], dw_sh[c][k]);
+  }
+  if (threadIdx.x < C && db) atomicAdd(&db[threadIdx.x], db_sh[threadIdx.x]);
+  if (threadIdx.x == 0) atomicAdd(loss, loss_sh * inv_n);
+}
+
+}  // namespace
+
+extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias,
+                                             const int64_t* d_labels, int64_t n, int32_t in_dim, int32_t n_classes,
+                                             float* d_loss, float* d_grad_a, int64_t ga_stride, float* d_grad_weight,
+                                             float* d_grad_bias, void* stream) {
+  PG_REQUIRE(d_weight && d_loss && d_grad_weight && n >= 0 && ((d_a && d_labels && d_grad_a) || n == 0),
+             "pg_linear_cross_entropy: bad arguments");
+  PG_REQUIRE(in_dim >= 1 && in_dim <= kHeadMaxK && n_classes >= 1 && n_classes <= kHeadMaxC,
+             "pg_linear_cross_entropy: in_dim and n_classes must be <= 64");
+  PG_REQUIRE(a_stride >= in_dim && ga_stride >= in_dim, "pg_linear_cross_entropy: stride smaller than in_dim");
+  int dev = 0;
+  PG_CUDA(cudaGetDevice(&dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  PG_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(float), st));
+  PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)n_classes * in_dim * sizeof(float), st));
+  if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, (size_t)n_classes * sizeof(float), st));
+  if (n == 0) return PG_OK;
+  const int grid = (int)std::min<int64_t>((n + kHeadWarps - 1) / kHeadWarps, (int64_t)pg::sm_count(dev));
+  const size_t smem = 3 * (size_t)kHeadMaxK * kHeadMaxC * sizeof(float);
+  PG_CUDA(cudaFuncSetAttribute(linear_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  linear_ce_kernel<<<grid, kHeadWarps * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
+                                                     1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight, d_grad_bias);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}

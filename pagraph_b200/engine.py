@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from .nodeflow import NodeBatch
-from .ops import _MODES
+from .ops import _MODES, LinearCrossEntropy
 
 _RING = 3          # ring slots: load runs up to 2 minibatches ahead of compute
 _BUCKET = 4096     # padded-shape granularity of the dense layers
@@ -240,12 +240,19 @@ class GCNTrainEngine:
                                        _MODES["mean"], None, float(p), self.drop_seed, _lib.ptr(self.step_counter), caps[1],
                                        _lib.stream_ptr()), "pg_aggregate_rows")
         h = m.layers[0](NodeBatch({"h": agg}))["activation"]
+        loss = None
         for i in range(1, self.L):
             if m.dropout is not None:
                 h = m.dropout(h)
             h = _BlockAggregateDyn.apply(h, nf["indptr"], nf["indices"], nf["meta"], i, caps[i + 1], "mean")
-            h = m.layers[i](NodeBatch({"h": h}))["activation"]
-        loss = self.loss_fcn(h[:n_valid], s.labels[:n_valid])
+            layer = m.layers[i]
+            if i == self.L - 1 and self._head_fusable(layer, h):
+                # last NodeUpdate (plain linear) + CrossEntropyLoss, forward and backward, in one kernel
+                loss = LinearCrossEntropy.apply(h[:n_valid], layer.linear.weight, layer.linear.bias, s.labels[:n_valid])
+            else:
+                h = layer(NodeBatch({"h": h}))["activation"]
+        if loss is None:
+            loss = self.loss_fcn(h[:n_valid], s.labels[:n_valid])
         if self.sync is not None:
             self.sync.zero_grad()
         else:
@@ -256,6 +263,12 @@ class GCNTrainEngine:
         self.opt.step()
         self.step_counter.add_(1)
         s.loss.copy_(loss.detach())
+
+    def _head_fusable(self, layer, h):
+        lf = self.loss_fcn
+        return (isinstance(lf, torch.nn.CrossEntropyLoss) and lf.reduction == "mean" and lf.weight is None
+                and lf.label_smoothing == 0.0 and layer.activation is None and not layer.concat and not layer.test
+                and LinearCrossEntropy.supported(h, layer.linear.weight))
 
     def _caps_for(self, s):
         meta = s.h_meta_np

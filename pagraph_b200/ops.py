@@ -107,3 +107,36 @@ class LinearConcat(torch.autograd.Function):
                                                        _lib.ptr(out), out.stride(0), n, K, 32, int(ctx.concat), _lib.ptr(gw),
                                                        _lib.ptr(gb), _lib.stream_ptr()), "pg_linear_concat_bwd")
         return None, gw, (gb if ctx.has_bias else None), None
+
+
+class LinearCrossEntropy(torch.autograd.Function):
+    """mean cross-entropy of (x W^T + b) against integer labels — the last NodeUpdate (no activation) followed by
+    torch.nn.CrossEntropyLoss — forward and backward in one kernel (pg_linear_cross_entropy)."""
+
+    @staticmethod
+    def supported(x, weight):
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] <= 64 and weight.shape[0] <= 64
+                and x.stride(1) == 1)
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, labels):
+        n, K = x.shape
+        C = weight.shape[0]
+        loss = torch.empty(1, dtype=torch.float32, device=x.device)
+        gx = torch.empty((n, K), dtype=torch.float32, device=x.device)
+        gw = torch.empty((C, K), dtype=torch.float32, device=x.device)
+        gb = torch.empty(C, dtype=torch.float32, device=x.device)
+        w = weight.contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().pg_linear_cross_entropy(_lib.ptr(x), x.stride(0), _lib.ptr(w), _lib.ptr(bias),
+                                                          _lib.ptr(labels), n, K, C, _lib.ptr(loss), _lib.ptr(gx),
+                                                          gx.stride(0), _lib.ptr(gw), _lib.ptr(gb), _lib.stream_ptr()),
+                       "pg_linear_cross_entropy")
+        ctx.save_for_backward(gx, gw, gb)
+        ctx.has_bias = bias is not None
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gx, gw, gb = ctx.saved_tensors
+        return gx * g, gw * g, (gb * g if ctx.has_bias else None), None

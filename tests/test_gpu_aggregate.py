@@ -141,3 +141,29 @@ def test_linear_concat_matches_torch(n, K, concat):
     (torch.cat((z, torch.relu(z)), 1) if concat else torch.relu(z)).backward(gout.double())
     torch.testing.assert_close(gw.double(), w64.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(gb.double(), b64.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("n,K,C", [(6000, 64, 60), (77, 64, 41), (1, 32, 7), (513, 50, 64), (0, 64, 60)])
+def test_linear_cross_entropy_matches_torch(n, K, C):
+    """Classifier head + CrossEntropyLoss in one kernel: loss and all three gradients against torch (float64)."""
+    import torch
+    from pagraph_b200.ops import LinearCrossEntropy
+    torch.manual_seed(n + K + C)
+    x = torch.randn(n, K, device="cuda", requires_grad=True)
+    lin = torch.nn.Linear(K, C).cuda()
+    y = torch.randint(0, C, (n,), device="cuda")
+    assert LinearCrossEntropy.supported(x, lin.weight)
+    loss = LinearCrossEntropy.apply(x, lin.weight, lin.bias, y)
+    (loss * 3.0).backward()
+    got = [t.clone() for t in (x.grad, lin.weight.grad, lin.bias.grad)]
+    if n == 0:
+        assert all((t == 0).all() for t in got)
+        return
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = lin.weight.detach().double().requires_grad_(True)
+    b64 = lin.bias.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(torch.nn.functional.linear(x64, w64, b64), y)
+    (ref * 3.0).backward()
+    torch.testing.assert_close(loss.double(), ref, rtol=1e-5, atol=1e-6)
+    for a, b in zip(got, (x64.grad, w64.grad, b64.grad)):
+        torch.testing.assert_close(a.double(), b, rtol=1e-4, atol=1e-6)

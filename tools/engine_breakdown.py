@@ -49,6 +49,49 @@ def main():
         b.record(eng.side)
     torch.cuda.synchronize()
     out["load_graph_only_ms"] = a.elapsed_time(b) / n
+    # the engine's own loop with the load stage stubbed out (slot data left as is): host overhead + compute chain
+    real_issue = eng._issue_load
+
+    def fake_issue(k):
+        sl = eng.slots[k % 3]
+        sl.n_valid, sl.k = eng.batch, k
+        eng.side.wait_event(sl.done)
+        sl.loaded.record(eng.side)
+    eng._issue_load = fake_issue
+    tr.run(10, record=False)
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    tr.run(n, record=False)
+    b.record()
+    torch.cuda.synchronize()
+    out["engine_loop_without_load_ms"] = a.elapsed_time(b) / n
+    eng._issue_load = real_issue
+    # and with the compute graph stubbed out: host overhead + load chain
+    real_compute = {}
+    for sl in eng.slots:
+        real_compute[id(sl)] = dict(sl.compute_graphs)
+
+    class _Nop:
+        def replay(self):
+            pass
+    for sl in eng.slots:
+        sl.compute_graphs = {k: (_Nop(), v[1]) for k, v in sl.compute_graphs.items()}
+    tr.run(10, record=False)
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    tr.run(n, record=False)
+    b.record()
+    torch.cuda.synchronize()
+    out["engine_loop_without_compute_ms"] = a.elapsed_time(b) / n
+    for sl in eng.slots:
+        sl.compute_graphs = real_compute[id(sl)]
+    import time
+    t0 = time.perf_counter()
+    tr.run(n, record=False)
+    out["host_issue_ms_per_step"] = (time.perf_counter() - t0) * 1e3 / n
+    torch.cuda.synchronize()
     out["caps"] = list(caps)
     print(json.dumps(out))
 
