@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
-    def __init__(self, dev, period=0.02):
+    def __init__(self, dev, period=0.004):
         super().__init__(daemon=True)
         self.period, self.samples, self._stop_ev, self.ok = period, [], threading.Event(), False
         try:

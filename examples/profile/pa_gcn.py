@@ -70,6 +70,8 @@ def trainer(rank, world_size, args, backend='nccl'):
     optimizer = torch.optim.Adam(sync.flat_parameters(), lr=args.lr, weight_decay=args.weight_decay)
 
     fanout = [int(x) for x in str(args.num_neighbors).split(',')]
+    if args.engine == 'graph' and not args.preprocess:
+        return train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fanout, num_hops, embed_names, remote_g)
     fanout = fanout[0] if len(fanout) == 1 else fanout
     sampler = NeighborSampler(g, args.batch_size, fanout, neighbor_type='in', shuffle=True,
                               num_workers=args.num_workers, num_hops=num_hops, seed_nodes=train_nid,
@@ -105,6 +107,42 @@ def trainer(rank, world_size, args, backend='nccl'):
             print('Epoch average miss rate: {:.4f}'.format(cacher.get_miss_rate()))
     toc = time.time()
     print('Total Time: {:.4f}s'.format(toc - tic))
+    if not args.keep_store:
+        remote_g.destroy()
+    dist.destroy_process_group()
+
+
+def train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fanout, num_hops, embed_names, remote_g):
+    """Same loop on pagraph_b200.engine.GCNTrainEngine: the minibatch work is two CUDA-graph replays (load + compute)."""
+    from pagraph_b200.engine import GCNTrainEngine
+    from pagraph_b200.parallel import equalised_num_batches
+    optimizer = torch.optim.Adam(sync.flat_parameters(), lr=args.lr, weight_decay=args.weight_decay, capturable=True, fused=True)
+    fanouts = fanout * num_hops if len(fanout) == 1 else fanout
+    engine = GCNTrainEngine(g, cacher, model, optimizer, train_nid, labels, args.batch_size, fanouts, sync=sync, seed=args.seed,
+                            shuffle=True)
+    steps_per_epoch = equalised_num_batches(engine.num_batches)
+    epoch_dur = []
+    tic = time.time()
+    model.train()
+    for epoch in range(args.n_epochs):
+        epoch_start_time = time.time()
+        engine.next_compute = engine.next_issue = epoch * engine.num_batches     # every epoch starts at its first minibatch
+        done = 0
+        while done < steps_per_epoch:
+            n = 1 if (epoch == 0 and done == 0) else min(20 - done % 20, steps_per_epoch - done)
+            loss = engine.steps(n)
+            done += n
+            if epoch == 0 and done == 1:
+                cacher.auto_cache(g, embed_names)
+            if rank == 0 and done % 20 == 0:
+                print('epoch [{}] step [{}]. Loss: {:.4f}'.format(epoch + 1, done, loss.item()))
+        torch.cuda.synchronize()
+        if rank == 0:
+            epoch_dur.append(time.time() - epoch_start_time)
+            print('Epoch average time: {:.4f}'.format(np.mean(np.array(epoch_dur[2:])) if len(epoch_dur) > 2
+                                                      else epoch_dur[-1]))
+    print('Total Time: {:.4f}s'.format(time.time() - tic))
+    engine.close()
     remote_g.destroy()
     dist.destroy_process_group()
 
@@ -132,6 +170,9 @@ def make_parser():
     parser.add_argument("--remote-sample", dest='remote_sample', action='store_true')
     parser.set_defaults(remote_sample=False)
     parser.add_argument("--seed", type=int, default=0, help="sampling RNG seed (the reference's is unseeded)")
+    parser.add_argument("--keep-store", action='store_true', help="do not tell the feature server this trainer is done")
+    parser.add_argument("--engine", default="graph", choices=["graph", "eager"],
+                        help="graph: GCNTrainEngine (CUDA-graph pipeline, default); eager: the reference's op-by-op loop")
     return parser
 
 

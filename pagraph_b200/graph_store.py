@@ -179,15 +179,33 @@ class SharedMemoryStoreServer:
                 os.unlink(os.path.join(_SHM_DIR, f))
 
 
+class _LazyFrame(dict):
+    """Field table of a client: a field the server publishes after the client attached is picked up on first use."""
+
+    def __init__(self, client):
+        super().__init__()
+        self._client = client
+
+    def __missing__(self, name):
+        self._client._attach(expect_fields=[name])
+        return dict.__getitem__(self, name)
+
+
 class SharedMemoryStoreClient:
     """Attaches to a server's segments; pins + maps them for the GPU."""
 
     def __init__(self, graph_name, wait_s=600.0, expect_fields=None):
         self.name = graph_name
+        self._wait_s = wait_s
         self._node_frame = _NodeFrame()
+        self._node_frame._frame = _LazyFrame(self)
         self._maps = []
         self._registered = []
         self.ndata = _NData(self)
+        self._attach(expect_fields)
+
+    def _attach(self, expect_fields=None):
+        graph_name = self.name
         t0 = time.time()
         while True:
             try:
@@ -197,10 +215,12 @@ class SharedMemoryStoreClient:
                     break
             except (FileNotFoundError, json.JSONDecodeError):
                 pass
-            if time.time() - t0 > wait_s:
-                raise TimeoutError("graph store %r did not appear under %s" % (graph_name, _SHM_DIR))
+            if time.time() - t0 > self._wait_s:
+                raise TimeoutError("graph store %r (fields %s) did not appear under %s" % (graph_name, expect_fields, _SHM_DIR))
             time.sleep(0.2)
         for name, m in meta["fields"].items():
+            if dict.__contains__(self._node_frame._frame, name):
+                continue
             fd = os.open(_seg_path(graph_name, name), os.O_RDWR)
             try:
                 mm = mmap.mmap(fd, m["rows"] * m["stride"] * 4, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
