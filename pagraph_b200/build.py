@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("PG_NVCC_DEFS", "").split(), "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

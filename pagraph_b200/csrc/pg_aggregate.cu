@@ -225,6 +225,10 @@ __device__ __forceinline__ void acc_drop4(float4& acc, const float4 v, uint64_t 
   if (hi >= thr_hi) acc.w = fmaf(v.w, scale, acc.w);
 }
 
+// ILP = rows consumed per round. ILP = 2 is the faster kernel in isolation (0.166 vs 0.197 ms at config 2) but needs 113
+// registers x 512 threads = 58 k of the SM's 64 k, which evicts the load stage's CTAs (sampler, gather) that should run
+// next to it on the other stream; ILP = 1 (64 registers) gives the faster pipelined step (0.510 vs 0.521 ms), and capping
+// ILP = 2 with __maxnreg__ (96 / 88 / 80) only spills. Hence ILP = 1 at 16 warps.
 template <int W, int CH, bool DROP, int ILP>
 __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a, int group, int depth) {
   constexpr int kRowsWarps = W;
@@ -395,8 +399,10 @@ pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, 
   const bool drop = a.drop_thr != 0;
   // 16 warps give enough thread-level parallelism; the 2-row unroll would only cost registers (the kernel must leave
   // register file for the sampler's CTAs that run next to it on the other stream)
-  constexpr int ILP = W >= 16 ? 1 : 2;
-  auto kern = drop ? agg_rows_tma_kernel<W, CH, true, ILP> : agg_rows_tma_kernel<W, CH, false, ILP>;
+  const char* env_i = getenv("PG_AGG_ILP");
+  const int ilp = env_i ? atoi(env_i) : (W >= 16 ? 1 : 2);
+  auto kern = ilp == 1 ? (drop ? agg_rows_tma_kernel<W, CH, true, 1> : agg_rows_tma_kernel<W, CH, false, 1>)
+                       : (drop ? agg_rows_tma_kernel<W, CH, true, 2> : agg_rows_tma_kernel<W, CH, false, 2>);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t rows = std::max(a.n_dst, a.zero_rows_to);
   const int64_t need = std::max<int64_t>(1, (rows + W - 1) / W);
@@ -418,6 +424,7 @@ pg_status launch_rows_tma(const pg::AggRowsArgs& a, int dev, cudaStream_t st) {
   const int warps = env_w ? atoi(env_w) : 16;
   pg_status s = PG_ERR_INVALID;
   if (warps >= 16) s = launch_rows_tma_w<16, CH>(a, dev, st, budget, depth);
+  if (s == PG_ERR_INVALID && warps >= 12) s = launch_rows_tma_w<12, CH>(a, dev, st, budget, depth);
   if (s == PG_ERR_INVALID && warps >= 8) s = launch_rows_tma_w<8, CH>(a, dev, st, budget, depth);
   if (s == PG_ERR_INVALID) s = launch_rows_tma_w<4, CH>(a, dev, st, budget, depth);
   return s;

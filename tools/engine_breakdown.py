@@ -87,6 +87,42 @@ def main():
     out["engine_loop_without_compute_ms"] = a.elapsed_time(b) / n
     for sl in eng.slots:
         sl.compute_graphs = real_compute[id(sl)]
+    # which part of the load stage is visible in the step? re-capture the load graphs with only one part each
+    import ctypes
+    from pagraph_b200 import _lib
+
+    def recapture(part):
+        def body(sl, n_seeds):
+            L, c = _lib.lib(), eng.cacher
+            st = _lib.stream_ptr()
+            if part in ("sample", "all"):
+                nfb = _lib.pg_nodeflow_buffers(*[_lib.ptr(sl.nf[k]) for k in ("node_mapping", "indptr", "indices", "edge_mapping", "meta")])
+                key = ctypes.c_void_p(sl.seeds_key.data_ptr() + 8 * eng.batch)
+                _lib.check(L.pg_sample_keyed(eng.sampler, _lib.ptr(sl.seeds_key), n_seeds, key, ctypes.byref(nfb), _lib.ptr(sl.h_meta), st), "s")
+            if part in ("fetch", "all"):
+                outs = (ctypes.c_void_p * len(sl.rest))(*[t.data_ptr() for t in sl.rest])
+                _lib.check(L.pg_cache_fetch_dyn(c._handle, _lib.ptr(sl.nf["node_mapping"]), eng._meta_ptr(sl, 5), eng._meta_ptr(sl, 4 + eng.L + 1),
+                                                eng.cap_rest, outs, None, 0, st), "f")
+                blk = _lib.pg_block(_lib.ptr(sl.nf["node_mapping"]), _lib.ptr(sl.nf["indptr"]), _lib.ptr(sl.nf["indices"]), 0, eng.cap_n0,
+                                    eng.cap_layer[-2], eng._meta_ptr(sl, 4))
+                _lib.check(L.pg_cache_resolve(c._handle, eng.fi, ctypes.byref(blk), _lib.ptr(sl.rowptr), _lib.ptr(sl.stage), eng.stage_rows, None, st), "r")
+        torch.cuda.synchronize()
+        for sl in eng.slots:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(eng.side):
+                with torch.cuda.graph(g2, stream=eng.side, capture_error_mode="thread_local"):
+                    body(sl, eng.batch)
+            sl.load_graph = g2
+    for part in ("sample", "fetch", "all"):
+        recapture(part)
+        tr.run(10, record=False)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        tr.run(n, record=False)
+        b.record()
+        torch.cuda.synchronize()
+        out["pipelined_with_load=%s_ms" % part] = a.elapsed_time(b) / n
     import time
     t0 = time.perf_counter()
     tr.run(n, record=False)
