@@ -177,7 +177,8 @@ pg_status pg_aggregate_bwd_dyn(const int64_t* d_indptr_base, const int64_t* d_co
  * (missed rows are first pulled over PCIe into a staging buffer, one TMA bulk copy per row). drop() is inverted
  * dropout with probability dropout_p, mask keyed by (dropout_seed + *d_step, source node, column) so that every
  * edge of a source node sees the same dropped row, as dropout-then-aggregate does; dropout_p = 0 disables it.
- * d_norm / mode as pg_aggregate_fwd. Rows [n_dst, zero_rows_to) of d_dst are zero-filled (fixed-shape buffers).
+ * d_norm / mode as pg_aggregate_fwd. Rows [n_dst, zero_rows_to) of d_dst are zero-filled (fixed-shape buffers); with
+ * device-resident extents a negative zero_rows_to = -g zero-fills up to n_dst rounded up to a multiple of g.
  * d_counts (optional int64[2]) is incremented by (n_src, misses) like pg_cache_fetch. */
 typedef struct {
   const int64_t* parent_ids; /* [n_src] parent (local) ids of the block's source layer               */

@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a,
   __syncwarp();
   const int64_t warp0 = (int64_t)blockIdx.x * kRowsWarps + w, nwarps = (int64_t)gridDim.x * kRowsWarps;
   const uint64_t seed = DROP ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
+  const int64_t cap_dst = a.n_dst;
   if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
+  a.zero_rows_to = pg::resolve_zero_rows(a.zero_rows_to, a.n_dst, cap_dst);
 
   auto issue = [&](const TaskCursor& c, int buf) {
     const int cnt = c.count(group);
@@ -361,7 +363,9 @@ __global__ void __launch_bounds__(kAggThreads) agg_rows_ldg_kernel(pg::AggRowsAr
   const int64_t nwarps = (int64_t)gridDim.x * (kAggThreads / 32);
   const uint32_t groups = (uint32_t)((a.dim + 3) >> 2);
   const uint64_t seed = a.drop_thr ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
+  const int64_t cap_dst = a.n_dst;
   if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
+  a.zero_rows_to = pg::resolve_zero_rows(a.zero_rows_to, a.n_dst, cap_dst);
   for (int64_t r = warp0; r < a.zero_rows_to || r < a.n_dst; r += nwarps) {
     if (r >= a.n_dst) {
       for (int col = lane; col < a.dim; col += 32) a.dst[r * a.dst_stride + col] = 0.f;
@@ -404,7 +408,7 @@ pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, 
   auto kern = ilp == 1 ? (drop ? agg_rows_tma_kernel<W, CH, true, 1> : agg_rows_tma_kernel<W, CH, false, 1>)
                        : (drop ? agg_rows_tma_kernel<W, CH, true, 2> : agg_rows_tma_kernel<W, CH, false, 2>);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t rows = std::max(a.n_dst, a.zero_rows_to);
+  const int64_t rows = std::max(a.n_dst, a.zero_rows_to);   // a negative zero_rows_to is bounded by the capacity n_dst
   const int64_t need = std::max<int64_t>(1, (rows + W - 1) / W);
   const int grid = (int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev));
   kern<<<grid, W * 32, smem, st>>>(a, group, depth);

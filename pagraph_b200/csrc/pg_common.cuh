@@ -79,7 +79,9 @@ struct AggRowsArgs {
   float* dst;
   int64_t dst_stride;
   int64_t n_dst;
-  int64_t zero_rows_to;        // rows [n_dst, zero_rows_to) of dst are zero-filled (padding of fixed-shape buffers)
+  int64_t zero_rows_to;        // rows [n_dst, zero_rows_to) of dst are zero-filled (padding of fixed-shape buffers);
+                               // a negative value -g means "up to n_dst rounded up to a multiple of g" (capped by the
+                               // capacity passed as n_dst), for device-resident extents
   int dim;
   int mode;
   const float* norm;
@@ -101,6 +103,12 @@ __device__ __forceinline__ int64_t apply_extents(const int64_t* lo, const int64_
   col_base = l0;
   n_dst = min(n_dst, l2 - l1);
   return l1 - l0;
+}
+// resolves AggRowsArgs::zero_rows_to (see there) once n_dst is final; cap = the capacity n_dst held before apply_extents
+__device__ __forceinline__ int64_t resolve_zero_rows(int64_t zero_rows_to, int64_t n_dst, int64_t cap) {
+  if (zero_rows_to >= 0) return zero_rows_to;
+  const int64_t g = -zero_rows_to;
+  return min(cap, (n_dst + g - 1) / g * g);
 }
 pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st);
 

@@ -626,6 +626,7 @@ pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, i
   PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_aggregate_rows: mode must be PG_AGG_SUM or PG_AGG_MEAN");
   PG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pg_aggregate_rows: dropout_p must be in [0, 1)");
   PG_REQUIRE(blk->n_dst >= 0 && dst_stride >= dim && (blk->indptr || blk->n_dst == 0), "pg_aggregate_rows: bad sizes");
+  PG_REQUIRE(zero_rows_to >= 0 || blk->d_layer_offsets, "pg_aggregate_rows: a rounding zero_rows_to needs device extents");
   if (std::max(blk->n_dst, zero_rows_to) == 0) return PG_OK;
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));

@@ -2,18 +2,21 @@
 
 The reference loop is `for nf in sampler: cacher.fetch_data(nf); label = ...; pred = model(nf); loss; backward;
 step`. Issued op by op it is launch-bound on a B200 (≈ 40 kernels, ≈ 0.65 ms of GPU work per minibatch at config 2).
-Here the same work is two captured graphs per minibatch, replayed:
+Here the same work is three captured graphs per minibatch, replayed on three streams that run one minibatch apart:
 
-  load graph (side stream, one per ring slot)     pg_sample_keyed -> pg_cache_fetch_dyn (layers 1..L frames) ->
-                                                  pg_cache_resolve (row pointers of the input layer + PCIe staging of
-                                                  its missed rows) [-> label gather]
-  compute graph (main stream, per slot x bucket)  pg_aggregate_rows (fused cache lookup + dropout + block-0 aggregation)
-                                                  -> NodeUpdate linears (cuBLAS) -> pg_aggregate_fwd_dyn -> ... -> loss ->
-                                                  backward (pg_aggregate_bwd_dyn) -> gradient all-reduce -> Adam
+  sample graph  (stream A, per ring slot)   pg_sample_keyed [-> label gather]: a chain of small latency-bound kernels
+  gather graph  (stream B, per ring slot)   pg_cache_fetch_dyn (layers 1..L frames) -> pg_cache_resolve (row pointers of
+                                            the input layer + PCIe staging of its missed rows) -> pg_aggregate_rows (fused
+                                            cache lookup + dropout + block-0 aggregation; it has no trainable input, so it
+                                            need not wait for the previous optimizer step): the HBM / PCIe-bound part
+  compute graph (main stream, per slot x bucket)  NodeUpdate linear (cuBLAS) + cat/relu -> dropout -> pg_aggregate_fwd_dyn
+                                            -> head + loss (pg_linear_cross_entropy) -> backward (pg_aggregate_bwd_dyn,
+                                            pg_linear_concat_bwd) -> gradient all-reduce -> Adam
 
+While minibatch k trains, minibatch k+1 is gathered and aggregated and minibatch k+2 is sampled.
 Nothing about a minibatch's size is needed on the host to launch it: every kernel reads the NodeFlow extents from
 the device (`meta`), the host only picks the padded-shape bucket of the dense layers from the pinned copy of `meta`
-that the load graph leaves behind two minibatches ahead. The PCIe transfer of minibatch k+1's missed rows runs under
+that the sample graph leaves behind two minibatches ahead. The PCIe transfer of minibatch k+1's missed rows runs under
 minibatch k's compute. Semantics (what is sampled, fetched, aggregated, and the model math) are those of the eager
 classes in this package; tests/test_gpu_engine.py checks the two paths against each other.
 """
@@ -25,7 +28,7 @@ from . import _lib
 from .nodeflow import NodeBatch
 from .ops import _MODES, LinearCrossEntropy
 
-_RING = 3          # ring slots: load runs up to 2 minibatches ahead of compute
+_RING = 4          # ring slots: sampling runs 2 minibatches ahead of compute, gathering 1
 _BUCKET = 4096     # padded-shape granularity of the dense layers
 
 
@@ -98,8 +101,8 @@ class GCNTrainEngine:
         with torch.cuda.device(self.dev):
             # the load stage is a chain of small latency-bound kernels: high priority lets them slip in between the
             # compute stage's full-GPU kernels instead of queueing behind them
-            import os
-            self.side = torch.cuda.Stream(device=self.dev, priority=int(os.environ.get("PG_ENGINE_SIDE_PRIORITY", "-1")))
+            self.side = torch.cuda.Stream(device=self.dev, priority=-1)     # stream A: sampling
+            self.gather = torch.cuda.Stream(device=self.dev)                # stream B: fetch / resolve / aggregate
             if self.host_inputs:
                 self.seeds_host = seeds.pin_memory()
                 self.labels_host = labels.cpu()
@@ -125,11 +128,13 @@ class GCNTrainEngine:
             _lib.check(L.pg_sampler_create(g.handle(self.dev.index), self.L, fan, self.seed, self.batch, self.cap_nodes,
                                            self.cap_edges, ctypes.byref(h)), "pg_sampler_create")
             self.sampler = h
-            self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # keys the fused dropout mask
+            self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # optimizer steps taken
+            self.load_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # minibatches loaded: keys the fused dropout mask
             self.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             self.slots = [self._make_slot() for _ in range(_RING)]
         self.pool = None
-        self.next_issue = 0          # global minibatch index of the next load to issue
+        self.next_issue = 0          # global minibatch index of the next stage A to issue
+        self.next_gather = 0         # ... of the next stage B
         self.next_compute = 0
         self.launches = 0            # kernels launched / replayed by this engine (bench.py's gpu_launches)
         self.size_log = None         # set to [] to record (layer offsets, block offsets) of every computed minibatch
@@ -153,9 +158,12 @@ class GCNTrainEngine:
         s.stage = torch.empty((max(self.stage_rows, 1), self.F), dtype=torch.float32, device=dev)
         s.rest = [torch.empty((self.cap_rest, self.cacher.dims[n]), dtype=torch.float32, device=dev)
                   for n in self.cacher._field_names]
+        cap1 = -(-self.cap_layer[-2] // _BUCKET) * _BUCKET
+        s.agg = torch.empty((cap1, self.F), dtype=torch.float32, device=dev)       # block-0 aggregate, padded rows zeroed
         s.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        s.loaded, s.done = torch.cuda.Event(), torch.cuda.Event()
-        s.load_graph, s.load_kernels = None, 0
+        s.sampled, s.loaded, s.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        s.sample_graph, s.sample_kernels = None, 0
+        s.gather_graph, s.gather_kernels = None, 0
         s.compute_graphs = {}
         s.n_valid = self.batch
         return s
@@ -164,29 +172,39 @@ class GCNTrainEngine:
         return ctypes.c_void_p(s.nf["meta"].data_ptr() + 8 * idx)
 
     # ------------------------------------------------------------------ load stage (side stream)
-    def _load_body(self, s, n_seeds):
-        """sample + fetch layers 1..L + resolve the input layer; everything sized on the device."""
-        L, c = _lib.lib(), self.cacher
+    def _sample_body(self, s, n_seeds):
+        """stage A: sample the minibatch (sizes stay on the device; meta also goes to pinned host for the bucket)."""
+        L = _lib.lib()
         nfb = _lib.pg_nodeflow_buffers(*[_lib.ptr(s.nf[k]) for k in
                                          ("node_mapping", "indptr", "indices", "edge_mapping", "meta")])
-        st = _lib.stream_ptr()
         key = ctypes.c_void_p(s.seeds_key.data_ptr() + 8 * self.batch)
         _lib.check(L.pg_sample_keyed(self.sampler, _lib.ptr(s.seeds_key), n_seeds, key, ctypes.byref(nfb), _lib.ptr(s.h_meta),
-                                     st), "pg_sample_keyed")
+                                     _lib.stream_ptr()), "pg_sample_keyed")
         if not self.host_inputs:
             torch.index_select(self.labels_dev, 0, s.seeds_key[:self.batch], out=s.labels)
+
+    def _gather_body(self, s):
+        """stage B: fetch layers 1..L, resolve + stage the input layer, aggregate block 0; all sized on the device."""
+        L, c = _lib.lib(), self.cacher
+        st = _lib.stream_ptr()
         counts = c._counts if (c.log and not c.full_cached) else None
         outs = (ctypes.c_void_p * len(s.rest))(*[t.data_ptr() for t in s.rest])
         _lib.check(L.pg_cache_fetch_dyn(c._handle, _lib.ptr(s.nf["node_mapping"]), self._meta_ptr(s, 4 + 1),
                                         self._meta_ptr(s, 4 + self.L + 1), self.cap_rest, outs, _lib.ptr(counts), 0, st),
                    "pg_cache_fetch_dyn")
         blk = _lib.pg_block(_lib.ptr(s.nf["node_mapping"]), _lib.ptr(s.nf["indptr"]), _lib.ptr(s.nf["indices"]), 0,
-                            self.cap_n0, self.cap_layer[-2], self._meta_ptr(s, 4))
+                            self.cap_n0, s.agg.shape[0], self._meta_ptr(s, 4))
         _lib.check(L.pg_cache_resolve(c._handle, self.fi, ctypes.byref(blk), _lib.ptr(s.rowptr), _lib.ptr(s.stage),
                                       self.stage_rows, _lib.ptr(counts), st), "pg_cache_resolve")
+        m = self.model
+        p = m.dropout.p if (m.dropout is not None and m.training) else 0.0
+        _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptr), ctypes.byref(blk), self.F, _lib.ptr(s.agg), s.agg.stride(0),
+                                       _MODES["mean"], None, float(p), self.drop_seed, _lib.ptr(self.load_counter), -_BUCKET,
+                                       st), "pg_aggregate_rows")
+        self.load_counter.add_(1)
 
-    def _issue_load(self, k):
-        """Enqueue the load stage of global minibatch k on the side stream."""
+    def _issue_sample(self, k):
+        """Enqueue stage A of global minibatch k."""
         s = self.slots[k % _RING]
         epoch, b = divmod(k, self.num_batches)
         lo = b * self.batch
@@ -208,37 +226,47 @@ class GCNTrainEngine:
                 s.stage_host[0] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
                 s.seeds_key[self.batch:].copy_(s.stage_host[:1], non_blocking=True)
             if self.use_graphs and n == self.batch:
-                if s.load_graph is None:
-                    self._capture_load(s)
-                s.load_graph.replay()
-                self.launches += s.load_kernels
+                if s.sample_graph is None:
+                    s.sample_graph, s.sample_kernels = self._capture(self.side, lambda: self._sample_body(s, self.batch))
+                s.sample_graph.replay()
+                self.launches += s.sample_kernels
             else:
                 l0 = _lib.launch_count()
-                self._load_body(s, n)
+                self._sample_body(s, n)
                 self.launches += _lib.launch_count() - l0
-            s.loaded.record(self.side)
+            s.sampled.record(self.side)
 
-    def _capture_load(self, s):
-        self._load_body(s, self.batch)                       # eager once: sizes every workspace outside the capture
-        self.side.synchronize()
+    def _issue_gather(self, k):
+        """Enqueue stage B of global minibatch k (after its stage A)."""
+        s = self.slots[k % _RING]
+        self.gather.wait_event(s.sampled)
+        with torch.cuda.stream(self.gather):
+            if self.use_graphs:
+                if s.gather_graph is None:
+                    s.gather_graph, s.gather_kernels = self._capture(self.gather, lambda: self._gather_body(s))
+                s.gather_graph.replay()
+                self.launches += s.gather_kernels
+            else:
+                l0 = _lib.launch_count()
+                self._gather_body(s)
+                self.launches += _lib.launch_count() - l0
+            s.loaded.record(self.gather)
+
+    def _capture(self, stream, body):
+        body()                                               # eager once: sizes every workspace outside the capture
+        stream.synchronize()
         g = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
-        with torch.cuda.graph(g, stream=self.side, capture_error_mode="thread_local"):
-            self._load_body(s, self.batch)
-        s.load_graph, s.load_kernels = g, _lib.launch_count() - l0
+        with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+            body()
+        return g, _lib.launch_count() - l0
 
     # ------------------------------------------------------------------ compute stage (main stream)
     def _compute_body(self, s, caps, n_valid):
         """caps[j]: padded row count of NodeFlow layer j (j = 1..L; caps[L] = batch)."""
         L, m = _lib.lib(), self.model
         nf = s.nf
-        p = m.dropout.p if (m.dropout is not None and m.training) else 0.0
-        agg = torch.empty((caps[1], self.F), dtype=torch.float32, device=self.dev)
-        blk = _lib.pg_block(_lib.ptr(nf["node_mapping"]), _lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), 0, self.cap_n0,
-                            caps[1], self._meta_ptr(s, 4))
-        _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptr), ctypes.byref(blk), self.F, _lib.ptr(agg), agg.stride(0),
-                                       _MODES["mean"], None, float(p), self.drop_seed, _lib.ptr(self.step_counter), caps[1],
-                                       _lib.stream_ptr()), "pg_aggregate_rows")
+        agg = s.agg[:caps[1]]                                 # aggregated by the load stage; rows >= n_1 are zero
         h = m.layers[0](NodeBatch({"h": agg}))["activation"]
         loss = None
         for i in range(1, self.L):
@@ -296,7 +324,7 @@ class GCNTrainEngine:
             self._cache_state = st
             new_stage = 0 if self.cacher.full_cached else int(min(self._stage_rows_req, self.cap_n0))
             for s in self.slots:
-                s.load_graph, s.compute_graphs = None, {}
+                s.sample_graph, s.gather_graph, s.compute_graphs = None, None, {}
                 if new_stage != self.stage_rows:
                     s.stage = torch.empty((max(new_stage, 1), self.F), dtype=torch.float32, device=self.dev)
             self.stage_rows = new_stage
@@ -308,15 +336,19 @@ class GCNTrainEngine:
         self._check_cache_state()
         main = torch.cuda.current_stream(self.dev)
         end = self.next_compute + count
-        # a previous call may have left loads in flight for minibatches < next_issue
-        while self.next_issue < min(end, self.next_compute + _RING - 1):
-            self._issue_load(self.next_issue)
+        self.next_gather = max(self.next_gather, self.next_compute)
+        self.next_issue = max(self.next_issue, self.next_gather)
+        while self.next_issue < min(end, self.next_compute + 2):       # prologue: A runs 2 ahead, B 1 ahead
+            self._issue_sample(self.next_issue)
             self.next_issue += 1
+        while self.next_gather < min(end, self.next_compute + 1):
+            self._issue_gather(self.next_gather)
+            self.next_gather += 1
         loss = None
         while self.next_compute < end:
             k = self.next_compute
             s = self.slots[k % _RING]
-            s.loaded.synchronize()                           # sampling is >= 1 minibatch ahead: normally no wait
+            s.sampled.synchronize()                          # sampling is 2 minibatches ahead: normally no wait
             if s.h_meta_np[0] != _lib.PG_OK:
                 raise _lib.PGError("sampler reported status %d for minibatch %d" % (int(s.h_meta_np[0]), k))
             main.wait_event(s.loaded)
@@ -338,8 +370,11 @@ class GCNTrainEngine:
             s.done.record(main)
             self.next_compute += 1
             if self.next_issue < end:
-                self._issue_load(self.next_issue)
+                self._issue_sample(self.next_issue)
                 self.next_issue += 1
+            if self.next_gather < end:
+                self._issue_gather(self.next_gather)
+                self.next_gather += 1
             loss = s.loss
             if read_loss:
                 loss = float(s.loss.item())                  # D2H read of the step's result
@@ -354,7 +389,7 @@ class GCNTrainEngine:
     def close(self):
         torch.cuda.synchronize(self.dev)
         for s in self.slots:
-            s.load_graph, s.compute_graphs = None, {}
+            s.sample_graph, s.gather_graph, s.compute_graphs = None, None, {}
         if self.sampler is not None:
             _lib.lib().pg_sampler_destroy(self.sampler)
             self.sampler = None
