@@ -48,6 +48,12 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_free_events;
 bool timing_enabled() { return g_timing.load(std::memory_order_relaxed); }
 
 void timing_begin(int slot, cudaStream_t st, int* token) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();   // a replayed graph has no host-side launch to bracket: no record for captured work
+    *token = -1;
+    return;
+  }
   std::lock_guard<std::mutex> lk(g_timing_mu);
   TimingRec r;
   r.slot = slot;

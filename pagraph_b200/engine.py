@@ -20,7 +20,9 @@ that the sample graph leaves behind two minibatches ahead. The PCIe transfer of 
 minibatch k's compute. Semantics (what is sampled, fetched, aggregated, and the model math) are those of the eager
 classes in this package; tests/test_gpu_engine.py checks the two paths against each other.
 """
+import contextlib
 import ctypes
+import gc
 
 import torch
 
@@ -62,6 +64,19 @@ class _BlockAggregateDyn(torch.autograd.Function):
 
 class _Slot:
     pass
+
+
+@contextlib.contextmanager
+def _capture_guard():
+    """No cyclic garbage collection while a stream capture is open: a collected GraphCacheServer / sampler / engine
+    would run its destructor (cudaFree, cudaDeviceSynchronize) on the capturing thread and invalidate the capture."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class GCNTrainEngine:
@@ -257,7 +272,7 @@ class GCNTrainEngine:
         stream.synchronize()
         g = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
-        with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+        with _capture_guard(), torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
             body()
         return g, _lib.launch_count() - l0
 
@@ -310,7 +325,7 @@ class GCNTrainEngine:
     def _capture_compute(self, s, caps):
         g = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
-        with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+        with _capture_guard(), torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
             self._compute_body(s, caps, self.batch)
         if self.pool is None:
             self.pool = g.pool()
