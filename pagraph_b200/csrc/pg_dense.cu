@@ -71,24 +71,42 @@ __global__ void __launch_bounds__(kBwdThreads, 1) linear_concat_bwd_kernel(const
 #pragma unroll
     for (int o = 0; o < kOut / 2; ++o) acc[j][o] = 0ull;
   float dbv = 0.f;
-  if (ntiles > 0 && t < 32) issue(0);
-  uint32_t phase = 0;                                 // bit b: parity to wait for on buffer b
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int buf = tile & 1;
+  // gz for one tile: each thread owns kTile*kOut/kBwdThreads entries; loaded into registers one tile ahead so that the
+  // global-load latency hides under the previous tile's FMA loop
+  constexpr int kPer = kTile * kOut / kBwdThreads;
+  float gnext[kPer];
+  auto load_gz = [&](int tile) {
     const int64_t r0 = r_begin + (int64_t)tile * kTile;
     const int rows = (int)min((int64_t)kTile, r_end - r0);
-    if (tile + 1 < ntiles && t < 32) issue(tile + 1);  // the other buffer was released by the barrier ending tile-1
-    for (int i = t; i < kTile * kOut; i += kBwdThreads) {
-      const int rr = i / kOut, o = i % kOut;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = t + q * kBwdThreads, rr = i / kOut, o = i % kOut;
       float v = 0.f;
       if (rr < rows) {
         const float* grow = g + (r0 + rr) * g_stride;
         const float* yrow = y + (r0 + rr) * y_stride;
         v = concat ? grow[o] + (yrow[kOut + o] > 0.f ? grow[kOut + o] : 0.f) : (yrow[o] > 0.f ? grow[o] : 0.f);
       }
-      gz[rr][o] = v;
+      gnext[q] = v;
+    }
+  };
+  if (ntiles > 0) {
+    if (t < 32) issue(0);
+    load_gz(0);
+  }
+  uint32_t phase = 0;                                 // bit b: parity to wait for on buffer b
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    const int64_t r0 = r_begin + (int64_t)tile * kTile;
+    const int rows = (int)min((int64_t)kTile, r_end - r0);
+    if (tile + 1 < ntiles && t < 32) issue(tile + 1);  // the other buffer was released by the barrier ending tile-1
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = t + q * kBwdThreads;
+      gz[i / kOut][i % kOut] = gnext[q];
     }
     __syncthreads();
+    if (tile + 1 < ntiles) load_gz(tile + 1);          // in flight during the FMA loop below
     while (!pg::mbar_try_wait(pg::smem_u32(&bars[buf]), (phase >> buf) & 1u)) {
     }
     phase ^= 1u << buf;
@@ -287,7 +305,7 @@ extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride,
   PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)n_classes * in_dim * sizeof(float), st));
   if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, (size_t)n_classes * sizeof(float), st));
   if (n == 0) return PG_OK;
-  const int grid = (int)std::min<int64_t>((n + kHeadWarps - 1) / kHeadWarps, (int64_t)pg::sm_count(dev));
+  const int grid = (int)std::min<int64_t>((n + kHeadWarps - 1) / kHeadWarps, (int64_t)pg::sm_count(dev) * 2);
   const size_t smem = 3 * (size_t)kHeadMaxK * kHeadMaxC * sizeof(float);
   PG_CUDA(cudaFuncSetAttribute(linear_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   linear_ce_kernel<<<grid, kHeadWarps * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
