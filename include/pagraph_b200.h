@@ -39,9 +39,12 @@ enum {
 typedef struct pg_graph pg_graph;     /* in-CSR adjacency resident in HBM */
 typedef struct pg_sampler pg_sampler; /* sampling workspace bound to one graph */
 typedef struct pg_cache pg_cache;     /* feature-cache lookup state (flag / l2c / nid_map / tables) */
+typedef struct pg_peer_group pg_peer_group; /* NVLink peer memory of the one-node gradient all-reduce */
 
 #define PG_MAX_FIELDS 4
 #define PG_MAX_HOPS 8
+#define PG_MAX_RANKS 8            /* GPUs of one node in a peer group */
+#define PG_IPC_HANDLE_BYTES 64    /* sizeof(cudaIpcMemHandle_t) */
 
 /* ---------------------------------------------------------------- runtime */
 int pg_version(void);
@@ -220,6 +223,24 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
 pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias,
                                   const int64_t* d_labels, int64_t n, int32_t in_dim, int32_t n_classes, float* d_loss,
                                   float* d_grad_a, int64_t ga_stride, float* d_grad_weight, float* d_grad_bias, void* stream);
+
+/* ---------------------------------------------------------------- gradient all-reduce fused with the optimizer step
+ * Replaces DistributedDataParallel's all-reduce of the flat gradient followed by Adam (examples/profile/pa_gcn.py:65,96-97)
+ * with ONE kernel over NVLink peer memory: every CTA pushes its slice of the gradient into every peer's receive area
+ * (CUDA-IPC mapped), raises a per-slice flag, waits for the peers' slices, sums them in rank order, divides by the world
+ * size and applies Adam to its slice in place. No NCCL call, no host synchronisation, capturable in a CUDA graph.
+ *   pg_peer_group_create: allocates this rank's receive area for n floats and returns its CUDA IPC handle (exchange the
+ *     handles of all ranks by any means, e.g. an all_gather); pg_peer_group_connect maps the peers' areas.
+ *   pg_allreduce_adam: d_grad is replaced by the rank-averaged gradient; d_param / d_exp_avg / d_exp_avg_sq are updated in
+ *     place with torch.optim.Adam's formulas (no amsgrad). d_step: the optimizer's step count for THIS step (float, on
+ *     the device, already incremented); d_step_id: a step number >= 1 on the device that is equal on all ranks and grows
+ *     by one per call (it is the flag value peers wait for). world == 1 degenerates to the optimizer step. */
+pg_status pg_peer_group_create(int world, int rank, int64_t n, int dev, pg_peer_group** out, unsigned char* handle_out);
+pg_status pg_peer_group_connect(pg_peer_group* g, const unsigned char* handles);
+void pg_peer_group_destroy(pg_peer_group* g);
+pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                            const float* d_step, const int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, void* stream);
 
 /* ---------------------------------------------------------------- offline partitioner (host code, host pointers)
  * The streaming "dg" assignment of PaGraph/partition/dg.py:59-103, same assignments bit for bit (see pg_partition.cu).

@@ -7,6 +7,8 @@ from . import build as _build
 
 PG_MAX_FIELDS = 4
 PG_MAX_HOPS = 8
+PG_MAX_RANKS = 8
+PG_IPC_HANDLE_BYTES = 64
 PG_META_LEN = 4 + (PG_MAX_HOPS + 2) + (PG_MAX_HOPS + 1)
 PG_OK, PG_ERR_INVALID, PG_ERR_CUDA, PG_ERR_OVERFLOW, PG_ERR_NOMEM = 0, 1, 2, 3, 4
 PG_AGG_SUM, PG_AGG_MEAN = 0, 1
@@ -86,6 +88,12 @@ SIGNATURES = {
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int, c_vp, c_vp, c_vp]),
     "pg_linear_cross_entropy": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32,
                                                ctypes.c_int32, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp]),
+    "pg_peer_group_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp),
+                                            c_vp]),
+    "pg_peer_group_connect": (ctypes.c_int, [c_vp, c_vp]),
+    "pg_peer_group_destroy": (None, [c_vp]),
+    "pg_allreduce_adam": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_float,
+                                         ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp]),
     "pg_partition_dg": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                        c_vp, c_vp]),
     "pg_measure_h2d": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int,

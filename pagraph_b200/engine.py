@@ -23,12 +23,14 @@ classes in this package; tests/test_gpu_engine.py checks the two paths against e
 import contextlib
 import ctypes
 import gc
+import os
 
 import torch
 
 from . import _lib
 from .nodeflow import NodeBatch
 from .ops import _MODES, LinearCrossEntropy
+from .parallel import PeerAdam
 
 _RING = 4          # ring slots: sampling runs 2 minibatches ahead of compute, gathering 1
 _BUCKET = 4096     # padded-shape granularity of the dense layers
@@ -147,6 +149,12 @@ class GCNTrainEngine:
             self.load_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # minibatches loaded: keys the fused dropout mask
             self.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             self.slots = [self._make_slot() for _ in range(_RING)]
+        self.fused_opt = None
+        if sync is not None and os.environ.get("PG_ENGINE_FUSED_OPT", "1") != "0" and PeerAdam.supported(sync, optimizer):
+            try:
+                self.fused_opt = PeerAdam(sync, optimizer)
+            except Exception as e:                          # e.g. CUDA IPC unavailable: NCCL all-reduce + optimizer.step()
+                print("GCNTrainEngine: fused all-reduce + Adam unavailable (%s); using all_reduce + optimizer.step()" % e)
         self.pool = None
         self.next_issue = 0          # global minibatch index of the next stage A to issue
         self.next_gather = 0         # ... of the next stage B
@@ -301,10 +309,14 @@ class GCNTrainEngine:
         else:
             self.opt.zero_grad(set_to_none=False)
         loss.backward()
-        if self.sync is not None:
-            self.sync()
-        self.opt.step()
-        self.step_counter.add_(1)
+        if self.fused_opt is not None:                       # gradient all-reduce + Adam: one kernel over NVLink peer memory
+            self.step_counter.add_(1)
+            self.fused_opt.step(self.step_counter)
+        else:
+            if self.sync is not None:
+                self.sync()
+            self.opt.step()
+            self.step_counter.add_(1)
         s.loss.copy_(loss.detach())
 
     def _head_fusable(self, layer, h):
@@ -408,6 +420,9 @@ class GCNTrainEngine:
         if self.sampler is not None:
             _lib.lib().pg_sampler_destroy(self.sampler)
             self.sampler = None
+        if self.fused_opt is not None:
+            self.fused_opt.close()
+            self.fused_opt = None
 
     def __del__(self):
         try:

@@ -84,3 +84,74 @@ def equalised_num_batches(local_num_batches, process_group=None):
     t = torch.tensor([int(local_num_batches)], dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=process_group)
     return int(t.item())
+
+
+class PeerAdam:
+    """Gradient all-reduce + Adam step as one kernel over NVLink peer memory (pg_allreduce_adam), standing where
+    `sync(); optimizer.step()` stands. The optimizer object keeps owning the hyper-parameters and the state tensors
+    (`exp_avg`, `exp_avg_sq`, `step`), which the kernel updates in place, so `optimizer.state_dict()` stays meaningful.
+
+    Usable when `optimizer` is a torch.optim.Adam (no amsgrad / maximize) over `sync.flat_parameters()` on a CUDA device,
+    with world_size <= 8 on one node. Hyper-parameters are read when `step()` is called (a captured CUDA graph bakes them)."""
+
+    @staticmethod
+    def supported(sync, optimizer):
+        if not isinstance(optimizer, torch.optim.Adam) or len(optimizer.param_groups) != 1:
+            return False
+        g = optimizer.param_groups[0]
+        flat = sync.flat_parameters()[0]
+        return (len(g["params"]) == 1 and g["params"][0] is flat and flat.is_cuda and flat.dtype == torch.float32
+                and not g.get("amsgrad") and not g.get("maximize") and not g.get("decoupled_weight_decay", False)
+                and sync.world <= 8)
+
+    def __init__(self, sync, optimizer):
+        import ctypes
+        from . import _lib
+        self._lib = _lib
+        self.sync, self.opt = sync, optimizer
+        self.flat = sync.flat_parameters()[0]
+        dev = self.flat.device
+        st = optimizer.state[self.flat]
+        if len(st) == 0:                                  # what Adam._init_group creates for capturable / fused
+            st["step"] = torch.zeros((), dtype=torch.float32, device=dev)
+            st["exp_avg"] = torch.zeros_like(self.flat, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(self.flat, memory_format=torch.preserve_format)
+        if not (torch.is_tensor(st["step"]) and st["step"].is_cuda):
+            st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32, device=dev)
+        self.state = st
+        world, rank = sync.world, (dist.get_rank(sync.group) if sync.world > 1 else 0)
+        h = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * _lib.PG_IPC_HANDLE_BYTES)()
+        _lib.check(_lib.lib().pg_peer_group_create(world, rank, self.flat.numel(), dev.index, ctypes.byref(h), handle),
+                   "pg_peer_group_create")
+        self._handle = h
+        if world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine, group=sync.group)
+            blob = bytes(torch.stack(allh).cpu().numpy().tobytes())
+            _lib.check(_lib.lib().pg_peer_group_connect(h, blob), "pg_peer_group_connect")
+            dist.barrier(group=sync.group)
+
+    def step(self, step_id):
+        """step_id: int64 CUDA scalar tensor, >= 1, equal on all ranks, +1 per call."""
+        _lib = self._lib
+        g = self.opt.param_groups[0]
+        self.state["step"].add_(1)
+        with torch.cuda.device(self.flat.device):
+            _lib.check(_lib.lib().pg_allreduce_adam(self._handle, _lib.ptr(self.flat), _lib.ptr(self.sync.flat_grad),
+                                                    _lib.ptr(self.state["exp_avg"]), _lib.ptr(self.state["exp_avg_sq"]),
+                                                    _lib.ptr(self.state["step"]), _lib.ptr(step_id), float(g["lr"]),
+                                                    float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                                    float(g["weight_decay"]), _lib.stream_ptr()), "pg_allreduce_adam")
+
+    def close(self):
+        if self._handle is not None:
+            self._lib.lib().pg_peer_group_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -105,3 +105,99 @@ def test_engine_dropout_trains_and_graph_replays_rekey():
     assert len(set(losses)) == len(losses)
     assert int(eng.step_counter.item()) == 24
     eng.close()
+
+
+def test_peer_adam_single_rank_matches_torch_adam():
+    """pg_allreduce_adam with world == 1 is torch.optim.Adam (capturable math) on the flat bucket."""
+    import torch
+    from pagraph_b200.parallel import FlatGradAllReduce, PeerAdam
+    torch.manual_seed(0)
+    make = lambda: torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.ReLU(), torch.nn.Linear(19, 5)).cuda()
+    a, b = make(), make()
+    b.load_state_dict(a.state_dict())
+    sync = FlatGradAllReduce(a)
+    opt_a = torch.optim.Adam(sync.flat_parameters(), lr=3e-2, weight_decay=1e-3, capturable=True)
+    assert PeerAdam.supported(sync, opt_a)
+    fused = PeerAdam(sync, opt_a)
+    opt_b = torch.optim.Adam(b.parameters(), lr=3e-2, weight_decay=1e-3)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(6):
+        x = torch.randn(64, 37, device="cuda")
+        for m in (a, b):
+            m.zero_grad(set_to_none=False) if m is b else sync.zero_grad()
+            m(x).square().mean().backward()
+        step.add_(1)
+        fused.step(step)
+        opt_b.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-4, atol=1e-6)
+    assert float(opt_a.state[sync.flat_parameters()[0]]["step"]) == 6.0
+    fused.close()
+
+
+def _two_rank_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    from pagraph_b200.parallel import FlatGradAllReduce, PeerAdam
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.ReLU(), torch.nn.Linear(19, 5)).cuda()
+    sync = FlatGradAllReduce(model)
+    opt = torch.optim.Adam(sync.flat_parameters(), lr=1e-2, capturable=True)
+    fused = PeerAdam(sync, opt)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(world * 32, 37, device="cuda", generator=g)
+    graph, static_x = None, x[rank * 32:(rank + 1) * 32].clone()
+    for it in range(40):                       # eager for 3 steps, then the same step as a replayed CUDA graph
+        def body():
+            sync.zero_grad()
+            model(static_x).square().mean().backward()
+            step.add_(1)
+            fused.step(step)
+        if it < 3:
+            body()
+        else:
+            if graph is None:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    body()
+            graph.replay()
+    torch.cuda.synchronize()
+    out[rank] = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
+    dist.barrier()
+    fused.close()
+    dist.destroy_process_group()
+
+
+def test_peer_adam_two_ranks_equals_global_batch():
+    """Two processes / two GPUs: the NVLink one-shot all-reduce + Adam keeps replicas identical and equals single-process
+    training on the concatenated batch (mean of the per-rank mean-gradients). Skipped with fewer than 2 GPUs."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_two_rank_worker, args=(2, port, out), nprocs=2, join=True)
+        res = dict(out)
+    np.testing.assert_array_equal(res[0], res[1])
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.ReLU(), torch.nn.Linear(19, 5)).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(64, 37, device="cuda", generator=g)
+    for _ in range(40):
+        opt.zero_grad()
+        (0.5 * (model(x[:32]).square().mean() + model(x[32:]).square().mean())).backward()
+        opt.step()
+    want = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
+    np.testing.assert_allclose(res[0], want, rtol=2e-3, atol=2e-5)
