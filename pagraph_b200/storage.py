@@ -286,12 +286,15 @@ class GraphCacheServer:
         self._drop_calls += 1
         return (self._drop_seed + self._drop_calls * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
 
-    def _gather(self, ids, names):
+    def _gather(self, ids, names, outs=None):
         """rows of `names` (all fields, or a subset -> all fields are gathered and the subset returned) for local
-        ids `ids` (CUDA int64), through pg_cache_fetch."""
+        ids `ids` (CUDA int64), through pg_cache_fetch. `outs`: optional preallocated [>= n, dim] buffers per field."""
         n = ids.numel()
-        outs = [torch.empty((n, self.dims[name]), dtype=torch.float32, device=self._dev)
-                for name in self._field_names]
+        if outs is None:
+            outs = [torch.empty((n, self.dims[name]), dtype=torch.float32, device=self._dev)
+                    for name in self._field_names]
+        else:
+            outs = [o[:n] for o in outs]
         mask = None
         if self.keep_hit_mask:
             mask = torch.empty(n, dtype=torch.bool, device=self._dev)
