@@ -207,14 +207,25 @@ pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float*
                              const float* d_norm, float dropout_p, uint64_t dropout_seed, const int64_t* d_step,
                              int64_t zero_rows_to, int64_t* d_counts, void* stream);
 
-/* ---------------------------------------------------------------- backward of the first NodeUpdate (PaGraph/model/gcn_nssc.py:14-24)
+/* ---------------------------------------------------------------- the first NodeUpdate (PaGraph/model/gcn_nssc.py:14-24, :64-70)
  * out = concat ? cat(z, relu(z)) : relu(z),  z = x W^T + b, x [n, in_dim] = the aggregated input block (needs no
- * gradient), W [32, in_dim], out [n, 64 | 32]. Computes grad_weight [32, in_dim] = gz^T x and grad_bias [32] = sum_r gz,
- * with gz (the gradient of z) recovered from grad_out and out: relu' and the concat split are folded in. Both outputs
- * are overwritten. One TMA-streamed pass over x. in_dim % 4 == 0, <= 768; out_dim == 32. */
+ * gradient), W [32, in_dim] contiguous, out [n, 64 | 32]. Both directions run on the tensor cores as error-compensated
+ * TF32 (3xTF32, fp32 accumulate: fp32-level accuracy). in_dim % 4 == 0, <= 768; out_dim == 32.
+ *   pg_linear_concat_fwd: writes out and, when d_out_drop != NULL, out_drop = dropout(out) (the `h = self.dropout(h)`
+ *     of gcn_nssc.py:66-67 ahead of the next block_compute) under the mask contract of pg_cache_aggregate: element
+ *     (row, col) is dropped when the (col % 4)-th 16-bit lane of hash(dropout_seed + *d_step, row, width/4, col/4) is
+ *     below round(p * 65536); kept values are scaled by 1/(1-p). d_step: optional int64 on the device.
+ *   pg_linear_concat_bwd: grad_weight [32, in_dim] = gz^T x and grad_bias [32] = sum_r gz, with gz (the gradient of z)
+ *     recovered from grad_out and out: relu' and the concat split are folded in; with dropout_p > 0 grad_out is the
+ *     gradient of out_drop and the mask is regenerated from the same (seed, *d_step). Both outputs are overwritten. */
+pg_status pg_linear_concat_fwd(const float* d_x, int64_t x_stride, const float* d_weight, const float* d_bias, int64_t n,
+                               int32_t in_dim, int32_t out_dim, int concat, float* d_out, int64_t out_stride,
+                               float* d_out_drop, int64_t od_stride, float dropout_p, uint64_t dropout_seed,
+                               const int64_t* d_step, void* stream);
 pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
                                const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int32_t out_dim, int concat,
-                               float* d_grad_weight, float* d_grad_bias, void* stream);
+                               float dropout_p, uint64_t dropout_seed, const int64_t* d_step, float* d_grad_weight,
+                               float* d_grad_bias, void* stream);
 
 /* Classifier head + loss in one pass (the last NodeUpdate, gcn_nssc.py:48, followed by torch.nn.CrossEntropyLoss,
  * examples/profile/pa_gcn.py:62,93-94): pred = a W^T + b, loss = mean_r(logsumexp(pred_r) - pred_r[label_r]); also emits

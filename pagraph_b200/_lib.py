@@ -84,8 +84,12 @@ SIGNATURES = {
                                         ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
     "pg_aggregate_bwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
+    "pg_linear_concat_fwd": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                            ctypes.c_int, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_float,
+                                            ctypes.c_uint64, c_vp, c_vp]),
     "pg_linear_concat_bwd": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int64,
-                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_int, c_vp, c_vp, c_vp]),
+                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_int, ctypes.c_float, ctypes.c_uint64,
+                                            c_vp, c_vp, c_vp, c_vp]),
     "pg_linear_cross_entropy": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32,
                                                ctypes.c_int32, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "pg_peer_group_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp),

@@ -111,6 +111,10 @@ __device__ __forceinline__ int64_t resolve_zero_rows(int64_t zero_rows_to, int64
   return min(cap, (n_dst + g - 1) / g * g);
 }
 pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st);
+// fp32-pipe dW kernel of pg_dense.cu (A/B baseline of the tensor-core kernel in pg_dense_mma.cu); outputs pre-zeroed
+pg_status linear_concat_bwd_simt(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
+                                 const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int concat,
+                                 float* d_grad_weight, float* d_grad_bias, cudaStream_t st);
 
 // Dropout mask contract (shared with oracle.dropout_mask): one 64-bit hash per (source row j, 4-column group g);
 // its k-th 16-bit lane decides column 4g+k.

@@ -154,25 +154,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) linear_concat_bwd_kernel(const
 
 }  // namespace
 
-extern "C" {
+namespace pg {
 
-pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
-                               const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int32_t out_dim, int concat,
-                               float* d_grad_weight, float* d_grad_bias, void* stream) {
-  PG_REQUIRE(d_grad_weight && n >= 0 && ((d_x && d_grad_out && d_out) || n == 0), "pg_linear_concat_bwd: bad arguments");
-  PG_REQUIRE(out_dim == kOut, "pg_linear_concat_bwd: out_dim must be 32");
-  PG_REQUIRE(in_dim >= 4 && in_dim % 4 == 0 && in_dim <= 3 * kBwdThreads && x_stride >= in_dim && x_stride % 4 == 0 &&
-                 (uintptr_t)d_x % 16 == 0,
-             "pg_linear_concat_bwd: in_dim must be a multiple of 4 (<= 768) with 16-byte aligned rows");
+// The fp32-pipe (FFMA2) dW kernel, kept for A/B measurements against the tensor-core kernel of pg_dense_mma.cu
+// (PG_DENSE_SIMT=1; no dropout support). Outputs must be zeroed by the caller.
+pg_status linear_concat_bwd_simt(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
+                                 const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int concat,
+                                 float* d_grad_weight, float* d_grad_bias, cudaStream_t st) {
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));
-  cudaStream_t st = (cudaStream_t)stream;
-  PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)kOut * in_dim * sizeof(float), st));
-  if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, kOut * sizeof(float), st));
-  if (n == 0) return PG_OK;
-  // Tile rows: 32 (2 x 77 KB at in_dim = 600) by default; PG_DENSE_TILE=16 halves the shared-memory footprint. Measured in
-  // the pipelined engine step the two are within 1 % (0.495 vs 0.501 ms), co-residency with the gather stream's
-  // aggregation kernel is not what limits the overlap.
   const char* env_t = getenv("PG_DENSE_TILE");
   const int tile = env_t ? atoi(env_t) : 32;
   auto launch = [&](auto kern, int kt) -> pg_status {
@@ -187,7 +177,7 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
   return tile >= 32 ? launch(linear_concat_bwd_kernel<32>, 32) : launch(linear_concat_bwd_kernel<16>, 16);
 }
 
-}  // extern "C"
+}  // namespace pg
 
 // ====================================================================== classifier head + loss, forward and backward
 // Reference: the last NodeUpdate (no activation, gcn_nssc.py:48 / :14-24) followed by torch.nn.CrossEntropyLoss

@@ -1,0 +1,484 @@
+// pg_dense_mma.cu — the first NodeUpdate of the GCN / GraphSAGE models on the tensor cores, forward and backward.
+//
+// Reference: PaGraph/model/gcn_nssc.py:14-24 (NodeUpdate.forward with concat=True) and :64-70 (dropout on the layer's
+// output before the next block_compute):
+//     z = Linear(x);  out = cat(z, relu(z));  out_drop = dropout(out)
+// x [n_1, F] is the aggregated input block (F = 600, n_1 ~ 35 k), Linear is F -> 32. Both products are tall-skinny fp32
+// GEMMs (1.36 GFLOP over 85 MB of x): on the fp32 pipe they are FMA-bound (cuBLAS SIMT sgemm 42 us forward; 81 us for
+// dW with packed FFMA2), 3-6x over the 13 us it takes to stream x from HBM. Here they run as error-compensated TF32
+// ("3xTF32": a = a_hi + a_lo, b = b_hi + b_lo, a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate), which keeps
+// fp32-level accuracy (the dropped term is 2^-22 relative), so the result stays within the reference's own fp32 noise.
+//
+// Shapes are far from the 128 x N tiles tcgen05 wants (N = 32 outputs, and both kernels are bound by the HBM stream of
+// x once the math is off the fp32 pipe), so the MMAs are warp-level mma.sync.m16n8k8 with operands loaded straight
+// from global memory into fragment registers:
+//   * the k index of a product is a dummy index, so its order is free: a lane fetches 4 consecutive floats (one 16-byte
+//     load) and feeds them to two k-steps; both operands use the same permutation. Same trick on the n index of dW
+//     (a column permutation of the output, undone when the accumulators are written).
+//   * forward: W is split once per CTA into hi / lo TF32 planes in shared memory (2 x 78 KB, conflict-free stride); each
+//     warp owns 32 rows of x, keeps 3 chunks of 16 columns in flight in registers, epilogue fuses bias, relu, the
+//     skip-concat and (optionally) the dropout mask of the next block.
+//   * backward: dW = gz^T x with gz = g[:, :32] + g[:, 32:] * (z > 0) (g first multiplied by the dropout mask, which is
+//     regenerated from the hash, not stored). One persistent CTA per SM walks a contiguous range of rows; gz tiles are
+//     staged (split hi / lo) in shared memory, each warp owns 64 columns of x / dW, partials go out as float atomics.
+#include <algorithm>
+#include <cstdlib>
+
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int kOut = 32;  // output width (n_hidden of the reference default)
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+// D += A (16x8, row) * B (8x8, col), TF32 inputs, fp32 accumulate.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float4 ld_stream4(const float* p) {  // read-once data: no L1 allocation
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+struct DropArgs {
+  uint32_t thr;        // drop when the 16-bit hash lane < thr (0 = no dropout)
+  float scale;         // 1 / (1 - p)
+  uint64_t seed;
+  const int64_t* step; // optional device counter added to the seed
+};
+// keep-scale factor of element (row, col) of a [*, width] activation under the drop_hash contract (pg_common.cuh)
+__device__ __forceinline__ float drop_factor(const DropArgs& d, uint64_t seed, int64_t row, int width, int col) {
+  const uint64_t h = pg::drop_hash(seed, (uint64_t)row, (uint32_t)(width >> 2), (uint32_t)(col >> 2));
+  return ((uint32_t)(h >> (16 * (col & 3))) & 0xffffu) < d.thr ? 0.f : d.scale;
+}
+
+// ====================================================================================================== forward
+constexpr int kFwdWarps = 8;
+constexpr int kFwdRowsPerWarp = 32;
+constexpr int kFwdDepth = 5;  // 16-column chunks of x in flight per warp (2 KB each)
+
+__host__ __device__ inline int fwd_wstride(int K) {  // row stride of the W planes: 16 mod 32 words -> conflict-free LDS.128
+  const int k16 = (K + 15) / 16 * 16;
+  return k16 + ((16 - k16 % 32) + 32) % 32;
+}
+
+__global__ void __launch_bounds__(kFwdWarps * 32, 1)
+    linear_concat_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ W,
+                             const float* __restrict__ bias, int64_t n, int K, int concat, float* __restrict__ out,
+                             int64_t out_stride, float* __restrict__ out_drop, int64_t od_stride, DropArgs drop) {
+  extern __shared__ __align__(16) uint32_t wsm[];  // [2][kOut][ws]: hi plane, lo plane
+  const int ws = fwd_wstride(K);
+  uint32_t* w_hi = wsm;
+  uint32_t* w_lo = wsm + (size_t)kOut * ws;
+  {  // W -> hi / lo planes: 16-byte loads, kPre of them in flight per thread before the first use
+    const int nvec = K >> 2, total = kOut * nvec;
+    constexpr int kPre = 10;
+    for (int base = 0; base < total; base += kFwdWarps * 32 * kPre) {
+      float4 v[kPre];
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int idx = base + u * kFwdWarps * 32 + (int)threadIdx.x;
+        v[u] = idx < total ? __ldg((const float4*)W + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int idx = base + u * kFwdWarps * 32 + (int)threadIdx.x;
+        if (idx < total) {
+          const int o = idx / nvec, k4 = idx - o * nvec;
+          uint4 hi, lo;
+          split_tf32(v[u].x, hi.x, lo.x);
+          split_tf32(v[u].y, hi.y, lo.y);
+          split_tf32(v[u].z, hi.z, lo.z);
+          split_tf32(v[u].w, hi.w, lo.w);
+          *(uint4*)(w_hi + o * ws + 4 * k4) = hi;
+          *(uint4*)(w_lo + o * ws + 4 * k4) = lo;
+        }
+      }
+    }
+    const int pad = ws - K;  // columns [K, ws) of every row: zero (the last chunk reads up to the next multiple of 16)
+    for (int i = threadIdx.x; i < kOut * pad; i += blockDim.x) {
+      const int o = i / pad, k = K + i % pad;
+      w_hi[o * ws + k] = 0u;
+      w_lo[o * ws + k] = 0u;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int nchunks = (K + 15) / 16;
+  const int64_t ntiles = (n + kFwdWarps * kFwdRowsPerWarp - 1) / (kFwdWarps * kFwdRowsPerWarp);
+  const uint64_t seed = drop.thr ? drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull) : 0ull;
+  const int width = concat ? 2 * kOut : kOut;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = (tile * kFwdWarps + warp) * kFwdRowsPerWarp;
+    if (r0 >= n) continue;
+    // rows of this lane: r0 + g + 8 i, i = 0..3 (m-tile i/2, half i%2)
+    const float* xrow[4];
+    bool rok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + g + 8 * i;
+      rok[i] = r < n;
+      xrow[i] = x + (rok[i] ? r : 0) * x_stride + 4 * t;
+    }
+    float acc[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+    float4 buf[kFwdDepth][4];
+    auto load = [&](float4(&b)[4], int chunk) {
+      const bool cok = chunk < nchunks && chunk * 16 + 4 * t < K;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = (cok && rok[i]) ? ld_stream4(xrow[i] + chunk * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+#pragma unroll
+    for (int d = 0; d < kFwdDepth; ++d) load(buf[d], d);
+    for (int c0 = 0; c0 < nchunks; c0 += kFwdDepth) {
+#pragma unroll
+      for (int d = 0; d < kFwdDepth; ++d) {
+        const int chunk = c0 + d;
+        if (chunk < nchunks) {
+          // A fragments of both k-steps of this chunk: [m-tile][k-step][a0..a3]
+          uint32_t ah[2][2][4], al[2][2][4];
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              split_tf32(comp(buf[d][2 * m], 2 * s), ah[m][s][0], al[m][s][0]);          // (row g,   k = t)
+              split_tf32(comp(buf[d][2 * m + 1], 2 * s), ah[m][s][1], al[m][s][1]);      // (row g+8, k = t)
+              split_tf32(comp(buf[d][2 * m], 2 * s + 1), ah[m][s][2], al[m][s][2]);      // (row g,   k = t+4)
+              split_tf32(comp(buf[d][2 * m + 1], 2 * s + 1), ah[m][s][3], al[m][s][3]);  // (row g+8, k = t+4)
+            }
+          load(buf[d], chunk + kFwdDepth);
+          uint4 bh[4], bl[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int off = (j * 8 + g) * ws + chunk * 16 + 4 * t;
+            bh[j] = *(const uint4*)(w_hi + off);
+            bl[j] = *(const uint4*)(w_lo + off);
+          }
+#pragma unroll
+          for (int term = 0; term < 3; ++term)  // small terms first
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+              for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t(&a)[4] = term == 0 ? al[m][s] : ah[m][s];
+                  const uint4& b = term == 1 ? bl[j] : bh[j];
+                  mma_tf32(acc[m][j], a[0], a[1], a[2], a[3], s == 0 ? b.x : b.z, s == 0 ? b.y : b.w);
+                }
+        }
+      }
+    }
+    // epilogue: acc[m][j] = {(row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)} of m-tile m, n-tile j
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t r = r0 + m * 16 + h * 8 + g;
+        if (r >= n) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = j * 8 + 2 * t;
+          float z0 = acc[m][j][2 * h], z1 = acc[m][j][2 * h + 1];
+          if (bias) {
+            z0 += bias[col];
+            z1 += bias[col + 1];
+          }
+          const float p0 = fmaxf(z0, 0.f), p1 = fmaxf(z1, 0.f);
+          float* orow = out + r * out_stride;
+          if (concat) {
+            *(float2*)(orow + col) = make_float2(z0, z1);
+            *(float2*)(orow + kOut + col) = make_float2(p0, p1);
+          } else {
+            *(float2*)(orow + col) = make_float2(p0, p1);
+          }
+          if (out_drop) {
+            float* drow = out_drop + r * od_stride;
+            if (concat) {
+              *(float2*)(drow + col) = make_float2(z0 * drop_factor(drop, seed, r, width, col),
+                                                   z1 * drop_factor(drop, seed, r, width, col + 1));
+              *(float2*)(drow + kOut + col) = make_float2(p0 * drop_factor(drop, seed, r, width, kOut + col),
+                                                          p1 * drop_factor(drop, seed, r, width, kOut + col + 1));
+            } else {
+              *(float2*)(drow + col) = make_float2(p0 * drop_factor(drop, seed, r, width, col),
+                                                   p1 * drop_factor(drop, seed, r, width, col + 1));
+            }
+          }
+        }
+      }
+  }
+}
+
+// ====================================================================================================== backward (dW, db)
+constexpr int kDwTile = 24;      // rows per gz tile = 3 k-steps of 8 rows, one per x register stage
+constexpr int kGzStride = 40;    // floats per gz row in shared memory: conflict-free LDS.128 of the A fragments
+constexpr int kDwMaxWarps = 12;  // 64 columns per warp -> in_dim <= 768
+
+template <int kWarps>            // CTA size; the warps beyond in_dim / 64 only help staging gz
+__global__ void __launch_bounds__(kWarps * 32, 1)
+    linear_concat_dw_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gout, int64_t g_stride,
+                            const float* __restrict__ y, int64_t y_stride, int64_t n, int K, int concat, DropArgs drop,
+                            float* dW, float* db) {
+  // gz tiles, double-buffered, split into hi / lo planes; element (row, o) lives at [row][(o % 8) * 4 + o / 8] so that
+  // lane (g, t) reads its four A values of row t (o = g, g+8, g+16, g+24) with one 16-byte load
+  __shared__ __align__(16) uint32_t gz_hi[2][kDwTile][kGzStride];
+  __shared__ __align__(16) uint32_t gz_lo[2][kDwTile][kGzStride];
+  __shared__ float db_sh[kOut];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (tid < kOut) db_sh[tid] = 0.f;
+  int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
+  rows_per_cta = (rows_per_cta + 7) / 8 * 8;  // whole k-steps; a partial last tile is zero-padded
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(n, r_begin + rows_per_cta);
+  if (r_begin >= r_end) return;
+  const int ntiles = (int)((r_end - r_begin + kDwTile - 1) / kDwTile);
+  const uint64_t seed = drop.thr ? drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull) : 0ull;
+  const int width = concat ? 2 * kOut : kOut;
+  // this warp's columns: blocks cb = 2 warp, 2 warp + 1 of 32 columns; lane fetches floats [32 cb + 4 g, +4)
+  const int col0 = warp * 64 + 4 * g;
+  const bool cok[2] = {col0 < K, col0 + 32 < K};
+  const bool cb_any[2] = {warp * 64 < K, warp * 64 + 32 < K};
+
+  // ---- gz of one tile into registers (global loads), then into shared memory
+  constexpr int kThreads = kWarps * 32;
+  constexpr int per = (kDwTile * kOut + kThreads - 1) / kThreads;  // gz values a thread stages per tile
+  // raw operands of gz, loaded one tile ahead (no arithmetic on them until store_gz: the loads stay in flight under
+  // the MMAs of the current tile)
+  float gr_a[per], gr_b[per], gr_y[per];
+  float dbv = 0.f;
+  auto load_gz = [&](int tile) {
+    const int64_t r0 = r_begin + (int64_t)tile * kDwTile;
+#pragma unroll
+    for (int q = 0; q < per; ++q) {
+      const int i = tid + q * kThreads;
+      const int rr = i / kOut, o = i % kOut;
+      const int64_t r = r0 + rr;
+      gr_a[q] = gr_b[q] = gr_y[q] = 0.f;
+      if (i < kDwTile * kOut && r < r_end) {
+        const float* grow = gout + r * g_stride;
+        const float* yrow = y + r * y_stride;
+        if (concat) {
+          gr_a[q] = __ldg(grow + o);
+          gr_b[q] = __ldg(grow + kOut + o);
+          gr_y[q] = __ldg(yrow + kOut + o);
+        } else {
+          gr_a[q] = __ldg(grow + o);
+          gr_y[q] = __ldg(yrow + o);
+        }
+      }
+    }
+  };
+  auto store_gz = [&](int tile, int buf) {
+    const int64_t r0 = r_begin + (int64_t)tile * kDwTile;
+#pragma unroll
+    for (int q = 0; q < per; ++q) {
+      const int i = tid + q * kThreads;
+      if (i < kDwTile * kOut) {
+        const int rr = i / kOut, o = i % kOut;
+        const int64_t r = r0 + rr;
+        float v;
+        if (concat) {
+          float ga = gr_a[q], gb = gr_y[q] > 0.f ? gr_b[q] : 0.f;
+          if (drop.thr) {
+            ga *= drop_factor(drop, seed, r, width, o);
+            gb *= drop_factor(drop, seed, r, width, kOut + o);
+          }
+          v = ga + gb;
+        } else {
+          v = gr_y[q] > 0.f ? gr_a[q] : 0.f;
+          if (drop.thr) v *= drop_factor(drop, seed, r, width, o);
+        }
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        gz_hi[buf][rr][(o & 7) * 4 + (o >> 3)] = hi;
+        gz_lo[buf][rr][(o & 7) * 4 + (o >> 3)] = lo;
+        dbv += v;  // o = tid % 32 for every q (the CTA size is a multiple of 32)
+      }
+    }
+  };
+
+  // ---- x stages: 8 rows (one k-step) x this warp's 64 columns; lane holds rows {t, t+4} x 2 blocks; 3 stages in flight
+  float4 xb[3][2][2];  // [stage buffer][block][row slot]
+  const int nstages = 3 * ntiles;
+  auto load_x = [&](float4(&b)[2][2], int stage) {
+    const int64_t rs = r_begin + (int64_t)stage * 8;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t r = rs + t + 4 * i;
+        b[c][i] = (stage < nstages && cok[c] && r < r_end) ? ld_stream4(x + r * x_stride + col0 + 32 * c)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  };
+  float acc[2][2][4][4];  // [m-tile][block][n-tile j][c0..c3]
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[m][c][j][q] = 0.f;
+
+  auto compute = [&](const float4(&b)[2][2], int buf, int ks) {  // k-step ks: rows [8 ks, 8 ks + 8) of the gz tile
+    const int rr = ks * 8;
+    // A: (m-tile 0: a0 a1 | m-tile 1: a0 a1) from row rr + t, (a2 a3 | a2 a3) from row rr + t + 4
+    const uint4 h0 = *(const uint4*)&gz_hi[buf][rr + t][g * 4], h1 = *(const uint4*)&gz_hi[buf][rr + t + 4][g * 4];
+    const uint4 l0 = *(const uint4*)&gz_lo[buf][rr + t][g * 4], l1 = *(const uint4*)&gz_lo[buf][rr + t + 4][g * 4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (!cb_any[c]) continue;  // warp-uniform
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        split_tf32(comp(b[c][0], j), bh[j][0], bl[j][0]);  // (k = t,   n = g) of n-tile j
+        split_tf32(comp(b[c][1], j), bh[j][1], bl[j][1]);  // (k = t+4, n = g)
+      }
+#pragma unroll
+      for (int term = 0; term < 3; ++term)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4& a0 = term == 0 ? l0 : h0;
+          const uint4& a1 = term == 0 ? l1 : h1;
+          const uint32_t b0 = term == 1 ? bl[j][0] : bh[j][0], b1 = term == 1 ? bl[j][1] : bh[j][1];
+          mma_tf32(acc[0][c][j], a0.x, a0.y, a1.x, a1.y, b0, b1);
+          mma_tf32(acc[1][c][j], a0.z, a0.w, a1.z, a1.w, b0, b1);
+        }
+    }
+  };
+
+#pragma unroll
+  for (int d = 0; d < 3; ++d) load_x(xb[d], d);
+  load_gz(0);
+  store_gz(0, 0);
+  __syncthreads();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) load_gz(tile + 1);  // in flight during the MMAs below
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      compute(xb[d], buf, d);
+      load_x(xb[d], 3 * tile + 3 + d);
+    }
+    if (tile + 1 < ntiles) store_gz(tile + 1, buf ^ 1);
+    __syncthreads();
+  }
+  // ---- write-out: acc[m][c][j] = {(o = 16m+g, nu = 2t), (o, 2t+1), (o+8, 2t), (o+8, 2t+1)}, column = 64 warp + 32 c + 4 nu + j
+  // the four n-tiles j of one (m, c, q) are four consecutive columns: one 16-byte vector atomic
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int o = 16 * m + g + 8 * (q >> 1);
+        const int col = warp * 64 + 32 * c + 4 * (2 * t + (q & 1));
+        if (col < K)
+          atomicAdd((float4*)&dW[(size_t)o * K + col],
+                    make_float4(acc[m][c][0][q], acc[m][c][1][q], acc[m][c][2][q], acc[m][c][3][q]));
+      }
+  if (db) {
+    atomicAdd(&db_sh[lane], dbv);
+    __syncthreads();
+    if (tid < kOut) atomicAdd(&db[tid], db_sh[tid]);
+  }
+}
+
+DropArgs make_drop(float p, uint64_t seed, const int64_t* d_step) {
+  DropArgs d;
+  d.thr = p > 0.f ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
+  d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  d.seed = seed;
+  d.step = d_step;
+  return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+pg_status pg_linear_concat_fwd(const float* d_x, int64_t x_stride, const float* d_weight, const float* d_bias, int64_t n,
+                               int32_t in_dim, int32_t out_dim, int concat, float* d_out, int64_t out_stride,
+                               float* d_out_drop, int64_t od_stride, float dropout_p, uint64_t dropout_seed,
+                               const int64_t* d_step, void* stream) {
+  PG_REQUIRE(d_weight && n >= 0 && ((d_x && d_out) || n == 0), "pg_linear_concat_fwd: bad arguments");
+  PG_REQUIRE(out_dim == kOut, "pg_linear_concat_fwd: out_dim must be 32");
+  PG_REQUIRE(in_dim >= 4 && in_dim % 4 == 0 && in_dim <= 768 && x_stride >= in_dim && x_stride % 4 == 0 &&
+                 (uintptr_t)d_x % 16 == 0 && (uintptr_t)d_weight % 16 == 0,
+             "pg_linear_concat_fwd: in_dim must be a multiple of 4 (<= 768) with 16-byte aligned rows and weight");
+  const int width = concat ? 2 * kOut : kOut;
+  PG_REQUIRE(out_stride >= width && out_stride % 2 == 0 && (uintptr_t)d_out % 8 == 0 &&
+                 (!d_out_drop || (od_stride >= width && od_stride % 2 == 0 && (uintptr_t)d_out_drop % 8 == 0)),
+             "pg_linear_concat_fwd: output rows must be 8-byte aligned");
+  PG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pg_linear_concat_fwd: dropout_p must be in [0, 1)");
+  if (n == 0) return PG_OK;
+  int dev = 0;
+  PG_CUDA(cudaGetDevice(&dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = 2 * (size_t)kOut * fwd_wstride(in_dim) * sizeof(uint32_t);
+  PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (n + kFwdWarps * kFwdRowsPerWarp - 1) / (kFwdWarps * kFwdRowsPerWarp);
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev));
+  linear_concat_fwd_kernel<<<grid, kFwdWarps * 32, smem, st>>>(d_x, x_stride, d_weight, d_bias, n, in_dim, concat, d_out,
+                                                                out_stride, d_out_drop, od_stride,
+                                                                make_drop(d_out_drop ? dropout_p : 0.f, dropout_seed, d_step));
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
+                               const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int32_t out_dim, int concat,
+                               float dropout_p, uint64_t dropout_seed, const int64_t* d_step, float* d_grad_weight,
+                               float* d_grad_bias, void* stream) {
+  PG_REQUIRE(d_grad_weight && n >= 0 && ((d_x && d_grad_out && d_out) || n == 0), "pg_linear_concat_bwd: bad arguments");
+  PG_REQUIRE(out_dim == kOut, "pg_linear_concat_bwd: out_dim must be 32");
+  PG_REQUIRE(in_dim >= 4 && in_dim % 4 == 0 && in_dim <= 64 * kDwMaxWarps && x_stride >= in_dim && x_stride % 4 == 0 &&
+                 (uintptr_t)d_x % 16 == 0 && (uintptr_t)d_grad_weight % 16 == 0,
+             "pg_linear_concat_bwd: in_dim must be a multiple of 4 (<= 768) with 16-byte aligned rows and grad_weight");
+  PG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pg_linear_concat_bwd: dropout_p must be in [0, 1)");
+  int dev = 0;
+  PG_CUDA(cudaGetDevice(&dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)kOut * in_dim * sizeof(float), st));
+  if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, kOut * sizeof(float), st));
+  if (n == 0) return PG_OK;
+  const char* simt = getenv("PG_DENSE_SIMT");
+  if (simt && atoi(simt) && dropout_p == 0.f)
+    return pg::linear_concat_bwd_simt(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim, concat, d_grad_weight,
+                                     d_grad_bias, st);
+  const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)pg::sm_count(dev));
+  const DropArgs drop = make_drop(dropout_p, dropout_seed, d_step);
+  auto launch = [&](auto kern, int warps) -> pg_status {
+    kern<<<grid, warps * 32, 0, st>>>(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim, concat, drop,
+                                      d_grad_weight, d_grad_bias);
+    PG_CHECK_LAUNCH();
+    return PG_OK;
+  };
+  if (in_dim <= 256) return launch(linear_concat_dw_kernel<4>, 4);
+  if (in_dim <= 640) return launch(linear_concat_dw_kernel<10>, 10);
+  return launch(linear_concat_dw_kernel<kDwMaxWarps>, kDwMaxWarps);
+}
+
+}  // extern "C"

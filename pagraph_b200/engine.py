@@ -29,7 +29,7 @@ import torch
 
 from . import _lib
 from .nodeflow import NodeBatch
-from .ops import _MODES, LinearCrossEntropy
+from .ops import _MODES, LinearConcat, LinearCrossEntropy, linear_concat_backward, linear_concat_forward
 from .parallel import PeerAdam
 
 _RING = 4          # ring slots: sampling runs 2 minibatches ahead of compute, gathering 1
@@ -148,6 +148,7 @@ class GCNTrainEngine:
             self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # optimizer steps taken
             self.load_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # minibatches loaded: keys the fused dropout mask
             self.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self.drop_seed_hidden = int(torch.randint(0, 2 ** 62, (1,)).item())
             self.slots = [self._make_slot() for _ in range(_RING)]
         self.fused_opt = None
         if sync is not None and os.environ.get("PG_ENGINE_FUSED_OPT", "1") != "0" and PeerAdam.supported(sync, optimizer):
@@ -155,6 +156,8 @@ class GCNTrainEngine:
                 self.fused_opt = PeerAdam(sync, optimizer)
             except Exception as e:                          # e.g. CUDA IPC unavailable: NCCL all-reduce + optimizer.step()
                 print("GCNTrainEngine: fused all-reduce + Adam unavailable (%s); using all_reduce + optimizer.step()" % e)
+        self._dense_ok = False
+        self.dense = None            # buffers of the fused dense stage (_compute_body_fused), made on first use
         self.pool = None
         self.next_issue = 0          # global minibatch index of the next stage A to issue
         self.next_gather = 0         # ... of the next stage B
@@ -287,6 +290,8 @@ class GCNTrainEngine:
     # ------------------------------------------------------------------ compute stage (main stream)
     def _compute_body(self, s, caps, n_valid):
         """caps[j]: padded row count of NodeFlow layer j (j = 1..L; caps[L] = batch)."""
+        if self._dense_ok:
+            return self._compute_body_fused(s, caps, n_valid)
         L, m = _lib.lib(), self.model
         nf = s.nf
         agg = s.agg[:caps[1]]                                 # aggregated by the load stage; rows >= n_1 are zero
@@ -318,6 +323,73 @@ class GCNTrainEngine:
             self.opt.step()
             self.step_counter.add_(1)
         s.loss.copy_(loss.detach())
+
+    # ---- fused dense stage: the standard 2-block GCN (NodeUpdate(F -> 32, relu, concat) -> NodeUpdate(64 -> classes) ->
+    # CrossEntropyLoss, gcn_nssc.py:43-48 with n_layers = 1) as six of our kernels writing the gradients straight into
+    # the parameters' .grad (the flat all-reduce bucket): tensor-core NodeUpdate forward (+ bias, relu, concat, dropout),
+    # block-1 aggregation, head + loss forward/backward, aggregation backward, tensor-core dW/db (+ dropout', relu',
+    # concat split), all-reduce + Adam. No autograd graph, no elementwise library kernels.
+    def _dense_fusable(self):
+        m = self.model
+        if os.environ.get("PG_ENGINE_FUSED_DENSE", "1") == "0" or self.L != 2 or len(m.layers) != 2:
+            return False
+        l0, l1 = m.layers[0], m.layers[1]
+        relu = l0.activation is torch.relu or l0.activation is torch.nn.functional.relu
+        w0, w1 = l0.linear.weight, l1.linear.weight
+        agg = self.slots[0].agg
+        ok = (relu and l0.concat and not l0.test and w0.shape == (32, self.F) and w1.shape[1] == 64
+              and LinearConcat.supported(agg, w0) and w0.is_contiguous() and w1.is_contiguous()
+              and (w0.grad is None or w0.grad.data_ptr() % 16 == 0)
+              and all(p.requires_grad for p in m.parameters())
+              and self._head_fusable(l1, torch.empty((1, 64), dtype=torch.float32, device=self.dev)))
+        return bool(ok)
+
+    def _dense_buffers(self):
+        if self.dense is None:
+            d, dev = _Slot(), self.dev
+            cap1 = self.slots[0].agg.shape[0]
+            f32 = dict(dtype=torch.float32, device=dev)
+            d.out = torch.zeros((cap1, 64), **f32)          # cat(z, relu z) of layer 0 (pre-dropout)
+            d.hd = torch.zeros((cap1, 64), **f32)           # dropout(out): source rows of block 1
+            d.ghd = torch.zeros((cap1, 64), **f32)          # d loss / d hd
+            d.a2 = torch.zeros((self.batch, 64), **f32)     # block-1 aggregate: input of the head
+            d.ga2 = torch.zeros((self.batch, 64), **f32)
+            for p in self.model.parameters():               # no sync object: plain .grad tensors the kernels overwrite
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            self.dense = d
+        return self.dense
+
+    def _compute_body_fused(self, s, caps, n_valid):
+        L, m, d = _lib.lib(), self.model, self._dense_buffers()
+        l0, l1 = m.layers[0], m.layers[1]
+        nf, st = s.nf, _lib.stream_ptr()
+        n1 = caps[1]
+        p = float(m.dropout.p) if (m.dropout is not None and m.training) else 0.0
+        x, out, hd, ghd = s.agg[:n1], d.out[:n1], d.hd[:n1], d.ghd[:n1]
+        w0, b0, w1, b1 = l0.linear.weight, l0.linear.bias, l1.linear.weight, l1.linear.bias
+        linear_concat_forward(x, w0, b0, True, out=out, out_drop=hd, dropout_p=p, seed=self.drop_seed_hidden,
+                              step=self.step_counter)
+        h = hd if p > 0 else out
+        lo = self._meta_ptr(s, 4 + 1)
+        _lib.check(L.pg_aggregate_fwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(h), 64,
+                                          _lib.ptr(d.a2), 64, caps[2], 64, _MODES["mean"], None, st), "pg_aggregate_fwd_dyn")
+        C = w1.shape[0]
+        _lib.check(L.pg_linear_cross_entropy(_lib.ptr(d.a2), 64, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(s.labels), n_valid, 64, C,
+                                             _lib.ptr(s.loss), _lib.ptr(d.ga2), 64, _lib.ptr(w1.grad),
+                                             _lib.ptr(b1.grad if b1 is not None else None), st), "pg_linear_cross_entropy")
+        _lib.check(L.pg_aggregate_bwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(d.ga2), 64,
+                                          _lib.ptr(ghd), 64, caps[2], n1, 64, _MODES["mean"], None, st), "pg_aggregate_bwd_dyn")
+        linear_concat_backward(x, ghd, out, True, w0.grad, b0.grad if b0 is not None else None, p, self.drop_seed_hidden,
+                               self.step_counter)
+        if self.fused_opt is not None:                       # gradient all-reduce + Adam: one kernel over NVLink peer memory
+            self.step_counter.add_(1)
+            self.fused_opt.step(self.step_counter)
+        else:
+            if self.sync is not None:
+                self.sync()
+            self.opt.step()
+            self.step_counter.add_(1)
 
     def _head_fusable(self, layer, h):
         lf = self.loss_fcn
@@ -361,6 +433,9 @@ class GCNTrainEngine:
         """Run `count` training minibatches (continuing from the previous call, wrapping over epochs). Returns the
         last loss (a CUDA scalar, or a float when read_loss — then every step's loss is read back)."""
         self._check_cache_state()
+        self._dense_ok = self._dense_fusable()               # decided (and buffers made) outside any stream capture
+        if self._dense_ok:
+            self._dense_buffers()
         main = torch.cuda.current_stream(self.dev)
         end = self.next_compute + count
         self.next_gather = max(self.next_gather, self.next_compute)

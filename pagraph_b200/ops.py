@@ -76,37 +76,67 @@ def cache_aggregate(cacher, field, parent_ids, indptr, cols, col_base, n_src, n_
     return out
 
 
+def linear_concat_forward(x, weight, bias, concat, out=None, out_drop=None, dropout_p=0.0, seed=0, step=None):
+    """out = cat(z, relu(z)) | relu(z), z = x W^T + b (pg_linear_concat_fwd, 3xTF32 tensor-core product); with
+    dropout_p > 0 also out_drop = dropout(out) under the hash-mask contract. Returns (out, out_drop | None)."""
+    n, K = x.shape
+    width = 64 if concat else 32
+    if out is None:
+        out = torch.empty((n, width), dtype=torch.float32, device=x.device)
+    if dropout_p > 0 and out_drop is None:
+        out_drop = torch.empty((n, width), dtype=torch.float32, device=x.device)
+    if dropout_p <= 0:
+        out_drop = None
+    w = weight.contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pg_linear_concat_fwd(_lib.ptr(x), x.stride(0), _lib.ptr(w), _lib.ptr(bias), n, K, 32, int(concat),
+                                                   _lib.ptr(out), out.stride(0), _lib.ptr(out_drop),
+                                                   out_drop.stride(0) if out_drop is not None else 0, float(dropout_p),
+                                                   int(seed) & (2 ** 64 - 1), _lib.ptr(step), _lib.stream_ptr()),
+                   "pg_linear_concat_fwd")
+    return out, out_drop
+
+
+def linear_concat_backward(x, grad_out, out, concat, gw, gb, dropout_p=0.0, seed=0, step=None):
+    """dW [32, K] -> gw, db [32] -> gb (both overwritten) of linear_concat_forward; grad_out is the gradient of out_drop
+    when dropout_p > 0 (the mask is regenerated from (seed, step)), else of out."""
+    n, K = x.shape
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().pg_linear_concat_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(grad_out), grad_out.stride(0),
+                                                   _lib.ptr(out), out.stride(0), n, K, 32, int(concat), float(dropout_p),
+                                                   int(seed) & (2 ** 64 - 1), _lib.ptr(step), _lib.ptr(gw), _lib.ptr(gb),
+                                                   _lib.stream_ptr()), "pg_linear_concat_bwd")
+
+
 class LinearConcat(torch.autograd.Function):
     """cat(z, relu(z)) (concat=True) or relu(z), z = x W^T + b, for an input x that needs no gradient (the aggregated
-    input block). Same math as NodeUpdate.forward (PaGraph/model/gcn_nssc.py:14-24). Forward: the tall-skinny GEMM stays
-    on cuBLAS; backward: pg_linear_concat_bwd — one TMA-streamed pass over x that folds relu', the concat split, dW and
-    db (cuBLAS needs a split-K GEMM plus four elementwise / reduction kernels for the same thing)."""
+    input block), optionally followed by dropout (hash mask keyed by (seed, *step, row, column); `step` an int64 CUDA
+    scalar that must not change between forward and backward). Same math as NodeUpdate.forward
+    (PaGraph/model/gcn_nssc.py:14-24) + the dropout of :66-67. Forward and backward are the tensor-core kernels of
+    pg_dense_mma.cu (3xTF32: fp32-level accuracy); bias, relu, the concat split, dropout, dW and db are fused into them."""
 
     @staticmethod
     def supported(x, weight):
         return (x.is_cuda and x.dtype == torch.float32 and not x.requires_grad and weight.shape[0] == 32
-                and x.shape[1] % 4 == 0 and x.shape[1] <= 768 and x.stride(1) == 1 and x.stride(0) % 4 == 0)
+                and x.shape[1] % 4 == 0 and x.shape[1] <= 768 and x.stride(1) == 1 and x.stride(0) % 4 == 0
+                and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0)
 
     @staticmethod
-    def forward(ctx, x, weight, bias, concat):
-        z = torch.nn.functional.linear(x, weight, bias)
-        out = torch.cat((z, torch.relu(z)), dim=1) if concat else torch.relu(z)
+    def forward(ctx, x, weight, bias, concat, dropout_p=0.0, seed=0, step=None):
+        out, out_drop = linear_concat_forward(x, weight, bias, concat, dropout_p=dropout_p, seed=seed, step=step)
         ctx.save_for_backward(x, out)
-        ctx.concat, ctx.has_bias = concat, bias is not None
-        return out
+        ctx.concat, ctx.has_bias, ctx.drop = concat, bias is not None, (float(dropout_p), seed, step)
+        return out_drop if out_drop is not None else out
 
     @staticmethod
     def backward(ctx, grad_out):
         x, out = ctx.saved_tensors
-        n, K = x.shape
         grad_out = grad_out.contiguous()
-        gw = torch.empty((32, K), dtype=torch.float32, device=x.device)
+        gw = torch.empty((32, x.shape[1]), dtype=torch.float32, device=x.device)
         gb = torch.empty(32, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().pg_linear_concat_bwd(_lib.ptr(x), x.stride(0), _lib.ptr(grad_out), grad_out.stride(0),
-                                                       _lib.ptr(out), out.stride(0), n, K, 32, int(ctx.concat), _lib.ptr(gw),
-                                                       _lib.ptr(gb), _lib.stream_ptr()), "pg_linear_concat_bwd")
-        return None, gw, (gb if ctx.has_bias else None), None
+        p, seed, step = ctx.drop
+        linear_concat_backward(x, grad_out, out, ctx.concat, gw, gb, p, seed, step)
+        return None, gw, (gb if ctx.has_bias else None), None, None, None, None
 
 
 class LinearCrossEntropy(torch.autograd.Function):

@@ -116,10 +116,11 @@ def test_autograd_function_matches_torch_sparse():
     torch.testing.assert_close(x.grad.double(), x64.grad, rtol=RTOL, atol=1e-12)
 
 
-@pytest.mark.parametrize("n,K", [(1000, 600), (37, 128), (4099, 64), (1, 600), (0, 600)])
+@pytest.mark.parametrize("n,K", [(1000, 600), (37, 128), (4099, 64), (1, 600), (0, 600), (300, 768), (513, 4), (2500, 260)])
 @pytest.mark.parametrize("concat", [True, False])
 def test_linear_concat_matches_torch(n, K, concat):
-    """Fused first NodeUpdate (linear + bias + cat(z, relu(z))) forward and its dW / db against torch autograd."""
+    """Fused first NodeUpdate (linear + bias + cat(z, relu(z))) forward and its dW / db against torch autograd (float64).
+    The kernels are 3xTF32 tensor-core products: the tolerance is fp32-level, not TF32-level."""
     import torch
     from pagraph_b200.ops import LinearConcat
     torch.manual_seed(n + K)
@@ -135,12 +136,48 @@ def test_linear_concat_matches_torch(n, K, concat):
     z = torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double())
     ref = torch.cat((z, torch.relu(z)), 1) if concat else torch.relu(z)
     torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+    if n:                                   # fp32-level: far below one TF32 ulp (2^-11) of the operands
+        assert (out.double() - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
     w64 = lin.weight.detach().double().requires_grad_(True)
     b64 = lin.bias.detach().double().requires_grad_(True)
     z = torch.nn.functional.linear(x.double(), w64, b64)
-    (torch.cat((z, torch.relu(z)), 1) if concat else torch.relu(z)).backward(gout.double())
+    # relu' is taken from the fp32 forward (z > 0 as the kernel saw it), like autograd does with the saved output
+    pos = (out[:, 32:] > 0) if concat else (out > 0)
+    gz = (gout[:, :32].double() + gout[:, 32:].double() * pos) if concat else gout.double() * pos
+    z.backward(gz)
     torch.testing.assert_close(gw.double(), w64.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(gb.double(), b64.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("n,K,p", [(1000, 600, 0.2), (77, 64, 0.5), (4100, 600, 0.2)])
+@pytest.mark.parametrize("concat", [True, False])
+def test_linear_concat_fused_dropout(n, K, p, concat):
+    """Dropout folded into the NodeUpdate kernels: out_drop = out * keep / (1 - p) with the oracle's hash mask (keyed by
+    seed + device step), and the backward regenerates the same mask."""
+    import torch
+    import oracle
+    from pagraph_b200.ops import LinearConcat, linear_concat_forward
+    torch.manual_seed(n + K)
+    width = 64 if concat else 32
+    x = torch.randn(n, K, device="cuda")
+    lin = torch.nn.Linear(K, 32).cuda()
+    gout = torch.randn(n, width, device="cuda")
+    seed = 0x1234567890ABCDEF
+    step = torch.tensor([7], dtype=torch.int64, device="cuda")
+    out, _ = linear_concat_forward(x, lin.weight, lin.bias, concat)
+    od = LinearConcat.apply(x, lin.weight, lin.bias, concat, p, seed - 7, step)
+    keep = torch.from_numpy(oracle.dropout_keep_mask(seed, n, width, p)).cuda()
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.02
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    want = torch.where(keep, out * float(scale), torch.zeros_like(out))
+    torch.testing.assert_close(od, want, rtol=0, atol=0)
+    od.backward(gout)
+    gw, gb = lin.weight.grad.clone(), lin.bias.grad.clone()
+    g = gout.double() * keep * float(scale)
+    pos = (out[:, 32:] > 0) if concat else (out > 0)
+    gz = (g[:, :32] + g[:, 32:] * pos) if concat else g * pos
+    torch.testing.assert_close(gw.double(), gz.t() @ x.double(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gb.double(), gz.sum(0), rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("n,K,C", [(6000, 64, 60), (77, 64, 41), (1, 32, 7), (513, 50, 64), (0, 64, 60)])

@@ -24,20 +24,20 @@ def _world(V=4000, nnz=60000, F=600, classes=7, seed=5):
     return g, store, labels, train, V, F, classes
 
 
-def _model(F, classes, dropout):
+def _model(F, classes, dropout, n_hidden=16):
     import torch
     from pagraph_b200.model.gcn_nssc import GCNSampling
     torch.manual_seed(0)
-    return GCNSampling(F, 16, classes, 1, torch.relu, dropout).cuda()
+    return GCNSampling(F, n_hidden, classes, 1, torch.relu, dropout).cuda()
 
 
-def _eager_losses(g, store, labels, train, V, F, classes, cap, batch, fanouts, steps):
+def _eager_losses(g, store, labels, train, V, F, classes, cap, batch, fanouts, steps, n_hidden=16):
     import torch
     from pagraph_b200.sampling import NeighborSampler
     from pagraph_b200.storage import GraphCacheServer
     cs = GraphCacheServer(store, V, torch.arange(V), 0)
     cs.init_field(["features", "norm"])
-    model = _model(F, classes, 0.0)
+    model = _model(F, classes, 0.0, n_hidden)
     opt = torch.optim.Adam(model.parameters(), lr=3e-2)
     sampler = NeighborSampler(g, batch, fanouts, num_hops=len(fanouts), seed_nodes=torch.from_numpy(train), seed=11)
     lab = labels.cuda()
@@ -85,6 +85,63 @@ def test_engine_matches_eager_loop(cap, use_graphs, host_inputs):
     assert eng.launches > 0
     if not cs.full_cached:
         assert cs.try_num > 0 and 0 < cs.miss_num <= cs.try_num
+    eng.close()
+
+
+@pytest.mark.parametrize("flat_bucket", [False, True])
+@pytest.mark.parametrize("use_graphs", [False, True])
+@pytest.mark.parametrize("cap", [900, 10 ** 9])
+def test_engine_fused_dense_stage_matches_eager_loop(cap, use_graphs, flat_bucket):
+    """n_hidden = 32 (the reference default): the engine's dense stage is the six-kernel fused path (tensor-core NodeUpdate
+    forward / dW, head + loss, gradients written straight into .grad / the flat bucket) — same losses and parameters as
+    the eager autograd loop."""
+    import torch
+    from pagraph_b200.engine import GCNTrainEngine
+    from pagraph_b200.parallel import FlatGradAllReduce
+    from pagraph_b200.storage import GraphCacheServer
+    g, store, labels, train, V, F, classes = _world()
+    batch, fanouts, steps = 256, [6, 4], 7
+    want, want_params = _eager_losses(g, store, labels, train, V, F, classes, cap, batch, fanouts, steps, n_hidden=32)
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(["features", "norm"])
+    model = _model(F, classes, 0.0, 32)
+    sync = FlatGradAllReduce(model) if flat_bucket else None
+    opt = torch.optim.Adam(sync.flat_parameters() if flat_bucket else model.parameters(), lr=3e-2, capturable=use_graphs)
+    eng = GCNTrainEngine(g, cs, model, opt, train, labels, batch, fanouts, sync=sync, seed=11, shuffle=False,
+                         use_graphs=use_graphs, stage_rows=300)
+    got = [eng.steps(1, read_loss=True)]
+    assert eng._dense_ok and (eng.fused_opt is not None) == flat_bucket
+    cs.auto_cache(g, ["features", "norm"], capability=cap)
+    got += [eng.steps(1, read_loss=True) for _ in range(2)]
+    last = eng.steps(steps - 3)
+    got_params = [p.detach().cpu().numpy() for p in model.parameters()]
+    np.testing.assert_allclose(got, want[:3], rtol=2e-4)
+    np.testing.assert_allclose(float(last), want[-1], rtol=2e-4)
+    for a, b in zip(got_params, want_params):
+        np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)
+    eng.close()
+
+
+def test_engine_fused_dense_stage_dropout():
+    """Dropout inside the fused dense stage (hash mask keyed by the device step counter, regenerated in the backward):
+    finite, re-keyed every replay, and the loss goes down on a learnable target."""
+    import torch
+    from pagraph_b200.engine import GCNTrainEngine
+    from pagraph_b200.storage import GraphCacheServer
+    g, store, labels, train, V, F, classes = _world(classes=3)
+    labels = (store.ndata["features"][:, 0] > 0.5).long()            # two of the three classes occur
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(["features", "norm"])
+    cs.auto_cache(g, ["features", "norm"], capability=V)
+    model = _model(F, 3, 0.3, 32)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, capturable=True)
+    eng = GCNTrainEngine(g, cs, model, opt, train[:1024], labels, 256, [6, 4], seed=3)
+    losses = [eng.steps(1, read_loss=True) for _ in range(24)]
+    assert eng._dense_ok
+    assert all(np.isfinite(losses))
+    assert len(set(losses)) == len(losses)
+    assert int(eng.step_counter.item()) == 24
+    assert np.mean(losses[-4:]) < np.mean(losses[:4])                # 3 classes, one never used: the loss must drop from ln 3
     eng.close()
 
 
