@@ -213,7 +213,7 @@ pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float*
  * TF32 (3xTF32, fp32 accumulate: fp32-level accuracy). in_dim % 4 == 0, <= 768; out_dim == 32.
  *   pg_linear_concat_fwd: writes out and, when d_out_drop != NULL, out_drop = dropout(out) (the `h = self.dropout(h)`
  *     of gcn_nssc.py:66-67 ahead of the next block_compute) under the mask contract of pg_cache_aggregate: element
- *     (row, col) is dropped when the (col % 4)-th 16-bit lane of hash(dropout_seed + *d_step, row, width/4, col/4) is
+ *     (row, col) is dropped when the (col % 4)-th 16-bit lane of hash(dropout_seed + *d_step, row, col/4) is
  *     below round(p * 65536); kept values are scaled by 1/(1-p). d_step: optional int64 on the device.
  *   pg_linear_concat_bwd: grad_weight [32, in_dim] = gz^T x and grad_bias [32] = sum_r gz, with gz (the gradient of z)
  *     recovered from grad_out and out: relu' and the concat split are folded in; with dropout_p > 0 grad_out is the
@@ -274,7 +274,11 @@ enum {
   PG_T_GATHER_MISS = 3, /* pinned-host row fetch (runs on a side stream) */
   PG_T_AGG_FWD = 4,
   PG_T_AGG_BWD = 5,
-  PG_T_FUSED = 6        /* fused cache-lookup + aggregation (pg_cache_aggregate) */
+  PG_T_FUSED = 6,       /* fused cache-lookup + aggregation (pg_cache_aggregate) */
+  PG_T_DENSE_FWD = 7,   /* pg_linear_concat_fwd                          */
+  PG_T_DENSE_BWD = 8,   /* pg_linear_concat_bwd (memsets + kernel)       */
+  PG_T_HEAD = 9,        /* pg_linear_cross_entropy (memsets + kernel)    */
+  PG_T_OPT = 10         /* pg_allreduce_adam                             */
 };
 pg_status pg_timing_enable(int enabled);
 pg_status pg_timing_drain(int32_t* slots, float* ms, int64_t cap, int64_t* n_out);

@@ -207,19 +207,28 @@ def aggregate_bwd(indptr, cols, col_base, grad_dst, n_src, mode):
     return out
 
 
-def dropout_keep_mask(seed, n_src, dim, p):
-    """Mask contract of the fused dropout (pagraph_b200/csrc/pg_common.cuh drop_hash): element (j, col) of the
-    source rows is KEPT iff the (col % 4)-th 16-bit lane of splitmix64(seed + j * groups + col // 4) is
-    >= round(p * 65536), groups = ceil(dim / 4). Returns bool [n_src, dim]."""
-    groups = (dim + 3) // 4
-    thr = np.uint64(int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)))
-    j = np.arange(n_src, dtype=np.uint64)[:, None]
-    g = np.arange(groups, dtype=np.uint64)[None, :]
+def _splitmix64(x):
     with np.errstate(over="ignore"):
-        x = np.uint64(seed & (2 ** 64 - 1)) + j * np.uint64(groups) + g + np.uint64(0x9E3779B97F4A7C15)
+        x = x + np.uint64(0x9E3779B97F4A7C15)
         x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        x = x ^ (x >> np.uint64(31))
+        return x ^ (x >> np.uint64(31))
+
+
+def dropout_keep_mask(seed, n_src, dim, p):
+    """Mask contract of the fused dropout (pagraph_b200/csrc/pg_common.cuh drop_hash): element (j, col) is KEPT iff
+    the (col % 4)-th 16-bit lane of  mix(rowkey ^ colkey)  is >= round(p * 65536), with
+    rowkey = splitmix64(splitmix64(seed) + j), colkey = splitmix64(0xD1B54A32D192ED03 + col // 4),
+    mix(x) = (x * 0x9E3779B97F4A7C15) ^ ((x * 0x9E3779B97F4A7C15) >> 32). `seed` = dropout seed + step.
+    Returns bool [n_src, dim]."""
+    groups = (dim + 3) // 4
+    thr = np.uint64(int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)))
+    with np.errstate(over="ignore"):
+        stepkey = _splitmix64(np.array([seed & (2 ** 64 - 1)], dtype=np.uint64))[0]
+        rk = _splitmix64(stepkey + np.arange(n_src, dtype=np.uint64))[:, None]
+        ck = _splitmix64(np.uint64(0xD1B54A32D192ED03) + np.arange(groups, dtype=np.uint64))[None, :]
+        x = (rk ^ ck) * np.uint64(0x9E3779B97F4A7C15)
+        x = x ^ (x >> np.uint64(32))
     lanes = np.stack([(x >> np.uint64(16 * k)) & np.uint64(0xFFFF) for k in range(4)], axis=-1)   # [n, groups, 4]
     keep = (lanes >= thr).reshape(n_src, groups * 4)[:, :dim]
     return keep

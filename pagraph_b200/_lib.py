@@ -153,7 +153,7 @@ def stream_ptr(stream=None):
     return ctypes.c_void_p(s.cuda_stream)
 
 
-T_SAMPLE, T_SPLIT, T_GATHER_HIT, T_GATHER_MISS, T_AGG_FWD, T_AGG_BWD, T_FUSED = range(7)
+T_SAMPLE, T_SPLIT, T_GATHER_HIT, T_GATHER_MISS, T_AGG_FWD, T_AGG_BWD, T_FUSED, T_DENSE_FWD, T_DENSE_BWD, T_HEAD, T_OPT = range(11)
 
 
 def timing_enable(on):

@@ -230,11 +230,12 @@ __device__ __forceinline__ void acc_drop4(float4& acc, const float4 v, uint64_t 
 // next to it on the other stream; ILP = 1 (64 registers) gives the faster pipelined step (0.510 vs 0.521 ms), and capping
 // ILP = 2 with __maxnreg__ (96 / 88 / 80) only spills. Hence ILP = 1 at 16 warps.
 template <int W, int CH, bool DROP, int ILP>
-__global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a, int group, int depth) {
+__global__ void __launch_bounds__(W * 32) __maxnreg__(ILP == 1 ? 80 : 96)
+    agg_rows_tma_kernel(pg::AggRowsArgs a, int group, int depth) {
   constexpr int kRowsWarps = W;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[kRowsWarps * kRowsMaxDepth];
-  __shared__ int src_idx[kRowsWarps][kRowsMaxDepth][kRowsMaxGroup];
+  __shared__ uint64_t row_key[kRowsWarps][kRowsMaxDepth][kRowsMaxGroup];  // dropout row key of every staged row
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nvec = a.dim >> 2;
   const uint32_t row_bytes = (uint32_t)a.dim * 4u;
@@ -243,7 +244,10 @@ __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a,
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
   const int64_t warp0 = (int64_t)blockIdx.x * kRowsWarps + w, nwarps = (int64_t)gridDim.x * kRowsWarps;
-  const uint64_t seed = DROP ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
+  const uint64_t stepkey = DROP ? pg::drop_stepkey(a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull)) : 0ull;
+  uint64_t col_key[CH];  // dropout column keys of this lane's float4 groups
+#pragma unroll
+  for (int c = 0; c < CH; ++c) col_key[c] = DROP ? pg::drop_colkey((uint32_t)(c * 32 + lane)) : 0ull;
   const int64_t cap_dst = a.n_dst;
   if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
   a.zero_rows_to = pg::resolve_zero_rows(a.zero_rows_to, a.n_dst, cap_dst);
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a,
     if (lane < cnt) {
       const int64_t j = a.cols[c.s + c.off + lane] - a.col_base;
       src = a.rowptr[j];
-      src_idx[w][buf][lane] = (int)j;
+      if (DROP) row_key[w][buf][lane] = pg::drop_rowkey(stepkey, (uint64_t)j);  // one hash per fetched row, lanes in parallel
     }
     if (lane == 0) pg::mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
     __syncwarp();
@@ -293,14 +297,14 @@ __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a,
           const int col = c * 32 + lane;
           if (col < nvec) { v0[c] = row0[col]; v1[c] = row1[col]; }
         }
-        const uint64_t j0 = DROP ? (uint64_t)src_idx[w][buf][k] : 0ull, j1 = DROP ? (uint64_t)src_idx[w][buf][k + 1] : 0ull;
+        const uint64_t j0 = DROP ? row_key[w][buf][k] : 0ull, j1 = DROP ? row_key[w][buf][k + 1] : 0ull;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const int col = c * 32 + lane;
           if (col < nvec) {
             if (DROP) {
-              acc_drop4(acc[c], v0[c], pg::drop_hash(seed, j0, (uint32_t)nvec, (uint32_t)col), thr_hi, a.keep_scale);
-              acc_drop4(acc[c], v1[c], pg::drop_hash(seed, j1, (uint32_t)nvec, (uint32_t)col), thr_hi, a.keep_scale);
+              acc_drop4(acc[c], v0[c], pg::drop_mix(j0, col_key[c]), thr_hi, a.keep_scale);
+              acc_drop4(acc[c], v1[c], pg::drop_mix(j1, col_key[c]), thr_hi, a.keep_scale);
             } else {
               acc[c].x = (acc[c].x + v0[c].x) + v1[c].x; acc[c].y = (acc[c].y + v0[c].y) + v1[c].y;
               acc[c].z = (acc[c].z + v0[c].z) + v1[c].z; acc[c].w = (acc[c].w + v0[c].w) + v1[c].w;
@@ -311,14 +315,14 @@ __global__ void __launch_bounds__(W * 32) agg_rows_tma_kernel(pg::AggRowsArgs a,
     }
     for (; k < cnt; ++k) {
       const float4* row = (const float4*)(base + (size_t)k * row_bytes);
-      const uint64_t j = DROP ? (uint64_t)src_idx[w][buf][k] : 0ull;
+      const uint64_t j = DROP ? row_key[w][buf][k] : 0ull;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const int col = c * 32 + lane;
         if (col < nvec) {
           const float4 v = row[col];
           if (DROP) {
-            acc_drop4(acc[c], v, pg::drop_hash(seed, j, (uint32_t)nvec, (uint32_t)col), thr_hi, a.keep_scale);
+            acc_drop4(acc[c], v, pg::drop_mix(j, col_key[c]), thr_hi, a.keep_scale);
           } else {
             acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
           }
@@ -361,7 +365,6 @@ __global__ void __launch_bounds__(kAggThreads) agg_rows_ldg_kernel(pg::AggRowsAr
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (kAggThreads / 32) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (kAggThreads / 32);
-  const uint32_t groups = (uint32_t)((a.dim + 3) >> 2);
   const uint64_t seed = a.drop_thr ? a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull) : 0ull;
   const int64_t cap_dst = a.n_dst;
   if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_rows_ldg_kernel(pg::AggRowsAr
         const int64_t j = a.cols[q] - a.col_base;
         float v = __ldg(a.rowptr[j] + col);
         if (a.drop_thr) {
-          const uint64_t h = pg::drop_hash(seed, (uint64_t)j, groups, (uint32_t)(col >> 2));
+          const uint64_t h = pg::drop_hash(seed, (uint64_t)j, (uint32_t)(col >> 2));
           v = ((uint32_t)((h >> (16 * (col & 3))) & 0xffff) < a.drop_thr) ? 0.f : v * a.keep_scale;
         }
         acc += v;

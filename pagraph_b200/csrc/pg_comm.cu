@@ -128,7 +128,7 @@ pg_status pg_peer_group_create(int world, int rank, int64_t n, int dev, pg_peer_
   g->args.rank = rank;
   g->args.n = n;
   g->args.n_pad = (n + 63) / 64 * 64;
-  g->ctas = (int)std::min<int64_t>(kCommMaxCtas, std::max<int64_t>(1, (n + 1023) / 1024));
+  g->ctas = (int)std::min<int64_t>(kCommMaxCtas, std::max<int64_t>(1, (n + 511) / 512));  // 2 elements per thread
   size_t flags_off = 0;
   g->region_bytes = region_layout(world, g->args.n_pad, &flags_off);
   if (cudaMalloc(&g->local, g->region_bytes) != cudaSuccess) {
@@ -186,6 +186,7 @@ pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, flo
     PG_REQUIRE(g->args.recv[p] != nullptr, "pg_allreduce_adam: peer group is not connected");
   pg::DeviceGuard guard(g->dev);
   AdamArgs ad{d_param, d_grad, d_exp_avg, d_exp_avg_sq, d_step, lr, beta1, beta2, eps, weight_decay};
+  pg::TimedScope timed(PG_T_OPT, (cudaStream_t)stream);
   allreduce_adam_kernel<<<g->ctas, kCommThreads, 0, (cudaStream_t)stream>>>(g->args, ad, d_step_id);
   PG_CHECK_LAUNCH();
   return PG_OK;

@@ -116,13 +116,29 @@ pg_status linear_concat_bwd_simt(const float* d_x, int64_t x_stride, const float
                                  const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int concat,
                                  float* d_grad_weight, float* d_grad_bias, cudaStream_t st);
 
-// Dropout mask contract (shared with oracle.dropout_mask): one 64-bit hash per (source row j, 4-column group g);
-// its k-th 16-bit lane decides column 4g+k.
-__host__ __device__ __forceinline__ uint64_t drop_hash(uint64_t seed, uint64_t j, uint32_t groups, uint32_t g) {
-  uint64_t x = seed + j * groups + g + 0x9E3779B97F4A7C15ull;
+// Dropout mask contract (shared with oracle.dropout_keep_mask). Element (row j, column c) of a dropped-out activation is
+// decided by the (c % 4)-th 16-bit lane of
+//     drop_mix(drop_rowkey(drop_stepkey(seed + step), j), drop_colkey(c / 4))
+// (dropped when the lane < round(p * 65536)). Row and column keys are full splitmix64 outputs; the per-element work is
+// one xor, one 64-bit multiply and one fold, so that the fused aggregation pays ~6 integer instructions per float4 in its
+// inner loop (the row key is computed once per fetched row, the column keys once per thread). Hashing the step into the
+// key first keeps the masks of consecutive steps unrelated.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t drop_stepkey(uint64_t seed_plus_step) { return splitmix64(seed_plus_step); }
+__host__ __device__ __forceinline__ uint64_t drop_rowkey(uint64_t stepkey, uint64_t j) { return splitmix64(stepkey + j); }
+__host__ __device__ __forceinline__ uint64_t drop_colkey(uint32_t g) { return splitmix64(0xD1B54A32D192ED03ull + g); }
+__host__ __device__ __forceinline__ uint64_t drop_mix(uint64_t rowkey, uint64_t colkey) {
+  uint64_t x = (rowkey ^ colkey) * 0x9E3779B97F4A7C15ull;
+  return x ^ (x >> 32);
+}
+// the whole chain for one (row, 4-column group); `seed` = dropout seed + step
+__host__ __device__ __forceinline__ uint64_t drop_hash(uint64_t seed, uint64_t j, uint32_t g) {
+  return drop_mix(drop_rowkey(drop_stepkey(seed), j), drop_colkey(g));
 }
 
 // ------------------------------------------------------------------ Philox4x32-10 (RNG contract, oracle/pg_oracle.cpp)

@@ -197,10 +197,12 @@ __global__ void __launch_bounds__(kHeadWarps * 32) linear_ce_kernel(const float*
                                                                    const int64_t* __restrict__ labels, int64_t n, int K, int C,
                                                                    float inv_n, float* loss, float* grad_a, int64_t ga_stride,
                                                                    float* dW, float* db) {
-  extern __shared__ __align__(16) float head_smem[];  // 3 x 16 KB: over the 48 KB static limit, hence dynamic
-  float (*w_kc)[kHeadMaxC] = (float (*)[kHeadMaxC])head_smem;                                  // w_kc[k][c] = W[c][k] (logits: lane = class)
-  float (*w_ck)[kHeadMaxK] = (float (*)[kHeadMaxK])(head_smem + kHeadMaxK * kHeadMaxC);        // w_ck[c][k] = W[c][k] (grad_a: lane = input column)
-  float (*dw_sh)[kHeadMaxK] = (float (*)[kHeadMaxK])(head_smem + 2 * kHeadMaxK * kHeadMaxC);
+  extern __shared__ __align__(16) float head_smem[];  // over the 48 KB static limit, hence dynamic
+  // w_kc[k][c] = W[c][k] (logits: lane = class; row stride 65 so that the transposing fill is conflict-free),
+  // w_ck[c][k] = W[c][k] (grad_a: lane = input column), dw_sh[c][k]: the CTA's partial of dW
+  float (*w_kc)[kHeadMaxC + 1] = (float (*)[kHeadMaxC + 1])head_smem;
+  float (*w_ck)[kHeadMaxK] = (float (*)[kHeadMaxK])(head_smem + kHeadMaxK * (kHeadMaxC + 1));
+  float (*dw_sh)[kHeadMaxK] = (float (*)[kHeadMaxK])(head_smem + kHeadMaxK * (kHeadMaxC + 1) + kHeadMaxK * kHeadMaxC);
   __shared__ float db_sh[kHeadMaxC];
   __shared__ float loss_sh;
   for (int i = threadIdx.x; i < kHeadMaxC * kHeadMaxK; i += blockDim.x) {
@@ -259,19 +261,32 @@ __global__ void __launch_bounds__(kHeadWarps * 32) linear_ce_kernel(const float*
     if (lane < K) grow[lane] = ga0;
     if (lane + 32 < K) grow[lane + 32] = ga1;
   }
-  // CTA reduction in shared memory, then one global atomic per output
+  // CTA reduction: the warps take turns adding their register partials into shared memory (plain read-modify-write,
+  // lanes on consecutive words), then one global atomic per output word (16-byte vector atomics when the layout allows)
+  for (int turn = 0; turn < kHeadWarps; ++turn) {
+    if (w == turn) {
 #pragma unroll
-  for (int c = 0; c < kHeadMaxC; ++c) {
-    atomicAdd(&dw_sh[c][lane], dwa[c][0]);
-    atomicAdd(&dw_sh[c][lane + 32], dwa[c][1]);
+      for (int c = 0; c < kHeadMaxC; ++c) {
+        dw_sh[c][lane] += dwa[c][0];
+        dw_sh[c][lane + 32] += dwa[c][1];
+      }
+      db_sh[lane] += dba0;
+      db_sh[lane + 32] += dba1;
+      if (lane == 0) loss_sh += loss_acc;
+    }
+    __syncthreads();
   }
-  atomicAdd(&db_sh[lane], dba0);
-  atomicAdd(&db_sh[lane + 32], dba1);
-  if (lane == 0) atomicAdd(&loss_sh, loss_acc);
-  __syncthreads();
-  for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
-    const int c = i / K, k = i % K;
-    atomicAdd(&dW[i], dw_sh[c][k]);
+  if ((K & 3) == 0 && ((uintptr_t)dW & 15) == 0) {
+    const int kv = K >> 2;
+    for (int i = threadIdx.x; i < C * kv; i += blockDim.x) {
+      const int c = i / kv, k = (i % kv) << 2;
+      atomicAdd((float4*)&dW[(size_t)c * K + k], *(const float4*)&dw_sh[c][k]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
+      const int c = i / K, k = i % K;
+      atomicAdd(&dW[i], dw_sh[c][k]);
+    }
   }
   if (threadIdx.x < C && db) atomicAdd(&db[threadIdx.x], db_sh[threadIdx.x]);
   if (threadIdx.x == 0) atomicAdd(loss, loss_sh * inv_n);
@@ -291,12 +306,14 @@ extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride,
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));
   cudaStream_t st = (cudaStream_t)stream;
+  pg::TimedScope timed(PG_T_HEAD, st);
   PG_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(float), st));
   PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)n_classes * in_dim * sizeof(float), st));
   if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, (size_t)n_classes * sizeof(float), st));
   if (n == 0) return PG_OK;
-  const int grid = (int)std::min<int64_t>((n + kHeadWarps - 1) / kHeadWarps, (int64_t)pg::sm_count(dev) * 2);
-  const size_t smem = 3 * (size_t)kHeadMaxK * kHeadMaxC * sizeof(float);
+  // one CTA per SM: the fixed cost per CTA (staging W twice, 4 k atomics for dW) is what the kernel's time is made of
+  const int grid = (int)std::min<int64_t>((n + kHeadWarps - 1) / kHeadWarps, (int64_t)pg::sm_count(dev));
+  const size_t smem = ((size_t)kHeadMaxK * (kHeadMaxC + 1) + 2 * (size_t)kHeadMaxK * kHeadMaxC) * sizeof(float);
   PG_CUDA(cudaFuncSetAttribute(linear_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   linear_ce_kernel<<<grid, kHeadWarps * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
                                                      1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight, d_grad_bias);

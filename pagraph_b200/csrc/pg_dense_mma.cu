@@ -61,43 +61,47 @@ struct DropArgs {
   uint64_t seed;
   const int64_t* step; // optional device counter added to the seed
 };
-// keep-scale factor of element (row, col) of a [*, width] activation under the drop_hash contract (pg_common.cuh)
-__device__ __forceinline__ float drop_factor(const DropArgs& d, uint64_t seed, int64_t row, int width, int col) {
-  const uint64_t h = pg::drop_hash(seed, (uint64_t)row, (uint32_t)(width >> 2), (uint32_t)(col >> 2));
+// keep-scale factor of column `col` of a row under the drop_hash contract (pg_common.cuh): rowkey = drop_rowkey(stepkey,
+// row), colkey = drop_colkey(col / 4), both hoisted by the callers
+__device__ __forceinline__ float drop_factor(const DropArgs& d, uint64_t rowkey, uint64_t colkey, int col) {
+  const uint64_t h = pg::drop_mix(rowkey, colkey);
   return ((uint32_t)(h >> (16 * (col & 3))) & 0xffffu) < d.thr ? 0.f : d.scale;
 }
 
 // ====================================================================================================== forward
-constexpr int kFwdWarps = 8;
-constexpr int kFwdRowsPerWarp = 32;
-constexpr int kFwdDepth = 5;  // 16-column chunks of x in flight per warp (2 KB each)
-
+// Template knobs (PG_FWD_VARIANT picks among the instantiations below; the default is the measured best):
+//   MT     m-tiles (16 rows) per warp: 2 halves the shared-memory reads of W per MMA, 1 halves the registers
+//   PAIR   16-column chunks fetched together: PAIR * 64 contiguous bytes per row and request burst (DRAM locality)
+//   DEPTH  load groups (PAIR chunks each) in flight per warp, held in registers
+//   WARPS  warps per CTA (one CTA per SM: the W planes take 156 KB of shared memory)
 __host__ __device__ inline int fwd_wstride(int K) {  // row stride of the W planes: 16 mod 32 words -> conflict-free LDS.128
   const int k16 = (K + 15) / 16 * 16;
   return k16 + ((16 - k16 % 32) + 32) % 32;
 }
 
-__global__ void __launch_bounds__(kFwdWarps * 32, 1)
+template <int MT, int PAIR, int DEPTH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
     linear_concat_fwd_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ W,
                              const float* __restrict__ bias, int64_t n, int K, int concat, float* __restrict__ out,
                              int64_t out_stride, float* __restrict__ out_drop, int64_t od_stride, DropArgs drop) {
+  constexpr int kThreads = WARPS * 32, kRowsPerWarp = 16 * MT, kRowsPerCta = WARPS * kRowsPerWarp;
   extern __shared__ __align__(16) uint32_t wsm[];  // [2][kOut][ws]: hi plane, lo plane
   const int ws = fwd_wstride(K);
   uint32_t* w_hi = wsm;
   uint32_t* w_lo = wsm + (size_t)kOut * ws;
   {  // W -> hi / lo planes: 16-byte loads, kPre of them in flight per thread before the first use
     const int nvec = K >> 2, total = kOut * nvec;
-    constexpr int kPre = 10;
-    for (int base = 0; base < total; base += kFwdWarps * 32 * kPre) {
+    constexpr int kPre = 8;
+    for (int base = 0; base < total; base += kThreads * kPre) {
       float4 v[kPre];
 #pragma unroll
       for (int u = 0; u < kPre; ++u) {
-        const int idx = base + u * kFwdWarps * 32 + (int)threadIdx.x;
+        const int idx = base + u * kThreads + (int)threadIdx.x;
         v[u] = idx < total ? __ldg((const float4*)W + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < kPre; ++u) {
-        const int idx = base + u * kFwdWarps * 32 + (int)threadIdx.x;
+        const int idx = base + u * kThreads + (int)threadIdx.x;
         if (idx < total) {
           const int o = idx / nvec, k4 = idx - o * nvec;
           uint4 hi, lo;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1)
       }
     }
     const int pad = ws - K;  // columns [K, ws) of every row: zero (the last chunk reads up to the next multiple of 16)
-    for (int i = threadIdx.x; i < kOut * pad; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kOut * pad; i += kThreads) {
       const int o = i / pad, k = K + i % pad;
       w_hi[o * ws + k] = 0u;
       w_lo[o * ws + k] = 0u;
@@ -121,82 +125,104 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int nchunks = (K + 15) / 16;
-  const int64_t ntiles = (n + kFwdWarps * kFwdRowsPerWarp - 1) / (kFwdWarps * kFwdRowsPerWarp);
-  const uint64_t seed = drop.thr ? drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull) : 0ull;
-  const int width = concat ? 2 * kOut : kOut;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r0 = (tile * kFwdWarps + warp) * kFwdRowsPerWarp;
-    if (r0 >= n) continue;
-    // rows of this lane: r0 + g + 8 i, i = 0..3 (m-tile i/2, half i%2)
-    const float* xrow[4];
-    bool rok[4];
+  const int ngroups = (nchunks + PAIR - 1) / PAIR;
+  const int64_t ntiles = (n + kRowsPerCta - 1) / kRowsPerCta;
+  const uint64_t stepkey = drop.thr ? pg::drop_stepkey(drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull)) : 0ull;
+  // dropout column keys of this lane's output columns: n-tile j covers columns 8 j + 2 t, + 1 (group 2 j + t / 2) of the
+  // z half and the same + 32 (group + 8) of the relu half
+  uint64_t ck_z[4], ck_p[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+  for (int j = 0; j < 4; ++j) {
+    ck_z[j] = drop.thr ? pg::drop_colkey((uint32_t)(2 * j + (t >> 1))) : 0ull;
+    ck_p[j] = drop.thr ? pg::drop_colkey((uint32_t)(8 + 2 * j + (t >> 1))) : 0ull;
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r0 = (tile * WARPS + warp) * kRowsPerWarp;
+    if (r0 >= n) continue;
+    // rows of this lane: r0 + g + 8 i, i = 0 .. 2 MT - 1 (m-tile i/2, half i%2)
+    const float* xrow[2 * MT];
+    bool rok[2 * MT];
+#pragma unroll
+    for (int i = 0; i < 2 * MT; ++i) {
       const int64_t r = r0 + g + 8 * i;
       rok[i] = r < n;
       xrow[i] = x + (rok[i] ? r : 0) * x_stride + 4 * t;
     }
-    float acc[2][4][4];
+    float acc[MT][4][4];
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
-    float4 buf[kFwdDepth][4];
-    auto load = [&](float4(&b)[4], int chunk) {
-      const bool cok = chunk < nchunks && chunk * 16 + 4 * t < K;
+    float4 buf[DEPTH][PAIR][2 * MT];
+    auto load = [&](float4(&b)[PAIR][2 * MT], int group) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = (cok && rok[i]) ? ld_stream4(xrow[i] + chunk * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pc = 0; pc < PAIR; ++pc) {
+        const int chunk = group * PAIR + pc;
+        const bool cok = chunk < nchunks && chunk * 16 + 4 * t < K;
+#pragma unroll
+        for (int i = 0; i < 2 * MT; ++i)
+          b[pc][i] = (cok && rok[i]) ? ld_stream4(xrow[i] + chunk * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
 #pragma unroll
-    for (int d = 0; d < kFwdDepth; ++d) load(buf[d], d);
-    for (int c0 = 0; c0 < nchunks; c0 += kFwdDepth) {
+    for (int d = 0; d < DEPTH; ++d) load(buf[d], d);
+    for (int g0 = 0; g0 < ngroups; g0 += DEPTH) {
 #pragma unroll
-      for (int d = 0; d < kFwdDepth; ++d) {
-        const int chunk = c0 + d;
-        if (chunk < nchunks) {
-          // A fragments of both k-steps of this chunk: [m-tile][k-step][a0..a3]
-          uint32_t ah[2][2][4], al[2][2][4];
+      for (int d = 0; d < DEPTH; ++d) {
+        const int group = g0 + d;
+        if (group < ngroups) {
+          // A fragments of every k-step of this group: [chunk][m-tile][k-step][a0..a3]
+          uint32_t ah[PAIR][MT][2][4], al[PAIR][MT][2][4];
 #pragma unroll
-          for (int m = 0; m < 2; ++m)
+          for (int pc = 0; pc < PAIR; ++pc)
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              split_tf32(comp(buf[d][2 * m], 2 * s), ah[m][s][0], al[m][s][0]);          // (row g,   k = t)
-              split_tf32(comp(buf[d][2 * m + 1], 2 * s), ah[m][s][1], al[m][s][1]);      // (row g+8, k = t)
-              split_tf32(comp(buf[d][2 * m], 2 * s + 1), ah[m][s][2], al[m][s][2]);      // (row g,   k = t+4)
-              split_tf32(comp(buf[d][2 * m + 1], 2 * s + 1), ah[m][s][3], al[m][s][3]);  // (row g+8, k = t+4)
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                split_tf32(comp(buf[d][pc][2 * m], 2 * s), ah[pc][m][s][0], al[pc][m][s][0]);          // (row g,   k = t)
+                split_tf32(comp(buf[d][pc][2 * m + 1], 2 * s), ah[pc][m][s][1], al[pc][m][s][1]);      // (row g+8, k = t)
+                split_tf32(comp(buf[d][pc][2 * m], 2 * s + 1), ah[pc][m][s][2], al[pc][m][s][2]);      // (row g,   k = t+4)
+                split_tf32(comp(buf[d][pc][2 * m + 1], 2 * s + 1), ah[pc][m][s][3], al[pc][m][s][3]);  // (row g+8, k = t+4)
+              }
+          load(buf[d], group + DEPTH);
+#pragma unroll
+          for (int pc = 0; pc < PAIR; ++pc) {
+            const int chunk = group * PAIR + pc;
+            if (chunk < nchunks) {
+              uint4 bh[4], bl[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int off = (j * 8 + g) * ws + chunk * 16 + 4 * t;
+                bh[j] = *(const uint4*)(w_hi + off);
+                bl[j] = *(const uint4*)(w_lo + off);
+              }
+#pragma unroll
+              for (int term = 0; term < 3; ++term)  // small terms first
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                  for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const uint32_t(&a)[4] = term == 0 ? al[pc][m][s] : ah[pc][m][s];
+                      const uint4& b = term == 1 ? bl[j] : bh[j];
+                      mma_tf32(acc[m][j], a[0], a[1], a[2], a[3], s == 0 ? b.x : b.z, s == 0 ? b.y : b.w);
+                    }
             }
-          load(buf[d], chunk + kFwdDepth);
-          uint4 bh[4], bl[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int off = (j * 8 + g) * ws + chunk * 16 + 4 * t;
-            bh[j] = *(const uint4*)(w_hi + off);
-            bl[j] = *(const uint4*)(w_lo + off);
           }
-#pragma unroll
-          for (int term = 0; term < 3; ++term)  // small terms first
-#pragma unroll
-            for (int s = 0; s < 2; ++s)
-#pragma unroll
-              for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint32_t(&a)[4] = term == 0 ? al[m][s] : ah[m][s];
-                  const uint4& b = term == 1 ? bl[j] : bh[j];
-                  mma_tf32(acc[m][j], a[0], a[1], a[2], a[3], s == 0 ? b.x : b.z, s == 0 ? b.y : b.w);
-                }
         }
       }
     }
     // epilogue: acc[m][j] = {(row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)} of m-tile m, n-tile j
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int64_t r = r0 + m * 16 + h * 8 + g;
         if (r >= n) continue;
+        const uint64_t rk = (out_drop && drop.thr) ? pg::drop_rowkey(stepkey, (uint64_t)r) : 0ull;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int col = j * 8 + 2 * t;
@@ -216,13 +242,11 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1)
           if (out_drop) {
             float* drow = out_drop + r * od_stride;
             if (concat) {
-              *(float2*)(drow + col) = make_float2(z0 * drop_factor(drop, seed, r, width, col),
-                                                   z1 * drop_factor(drop, seed, r, width, col + 1));
-              *(float2*)(drow + kOut + col) = make_float2(p0 * drop_factor(drop, seed, r, width, kOut + col),
-                                                          p1 * drop_factor(drop, seed, r, width, kOut + col + 1));
+              *(float2*)(drow + col) = make_float2(z0 * drop_factor(drop, rk, ck_z[j], col), z1 * drop_factor(drop, rk, ck_z[j], col + 1));
+              *(float2*)(drow + kOut + col) =
+                  make_float2(p0 * drop_factor(drop, rk, ck_p[j], col), p1 * drop_factor(drop, rk, ck_p[j], col + 1));
             } else {
-              *(float2*)(drow + col) = make_float2(p0 * drop_factor(drop, seed, r, width, col),
-                                                   p1 * drop_factor(drop, seed, r, width, col + 1));
+              *(float2*)(drow + col) = make_float2(p0 * drop_factor(drop, rk, ck_z[j], col), p1 * drop_factor(drop, rk, ck_z[j], col + 1));
             }
           }
         }
@@ -235,8 +259,8 @@ constexpr int kDwTile = 24;      // rows per gz tile = 3 k-steps of 8 rows, one 
 constexpr int kGzStride = 40;    // floats per gz row in shared memory: conflict-free LDS.128 of the A fragments
 constexpr int kDwMaxWarps = 12;  // 64 columns per warp -> in_dim <= 768
 
-template <int kWarps>            // CTA size; the warps beyond in_dim / 64 only help staging gz
-__global__ void __launch_bounds__(kWarps * 32, 1)
+template <int kWarps, int kMaxReg>  // CTA size (the warps beyond in_dim / 64 only help staging gz); register cap
+__global__ void __launch_bounds__(kWarps * 32) __maxnreg__(kMaxReg)
     linear_concat_dw_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gout, int64_t g_stride,
                             const float* __restrict__ y, int64_t y_stride, int64_t n, int K, int concat, DropArgs drop,
                             float* dW, float* db) {
@@ -253,8 +277,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(n, r_begin + rows_per_cta);
   if (r_begin >= r_end) return;
   const int ntiles = (int)((r_end - r_begin + kDwTile - 1) / kDwTile);
-  const uint64_t seed = drop.thr ? drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull) : 0ull;
-  const int width = concat ? 2 * kOut : kOut;
+  const uint64_t stepkey = drop.thr ? pg::drop_stepkey(drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull)) : 0ull;
+  // a thread stages gz[.][o] for one fixed o = tid % 32: dropout column keys of columns o and 32 + o
+  const uint64_t ck_a = drop.thr ? pg::drop_colkey((uint32_t)((tid & 31) >> 2)) : 0ull;
+  const uint64_t ck_b = drop.thr ? pg::drop_colkey((uint32_t)(8 + ((tid & 31) >> 2))) : 0ull;
   // this warp's columns: blocks cb = 2 warp, 2 warp + 1 of 32 columns; lane fetches floats [32 cb + 4 g, +4)
   const int col0 = warp * 64 + 4 * g;
   const bool cok[2] = {col0 < K, col0 + 32 < K};
@@ -298,16 +324,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
         const int rr = i / kOut, o = i % kOut;
         const int64_t r = r0 + rr;
         float v;
+        const uint64_t rk = drop.thr ? pg::drop_rowkey(stepkey, (uint64_t)r) : 0ull;
         if (concat) {
           float ga = gr_a[q], gb = gr_y[q] > 0.f ? gr_b[q] : 0.f;
           if (drop.thr) {
-            ga *= drop_factor(drop, seed, r, width, o);
-            gb *= drop_factor(drop, seed, r, width, kOut + o);
+            ga *= drop_factor(drop, rk, ck_a, o);
+            gb *= drop_factor(drop, rk, ck_b, o);   // column 32 + o: same lane (o % 4) of group 8 + o / 4
           }
           v = ga + gb;
         } else {
           v = gr_y[q] > 0.f ? gr_a[q] : 0.f;
-          if (drop.thr) v *= drop_factor(drop, seed, r, width, o);
+          if (drop.thr) v *= drop_factor(drop, rk, ck_a, o);
         }
         uint32_t hi, lo;
         split_tf32(v, hi, lo);
@@ -437,15 +464,27 @@ pg_status pg_linear_concat_fwd(const float* d_x, int64_t x_stride, const float* 
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));
   cudaStream_t st = (cudaStream_t)stream;
+  pg::TimedScope timed(PG_T_DENSE_FWD, st);
   const size_t smem = 2 * (size_t)kOut * fwd_wstride(in_dim) * sizeof(uint32_t);
-  PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t ntiles = (n + kFwdWarps * kFwdRowsPerWarp - 1) / (kFwdWarps * kFwdRowsPerWarp);
-  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev));
-  linear_concat_fwd_kernel<<<grid, kFwdWarps * 32, smem, st>>>(d_x, x_stride, d_weight, d_bias, n, in_dim, concat, d_out,
-                                                                out_stride, d_out_drop, od_stride,
-                                                                make_drop(d_out_drop ? dropout_p : 0.f, dropout_seed, d_step));
-  PG_CHECK_LAUNCH();
-  return PG_OK;
+  const DropArgs drop = make_drop(d_out_drop ? dropout_p : 0.f, dropout_seed, d_step);
+  auto launch = [&](auto kern, int warps, int rows_per_warp) -> pg_status {
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (n + warps * rows_per_warp - 1) / (warps * rows_per_warp);
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev));
+    kern<<<grid, warps * 32, smem, st>>>(d_x, x_stride, d_weight, d_bias, n, in_dim, concat, d_out, out_stride, d_out_drop,
+                                         od_stride, drop);
+    PG_CHECK_LAUNCH();
+    return PG_OK;
+  };
+  const char* env_v = getenv("PG_FWD_VARIANT");
+  switch (env_v ? atoi(env_v) : 0) {
+    case 1: return launch(linear_concat_fwd_kernel<2, 1, 5, 8>, 8, 32);
+    case 2: return launch(linear_concat_fwd_kernel<2, 2, 3, 8>, 8, 32);
+    case 3: return launch(linear_concat_fwd_kernel<1, 2, 4, 12>, 12, 16);
+    case 4: return launch(linear_concat_fwd_kernel<1, 4, 2, 12>, 12, 16);
+    case 5: return launch(linear_concat_fwd_kernel<1, 2, 3, 16>, 16, 16);
+    default: return launch(linear_concat_fwd_kernel<2, 2, 3, 8>, 8, 32);
+  }
 }
 
 pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
@@ -461,6 +500,7 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));
   cudaStream_t st = (cudaStream_t)stream;
+  pg::TimedScope timed(PG_T_DENSE_BWD, st);
   PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)kOut * in_dim * sizeof(float), st));
   if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, kOut * sizeof(float), st));
   if (n == 0) return PG_OK;
@@ -476,9 +516,9 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
     PG_CHECK_LAUNCH();
     return PG_OK;
   };
-  if (in_dim <= 256) return launch(linear_concat_dw_kernel<4>, 4);
-  if (in_dim <= 640) return launch(linear_concat_dw_kernel<10>, 10);
-  return launch(linear_concat_dw_kernel<kDwMaxWarps>, kDwMaxWarps);
+  if (in_dim <= 256) return launch(linear_concat_dw_kernel<4, 255>, 4);
+  if (in_dim <= 640) return launch(linear_concat_dw_kernel<10, 168>, 10);
+  return launch(linear_concat_dw_kernel<kDwMaxWarps, 168>, kDwMaxWarps);
 }
 
 }  // extern "C"

@@ -156,6 +156,7 @@ class GCNTrainEngine:
                 self.fused_opt = PeerAdam(sync, optimizer)
             except Exception as e:                          # e.g. CUDA IPC unavailable: NCCL all-reduce + optimizer.step()
                 print("GCNTrainEngine: fused all-reduce + Adam unavailable (%s); using all_reduce + optimizer.step()" % e)
+        self.serialize = False       # True: every stage runs alone (host sync after each) — per-kernel timing passes
         self._dense_ok = False
         self.dense = None            # buffers of the fused dense stage (_compute_body_fused), made on first use
         self.pool = None
@@ -261,6 +262,8 @@ class GCNTrainEngine:
                 self._sample_body(s, n)
                 self.launches += _lib.launch_count() - l0
             s.sampled.record(self.side)
+        if self.serialize:
+            torch.cuda.synchronize(self.dev)
 
     def _issue_gather(self, k):
         """Enqueue stage B of global minibatch k (after its stage A)."""
@@ -277,6 +280,8 @@ class GCNTrainEngine:
                 self._gather_body(s)
                 self.launches += _lib.launch_count() - l0
             s.loaded.record(self.gather)
+        if self.serialize:
+            torch.cuda.synchronize(self.dev)
 
     def _capture(self, stream, body):
         body()                                               # eager once: sizes every workspace outside the capture
@@ -470,6 +475,8 @@ class GCNTrainEngine:
                 self.launches += _lib.launch_count() - l0
                 self._warm = True                            # optimizer state exists after the first eager step
             s.done.record(main)
+            if self.serialize:
+                torch.cuda.synchronize(self.dev)
             self.next_compute += 1
             if self.next_issue < end:
                 self._issue_sample(self.next_issue)

@@ -14,7 +14,8 @@ for m, r in d['variants'].items():
         print(' ', m, k, 'mb/s', round(x['minibatches_per_s'], 1), 'ms', round(x['ms_per_step'], 3), 'wall', round(x['wall_ms_per_step'], 3),
               'hit', round(x['hit_rate'], 3), 'launches', x['launches'])
         for kn, kv in x['kernels'].items():
-            print('       %-58s avg_ms %.4f  GB/s %8.1f  frac %.3f (%s)' % (kn, kv['avg_ms'], kv['achieved_gbs'], kv['frac'], kv['bound']))
+            print('       %-58s avg_ms %.4f  (in pipeline %s)  GB/s %8.1f  frac %.3f (%s)' % (
+                kn, kv['avg_ms'], ('%.4f' % kv['avg_ms_in_pipeline']) if 'avg_ms_in_pipeline' in kv else '-', kv['achieved_gbs'], kv['frac'], kv['bound']))
         if x.get('gather'):
             g = x['gather']
             print('     gather: %.1f GB/s payload, %.3f ms/batch, hit %.3f; hit kernel frac %.3f' % (g['gather_gbs'], g['ms_per_batch'], g['hit_rate'], g['hit']['frac']),
