@@ -225,10 +225,10 @@ __device__ __forceinline__ void acc_drop4(float4& acc, const float4 v, uint64_t 
   if (hi >= thr_hi) acc.w = fmaf(v.w, scale, acc.w);
 }
 
-// ILP = rows consumed per round. ILP = 2 is the faster kernel in isolation (0.166 vs 0.197 ms at config 2) but needs 113
-// registers x 512 threads = 58 k of the SM's 64 k, which evicts the load stage's CTAs (sampler, gather) that should run
-// next to it on the other stream; ILP = 1 (64 registers) gives the faster pipelined step (0.510 vs 0.521 ms), and capping
-// ILP = 2 with __maxnreg__ (96 / 88 / 80) only spills. Hence ILP = 1 at 16 warps.
+// ILP = rows consumed per round. With the row-key x column-key mask (one multiply per float4) ILP = 2 fits in 96
+// registers (512 threads x 96 = 48 k of the SM's 64 k registers, so the sampler's small CTAs on the other stream still find
+// room next to it) and is the faster choice both alone (gather stage 0.203 vs 0.225 ms at config 2) and in the pipelined
+// step (0.388 vs 0.408 ms); ILP = 1 (72 registers) stays selectable with PG_AGG_ILP=1.
 template <int W, int CH, bool DROP, int ILP>
 __global__ void __launch_bounds__(W * 32) __maxnreg__(ILP == 1 ? 80 : 96)
     agg_rows_tma_kernel(pg::AggRowsArgs a, int group, int depth) {
@@ -404,10 +404,8 @@ pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, 
   const int group = std::min(kRowsMaxGroup, slots / depth);
   const size_t smem = (size_t)W * depth * group * row_bytes;
   const bool drop = a.drop_thr != 0;
-  // 16 warps give enough thread-level parallelism; the 2-row unroll would only cost registers (the kernel must leave
-  // register file for the sampler's CTAs that run next to it on the other stream)
   const char* env_i = getenv("PG_AGG_ILP");
-  const int ilp = env_i ? atoi(env_i) : (W >= 16 ? 1 : 2);
+  const int ilp = env_i ? atoi(env_i) : 2;
   auto kern = ilp == 1 ? (drop ? agg_rows_tma_kernel<W, CH, true, 1> : agg_rows_tma_kernel<W, CH, false, 1>)
                        : (drop ? agg_rows_tma_kernel<W, CH, true, 2> : agg_rows_tma_kernel<W, CH, false, 2>);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

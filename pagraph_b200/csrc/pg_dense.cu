@@ -311,6 +311,12 @@ extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride,
   PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)n_classes * in_dim * sizeof(float), st));
   if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, (size_t)n_classes * sizeof(float), st));
   if (n == 0) return PG_OK;
+  const char* env_s = getenv("PG_HEAD_SIMT");
+  if (!(env_s && atoi(env_s))) {   // tensor-core kernel (pg_dense_mma.cu) whenever the layout allows 16-byte accesses
+    const pg_status s = pg::linear_ce_mma(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes, d_loss, d_grad_a,
+                                          ga_stride, d_grad_weight, d_grad_bias, st);
+    if (s != PG_ERR_INVALID) return s;
+  }
   // one CTA per SM: the fixed cost per CTA (staging W twice, 4 k atomics for dW) is what the kernel's time is made of
   const int grid = (int)std::min<int64_t>((n + kHeadWarps - 1) / kHeadWarps, (int64_t)pg::sm_count(dev));
   const size_t smem = ((size_t)kHeadMaxK * (kHeadMaxC + 1) + 2 * (size_t)kHeadMaxK * kHeadMaxC) * sizeof(float);

@@ -433,6 +433,270 @@ __global__ void __launch_bounds__(kWarps * 32) __maxnreg__(kMaxReg)
   }
 }
 
+// ====================================================================================================== classifier head + loss
+// pred = a W^T + b, loss = mean_r(logsumexp(pred_r) - pred_r[label_r]) and all three gradients (reference: the last
+// NodeUpdate, gcn_nssc.py:48, + CrossEntropyLoss, pa_gcn.py:62,93-94) as three chained tensor-core products per CTA of
+// 64 rows (4 warps x 16 rows), 3xTF32 like the kernels above:
+//   1. logits = a W^T            per warp; softmax / loss / G = d loss / d logits on the accumulator fragments
+//   2. grad_a = G W              per warp; the accumulator fragment of (1) IS the A fragment of (2) under the free
+//                                permutation of the summed index (class 8j+2t <-> k = t, class 8j+2t+1 <-> k = t+4)
+//   3. dW    += G^T a            per CTA, G and a staged in shared memory, warp w owns classes [16 w, 16 w + 16);
+//                                one 16-byte vector atomic per 4 outputs, db / loss by warp-reduced scalar atomics
+// in_dim, n_classes <= 64 (zero-padded to 64), in_dim % 4 == 0.
+constexpr int kHeadWarpsM = 4;
+constexpr int kHeadWS = 84;   // row stride (words) of the W planes: conflict-free for both operand access patterns
+constexpr int kHeadGS = 66;   // ... of the G planes (8-byte loads, 4 rows x 8 class groups per half-warp)
+constexpr int kHeadAS = 72;   // ... of the staged a tile (16-byte loads, 4 rows x 2 column groups per quarter-warp)
+
+__global__ void __launch_bounds__(kHeadWarpsM * 32)
+    linear_ce_mma_kernel(const float* __restrict__ a, int64_t a_stride, const float* __restrict__ W,
+                         const float* __restrict__ bias, const int64_t* __restrict__ labels, int64_t n, int K, int C,
+                         float inv_n, float* loss, float* grad_a, int64_t ga_stride, float* dW, float* db) {
+  extern __shared__ __align__(16) uint32_t hsm[];
+  uint32_t* w_hi = hsm;                                   // [64][kHeadWS]  w[class][k]
+  uint32_t* w_lo = w_hi + 64 * kHeadWS;
+  uint32_t* g_hi = w_lo + 64 * kHeadWS;                   // [64 rows][kHeadGS], class c at word (c % 8) * 8 + c / 8
+  uint32_t* g_lo = g_hi + 64 * kHeadGS;
+  float* a_s = (float*)(g_lo + 64 * kHeadGS);             // [64 rows][kHeadAS]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- phase 0: W -> hi / lo planes (zero-padded to 64 x 64)
+  for (int idx = tid; idx < 64 * 16; idx += kHeadWarpsM * 32) {
+    const int c = idx >> 4, k4 = (idx & 15) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C && k4 < K) v = __ldg((const float4*)(W + (size_t)c * K + k4));
+    uint4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+    *(uint4*)(w_hi + c * kHeadWS + k4) = hi;
+    *(uint4*)(w_lo + c * kHeadWS + k4) = lo;
+  }
+  // ---- this warp's 16 rows of a: fragments (rows g, g+8; columns 16 c + 4 t ..) and a copy in shared memory
+  const int64_t r0 = ((int64_t)blockIdx.x * kHeadWarpsM + w) * 16;
+  const int64_t ra = r0 + g, rb = r0 + g + 8;
+  const bool va = ra < n, vb = rb < n;
+  float4 xa[4], xb[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col = 16 * c + 4 * t;
+    xa[c] = (va && col < K) ? __ldg((const float4*)(a + ra * a_stride + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xb[c] = (vb && col < K) ? __ldg((const float4*)(a + rb * a_stride + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *(float4*)(a_s + (w * 16 + g) * kHeadAS + col) = xa[c];
+    *(float4*)(a_s + (w * 16 + g + 8) * kHeadAS + col) = xb[c];
+  }
+  const int64_t ya = va ? labels[ra] : -1, yb = vb ? labels[rb] : -1;
+  __syncthreads();
+  // ---- phase 1: logits (acc[j] = n-tile j = classes 8 j .. 8 j + 7; lane holds classes 8 j + 2 t, + 1 of rows g, g+8)
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      split_tf32(comp(xa[c], 2 * s), ah[s][0], al[s][0]);
+      split_tf32(comp(xb[c], 2 * s), ah[s][1], al[s][1]);
+      split_tf32(comp(xa[c], 2 * s + 1), ah[s][2], al[s][2]);
+      split_tf32(comp(xb[c], 2 * s + 1), ah[s][3], al[s][3]);
+    }
+    uint4 bh[8], bl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int off = (8 * j + g) * kHeadWS + 16 * c + 4 * t;
+      bh[j] = *(const uint4*)(w_hi + off);
+      bl[j] = *(const uint4*)(w_lo + off);
+    }
+#pragma unroll
+    for (int term = 0; term < 3; ++term)
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t(&av)[4] = term == 0 ? al[s] : ah[s];
+          const uint4& b = term == 1 ? bl[j] : bh[j];
+          mma_tf32(acc[j], av[0], av[1], av[2], av[3], s == 0 ? b.x : b.z, s == 0 ? b.y : b.w);
+        }
+  }
+  // ---- softmax, loss, G (overwrites acc): rows g (q = 0, 1) and g + 8 (q = 2, 3)
+  float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = 8 * j + 2 * t + (q & 1);
+      float z = acc[j][q] + ((bias && col < C) ? bias[col] : 0.f);
+      if (col >= C) z = -INFINITY;
+      acc[j][q] = z;
+      if (q < 2) ma = fmaxf(ma, z);
+      else mb = fmaxf(mb, z);
+    }
+  ma = fmaxf(ma, __shfl_xor_sync(pg::kFullMask, ma, 1));
+  ma = fmaxf(ma, __shfl_xor_sync(pg::kFullMask, ma, 2));
+  mb = fmaxf(mb, __shfl_xor_sync(pg::kFullMask, mb, 1));
+  mb = fmaxf(mb, __shfl_xor_sync(pg::kFullMask, mb, 2));
+  float sa = 0.f, sb = 0.f, la = 0.f, lb = 0.f;   // sum of exp, logit at the label
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = 8 * j + 2 * t + (q & 1);
+      const float z = acc[j][q];
+      const float e = col < C ? expf(z - (q < 2 ? ma : mb)) : 0.f;
+      if (q < 2) {
+        sa += e;
+        if (col == ya) la = z;
+      } else {
+        sb += e;
+        if (col == yb) lb = z;
+      }
+      acc[j][q] = e;
+    }
+#pragma unroll
+  for (int d = 1; d <= 2; d <<= 1) {
+    sa += __shfl_xor_sync(pg::kFullMask, sa, d);
+    sb += __shfl_xor_sync(pg::kFullMask, sb, d);
+    la += __shfl_xor_sync(pg::kFullMask, la, d);
+    lb += __shfl_xor_sync(pg::kFullMask, lb, d);
+  }
+  float lsum = 0.f;
+  if (t == 0) lsum = (va ? (ma + logf(sa)) - la : 0.f) + (vb ? (mb + logf(sb)) - lb : 0.f);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) lsum += __shfl_xor_sync(pg::kFullMask, lsum, d);
+  if (lane == 0) atomicAdd(loss, lsum * inv_n);
+  const float isa = va ? inv_n / sa : 0.f, isb = vb ? inv_n / sb : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = 8 * j + 2 * t + (q & 1);
+      const bool up = q < 2;
+      float gv = acc[j][q] * (up ? isa : isb);
+      if (col == (up ? ya : yb)) gv -= inv_n;          // ya / yb = -1 for rows beyond n: never matches
+      if (col >= C || !(up ? va : vb)) gv = 0.f;
+      acc[j][q] = gv;
+    }
+  // db: column sums over this warp's rows -> lanes g == 0 -> global
+  if (db) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d0 = acc[j][0] + acc[j][2], d1 = acc[j][1] + acc[j][3];
+#pragma unroll
+      for (int d = 4; d <= 16; d <<= 1) {
+        d0 += __shfl_xor_sync(pg::kFullMask, d0, d);
+        d1 += __shfl_xor_sync(pg::kFullMask, d1, d);
+      }
+      if (g == 0) {
+        const int col = 8 * j + 2 * t;
+        if (col < C) atomicAdd(&db[col], d0);
+        if (col + 1 < C) atomicAdd(&db[col + 1], d1);
+      }
+    }
+  }
+  // ---- phase 2: grad_a = G W; k-step j sums classes 8 j .. 8 j + 7 with A = the G fragment as it stands; the output
+  // column of n-tile 4 h + i, n = nu, is 32 h + 4 nu + i (a lane's four n-tiles of a half are 4 consecutive columns)
+  float acc2[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc2[j][q] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t ah[4], al[4];
+    split_tf32(acc[j][0], ah[0], al[0]);   // (row g,   class 8j+2t)   = A[g][k = t]
+    split_tf32(acc[j][2], ah[1], al[1]);   // (row g+8, class 8j+2t)   = A[g+8][t]
+    split_tf32(acc[j][1], ah[2], al[2]);   // (row g,   class 8j+2t+1) = A[g][t+4]
+    split_tf32(acc[j][3], ah[3], al[3]);   // (row g+8, class 8j+2t+1) = A[g+8][t+4]
+    // stage G for phase 3
+    {
+      const int ra_s = (w * 16 + g) * kHeadGS, rb_s = (w * 16 + g + 8) * kHeadGS;
+      const int p0 = (2 * t) * 8 + j, p1 = (2 * t + 1) * 8 + j;
+      g_hi[ra_s + p0] = ah[0]; g_lo[ra_s + p0] = al[0];
+      g_hi[rb_s + p0] = ah[1]; g_lo[rb_s + p0] = al[1];
+      g_hi[ra_s + p1] = ah[2]; g_lo[ra_s + p1] = al[2];
+      g_hi[rb_s + p1] = ah[3]; g_lo[rb_s + p1] = al[3];
+    }
+    uint4 bh0[2], bh1[2], bl0[2], bl1[2];   // [half]: W[class 8j+2t][32 h + 4 g ..], W[class 8j+2t+1][..]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o0 = (8 * j + 2 * t) * kHeadWS + 32 * h + 4 * g, o1 = o0 + kHeadWS;
+      bh0[h] = *(const uint4*)(w_hi + o0);
+      bh1[h] = *(const uint4*)(w_hi + o1);
+      bl0[h] = *(const uint4*)(w_lo + o0);
+      bl1[h] = *(const uint4*)(w_lo + o1);
+    }
+#pragma unroll
+    for (int term = 0; term < 3; ++term)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t(&av)[4] = term == 0 ? al : ah;
+          const uint4& b0 = term == 1 ? bl0[h] : bh0[h];
+          const uint4& b1 = term == 1 ? bl1[h] : bh1[h];
+          const uint32_t x0 = i == 0 ? b0.x : i == 1 ? b0.y : i == 2 ? b0.z : b0.w;
+          const uint32_t x1 = i == 0 ? b1.x : i == 1 ? b1.y : i == 2 ? b1.z : b1.w;
+          mma_tf32(acc2[4 * h + i], av[0], av[1], av[2], av[3], x0, x1);
+        }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t r = (q < 2) ? ra : rb;
+      const int col = 32 * h + 8 * t + 4 * (q & 1);
+      if (r < n && col < K)
+        *(float4*)(grad_a + r * ga_stride + col) =
+            make_float4(acc2[4 * h][q], acc2[4 * h + 1][q], acc2[4 * h + 2][q], acc2[4 * h + 3][q]);
+    }
+  __syncthreads();
+  // ---- phase 3: dW[16 w + .][.] += G^T a over the CTA's 64 rows (8 k-steps of 8 rows)
+  float acc3[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc3[j][q] = 0.f;
+#pragma unroll 2
+  for (int ks = 0; ks < 8; ++ks) {
+    const int rt = 8 * ks + t;
+    const uint2 h0 = *(const uint2*)(g_hi + rt * kHeadGS + g * 8 + 2 * w), h1 = *(const uint2*)(g_hi + (rt + 4) * kHeadGS + g * 8 + 2 * w);
+    const uint2 l0 = *(const uint2*)(g_lo + rt * kHeadGS + g * 8 + 2 * w), l1 = *(const uint2*)(g_lo + (rt + 4) * kHeadGS + g * 8 + 2 * w);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 v0 = *(const float4*)(a_s + rt * kHeadAS + 32 * h + 4 * g);
+      const float4 v1 = *(const float4*)(a_s + (rt + 4) * kHeadAS + 32 * h + 4 * g);
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        split_tf32(comp(v0, i), bh[i][0], bl[i][0]);
+        split_tf32(comp(v1, i), bh[i][1], bl[i][1]);
+      }
+#pragma unroll
+      for (int term = 0; term < 3; ++term)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint2& a0 = term == 0 ? l0 : h0;
+          const uint2& a1 = term == 0 ? l1 : h1;
+          mma_tf32(acc3[4 * h + i], a0.x, a0.y, a1.x, a1.y, term == 1 ? bl[i][0] : bh[i][0], term == 1 ? bl[i][1] : bh[i][1]);
+        }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = 16 * w + g + 8 * (q >> 1);
+      const int col = 32 * h + 8 * t + 4 * (q & 1);
+      if (c < C && col < K)
+        atomicAdd((float4*)&dW[(size_t)c * K + col],
+                  make_float4(acc3[4 * h][q], acc3[4 * h + 1][q], acc3[4 * h + 2][q], acc3[4 * h + 3][q]));
+    }
+}
+
 DropArgs make_drop(float p, uint64_t seed, const int64_t* d_step) {
   DropArgs d;
   d.thr = p > 0.f ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
@@ -443,6 +707,28 @@ DropArgs make_drop(float p, uint64_t seed, const int64_t* d_step) {
 }
 
 }  // namespace
+
+namespace pg {
+
+// Tensor-core head kernel; outputs (loss, grad_weight, grad_bias) must be zeroed by the caller. Returns PG_ERR_INVALID
+// without launching when the layout does not allow 16-byte accesses (the caller then uses the scalar kernel).
+pg_status linear_ce_mma(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias, const int64_t* d_labels,
+                        int64_t n, int32_t in_dim, int32_t n_classes, float* d_loss, float* d_grad_a, int64_t ga_stride,
+                        float* d_grad_weight, float* d_grad_bias, cudaStream_t st) {
+  const bool ok = in_dim % 4 == 0 && in_dim <= 64 && n_classes <= 64 && a_stride % 4 == 0 && ga_stride % 4 == 0 &&
+                  (((uintptr_t)d_a | (uintptr_t)d_weight | (uintptr_t)d_grad_a | (uintptr_t)d_grad_weight) & 15) == 0;
+  if (!ok) return PG_ERR_INVALID;
+  const size_t smem = (2 * 64 * (size_t)kHeadWS + 2 * 64 * (size_t)kHeadGS + 64 * (size_t)kHeadAS) * sizeof(uint32_t);
+  PG_CUDA(cudaFuncSetAttribute(linear_ce_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)((n + 16 * kHeadWarpsM - 1) / (16 * kHeadWarpsM));
+  linear_ce_mma_kernel<<<grid, kHeadWarpsM * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
+                                                             1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight,
+                                                             d_grad_bias);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+}  // namespace pg
 
 extern "C" {
 
@@ -478,10 +764,9 @@ pg_status pg_linear_concat_fwd(const float* d_x, int64_t x_stride, const float* 
   };
   const char* env_v = getenv("PG_FWD_VARIANT");
   switch (env_v ? atoi(env_v) : 0) {
+    // measured at config 2 (tools/micro_dense.py, us): <2,1,5,8> 45.5, <2,2,3,8> 41.4, <1,2,4,12> 53.7, <1,4,2,12> 61.9,
+    // <1,2,3,16> 41.4; cuBLAS fp32 SIMT sgemm + bias 51.7
     case 1: return launch(linear_concat_fwd_kernel<2, 1, 5, 8>, 8, 32);
-    case 2: return launch(linear_concat_fwd_kernel<2, 2, 3, 8>, 8, 32);
-    case 3: return launch(linear_concat_fwd_kernel<1, 2, 4, 12>, 12, 16);
-    case 4: return launch(linear_concat_fwd_kernel<1, 4, 2, 12>, 12, 16);
     case 5: return launch(linear_concat_fwd_kernel<1, 2, 3, 16>, 16, 16);
     default: return launch(linear_concat_fwd_kernel<2, 2, 3, 8>, 8, 32);
   }

@@ -2,7 +2,7 @@
 """Micro-benchmark of the dense-stage kernels at bench.py scale (config 2: n_1 = 36 864 padded rows, F = 600, hidden 32,
 6000 seeds, 60 classes) on synthetic inputs — no graph, no cache: seconds to set up, so it is also the cheap target for
 `ncu --set full`. Inputs rotate over buffers larger than L2. CUDA events, median.
-    python tools/micro_dense.py [--iters 30] [--fwd-variants 1,2,3,4,5] [--only fwd|bwd|head]
+    python tools/micro_dense.py [--iters 30] [--fwd-variants 0,1,5] [--only fwd|bwd|head]
 """
 import argparse
 import json
@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--n", type=int, default=36864)
     ap.add_argument("--F", type=int, default=600)
-    ap.add_argument("--fwd-variants", default="1,2,3,4,5")
+    ap.add_argument("--fwd-variants", default="0,1,5")
     ap.add_argument("--only", default="")
     ap.add_argument("--p", type=float, default=0.2)
     a = ap.parse_args()
