@@ -433,6 +433,173 @@ __global__ void __launch_bounds__(kWarps * 32) __maxnreg__(kMaxReg)
   }
 }
 
+// ------------------------------------------------------------------------------------------------------ dW, one warp per column block
+// Same product as linear_concat_dw_kernel, restructured after its ncu profile (tensor pipe 28 % busy: 2.5 warps per
+// scheduler do not hide the MMA issue latency, the 10 column warps split 3/3/2/2 over the 4 schedulers, every warp
+// stalls on the gz operand loads and then on the per-tile barrier):
+//   * one warp per 32-column block of x / dW: 19 warps at in_dim = 600 (5/5/5/4 per scheduler), 96 registers;
+//   * gz for a whole super-tile of 256 rows (the CTA's share at config 2) is built ONCE, by all warps together, into
+//     shared memory (hi / lo planes, 80 KB) while the first x stages are already in flight; after that barrier the warps
+//     run their k-steps without synchronising.
+constexpr int kDw2Super = 256;        // rows per gz super-tile (32 k-steps)
+constexpr int kDw2MaxWarps = 19;      // in_dim <= 608
+constexpr int kDw2Batch = 5;          // gz elements a thread loads together in the prologue
+
+__global__ void __maxnreg__(96)       // 19 warps x 32 x 96 registers = 57 k of the SM's 64 k, <= 5 warps per scheduler
+    linear_concat_dw2_kernel(const float* __restrict__ x, int64_t x_stride, const float* __restrict__ gout, int64_t g_stride,
+                             const float* __restrict__ y, int64_t y_stride, int64_t n, int K, int concat, DropArgs drop,
+                             float* dW, float* db) {
+  extern __shared__ __align__(16) uint32_t gzs[];     // [2 planes][kDw2Super][kGzStride]
+  uint32_t* gz_hi = gzs;
+  uint32_t* gz_lo = gzs + kDw2Super * kGzStride;
+  __shared__ float db_part[kDw2MaxWarps][kOut];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
+  rows_per_cta = (rows_per_cta + 7) / 8 * 8;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(n, r_begin + rows_per_cta);
+  if (r_begin >= r_end) return;
+  const int nsuper = (int)((r_end - r_begin + kDw2Super - 1) / kDw2Super);
+  const int nstages = (int)((r_end - r_begin + 7) / 8);   // k-steps of the whole CTA
+  // ---- gz prologue state: this thread stages gz[rows warp + nwarps q][o = lane]
+  const int o = lane;
+  const uint64_t stepkey = drop.thr ? pg::drop_stepkey(drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull)) : 0ull;
+  const uint64_t ck_a = drop.thr ? pg::drop_colkey((uint32_t)(o >> 2)) : 0ull;
+  const uint64_t ck_b = drop.thr ? pg::drop_colkey((uint32_t)(8 + (o >> 2))) : 0ull;
+  float dbv = 0.f;
+  auto build_gz = [&](int64_t s0) {                    // rows [s0, s0 + kDw2Super) of the CTA's range
+#pragma unroll 1
+    for (int rr0 = warp; rr0 < kDw2Super; rr0 += nwarps * kDw2Batch) {
+      float ra[kDw2Batch], rb[kDw2Batch], ry[kDw2Batch];
+#pragma unroll
+      for (int q = 0; q < kDw2Batch; ++q) {            // the batch's loads are in flight before the first use
+        const int rr = rr0 + q * nwarps;
+        const int64_t r = s0 + rr;
+        ra[q] = rb[q] = ry[q] = 0.f;
+        if (rr < kDw2Super && r < r_end) {
+          const float* grow = gout + r * g_stride;
+          const float* yrow = y + r * y_stride;
+          ra[q] = __ldg(grow + o);
+          if (concat) {
+            rb[q] = __ldg(grow + kOut + o);
+            ry[q] = __ldg(yrow + kOut + o);
+          } else {
+            ry[q] = __ldg(yrow + o);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kDw2Batch; ++q) {
+        const int rr = rr0 + q * nwarps;
+        if (rr >= kDw2Super) continue;
+        const int64_t r = s0 + rr;
+        const uint64_t rk = drop.thr ? pg::drop_rowkey(stepkey, (uint64_t)r) : 0ull;
+        float v;
+        if (concat) {
+          float ga = ra[q], gb = ry[q] > 0.f ? rb[q] : 0.f;
+          if (drop.thr) {
+            ga *= drop_factor(drop, rk, ck_a, o);
+            gb *= drop_factor(drop, rk, ck_b, o);
+          }
+          v = ga + gb;
+        } else {
+          v = ry[q] > 0.f ? ra[q] : 0.f;
+          if (drop.thr) v *= drop_factor(drop, rk, ck_a, o);
+        }
+        uint32_t hi, lo;
+        split_tf32(v, hi, lo);
+        gz_hi[rr * kGzStride + (o & 7) * 4 + (o >> 3)] = hi;
+        gz_lo[rr * kGzStride + (o & 7) * 4 + (o >> 3)] = lo;
+        dbv += v;
+      }
+    }
+  };
+  // ---- x: columns [32 warp, 32 warp + 32); 3 k-steps (8 rows each) in flight in registers
+  const int col0 = warp * 32 + 4 * g;
+  const bool cok = col0 < K;
+  float4 xb[3][2];  // [ring slot][row slot]: rows t, t + 4 of the k-step
+  auto load_x = [&](float4(&b)[2], int stage) {
+    const int64_t rs = r_begin + (int64_t)stage * 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t r = rs + t + 4 * i;
+      b[i] = (stage < nstages && cok && r < r_end) ? ld_stream4(x + r * x_stride + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float acc[2][4][4];  // [m-tile][n-tile j][c0..c3]
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+  auto compute = [&](const float4(&b)[2], int rr) {      // k-step at rows [rr, rr + 8) of the super-tile
+    const uint4 h0 = *(const uint4*)(gz_hi + (rr + t) * kGzStride + g * 4), h1 = *(const uint4*)(gz_hi + (rr + t + 4) * kGzStride + g * 4);
+    const uint4 l0 = *(const uint4*)(gz_lo + (rr + t) * kGzStride + g * 4), l1 = *(const uint4*)(gz_lo + (rr + t + 4) * kGzStride + g * 4);
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      split_tf32(comp(b[0], j), bh[j][0], bl[j][0]);
+      split_tf32(comp(b[1], j), bh[j][1], bl[j][1]);
+    }
+#pragma unroll
+    for (int term = 0; term < 3; ++term)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4& a0 = term == 0 ? l0 : h0;
+        const uint4& a1 = term == 0 ? l1 : h1;
+        const uint32_t b0 = term == 1 ? bl[j][0] : bh[j][0], b1 = term == 1 ? bl[j][1] : bh[j][1];
+        mma_tf32(acc[0][j], a0.x, a0.y, a1.x, a1.y, b0, b1);
+        mma_tf32(acc[1][j], a0.z, a0.w, a1.z, a1.w, b0, b1);
+      }
+  };
+#pragma unroll
+  for (int d = 0; d < 3; ++d) load_x(xb[d], d);
+  int stage = 0;                                          // next k-step to compute (its x is in ring slot stage % 3)
+  for (int sp = 0; sp < nsuper; ++sp) {
+    if (sp) __syncthreads();                              // every warp is done reading the previous super-tile's gz
+    build_gz(r_begin + (int64_t)sp * kDw2Super);
+    __syncthreads();
+    const int ks_end = min(nstages, (sp + 1) * (kDw2Super / 8));
+    // the ring has 3 slots and a super-tile 32 k-steps: unroll by 3 with the slot = position in the unrolled body; the
+    // global k-step index stays aligned with the ring because every super-tile but the last has 32 = 3 * 10 + 2 k-steps,
+    // handled by rotating the starting slot
+    while (stage < ks_end) {
+      const int slot = stage % 3;
+      const int rr = (stage - sp * (kDw2Super / 8)) * 8;
+      if (slot == 0) {
+        compute(xb[0], rr);
+        load_x(xb[0], stage + 3);
+      } else if (slot == 1) {
+        compute(xb[1], rr);
+        load_x(xb[1], stage + 3);
+      } else {
+        compute(xb[2], rr);
+        load_x(xb[2], stage + 3);
+      }
+      ++stage;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int oc = 16 * m + g + 8 * (q >> 1);
+      const int col = warp * 32 + 4 * (2 * t + (q & 1));
+      if (col < K)
+        atomicAdd((float4*)&dW[(size_t)oc * K + col], make_float4(acc[m][0][q], acc[m][1][q], acc[m][2][q], acc[m][3][q]));
+    }
+  if (db) {
+    db_part[warp][lane] = dbv;
+    __syncthreads();
+    if (warp == 0) {
+      float sum = 0.f;
+      for (int w2 = 0; w2 < nwarps; ++w2) sum += db_part[w2][lane];
+      atomicAdd(&db[lane], sum);
+    }
+  }
+}
+
 // ====================================================================================================== classifier head + loss
 // pred = a W^T + b, loss = mean_r(logsumexp(pred_r) - pred_r[label_r]) and all three gradients (reference: the last
 // NodeUpdate, gcn_nssc.py:48, + CrossEntropyLoss, pa_gcn.py:62,93-94) as three chained tensor-core products per CTA of
@@ -801,6 +968,16 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
     PG_CHECK_LAUNCH();
     return PG_OK;
   };
+  const char* env_d = getenv("PG_DW_VARIANT");   // 1 = the 10-warp kernel with per-tile barriers
+  if (in_dim <= 32 * kDw2MaxWarps && !(env_d && atoi(env_d) == 1)) {
+    const int warps = (in_dim + 31) / 32;
+    const size_t smem = 2 * (size_t)kDw2Super * kGzStride * sizeof(uint32_t);
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linear_concat_dw2_kernel<<<grid, warps * 32, smem, st>>>(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim,
+                                                             concat, drop, d_grad_weight, d_grad_bias);
+    PG_CHECK_LAUNCH();
+    return PG_OK;
+  }
   if (in_dim <= 256) return launch(linear_concat_dw_kernel<4, 255>, 4);
   if (in_dim <= 640) return launch(linear_concat_dw_kernel<10, 168>, 10);
   return launch(linear_concat_dw_kernel<kDwMaxWarps, 168>, kDwMaxWarps);
