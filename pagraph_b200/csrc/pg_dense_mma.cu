@@ -533,15 +533,18 @@ __global__ void __maxnreg__(96)       // 19 warps x 32 x 96 registers = 57 k of 
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
-  auto compute = [&](const float4(&b)[2], int rr) {      // k-step at rows [rr, rr + 8) of the super-tile
-    const uint4 h0 = *(const uint4*)(gz_hi + (rr + t) * kGzStride + g * 4), h1 = *(const uint4*)(gz_hi + (rr + t + 4) * kGzStride + g * 4);
-    const uint4 l0 = *(const uint4*)(gz_lo + (rr + t) * kGzStride + g * 4), l1 = *(const uint4*)(gz_lo + (rr + t + 4) * kGzStride + g * 4);
+  // k-step at rows [rr, rr + 8) of the super-tile from ring slot b; the slot is refilled with k-step `next` as soon as
+  // its values have been split into the B fragments, i.e. before the MMAs: three full k-steps of lead time for the load
+  auto compute = [&](float4(&b)[2], int rr, int next) {
     uint32_t bh[4][2], bl[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       split_tf32(comp(b[0], j), bh[j][0], bl[j][0]);
       split_tf32(comp(b[1], j), bh[j][1], bl[j][1]);
     }
+    load_x(b, next);
+    const uint4 h0 = *(const uint4*)(gz_hi + (rr + t) * kGzStride + g * 4), h1 = *(const uint4*)(gz_hi + (rr + t + 4) * kGzStride + g * 4);
+    const uint4 l0 = *(const uint4*)(gz_lo + (rr + t) * kGzStride + g * 4), l1 = *(const uint4*)(gz_lo + (rr + t + 4) * kGzStride + g * 4);
 #pragma unroll
     for (int term = 0; term < 3; ++term)
 #pragma unroll
@@ -567,16 +570,9 @@ __global__ void __maxnreg__(96)       // 19 warps x 32 x 96 registers = 57 k of 
     while (stage < ks_end) {
       const int slot = stage % 3;
       const int rr = (stage - sp * (kDw2Super / 8)) * 8;
-      if (slot == 0) {
-        compute(xb[0], rr);
-        load_x(xb[0], stage + 3);
-      } else if (slot == 1) {
-        compute(xb[1], rr);
-        load_x(xb[1], stage + 3);
-      } else {
-        compute(xb[2], rr);
-        load_x(xb[2], stage + 3);
-      }
+      if (slot == 0) compute(xb[0], rr, stage + 3);
+      else if (slot == 1) compute(xb[1], rr, stage + 3);
+      else compute(xb[2], rr, stage + 3);
       ++stage;
     }
   }
