@@ -285,6 +285,13 @@ pg_status pg_timing_drain(int32_t* slots, float* ms, int64_t cap, int64_t* n_out
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t pg_launch_count(void);
 
+/* The dropout mask contract of pg_cache_aggregate / pg_aggregate_rows / pg_linear_concat_fwd / _bwd, evaluated on the host
+ * (no GPU work): keep_out[j * dim + c] = 1 iff element (row j, column c) is kept for dropout probability p under
+ * seed_plus_step = dropout_seed + *d_step. Element (j, c) is decided by the (c % 4)-th 16-bit lane of
+ * mix(rowkey ^ colkey), rowkey = splitmix64(splitmix64(seed_plus_step) + j), colkey = splitmix64(0xD1B54A32D192ED03 + c / 4),
+ * mix(x) = (x * 0x9E3779B97F4A7C15) ^ ((x * 0x9E3779B97F4A7C15) >> 32); dropped when the lane < round(p * 65536). */
+pg_status pg_dropout_keep_mask(uint64_t seed_plus_step, int64_t n_rows, int32_t dim, float p, unsigned char* keep_out);
+
 #ifdef __cplusplus
 }
 #endif

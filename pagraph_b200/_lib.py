@@ -106,6 +106,7 @@ SIGNATURES = {
     "pg_timing_drain": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float),
                                        ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
     "pg_launch_count": (ctypes.c_int64, []),
+    "pg_dropout_keep_mask": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, c_vp]),
 }
 
 _LIB = None

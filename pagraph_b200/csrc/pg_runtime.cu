@@ -110,6 +110,22 @@ const char* pg_last_error(void) { return pg::g_err; }
 
 int64_t pg_launch_count(void) { return pg::g_launches.load(); }
 
+// Host evaluation of the dropout mask contract (pg_common.cuh drop_hash, the function the kernels inline): lets the CPU
+// test-suite pin kernels and oracle to the same mask without a GPU.
+pg_status pg_dropout_keep_mask(uint64_t seed_plus_step, int64_t n_rows, int32_t dim, float p, unsigned char* keep_out) {
+  PG_REQUIRE(keep_out && n_rows >= 0 && dim >= 1 && p >= 0.f && p < 1.f, "pg_dropout_keep_mask: bad arguments");
+  const uint32_t thr = p > 0.f ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
+  const uint64_t stepkey = pg::drop_stepkey(seed_plus_step);
+  for (int64_t j = 0; j < n_rows; ++j) {
+    const uint64_t rk = pg::drop_rowkey(stepkey, (uint64_t)j);
+    for (int32_t c = 0; c < dim; ++c) {
+      const uint64_t h = pg::drop_mix(rk, pg::drop_colkey((uint32_t)(c >> 2)));
+      keep_out[j * dim + c] = ((uint32_t)(h >> (16 * (c & 3))) & 0xffffu) >= thr;
+    }
+  }
+  return PG_OK;
+}
+
 pg_status pg_device_info(int dev, int* sm, size_t* total_mem, size_t* free_mem) {
   pg::DeviceGuard guard(dev);
   if (sm) *sm = pg::sm_count(dev);

@@ -231,3 +231,47 @@ def test_aggregate_zero_degree_rows_are_zero():
     x = np.ones((2, 4), np.float32) * 3
     out = oracle.aggregate(indptr, cols, 10, x, "mean")
     np.testing.assert_array_equal(out, [[0] * 4, [3] * 4, [0] * 4])
+
+
+@pytest.mark.parametrize("seed,n,dim,p", [(0, 7, 600, 0.2), (0xDEADBEEF12345, 300, 602, 0.5), (2 ** 64 - 3, 50, 64, 0.2),
+                                          (41, 33, 13, 0.9), (5, 10, 32, 0.0)])
+def test_dropout_mask_contract_library_vs_oracle(seed, n, dim, p):
+    """The kernels' mask function (pg_common.cuh drop_hash, evaluated on the host by pg_dropout_keep_mask: no GPU work)
+    and the oracle's numpy restatement are the same function."""
+    import ctypes
+    from pagraph_b200 import _lib
+    out = np.zeros((n, dim), dtype=np.uint8)
+    _lib.check(_lib.lib().pg_dropout_keep_mask(seed, n, dim, p, out.ctypes.data_as(ctypes.c_void_p)), "pg_dropout_keep_mask")
+    want = oracle.dropout_keep_mask(seed, n, dim, p)
+    assert np.array_equal(out.astype(bool), want)
+    if p == 0.0:
+        assert out.all()
+
+
+def test_dropout_mask_statistics():
+    """Bernoulli(1 - p) marginals per 16-bit lane, no correlation between neighbouring columns / rows / steps, and the
+    step is hashed into the key (consecutive steps do not shift the mask)."""
+    keep = oracle.dropout_keep_mask(12345, 4000, 600, 0.2)
+    assert abs(keep.mean() - 0.8) < 2e-3
+    for lane in range(4):
+        assert abs(keep[:, lane::4].mean() - 0.8) < 4e-3
+    x = keep.astype(np.float64) - keep.mean()
+    var = x.var()
+    assert abs((x[:, :-1] * x[:, 1:]).mean() / var) < 5e-3
+    assert abs((x[:, :-4] * x[:, 4:]).mean() / var) < 5e-3
+    assert abs((x[:-1] * x[1:]).mean() / var) < 5e-3
+    nxt = oracle.dropout_keep_mask(12346, 4000, 600, 0.2).astype(np.float64) - 0.8
+    for a, b in ((x, nxt), (x[:, 4:], nxt[:, :-4]), (x[1:], nxt[:-1]), (x[:, :-4], nxt[:, 4:])):
+        assert abs((a * b).mean() / var) < 5e-3
+    # a golden word pins the constants (computed with Python integers)
+    M = 2 ** 64 - 1
+
+    def sm(v):
+        v = (v + 0x9E3779B97F4A7C15) & M
+        v = ((v ^ (v >> 30)) * 0xBF58476D1CE4E5B9) & M
+        v = ((v ^ (v >> 27)) * 0x94D049BB133111EB) & M
+        return v ^ (v >> 31)
+    seed, j, c = 12345, 17, 42
+    h = ((sm((sm(seed) + j) & M) ^ sm(0xD1B54A32D192ED03 + c // 4)) * 0x9E3779B97F4A7C15) & M
+    h ^= h >> 32
+    assert bool(keep[j, c]) == (((h >> (16 * (c % 4))) & 0xFFFF) >= int(np.float32(0.2) * np.float32(65536.0) + np.float32(0.5)))
