@@ -1,4 +1,4 @@
-"""GCNTrainEngine — the training loop of examples/profile/pa_gcn.py:86-97 as a two-stream, CUDA-graph pipeline.
+"""GCNTrainEngine — the training loop of examples/profile/pa_gcn.py:86-97 as a three-stream, CUDA-graph pipeline.
 
 The reference loop is `for nf in sampler: cacher.fetch_data(nf); label = ...; pred = model(nf); loss; backward;
 step`. Issued op by op it is launch-bound on a B200 (≈ 40 kernels, ≈ 0.65 ms of GPU work per minibatch at config 2).
@@ -9,9 +9,13 @@ Here the same work is three captured graphs per minibatch, replayed on three str
                                             the input layer + PCIe staging of its missed rows) -> pg_aggregate_rows (fused
                                             cache lookup + dropout + block-0 aggregation; it has no trainable input, so it
                                             need not wait for the previous optimizer step): the HBM / PCIe-bound part
-  compute graph (main stream, per slot x bucket)  NodeUpdate linear (cuBLAS) + cat/relu -> dropout -> pg_aggregate_fwd_dyn
-                                            -> head + loss (pg_linear_cross_entropy) -> backward (pg_aggregate_bwd_dyn,
-                                            pg_linear_concat_bwd) -> gradient all-reduce -> Adam
+  compute graph (main stream, per slot x bucket)  first NodeUpdate + dropout (pg_linear_concat_fwd, tensor cores) ->
+                                            pg_aggregate_fwd_dyn -> head + loss forward/backward (pg_linear_cross_entropy)
+                                            -> pg_aggregate_bwd_dyn -> dW / db (pg_linear_concat_bwd) -> gradient
+                                            all-reduce + Adam (pg_allreduce_adam): six kernels writing the gradients
+                                            straight into the flat bucket when the model is the standard 2-block GCN
+                                            with n_hidden = 32 (_compute_body_fused); any other shape runs the same
+                                            stage through torch autograd over the ops of pagraph_b200.ops
 
 While minibatch k trains, minibatch k+1 is gathered and aggregated and minibatch k+2 is sampled.
 Nothing about a minibatch's size is needed on the host to launch it: every kernel reads the NodeFlow extents from

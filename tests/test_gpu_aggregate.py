@@ -149,6 +149,29 @@ def test_linear_concat_matches_torch(n, K, concat):
     torch.testing.assert_close(gb.double(), b64.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("n,K", [(40000, 600), (80003, 64)])
+def test_linear_concat_large_row_counts(n, K):
+    """More rows than one pass of the persistent kernels covers: the forward loops over row tiles (n > 148 x 256), the dW
+    kernel walks several 256-row gz super-tiles per CTA with its x register ring running across them. Norm-wise
+    tolerance: the tensor-core accumulators truncate, so the error grows with the number of MMAs per accumulator."""
+    import torch
+    from pagraph_b200.ops import LinearConcat
+    torch.manual_seed(7)
+    x = torch.randn(n, K, device="cuda")
+    lin = torch.nn.Linear(K, 32).cuda()
+    gout = torch.randn(n, 64, device="cuda")
+    out = LinearConcat.apply(x, lin.weight, lin.bias, True)
+    out.backward(gout)
+    z = torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double())
+    ref = torch.cat((z, torch.relu(z)), 1)
+    assert (out.double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    pos = out[:, 32:] > 0
+    gz = gout[:, :32].double() + gout[:, 32:].double() * pos
+    gw_ref, gb_ref = gz.t() @ x.double(), gz.sum(0)
+    assert (lin.weight.grad.double() - gw_ref).abs().max().item() < 3e-5 * gw_ref.abs().max().item()
+    assert (lin.bias.grad.double() - gb_ref).abs().max().item() < 1e-5 * max(gb_ref.abs().max().item(), n ** 0.5)
+
+
 @pytest.mark.parametrize("n,K,p", [(1000, 600, 0.2), (77, 64, 0.5), (4100, 600, 0.2)])
 @pytest.mark.parametrize("concat", [True, False])
 def test_linear_concat_fused_dropout(n, K, p, concat):
