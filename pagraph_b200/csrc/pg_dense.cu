@@ -1,16 +1,16 @@
-// pg_dense.cu — backward of the first NodeUpdate of the GCN / GraphSAGE models, fused around its tall-skinny GEMM.
+// pg_dense.cu — the fp32-pipe (SIMT) kernels of the dense stage: the baselines / fallbacks of pg_dense_mma.cu.
 //
 // Reference: PaGraph/model/gcn_nssc.py:14-24 (NodeUpdate.forward with concat=True):
 //     h = Linear(h);  h = cat(h, relu(h))
 // applied to the aggregated input block x [n_1, F] (F = 600, n_1 ~ 35 k, out = 32). x needs no gradient (it is an
 // aggregate of constant input features), so the backward is only dW = gz^T x and db = sum gz, with
-// gz = g[:, :32] + g[:, 32:] * (z > 0). In fp32 that is a memory-bound product (85 MB of activations, K = n_1): cuBLAS
-// takes 152 us for the split-K GEMM plus four more kernels (relu', slice-add, bias-grad reduction, split-K reduce).
-// linear_concat_bwd makes one pass over x: tiles of x arrive in shared memory by TMA bulk copies (double-buffered),
-// relu' and the concat split are folded into a per-tile gz, every CTA accumulates a [32, F] partial of dW (and db) in
-// registers and adds it to the result with float atomics.
-// The forward stays on cuBLAS (a plain library GEMM, 42 us); fp32 SIMT here on purpose: TF32 tensor cores would drop
-// below the reference's precision and the op is HBM-bound anyway.
+// gz = g[:, :32] + g[:, 32:] * (z > 0). cuBLAS takes 152 us for the split-K GEMM plus four more kernels (relu',
+// slice-add, bias-grad reduction, split-K reduce). linear_concat_bwd_kernel makes one pass over x: tiles of x arrive in
+// shared memory by TMA bulk copies (double-buffered), relu' and the concat split are folded into a per-tile gz, every CTA
+// accumulates a [32, F] partial of dW (and db) in registers (packed FFMA2) and adds it to the result with float atomics:
+// 81-86 us, FMA-bound. The product path is now the 3xTF32 tensor-core kernel of pg_dense_mma.cu (51 us); this one is kept
+// for A/B measurements (PG_DENSE_SIMT=1, tools/micro_dense.py). The scalar head + loss kernel below is what
+// pg_linear_cross_entropy falls back to when the layout rules out 16-byte accesses (in_dim % 4 != 0).
 #include <algorithm>
 #include <cstdlib>
 

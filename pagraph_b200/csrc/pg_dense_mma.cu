@@ -7,20 +7,26 @@
 // GEMMs (1.36 GFLOP over 85 MB of x): on the fp32 pipe they are FMA-bound (cuBLAS SIMT sgemm 42 us forward; 81 us for
 // dW with packed FFMA2), 3-6x over the 13 us it takes to stream x from HBM. Here they run as error-compensated TF32
 // ("3xTF32": a = a_hi + a_lo, b = b_hi + b_lo, a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate), which keeps
-// fp32-level accuracy (the dropped term is 2^-22 relative), so the result stays within the reference's own fp32 noise.
+// fp32-level accuracy (the dropped term is 2^-22 relative).
 //
-// Shapes are far from the 128 x N tiles tcgen05 wants (N = 32 outputs, and both kernels are bound by the HBM stream of
-// x once the math is off the fp32 pipe), so the MMAs are warp-level mma.sync.m16n8k8 with operands loaded straight
-// from global memory into fragment registers:
+// Shapes are far from the 128 x N tiles tcgen05 wants (N = 32 outputs) and the hi / lo split has to pass through
+// registers, so in this round the MMAs are warp-level mma.sync.m16n8k8 with operands loaded straight from global memory
+// into fragment registers (ncu: ~8 cycles of tensor pipe per HMMA.1688.F32.TF32 and scheduler, i.e. a ~17 us floor for
+// the 2.07 M HMMAs of one product, against a 13.5 us HBM stream; DESIGN.md lists the tcgen05 version as round-2 work):
 //   * the k index of a product is a dummy index, so its order is free: a lane fetches 4 consecutive floats (one 16-byte
 //     load) and feeds them to two k-steps; both operands use the same permutation. Same trick on the n index of dW
-//     (a column permutation of the output, undone when the accumulators are written).
+//     (a column permutation of the output, undone when the accumulators are written) and on the class index of the head.
 //   * forward: W is split once per CTA into hi / lo TF32 planes in shared memory (2 x 78 KB, conflict-free stride); each
-//     warp owns 32 rows of x, keeps 3 chunks of 16 columns in flight in registers, epilogue fuses bias, relu, the
-//     skip-concat and (optionally) the dropout mask of the next block.
+//     warp owns 32 rows of x, keeps 3 load groups of 2 x 16 columns in flight in registers, epilogue fuses bias, relu,
+//     the skip-concat and (optionally) the dropout mask of the next block.
 //   * backward: dW = gz^T x with gz = g[:, :32] + g[:, 32:] * (z > 0) (g first multiplied by the dropout mask, which is
-//     regenerated from the hash, not stored). One persistent CTA per SM walks a contiguous range of rows; gz tiles are
-//     staged (split hi / lo) in shared memory, each warp owns 64 columns of x / dW, partials go out as float atomics.
+//     regenerated from the hash, not stored). One persistent CTA per SM walks a contiguous range of rows; gz is built
+//     (split hi / lo) in shared memory once per 256 rows by the whole CTA, each warp owns 32 columns of x / dW, partials
+//     go out as 16-byte vector atomics (linear_concat_dw2_kernel; linear_concat_dw_kernel is its wider-tile predecessor,
+//     still used for in_dim > 608).
+//   * head: logits, softmax / loss, grad_a and dW of the classifier as three chained products (linear_ce_mma_kernel).
+// Accuracy: the tensor-core accumulators truncate, so the error grows with the number of MMAs per accumulator; measured
+// <= 1.5e-5 absolute on O(1) forward outputs and <= 3e-5 of the largest entry of dW at 80 k rows (tests/test_gpu_aggregate.py).
 #include <algorithm>
 #include <cstdlib>
 
