@@ -202,3 +202,30 @@ def test_entry_scripts_end_to_end(tmp_path):
     finally:
         if server.poll() is None:
             server.kill()
+
+
+def test_graphsage_entry_script_end_to_end(tmp_path):
+    """hash partition -> pa_server.py --model graphsage -> pa_gs.py (1 GPU, 2 epochs), the reference's GraphSAGE entry
+    (examples/profile/pa_gs.py) on the drop-in classes."""
+    from pagraph_b200 import data
+    ds = str(tmp_path / "tiny_gs")
+    V = 3000
+    adj = data.rmat_adj(V, 30000, seed=2)
+    data.write_dataset(ds, adj, data.random_feature(V, 600), data.random_label(V, 60), data.split_dataset(V))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, "-m", "pagraph_b200.partition.hash", "--dataset", ds, "--partition", "1", "--num-hops", "2",
+                    "--seed", "0"], check=True, env=env, cwd=ROOT, timeout=300)
+    server = subprocess.Popen([sys.executable, os.path.join(ROOT, "server", "pa_server.py"), "--dataset", ds, "--num-workers", "1",
+                               "--model", "graphsage"], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True)
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "profile", "pa_gs.py"), "--dataset", ds, "--gpu", "0",
+                              "--n-epochs", "2", "--batch-size", "500", "--num-neighbors", "5,3"],
+                             env=dict(env, MASTER_PORT="29535"), cwd=ROOT, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert "Total Time" in out.stdout and "Epoch average time" in out.stdout
+        server.wait(timeout=60)
+        assert server.returncode == 0
+    finally:
+        if server.poll() is None:
+            server.kill()
