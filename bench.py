@@ -62,6 +62,7 @@ def parse_args():
     p.add_argument("--gather-batches", type=int, default=50, help="minibatches of the gather-only measurement")
     p.add_argument("--cpu-batches", type=int, default=32, help="minibatches of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-parity-gate", action="store_true", help="skip the oracle check of one minibatch before timing")
     p.add_argument("--seed", type=int, default=1)
     return p.parse_args()
 
@@ -196,7 +197,9 @@ class Workload:
         self.R = 4 * (Fdim + 1)
 
     def host_graph(self):
-        return self.indptr.cpu().numpy(), self.indices.cpu().numpy()
+        if getattr(self, "_host_graph", None) is None:
+            self._host_graph = (self.indptr.cpu().numpy(), self.indices.cpu().numpy())
+        return self._host_graph
 
     def close(self):
         if self.world > 1:
@@ -444,6 +447,22 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
     res = {}
     for host_inputs in (False, True):
         tr = Trainer(wl, mode, host_inputs)
+        gate = None
+        if not host_inputs and not args.no_parity_gate:
+            # rank 0 checks one minibatch of ITS partition against the oracle; every rank learns the outcome
+            err = ""
+            if wl.rank == 0:
+                try:
+                    gate = parity_gate(wl, tr)
+                except SystemExit as ex:
+                    err = str(ex)
+            if world > 1:
+                flag = torch.tensor([1 if err else 0], device=wl.dev)
+                dist.all_reduce(flag)
+                if flag.item() and not err:
+                    err = "parity gate failed on rank 0"
+            if err:
+                raise SystemExit(err)
         tr.run(args.warmup, record=False, read_loss=host_inputs)
         clock = None
         if wl.rank == 0:
@@ -456,6 +475,9 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
         reg = timed_region(tr, args.steps, host_inputs, clock, world)
         if prof:
             torch.cuda.profiler.stop()
+        replicas = replica_check(tr, world)
+        if not replicas:
+            raise SystemExit("replica check: ranks hold different parameters after %d steps" % args.steps)
         if clock is not None and clock.ok:
             clock.stop()
         if tr.engine is not None:
@@ -483,15 +505,17 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
         steps = args.steps
         mbps = world * steps / (reg["ms"] * 1e-3)
         r = dict(minibatches_per_s=mbps, ms_per_step=reg["ms"] / steps, wall_ms_per_step=reg["wall_ms"] / steps,
-                 rows_per_step=N / steps, miss_rows_per_step=M / steps, hit_rate=1.0 - M / max(N, 1),
+                 rows_per_step=N / steps, miss_rows_per_step=M / steps,
+                 hit_rate=(1.0 - reg["misses"] / reg["tries"]) if reg["tries"] else 1.0,   # over the rows the step looked up
                  fetch_ms_per_step=reg["fetch_ms"] / steps, gather=gather,
                  launches=reg["launches"], loss=reg["loss"], clocks=reg["clocks"], kernels=kern,
-                 full_cached=tr.cacher.full_cached, cached_rows=tr.cacher.cached_num,
+                 full_cached=tr.cacher.full_cached, cached_rows=tr.cacher.cached_num, parity_gate=gate,
+                 replicas_identical=replicas,
                  layer_sizes=[int(np.mean([lo[i + 1] - lo[i] for lo, _ in tr.sizes])) for i in range(3)],
                  block_edges=[int(np.mean([bo[i + 1] - bo[i] for _, bo in tr.sizes])) for i in range(2)])
         if host_inputs:
             b = args.batch_size * ID_BYTES
-            r["h2d_bytes_per_step"] = int(2 * b + wl.R * M / steps)     # seeds + labels + missed rows over PCIe
+            r["h2d_bytes_per_step"] = int(2 * b + 4 * args.feat_size * M / steps)   # seeds + labels + missed input rows over PCIe
             r["d2h_bytes_per_step"] = int(4 + 8 * 23)                   # loss + NodeFlow meta block
         res["e2e" if host_inputs else "value"] = r
         del tr
@@ -606,9 +630,126 @@ def host_threads():
 
 
 def workload_name(args):
-    return ("PaRMAT-style R-MAT %d vtx / %d edges, feat=%d, 2-layer GCN (n_hidden %d, %d classes), fanout %s, "
-            "batch %d, hash partition per GPU" % (args.vnum, args.nnz, args.feat_size, args.n_hidden, args.n_classes,
-                                                  args.fanout.replace(",", "/"), args.batch_size))
+    return ("R-MAT %.3gM vtx/%.3gM edges f%d, GCN-2L h%d c%d, fanout %s, batch %d"
+            % (args.vnum / 1e6, args.nnz / 1e6, args.feat_size, args.n_hidden, args.n_classes,
+               args.fanout.replace(",", "/"), args.batch_size))
+
+
+
+# ------------------------------------------------------------------------------------ parity gate / replica check
+def parity_gate(wl, tr, batch_idx=3):
+    """One minibatch at the benchmarked size through the CUDA path against the CPU oracle, before any timing
+    (reference loop examples/profile/pa_gcn.py:86-97): pg_sample vs oracle.sample bit-exact (ids, CSR, edge ids),
+    the cache fetch of EVERY layer bit-exact against the host feature table, the fused block-0 aggregation within
+    1e-5 relative of the float64 oracle. The oracle is the checker here, never the measured path. Raises on mismatch."""
+    import oracle
+    from pagraph_b200 import ops
+    a = wl.args
+    indptr, indices = wl.host_graph()
+    sm = tr.sampler
+    nf = sm.sample_batch(batch_idx, epoch=0)
+    seeds = sm._seeds_cpu[batch_idx * a.batch_size:(batch_idx + 1) * a.batch_size].numpy()
+    ref = oracle.sample(indptr, indices, None, seeds, wl.fanouts, seed=a.seed, epoch=0, batch=batch_idx)
+    ok = nf._layer_offsets == ref.layer_offsets.tolist()
+    ok = ok and np.array_equal(nf._node_mapping.tousertensor().cpu().numpy(), ref.node_mapping)
+    ok = ok and np.array_equal(nf._indptr.cpu().numpy(), ref.indptr)
+    ok = ok and np.array_equal(nf._indices.cpu().numpy(), ref.indices)
+    ok = ok and np.array_equal(nf._edge_mapping.tousertensor().cpu().numpy(), ref.edge_mapping)
+    if not ok:
+        raise SystemExit("parity gate: sampled NodeFlow differs from the oracle (config size, batch %d)" % batch_idx)
+    c = tr.cacher
+    ids = nf._node_mapping.tousertensor()
+    outs = c._gather(ids, c._field_names)
+    ids_cpu = torch.from_numpy(ref.node_mapping)
+    for name, got in zip(c._field_names, outs):
+        want = wl.store.ndata[name][ids_cpu]
+        if not torch.equal(got.cpu().view(torch.int32), want.view(torch.int32)):
+            raise SystemExit("parity gate: fetched rows of %r differ from the host table" % name)
+    bi, bc, bb, n_dst, n_src = nf.block_csr(0)
+    got = ops.cache_aggregate(c, "features", nf.layer_parent_nid_dev(0), bi, bc, bb, n_src, n_dst, "mean").cpu().numpy()
+    ip, cols, base = ref.block(0)
+    feats0 = wl.store.ndata["features"][torch.from_numpy(ref.layer_parent_nid(0))].numpy()
+    want = oracle.aggregate(ip, cols, base, feats0, "mean", threads=host_threads())
+    err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
+    if not err <= 1e-5:
+        raise SystemExit("parity gate: block-0 aggregate off by %.3g relative (> 1e-5)" % err)
+    return {"status": "ok", "nodes": int(ref.layer_offsets[-1]), "edges": int(len(ref.indices)), "agg_max_rel_err": err}
+
+
+def replica_check(tr, world):
+    """After the timed steps every rank must hold bit-identical parameters (the gradient all-reduce is the only
+    exchange, pa_gcn.py:65,96): all-gather the flat bucket's checksum and first/last words."""
+    flat = tr.sync.flat_param.detach()
+    sig = torch.stack([flat.double().sum(), flat.double().abs().sum(), flat[0].double(), flat[-1].double()])
+    bits = flat.view(torch.int32).to(torch.int64)
+    sig = torch.cat([sig, torch.stack([(bits * (torch.arange(bits.numel(), device=bits.device) % 8191 + 1)).sum().double()])])
+    if world == 1:
+        return True
+    allsig = [torch.empty_like(sig) for _ in range(world)]
+    dist.all_gather(allsig, sig)
+    return all(torch.equal(allsig[0], x) for x in allsig[1:])
+
+
+# ------------------------------------------------------------------------------------ the driver-facing JSON line
+def _r(x, nd=5):
+    """round to nd significant digits (keeps the line short)"""
+    if x is None or isinstance(x, (bool, int, str)):
+        return x
+    x = float(x)
+    if x == 0 or x != x or x in (float("inf"), float("-inf")):
+        return x if x == x and abs(x) != float("inf") else None
+    from math import floor, log10
+    return round(x, nd - 1 - int(floor(log10(abs(x)))))
+
+
+def compact_line(d):
+    """The LAST stdout line: < 1150 bytes (the driver keeps a 1500-byte tail), every string <= 120 chars, one JSON object the driver parses. `d` is the full
+    detail record (written to gpurun_out/bench_detail_n{N}.json); only the contract keys and the headline split go here."""
+    rf, cpu, e, ck = d["roofline"], d.get("cpu_baseline"), d["e2e"], d.get("clocks") or {}
+    line = {
+        "metric": "minibatches/s", "value": _r(d["value"], 6), "unit": "minibatches/s", "n_gpus": d["n_gpus"],
+        "steps": d["steps"], "warmup": d["warmup"], "ms_per_step": _r(d["ms_per_step"]), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": d["config"]["workload"][:120], "cache_mode": d["config"]["cache_mode"],
+                   "path": d["config"]["path"], "l2": "inputs>L2 (24GB table, new batch/step)"},
+        "e2e": {"value": _r(e["value"], 6), "unit": "minibatches/s", "h2d_bytes_per_step": e["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": e["d2h_bytes_per_step"]},
+        "gpu_launches": d["gpu_launches"],
+        "roofline": {"bound": rf["bound"], "kernel": rf["kernel"].split("(")[-1].split(",")[0].rstrip(")")[:40], "achieved": _r(rf["achieved"]), "peak": _r(rf["peak"]),
+                     "unit": "GB/s", "frac": _r(rf["frac"], 4), "traffic": rf.get("traffic"),
+                     "alg_bytes_per_launch": _r(rf["alg_bytes_per_launch"], 6), "avg_ms": _r(rf["avg_ms"], 4)},
+        "cpu_baseline": None if not cpu else {"value": _r(cpu["value"], 4), "unit": "minibatches/s", "cores": cpu["cores"],
+                                              "kind": cpu["kind"], "sample": cpu["sample"][:64]},
+        "clocks": {"sm_mhz": ck.get("sm_mhz"), "sm_max_mhz": ck.get("sm_max_mhz"), "reasons": ck.get("reasons", [])},
+        "gather_gbs": _r(d.get("gather_gbs"), 4), "hit_rate": _r(d.get("hit_rate"), 4),
+        "parity_gate": d.get("parity_gate"), "replicas_identical": d.get("replicas_identical"),
+    }
+    v20 = d.get("vtx20")
+    if v20:
+        line["vtx20"] = {k: _r(v20.get(k), 4) for k in ("value", "e2e", "gather_gbs", "hit_rate", "miss_frac_pcie")}
+    out = json.dumps(line, separators=(",", ":"))
+    # never let the line grow past what the driver keeps: shorten the free-text strings first, then drop the optional tail
+    for shrink in (lambda: line["cpu_baseline"] and line["cpu_baseline"].update(sample=line["cpu_baseline"]["sample"][:48]),
+                   lambda: line["roofline"].update(kernel=line["roofline"]["kernel"][:32]),
+                   lambda: line["config"].update(l2="inputs>L2"),
+                   lambda: line.pop("vtx20", None), lambda: line.pop("gather_gbs", None)):
+        if len(out) < 1150:
+            break
+        shrink()
+        out = json.dumps(line, separators=(",", ":"))
+    return out
+
+
+def write_detail(detail, n):
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        path = os.path.join(ROOT, "gpurun_out", "bench_detail_n%d.json" % n)
+        with open(path, "w") as f:
+            json.dump(detail, f, indent=1)
+        return os.path.relpath(path, ROOT)
+    except Exception as ex:   # read-only checkout: the detail goes to stderr instead
+        print(json.dumps(detail), file=sys.stderr)
+        return "stderr (%s)" % type(ex).__name__
 
 
 # ------------------------------------------------------------------------------------ reference arm
@@ -652,18 +793,19 @@ def main_reference(args):
     cpu_path(args, indptr, indices, tables, seeds, args.warmup, threads, first_batch=0)
     t, stage = cpu_path(args, indptr, indices, tables, seeds, args.steps, threads, first_batch=args.warmup)
     v = args.steps / t
-    line = {"impl": "reference", "metric": "minibatches/sec (sample + cache fetch + GCN train step)", "value": v,
+    line = {"impl": "reference", "metric": "minibatches/s", "value": v,
             "unit": "minibatches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "cache": "none (CPU arm: every row gathered from the host table)"},
+            "config": {"workload": workload_name(args), "cache_mode": "none (CPU arm: every row from the host table)",
+                       "path": "oracle port, 1 process (also at n_gpus > 1)"},
             "cpu_baseline": {"value": v, "unit": "minibatches/s", "cores": threads, "kind": "port",
-                             "sample": "%d full minibatches (sample %d threads over batches; gather+aggregate %d threads)"
+                             "sample": "%d full minibatches; sample %d thr over batches, gather+aggregate %d thr"
                                        % (args.steps, threads, threads),
-                             "stage_s": stage},
+                             "stage_s": {k: round(x, 3) for k, x in stage.items()}},
             "e2e": {"value": v, "unit": "minibatches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line, separators=(",", ":")), flush=True)
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -702,9 +844,7 @@ def main_ours(args):
         torch.set_num_threads(threads)
         t, stage = cpu_path(args, indptr, indices, tables, seeds, args.cpu_batches, threads)
         cpu = {"value": args.cpu_batches / t, "unit": "minibatches/s", "cores": threads, "kind": "port",
-               "sample": "%d full minibatches of the same workload (oracle/: DGL-style sampling, %d threads over batches; "
-                         "host gather of all layers' rows + float64 mean aggregation with %d threads; GCN step on torch-CPU)"
-                         % (args.cpu_batches, threads, threads),
+               "sample": "%d full minibatches, oracle port, %d threads" % (args.cpu_batches, threads),
                "stage_s": {k: round(v, 3) for k, v in stage.items()}}
     wl.close()
     if rank != 0:
@@ -723,22 +863,21 @@ def main_ours(args):
                 traffic = traffic.get("bytes_per_launch")
     except Exception:
         pass
-    line = {
+    detail = {
         "metric": "minibatches/sec (sample + cache fetch + GCN train step) + feature-gather GB/s",
         "value": v["minibatches_per_s"], "unit": "minibatches/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "cache_mode": modes[0], "path": args.path,
                    "cache": "hbm20 = capacity 20% of HBM bytes (>= the 24 GB table -> full_cached, headline); "
-                            "vtx20 = top-20%-out-degree vertices cached (under variants)",
+                            "vtx20 = top-20%-out-degree vertices cached (real hit/miss split)",
                    "dropout": args.dropout, "optimizer": "Adam lr %g" % args.lr,
                    "l2": "inputs larger than L2 (24 GB feature table, new random minibatch every step); no flush",
                    "kernel_timing": ("pg_timing_* CUDA-event pairs on the launching stream; with --path engine the timed region "
                                      "replays CUDA graphs (no host-side launch to bracket), so the per-kernel numbers come from "
                                      "instrumented un-graphed passes of the same pipeline over %d further minibatches each: "
                                      "avg_ms / achieved / roofline = stages serialised, every kernel alone on the GPU (as ncu "
-                                     "sees it); avg_ms_in_pipeline = the three streams overlapped as in the timed region; "
-                                     "all-reduce kernel (NVLink peer memory) + flat-bucket Adam fused"
+                                     "sees it); avg_ms_in_pipeline = the three streams overlapped as in the timed region"
                                      % min(args.kernel_steps, args.steps)) if args.path == "engine" else
                                     "pg_timing_* CUDA-event pairs on the launching stream inside the timed region",
                    "parallelism": "dp%d (one partition per GPU; flat-bucket gradient all-reduce fused with Adam over NVLink peer memory)" % world},
@@ -754,11 +893,21 @@ def main_ours(args):
                      "alg_bytes_per_launch": tk["alg_bytes_per_launch"], "avg_ms": tk["avg_ms"]},
         "pcie": {"peak_gbs_measured_h2d": pcie_peak},
         "cpu_baseline": cpu,
+        "parity_gate": (v.get("parity_gate") or {}).get("status"),
+        "replicas_identical": bool(v["replicas_identical"] and e["replicas_identical"]),
         "kernels": v["kernels"],
         "variants": {m: results[m] for m in modes},
         "setup_s": round(t_setup, 1),
     }
-    print(json.dumps(line))
+    if "vtx20" in results and modes[0] != "vtx20":
+        x = results["vtx20"]
+        g = x["value"]["gather"] or {}
+        detail["vtx20"] = {"value": x["value"]["minibatches_per_s"], "e2e": x["e2e"]["minibatches_per_s"],
+                           "gather_gbs": g.get("gather_gbs"), "hit_rate": g.get("hit_rate"),
+                           "miss_frac_pcie": (g.get("miss") or {}).get("frac")}
+    detail["detail_file"] = write_detail(detail, world)
+    sys.stdout.flush()
+    print(compact_line(detail), flush=True)
 
 
 if __name__ == "__main__":

@@ -197,9 +197,12 @@ typedef struct {
 /* The two stages of pg_cache_aggregate, callable separately so that stage 1 (with its PCIe transfer of the missed rows)
  * can run ahead on another stream while the previous minibatch computes. d_rowptr: caller-owned float*[n_src];
  * d_stage: caller-owned [stage_rows, dim]. Misses beyond stage_rows are not staged: their row pointer addresses the
- * pinned host table directly (slower, still correct). */
+ * pinned host table directly (slower, still correct). d_ws: optional caller-owned workspace int64[2 + stage_rows] (miss
+ * counters + the host rows of the staged misses); a pipeline that replays captured graphs passes one per ring slot so
+ * that calls on other streams (an eager fetch_data, an evaluation NodeFlow) can neither move nor race it. NULL = the
+ * handle's shared workspace (grown on demand; replaced buffers stay allocated until pg_cache_destroy). */
 pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const float** d_rowptr, float* d_stage,
-                           int64_t stage_rows, int64_t* d_counts, void* stream);
+                           int64_t stage_rows, int64_t* d_counts, int64_t* d_ws, void* stream);
 pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, int32_t dim, float* d_dst,
                             int64_t dst_stride, int mode, const float* d_norm, float dropout_p, uint64_t dropout_seed,
                             const int64_t* d_step, int64_t zero_rows_to, void* stream);

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "pg_common.cuh"
 
@@ -312,12 +313,15 @@ struct pg_cache {
   int64_t rowptr_cap = 0;
   float* stage = nullptr;
   int64_t stage_floats = 0;
+  // buffers replaced by a larger workspace: kept until destroy, because a captured CUDA graph may still address them
+  std::vector<void*> retired;
 };
 
 static pg_status ensure_ws(pg_cache* c, int64_t n) {
   if (n <= c->ws_cap) return PG_OK;
   const int64_t cap = std::max<int64_t>(n + n / 4, 1 << 16);
-  cudaFree(c->hit_pos); cudaFree(c->hit_row); cudaFree(c->miss_pos); cudaFree(c->miss_row);
+  for (void* p : {(void*)c->hit_pos, (void*)c->hit_row, (void*)c->miss_pos, (void*)c->miss_row})
+    if (p) c->retired.push_back(p);
   c->hit_pos = c->hit_row = c->miss_pos = c->miss_row = nullptr;
   c->ws_cap = 0;
   const size_t b = (size_t)cap * sizeof(int64_t);
@@ -432,6 +436,7 @@ void pg_cache_destroy(pg_cache* c) {
   cudaFree(c->list_counts);
   cudaFree(c->hit_pos); cudaFree(c->hit_row); cudaFree(c->miss_pos); cudaFree(c->miss_row);
   cudaFree((void*)c->rowptr); cudaFree(c->stage);
+  for (void* p : c->retired) cudaFree(p);
   if (c->miss_stream) cudaStreamDestroy(c->miss_stream);
   for (cudaEvent_t e : {c->ev_split, c->ev_miss_done})
     if (e) cudaEventDestroy(e);
@@ -552,7 +557,7 @@ static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int6
 
 static pg_status ensure_fused_ws(pg_cache* c, int64_t n_src, int dim, bool need_stage) {
   if (n_src > c->rowptr_cap) {
-    cudaFree((void*)c->rowptr);
+    if (c->rowptr) c->retired.push_back((void*)c->rowptr);
     c->rowptr = nullptr;
     c->rowptr_cap = 0;
     const int64_t cap = std::max<int64_t>(n_src + n_src / 4, 1 << 16);
@@ -566,7 +571,7 @@ static pg_status ensure_fused_ws(pg_cache* c, int64_t n_src, int dim, bool need_
   if (need_stage) {
     const int64_t need = std::max<int64_t>(n_src, 1) * dim;
     if (need > c->stage_floats) {
-      cudaFree(c->stage);
+      if (c->stage) c->retired.push_back(c->stage);
       c->stage = nullptr;
       c->stage_floats = 0;
       const int64_t cap = need + need / 4;
@@ -582,7 +587,7 @@ static pg_status ensure_fused_ws(pg_cache* c, int64_t n_src, int dim, bool need_
 }
 
 pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const float** d_rowptr, float* d_stage,
-                           int64_t stage_rows, int64_t* d_counts, void* stream) {
+                           int64_t stage_rows, int64_t* d_counts, int64_t* d_ws, void* stream) {
   PG_REQUIRE(c && blk && d_rowptr, "pg_cache_resolve: bad arguments");
   PG_REQUIRE(field >= 0 && field < c->nfields, "pg_cache_resolve: no such field");
   const int64_t n_src = blk->n_src;
@@ -593,17 +598,25 @@ pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int dim = c->fields[field].dim;
   const bool full = c->is_full;
-  if (!full) {
+  // miss list + its counters: the caller's workspace (a pipeline that replays captured graphs owns one per slot, so an
+  // eager fetch on another stream can neither move nor race it), else the handle's shared one
+  unsigned long long* list_counts = c->list_counts;
+  int64_t* miss_row = nullptr;
+  if (d_ws) {
+    list_counts = (unsigned long long*)d_ws;
+    miss_row = d_ws + 2;
+  } else if (!full) {
     pg_status s = ensure_ws(c, n_src);
     if (s != PG_OK) return s;
+    miss_row = c->miss_row;
   }
   {
     pg::TimedScope timed(PG_T_SPLIT, st);
-    if (!full) PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
+    if (!full) PG_CUDA(cudaMemsetAsync(list_counts, 0, 16, st));
     const int grid = (int)std::min<int64_t>((n_src + kSplitThreads - 1) / kSplitThreads, (int64_t)pg::sm_count(c->dev) * 8);
     resolve_kernel<<<grid, kSplitThreads, 0, st>>>(blk->parent_ids, n_src, c->flag, c->l2c, c->nid_map, full ? 1 : 0,
                                                   c->cache_tables[field], dim, d_stage, dim, stage_rows, c->host_dev[field],
-                                                  c->fields[field].host_stride, d_rowptr, c->miss_row, c->list_counts,
+                                                  c->fields[field].host_stride, d_rowptr, miss_row, list_counts,
                                                   (unsigned long long*)d_counts, blk->d_layer_offsets);
     PG_CHECK_LAUNCH();
   }
@@ -612,7 +625,7 @@ pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const fl
     const float* src[1] = {c->host_dev[field]};
     const int64_t stride[1] = {c->fields[field].host_stride};
     float* dst[1] = {d_stage};
-    pg_status s = launch_rows(c, src, stride, dst, nullptr, c->miss_row, c->list_counts + 1, std::min(n_src, stage_rows),
+    pg_status s = launch_rows(c, src, stride, dst, nullptr, miss_row, list_counts + 1, std::min(n_src, stage_rows),
                               env_int("PG_MISS_MODE", 2) == 2, st, field, 1);
     if (s != PG_OK) return s;
   }
@@ -656,7 +669,7 @@ pg_status pg_cache_aggregate(pg_cache* c, int field, const pg_block* blk, float*
   // workspaces grow outside of any stream capture: size them with one eager call first
   pg_status s = ensure_fused_ws(c, blk->n_src, dim, !c->is_full);
   if (s != PG_OK) return s;
-  s = pg_cache_resolve(c, field, blk, c->rowptr, c->stage, c->is_full ? 0 : blk->n_src, d_counts, stream);
+  s = pg_cache_resolve(c, field, blk, c->rowptr, c->stage, c->is_full ? 0 : blk->n_src, d_counts, nullptr, stream);
   if (s != PG_OK) return s;
   return pg_aggregate_rows(c->rowptr, blk, dim, d_dst, dst_stride, mode, d_norm, dropout_p, dropout_seed, d_step,
                            zero_rows_to, stream);

@@ -5,7 +5,7 @@ step`. Issued op by op it is launch-bound on a B200 (≈ 40 kernels, ≈ 0.65 ms
 Here the same work is three captured graphs per minibatch, replayed on three streams that run one minibatch apart:
 
   sample graph  (stream A, per ring slot)   pg_sample_keyed [-> label gather]: a chain of small latency-bound kernels
-  gather graph  (stream B, per ring slot)   pg_cache_fetch_dyn (layers 1..L frames) -> pg_cache_resolve (row pointers of
+  gather graph  (stream B, per ring slot)   pg_cache_resolve (row pointers of
                                             the input layer + PCIe staging of its missed rows) -> pg_aggregate_rows (fused
                                             cache lookup + dropout + block-0 aggregation; it has no trainable input, so it
                                             need not wait for the previous optimizer step): the HBM / PCIe-bound part
@@ -28,6 +28,7 @@ import contextlib
 import ctypes
 import gc
 import os
+import sys
 
 import torch
 
@@ -114,6 +115,10 @@ class GCNTrainEngine:
         self.fi = cacher._field_names.index(self.field)
         self.F = cacher.dims[self.field]
         seeds = torch.as_tensor(train_nid, dtype=torch.int64).cpu()
+        if torch.unique(seeds).numel() != seeds.numel():
+            # labels are gathered by seed position (s.labels[i] belongs to seeds[i]); the sampler's seed layer drops
+            # duplicates (first occurrence wins), which would shift every later row against its label
+            raise ValueError("GCNTrainEngine: train_nid must not contain duplicates")
         if shuffle:                                   # once, like NeighborSampler
             seeds = seeds[torch.randperm(len(seeds))]
         self.num_batches = (len(seeds) + self.batch - 1) // self.batch
@@ -156,10 +161,11 @@ class GCNTrainEngine:
             self.slots = [self._make_slot() for _ in range(_RING)]
         self.fused_opt = None
         if sync is not None and os.environ.get("PG_ENGINE_FUSED_OPT", "1") != "0" and PeerAdam.supported(sync, optimizer):
-            try:
+            try:                                            # PeerAdam agrees on the outcome across ranks before it returns
                 self.fused_opt = PeerAdam(sync, optimizer)
             except Exception as e:                          # e.g. CUDA IPC unavailable: NCCL all-reduce + optimizer.step()
-                print("GCNTrainEngine: fused all-reduce + Adam unavailable (%s); using all_reduce + optimizer.step()" % e)
+                print("GCNTrainEngine: fused all-reduce + Adam unavailable (%s); using all_reduce + optimizer.step()" % e,
+                      file=sys.stderr)
         self.serialize = False       # True: every stage runs alone (host sync after each) — per-kernel timing passes
         self._dense_ok = False
         self.dense = None            # buffers of the fused dense stage (_compute_body_fused), made on first use
@@ -187,8 +193,7 @@ class GCNTrainEngine:
         s.h_meta_np = s.h_meta.numpy()
         s.rowptr = torch.zeros(self.cap_n0, **i64)
         s.stage = torch.empty((max(self.stage_rows, 1), self.F), dtype=torch.float32, device=dev)
-        s.rest = [torch.empty((self.cap_rest, self.cacher.dims[n]), dtype=torch.float32, device=dev)
-                  for n in self.cacher._field_names]
+        s.ws = torch.zeros(2 + max(self.stage_rows, 1), **i64)              # this slot's miss list (pg_cache_resolve d_ws)
         cap1 = -(-self.cap_layer[-2] // _BUCKET) * _BUCKET
         s.agg = torch.empty((cap1, self.F), dtype=torch.float32, device=dev)       # block-0 aggregate, padded rows zeroed
         s.loss = torch.zeros((), dtype=torch.float32, device=dev)
@@ -215,18 +220,16 @@ class GCNTrainEngine:
             torch.index_select(self.labels_dev, 0, s.seeds_key[:self.batch], out=s.labels)
 
     def _gather_body(self, s):
-        """stage B: fetch layers 1..L, resolve + stage the input layer, aggregate block 0; all sized on the device."""
+        """stage B: resolve + stage the input layer, aggregate block 0; all sized on the device. The frames of layers
+        1..L (which the reference's fetch_data also fills, storage.py:173-187) have no reader in the training step —
+        GCN / GraphSAGE consume the input layer only (gcn_nssc.py:64) — so they are not gathered here."""
         L, c = _lib.lib(), self.cacher
         st = _lib.stream_ptr()
         counts = c._counts if (c.log and not c.full_cached) else None
-        outs = (ctypes.c_void_p * len(s.rest))(*[t.data_ptr() for t in s.rest])
-        _lib.check(L.pg_cache_fetch_dyn(c._handle, _lib.ptr(s.nf["node_mapping"]), self._meta_ptr(s, 4 + 1),
-                                        self._meta_ptr(s, 4 + self.L + 1), self.cap_rest, outs, _lib.ptr(counts), 0, st),
-                   "pg_cache_fetch_dyn")
         blk = _lib.pg_block(_lib.ptr(s.nf["node_mapping"]), _lib.ptr(s.nf["indptr"]), _lib.ptr(s.nf["indices"]), 0,
                             self.cap_n0, s.agg.shape[0], self._meta_ptr(s, 4))
         _lib.check(L.pg_cache_resolve(c._handle, self.fi, ctypes.byref(blk), _lib.ptr(s.rowptr), _lib.ptr(s.stage),
-                                      self.stage_rows, _lib.ptr(counts), st), "pg_cache_resolve")
+                                      self.stage_rows, _lib.ptr(counts), _lib.ptr(s.ws), st), "pg_cache_resolve")
         m = self.model
         p = m.dropout.p if (m.dropout is not None and m.training) else 0.0
         _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptr), ctypes.byref(blk), self.F, _lib.ptr(s.agg), s.agg.stride(0),
@@ -435,6 +438,7 @@ class GCNTrainEngine:
                 s.sample_graph, s.gather_graph, s.compute_graphs = None, None, {}
                 if new_stage != self.stage_rows:
                     s.stage = torch.empty((max(new_stage, 1), self.F), dtype=torch.float32, device=self.dev)
+                    s.ws = torch.zeros(2 + max(new_stage, 1), dtype=torch.int64, device=self.dev)
             self.stage_rows = new_stage
             self.pool = None
 

@@ -103,8 +103,20 @@ class LocalGraphStore:
         self.close()
 
 
-def _seg_path(graph_name, field):
-    return os.path.join(_SHM_DIR, "pagraph_%s__%s.f32" % (graph_name, field))
+def _seg_path(graph_name, field, gen=""):
+    """One segment per (field, server generation): a restarted server never rewrites a segment that a client of the
+    previous run may still have mapped."""
+    return os.path.join(_SHM_DIR, "pagraph_%s__%s%s.f32" % (graph_name, field, "." + gen if gen else ""))
+
+
+def _purge(graph_name):
+    """Remove every file a previous (possibly crashed) server of this name left under /dev/shm."""
+    for f in os.listdir(_SHM_DIR):
+        if f.startswith("pagraph_%s." % graph_name) or f.startswith("pagraph_%s__" % graph_name):
+            try:
+                os.unlink(os.path.join(_SHM_DIR, f))
+            except FileNotFoundError:
+                pass
 
 
 def _meta_path(graph_name):
@@ -117,19 +129,18 @@ class SharedMemoryStoreServer:
     def __init__(self, graph, graph_name, num_workers=1):
         self.graph, self.name, self.num_workers = graph, graph_name, num_workers
         self._node_frame = _NodeFrame()
-        self._meta = {"fields": {}, "num_workers": num_workers}
+        self.gen = "%x%x" % (os.getpid(), int(time.time() * 1e3))
+        self._meta = {"fields": {}, "num_workers": num_workers, "gen": self.gen}
         self._maps = []
         self._pending = {}
         self.ndata = _NData(self)
-        for f in os.listdir(_SHM_DIR):
-            if f.startswith("pagraph_%s." % graph_name) and f.endswith(".done"):
-                os.unlink(os.path.join(_SHM_DIR, f))
+        _purge(graph_name)          # stale metadata / segments / .done markers of an earlier run, before any alloc
 
     def alloc_field(self, name, rows, dim):
         """Create the shared segment of field `name` and return its [rows, dim] tensor to be filled in
         place (no staging copy of a 24 GB table); `commit()` then makes it visible to clients."""
         stride = _padded_stride(dim)
-        path = _seg_path(self.name, name)
+        path = _seg_path(self.name, name, self.gen)
         arr = np.memmap(path, mode="w+", dtype=np.float32, shape=(rows, stride))
         self._maps.append(arr)
         t = torch.from_numpy(arr)[:, :dim]
@@ -169,14 +180,7 @@ class SharedMemoryStoreServer:
     def destroy(self):
         self._node_frame._frame.clear()
         self._maps = []
-        for name in list(self._meta["fields"]):
-            try:
-                os.unlink(_seg_path(self.name, name))
-            except FileNotFoundError:
-                pass
-        for f in os.listdir(_SHM_DIR):
-            if f.startswith("pagraph_%s." % self.name):
-                os.unlink(os.path.join(_SHM_DIR, f))
+        _purge(self.name)
 
 
 class _LazyFrame(dict):
@@ -218,10 +222,19 @@ class SharedMemoryStoreClient:
             if time.time() - t0 > self._wait_s:
                 raise TimeoutError("graph store %r (fields %s) did not appear under %s" % (graph_name, expect_fields, _SHM_DIR))
             time.sleep(0.2)
+        gen = meta.get("gen", "")
+        if getattr(self, "_gen", None) not in (None, gen):
+            raise RuntimeError("graph store %r was restarted (generation %s -> %s) under a live client" % (graph_name, self._gen, gen))
+        self._gen = gen
         for name, m in meta["fields"].items():
             if dict.__contains__(self._node_frame._frame, name):
                 continue
-            fd = os.open(_seg_path(graph_name, name), os.O_RDWR)
+            try:
+                fd = os.open(_seg_path(graph_name, name, gen), os.O_RDWR)
+            except FileNotFoundError:      # metadata of a server that has just been replaced: wait for the new one
+                self._gen = None
+                time.sleep(0.2)
+                return self._attach(expect_fields)
             try:
                 mm = mmap.mmap(fd, m["rows"] * m["stride"] * 4, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
             finally:

@@ -122,16 +122,35 @@ class PeerAdam:
         world, rank = sync.world, (dist.get_rank(sync.group) if sync.world > 1 else 0)
         h = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * _lib.PG_IPC_HANDLE_BYTES)()
-        _lib.check(_lib.lib().pg_peer_group_create(world, rank, self.flat.numel(), dev.index, ctypes.byref(h), handle),
-                   "pg_peer_group_create")
-        self._handle = h
+        self._handle = None
+        # Every rank walks the same sequence of collectives whatever happens locally, and the outcome is agreed with an
+        # all-reduce(MIN) of a success flag: if CUDA IPC / peer access fails on ONE rank, all ranks raise (and fall back
+        # to NCCL together) instead of some of them spinning in the kernel on flags that never arrive.
+        err = None
+        try:
+            _lib.check(_lib.lib().pg_peer_group_create(world, rank, self.flat.numel(), dev.index, ctypes.byref(h), handle),
+                       "pg_peer_group_create")
+            self._handle = h
+        except Exception as e:
+            err = e
         if world > 1:
             mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
             allh = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allh, mine, group=sync.group)
-            blob = bytes(torch.stack(allh).cpu().numpy().tobytes())
-            _lib.check(_lib.lib().pg_peer_group_connect(h, blob), "pg_peer_group_connect")
-            dist.barrier(group=sync.group)
+            if err is None:
+                try:
+                    blob = bytes(torch.stack(allh).cpu().numpy().tobytes())
+                    _lib.check(_lib.lib().pg_peer_group_connect(h, blob), "pg_peer_group_connect")
+                except Exception as e:
+                    err = e
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=sync.group)
+            if int(ok.item()) == 0:
+                self.close()
+                raise RuntimeError("peer-memory all-reduce unavailable on at least one rank%s"
+                                   % ("" if err is None else " (this rank: %s)" % err))
+        elif err is not None:
+            raise err
 
     def step(self, step_id):
         """step_id: int64 CUDA scalar tensor, >= 1, equal on all ranks, +1 per call."""

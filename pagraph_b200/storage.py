@@ -6,6 +6,7 @@ missed rows straight from the pinned host table, for all NodeFlow layers in one 
 synchronisation (the reference: ~10 torch kernels and >= 3 syncs per layer, CPU gather of misses).
 """
 import ctypes
+import sys
 
 import torch
 
@@ -169,7 +170,7 @@ class GraphCacheServer:
         for name in embed_names:
             self.dims[name] = self._table(name).size(1)
             self.total_dim += self.dims[name]
-        print('total dims: {}'.format(self.total_dim))
+        print('total dims: {}'.format(self.total_dim), file=sys.stderr)
 
     def auto_cache(self, dgl_g, embed_names, capability=None):
         """
@@ -187,13 +188,13 @@ class GraphCacheServer:
         total_mem = torch.cuda.get_device_properties(self.gpuid).total_memory
         available = total_mem - peak_allocated_mem - peak_cached_mem - 1024 * 1024 * 1024
         self.capability = int(available / (self.total_dim * 4)) if capability is None else int(capability)
-        print('Cache Memory: {:.2f}G. Capability: {}'.format(available / 1024 / 1024 / 1024, self.capability))
+        print('Cache Memory: {:.2f}G. Capability: {}'.format(available / 1024 / 1024 / 1024, self.capability), file=sys.stderr)
         if self.capability >= self.node_num:
-            print('cache the full graph...')
+            print('cache the full graph...', file=sys.stderr)
             nids = torch.arange(self.node_num, device=self._dev)
             self._fill(nids, is_full=True)
         else:
-            print('cache the part of graph... caching percentage: {:.4f}'.format(self.capability / self.node_num))
+            print('cache the part of graph... caching percentage: {:.4f}'.format(self.capability / self.node_num), file=sys.stderr)
             out_degrees = dgl_g.out_degrees().to(self._dev)
             sort_nid = torch.sort(out_degrees, descending=True, stable=True).indices
             self._fill(sort_nid[:max(self.capability, 0)].contiguous(), is_full=False)

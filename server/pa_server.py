@@ -38,6 +38,8 @@ def preprocess_features(graph, features, norm, device="cuda:0", rows_per_block=1
 
 
 def main(args):
+    if args.sample:        # refused before anything is published
+        raise SystemExit("--sample: server-side sampling is replaced by the GPU sampler in each trainer")
     coo_adj, feat = data.get_graph_data(args.dataset)
     graph = DGLGraph(coo_adj, readonly=True)
     features = torch.as_tensor(np.asarray(feat), dtype=torch.float32)
@@ -60,8 +62,6 @@ def main(args):
             print('preprocessing: warning: jusy copy')
             g.ndata['neigh'] = features
         g.ndata['features'] = features
-    if args.sample:
-        raise SystemExit("--sample: server-side sampling is replaced by the GPU sampler in each trainer")
     print('start running graph server on dataset: {}'.format(graph_name))
     g.run()
 
