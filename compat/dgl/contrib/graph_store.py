@@ -1,0 +1,5 @@
+"""Alias: this module IS pagraph_b200.graph_store (see compat/README.md)."""
+import importlib
+import sys
+
+sys.modules[__name__] = importlib.import_module("pagraph_b200.graph_store")

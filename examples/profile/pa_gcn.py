@@ -23,7 +23,7 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 from pagraph_b200 import DGLGraph  # noqa: E402
-from pagraph_b200 import data, graph_store, storage  # noqa: E402
+from pagraph_b200 import data, graph_store, profiling, storage  # noqa: E402
 from pagraph_b200.model.gcn_nssc import GCNSampling  # noqa: E402
 from pagraph_b200.parallel import FlatGradAllReduce, equalised_num_batches  # noqa: E402
 from pagraph_b200.sampling import NeighborSampler  # noqa: E402
@@ -85,14 +85,16 @@ def trainer(rank, world_size, args, backend='nccl'):
         epoch_start_time = time.time()
         step = 0
         for nf in sampler.batches(0, steps_per_epoch, epoch):
-            cacher.fetch_data(nf)                                    # 'gpu-load'
-            label = labels[nf.layer_parent_nid_dev(-1)]
-            pred = model(nf)                                         # 'gpu-compute'
-            loss = loss_fcn(pred, label)
-            sync.zero_grad()
-            loss.backward()
-            sync()
-            optimizer.step()
+            with profiling.range('gpu-load'):                        # pa_gcn.py:87-91
+                cacher.fetch_data(nf)
+                label = labels[nf.layer_parent_nid_dev(-1)]
+            with profiling.range('gpu-compute'):                     # pa_gcn.py:92-97
+                pred = model(nf)
+                loss = loss_fcn(pred, label)
+                sync.zero_grad()
+                loss.backward()
+                sync()
+                optimizer.step()
             step += 1
             if epoch == 0 and step == 1:
                 cacher.auto_cache(g, embed_names)
@@ -105,11 +107,21 @@ def trainer(rank, world_size, args, backend='nccl'):
                                                       else epoch_dur[-1]))
         if cacher.log:
             print('Epoch average miss rate: {:.4f}'.format(cacher.get_miss_rate()))
+        save_checkpoint(args, model, epoch, rank)
     toc = time.time()
     print('Total Time: {:.4f}s'.format(toc - tic))
     if not args.keep_store:
         remote_g.destroy()
     dist.destroy_process_group()
+
+
+def save_checkpoint(args, model, epoch, rank):
+    """`--ckpt DIR` (extension): rank 0 saves the parameters after every epoch as DIR/gcn-nssc_{epoch}, the file name
+    examples/eval.py loads (the reference's eval.py:28-32 expects them; nothing in its tree writes them)."""
+    if args.ckpt and rank == 0:
+        os.makedirs(args.ckpt, exist_ok=True)
+        torch.save({k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
+                   os.path.join(args.ckpt, 'gcn-nssc_{}'.format(epoch)))
 
 
 def train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fanout, num_hops, embed_names, remote_g):
@@ -141,6 +153,7 @@ def train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fan
             epoch_dur.append(time.time() - epoch_start_time)
             print('Epoch average time: {:.4f}'.format(np.mean(np.array(epoch_dur[2:])) if len(epoch_dur) > 2
                                                       else epoch_dur[-1]))
+        save_checkpoint(args, model, epoch, rank)
     print('Total Time: {:.4f}s'.format(time.time() - tic))
     engine.close()
     remote_g.destroy()
@@ -170,6 +183,7 @@ def make_parser():
     parser.add_argument("--remote-sample", dest='remote_sample', action='store_true')
     parser.set_defaults(remote_sample=False)
     parser.add_argument("--seed", type=int, default=0, help="sampling RNG seed (the reference's is unseeded)")
+    parser.add_argument("--ckpt", type=str, default=None, help="directory for per-epoch checkpoints (read by examples/eval.py)")
     parser.add_argument("--keep-store", action='store_true', help="do not tell the feature server this trainer is done")
     parser.add_argument("--engine", default="graph", choices=["graph", "eager"],
                         help="graph: GCNTrainEngine (CUDA-graph pipeline, default); eager: the reference's op-by-op loop")

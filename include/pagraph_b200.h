@@ -102,8 +102,12 @@ pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int6
 /* Same with the minibatch key read from device memory (uint32[2], as produced by pg_minibatch_key): the launch
  * sequence then depends on nothing but pointers, so one captured CUDA graph samples every minibatch. */
 void pg_minibatch_key(uint64_t seed, int64_t epoch, int64_t batch, uint32_t* key);
+/* d_labels / d_seed_labels (optional, both or neither): `label = labels[nf.layer_parent_nid(-1)]` of the trainer
+ * (examples/profile/pa_gcn.py:89-90) done in the same pass — d_seed_labels[i] = d_labels[parent id of seed-layer row i],
+ * i.e. in the order of the DEDUPLICATED seed layer, which is the row order of the model's output. */
 pg_status pg_sample_keyed(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, const uint32_t* d_key,
-                          const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream);
+                          const pg_nodeflow_buffers* out, int64_t* h_meta, const int64_t* d_labels, int64_t* d_seed_labels,
+                          void* stream);
 
 /* ---------------------------------------------------------------- feature cache (replaces PaGraph/storage/storage.py) */
 typedef struct {
@@ -233,10 +237,13 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
 /* Classifier head + loss in one pass (the last NodeUpdate, gcn_nssc.py:48, followed by torch.nn.CrossEntropyLoss,
  * examples/profile/pa_gcn.py:62,93-94): pred = a W^T + b, loss = mean_r(logsumexp(pred_r) - pred_r[label_r]); also emits
  * d loss/d a [n, in_dim], d loss/d W [n_classes, in_dim] and d loss/d b [n_classes] (all overwritten). in_dim, n_classes <= 64;
- * labels in [0, n_classes). */
+ * labels in [0, n_classes). d_lo (optional, device): int64[2]; the row count is then min(n, d_lo[1] - d_lo[0]) read on the
+ * device — the seed layer's extent &meta[4 + L] of a sampled NodeFlow, whose size the host does not know when a captured
+ * graph is replayed (duplicate seeds are dropped by the sampler). */
 pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias,
                                   const int64_t* d_labels, int64_t n, int32_t in_dim, int32_t n_classes, float* d_loss,
-                                  float* d_grad_a, int64_t ga_stride, float* d_grad_weight, float* d_grad_bias, void* stream);
+                                  float* d_grad_a, int64_t ga_stride, float* d_grad_weight, float* d_grad_bias,
+                                  const int64_t* d_lo, void* stream);
 
 /* ---------------------------------------------------------------- gradient all-reduce fused with the optimizer step
  * Replaces DistributedDataParallel's all-reduce of the flat gradient followed by Adam (examples/profile/pa_gcn.py:65,96-97)

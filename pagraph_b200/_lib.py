@@ -72,7 +72,7 @@ SIGNATURES = {
                                           ctypes.c_int, c_vp]),
     "pg_minibatch_key": (None, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint32)]),
     "pg_sample_keyed": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.POINTER(pg_nodeflow_buffers), c_vp,
-                                       c_vp]),
+                                       c_vp, c_vp, c_vp]),
     "pg_aggregate_fwd_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_int32, ctypes.c_int, c_vp, c_vp]),
     "pg_aggregate_bwd_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int64,
@@ -91,7 +91,7 @@ SIGNATURES = {
                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_int, ctypes.c_float, ctypes.c_uint64,
                                             c_vp, c_vp, c_vp, c_vp]),
     "pg_linear_cross_entropy": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32,
-                                               ctypes.c_int32, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp]),
+                                               ctypes.c_int32, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "pg_peer_group_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp),
                                             c_vp]),
     "pg_peer_group_connect": (ctypes.c_int, [c_vp, c_vp]),

@@ -196,8 +196,12 @@ __global__ void __launch_bounds__(kHeadWarps * 32) linear_ce_kernel(const float*
                                                                    const float* __restrict__ W, const float* __restrict__ bias,
                                                                    const int64_t* __restrict__ labels, int64_t n, int K, int C,
                                                                    float inv_n, float* loss, float* grad_a, int64_t ga_stride,
-                                                                   float* dW, float* db) {
+                                                                   float* dW, float* db, const int64_t* __restrict__ lo) {
   extern __shared__ __align__(16) float head_smem[];  // over the 48 KB static limit, hence dynamic
+  if (lo) {  // device-resident row count: n is a capacity
+    n = min(n, lo[1] - lo[0]);
+    inv_n = 1.0f / (float)max(n, (int64_t)1);
+  }
   // w_kc[k][c] = W[c][k] (logits: lane = class; row stride 65 so that the transposing fill is conflict-free),
   // w_ck[c][k] = W[c][k] (grad_a: lane = input column), dw_sh[c][k]: the CTA's partial of dW
   float (*w_kc)[kHeadMaxC + 1] = (float (*)[kHeadMaxC + 1])head_smem;
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) linear_ce_kernel(const float*
 extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias,
                                              const int64_t* d_labels, int64_t n, int32_t in_dim, int32_t n_classes,
                                              float* d_loss, float* d_grad_a, int64_t ga_stride, float* d_grad_weight,
-                                             float* d_grad_bias, void* stream) {
+                                             float* d_grad_bias, const int64_t* d_lo, void* stream) {
   PG_REQUIRE(d_weight && d_loss && d_grad_weight && n >= 0 && ((d_a && d_labels && d_grad_a) || n == 0),
              "pg_linear_cross_entropy: bad arguments");
   PG_REQUIRE(in_dim >= 1 && in_dim <= kHeadMaxK && n_classes >= 1 && n_classes <= kHeadMaxC,
@@ -314,7 +318,7 @@ extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride,
   const char* env_s = getenv("PG_HEAD_SIMT");
   if (!(env_s && atoi(env_s))) {   // tensor-core kernel (pg_dense_mma.cu) whenever the layout allows 16-byte accesses
     const pg_status s = pg::linear_ce_mma(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes, d_loss, d_grad_a,
-                                          ga_stride, d_grad_weight, d_grad_bias, st);
+                                          ga_stride, d_grad_weight, d_grad_bias, d_lo, st);
     if (s != PG_ERR_INVALID) return s;
   }
   // one CTA per SM: the fixed cost per CTA (staging W twice, 4 k atomics for dW) is what the kernel's time is made of
@@ -322,7 +326,8 @@ extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride,
   const size_t smem = ((size_t)kHeadMaxK * (kHeadMaxC + 1) + 2 * (size_t)kHeadMaxK * kHeadMaxC) * sizeof(float);
   PG_CUDA(cudaFuncSetAttribute(linear_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   linear_ce_kernel<<<grid, kHeadWarps * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
-                                                     1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight, d_grad_bias);
+                                                     1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight, d_grad_bias,
+                                                     d_lo);
   PG_CHECK_LAUNCH();
   return PG_OK;
 }

@@ -620,8 +620,13 @@ constexpr int kHeadAS = 72;   // ... of the staged a tile (16-byte loads, 4 rows
 __global__ void __launch_bounds__(kHeadWarpsM * 32)
     linear_ce_mma_kernel(const float* __restrict__ a, int64_t a_stride, const float* __restrict__ W,
                          const float* __restrict__ bias, const int64_t* __restrict__ labels, int64_t n, int K, int C,
-                         float inv_n, float* loss, float* grad_a, int64_t ga_stride, float* dW, float* db) {
+                         float inv_n, float* loss, float* grad_a, int64_t ga_stride, float* dW, float* db,
+                         const int64_t* __restrict__ lo) {
   extern __shared__ __align__(16) uint32_t hsm[];
+  if (lo) {  // device-resident row count: n is a capacity
+    n = min(n, lo[1] - lo[0]);
+    inv_n = 1.0f / (float)max(n, (int64_t)1);
+  }
   uint32_t* w_hi = hsm;                                   // [64][kHeadWS]  w[class][k]
   uint32_t* w_lo = w_hi + 64 * kHeadWS;
   uint32_t* g_hi = w_lo + 64 * kHeadWS;                   // [64 rows][kHeadGS], class c at word (c % 8) * 8 + c / 8
@@ -883,7 +888,7 @@ namespace pg {
 // without launching when the layout does not allow 16-byte accesses (the caller then uses the scalar kernel).
 pg_status linear_ce_mma(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias, const int64_t* d_labels,
                         int64_t n, int32_t in_dim, int32_t n_classes, float* d_loss, float* d_grad_a, int64_t ga_stride,
-                        float* d_grad_weight, float* d_grad_bias, cudaStream_t st) {
+                        float* d_grad_weight, float* d_grad_bias, const int64_t* d_lo, cudaStream_t st) {
   const bool ok = in_dim % 4 == 0 && in_dim <= 64 && n_classes <= 64 && a_stride % 4 == 0 && ga_stride % 4 == 0 &&
                   (((uintptr_t)d_a | (uintptr_t)d_weight | (uintptr_t)d_grad_a | (uintptr_t)d_grad_weight) & 15) == 0;
   if (!ok) return PG_ERR_INVALID;
@@ -892,7 +897,7 @@ pg_status linear_ce_mma(const float* d_a, int64_t a_stride, const float* d_weigh
   const int grid = (int)((n + 16 * kHeadWarpsM - 1) / (16 * kHeadWarpsM));
   linear_ce_mma_kernel<<<grid, kHeadWarpsM * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
                                                              1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight,
-                                                             d_grad_bias);
+                                                             d_grad_bias, d_lo);
   PG_CHECK_LAUNCH();
   return PG_OK;
 }

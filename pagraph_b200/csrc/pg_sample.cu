@@ -22,9 +22,10 @@ namespace {
 
 using pg::kFullMask;
 
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 4;
-constexpr int kTile = kScanThreads * kScanItems;
+constexpr int kSeedThreads = 256;    // seed kernel CTA: 256 x 64 registers fits beside the aggregation kernel's CTA
+constexpr int kSeedItems = 8;        // frontier vertices per thread per round of its row-offset scan
+constexpr int kBitsThreads = 256;    // bitmap -> layer kernel: 4 words per thread
+constexpr int kBitsTile = kBitsThreads * 4;
 constexpr int kPickWarps = 8;        // warps per CTA in the pick kernel
 constexpr int kSmemPicks = 64;       // accepted-position slots per warp kept in shared memory
 constexpr int64_t kEmptyKey = -1;
@@ -36,75 +37,14 @@ struct Counts {
   int64_t overflow;
 };
 
-// ------------------------------------------------------------------ generic two-pass device scan
-// pass1: per-tile sums; the last CTA to finish turns them into exclusive tile prefixes (+ total).
-// pass2: recomputes the values, adds the tile prefix and calls emit(i, exclusive_prefix, value).
-template <class F>
-__global__ void __launch_bounds__(kScanThreads) scan_pass1(F f, int64_t* tile_sums, unsigned* ticket,
-                                                           int64_t* total_out) {
-  __shared__ int64_t sh[kScanThreads / 32 + 1];
-  __shared__ bool is_last;
-  const int64_t n = f.size();
-  const int64_t ntiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t base = tile * kTile + (int64_t)threadIdx.x * kScanItems;
-    int64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k)
-      if (base + k < n) s += f.value(base + k);
-    int64_t total;
-    pg::block_exclusive_scan(s, total, sh);
-    if (threadIdx.x == 0) tile_sums[tile] = total;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const int64_t chunk = (ntiles + kScanThreads - 1) / kScanThreads;
-  const int64_t lo = min((int64_t)threadIdx.x * chunk, ntiles), hi = min(lo + chunk, ntiles);
-  int64_t local = 0;
-  for (int64_t i = lo; i < hi; ++i) local += __ldcg(tile_sums + i);
-  int64_t total;
-  int64_t run = pg::block_exclusive_scan(local, total, sh);
-  for (int64_t i = lo; i < hi; ++i) {
-    const int64_t t = __ldcg(tile_sums + i);
-    tile_sums[i] = run;
-    run += t;
-  }
-  if (threadIdx.x == 0) {
-    *total_out = total;
-    *ticket = 0;
-    f.finish(total);
-  }
-}
+// Work-distribution state of the per-hop bitmap kernels (zeroed by the seed kernel of every call).
+struct Control {
+  unsigned tile_ctr1[PG_MAX_HOPS + 1];   // next tile of phase 1 (tile sums)
+  unsigned tiles_done[PG_MAX_HOPS + 1];  // tiles whose sums are published
+  unsigned tile_ctr2[PG_MAX_HOPS + 1];   // next tile of phase 2 (emit)
+  unsigned ready[PG_MAX_HOPS + 1];       // tile prefixes are final
+};
 
-template <class F>
-__global__ void __launch_bounds__(kScanThreads) scan_pass2(F f, const int64_t* tile_sums) {
-  __shared__ int64_t sh[kScanThreads / 32 + 1];
-  const int64_t n = f.size();
-  const int64_t ntiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t base = tile * kTile + (int64_t)threadIdx.x * kScanItems;
-    int64_t vals[kScanItems];
-    int64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-      vals[k] = (base + k < n) ? f.value(base + k) : 0;
-      s += vals[k];
-    }
-    int64_t total;
-    int64_t excl = pg::block_exclusive_scan(s, total, sh) + tile_sums[tile];
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-      if (base + k < n) f.emit(base + k, excl, vals[k]);
-      excl += vals[k];
-    }
-  }
-}
-
-// ------------------------------------------------------------------ seed layer: ordered dedup (first occurrence wins)
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
   x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
@@ -112,59 +52,124 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 
-__global__ void seed_insert_kernel(const int64_t* __restrict__ seeds, int64_t n, int64_t* keys, int* minpos,
-                                   uint64_t mask) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t v = seeds[i];
-    uint64_t slot = mix64((uint64_t)v) & mask;
-    while (true) {
-      const int64_t old = (int64_t)atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey,
-                                             (unsigned long long)v);
-      if (old == kEmptyKey || old == v) {
-        atomicMin(&minpos[slot], (int)i);
-        break;
-      }
-      slot = (slot + 1) & mask;
-    }
-  }
-}
-
-struct SeedKeep {
+// ------------------------------------------------------------------ kernel 1 of a call: the seed layer
+// CTA 0: ordered dedup of the seeds (first occurrence wins, Appendix A.3) and the row offsets of hop 1.
+//   Duplicates are detected with a V-bit scratch bitmap (atomicOr returns the old bit): a duplicate-free batch — every
+//   training batch — is copied through; only a batch that does contain duplicates takes the exact path (open-addressing
+//   table keyed by vertex with the minimum position, then an ordered compaction). The scratch bits are cleared again
+//   through the seed list itself (work proportional to the batch, not to V).
+// CTAs 1..: zero the per-hop bitmaps for this call (one contiguous range) — the only work proportional to V, written
+//   at HBM/L2 speed while CTA 0 is busy with its latency chain.
+struct SeedArgs {
   const int64_t* seeds;
   int64_t n;
-  const int64_t* keys;
-  const int* minpos;
-  uint64_t mask;
+  const int64_t* indptr;
+  int64_t fanout0;
+  uint32_t* seedbits;
+  int64_t* hash_keys;
+  int* hash_minpos;
+  uint64_t hash_mask;
   int64_t* layer0;
-  __device__ int64_t size() const { return n; }
-  __device__ int64_t value(int64_t i) const {
-    const int64_t v = seeds[i];
-    uint64_t slot = mix64((uint64_t)v) & mask;
-    while (keys[slot] != v) slot = (slot + 1) & mask;
-    return minpos[slot] == (int)i ? 1 : 0;
-  }
-  __device__ void emit(int64_t i, int64_t excl, int64_t val) const {
-    if (val) layer0[excl] = seeds[i];
-  }
-  __device__ void finish(int64_t) const {}
+  int64_t* row_off1;
+  Counts* counts;
+  Control* ctl;
+  uint4* zero_base;
+  int64_t zero_vec;   // uint4 count
 };
 
-// ------------------------------------------------------------------ per-hop: row counts -> offsets
-struct FrontCount {
-  const int64_t* indptr;
-  const int64_t* front;      // layer h-1
-  const int64_t* n_front;    // device count
-  int64_t cap_front;         // capacity of `front`
-  int64_t fanout;
-  int64_t* row_off;          // [cap_front + 1]
-  __device__ int64_t size() const { return min(*n_front, cap_front); }
-  __device__ int64_t value(int64_t i) const {
-    const int64_t v = front[i];
-    return min(indptr[v + 1] - indptr[v], fanout);
+__global__ void __launch_bounds__(kSeedThreads) seed_kernel(SeedArgs a) {
+  __shared__ int64_t sh[kSeedThreads / 32 + 1];
+  const int tid = threadIdx.x;
+  if (blockIdx.x != 0 || gridDim.x == 1) {
+    const int64_t nz = gridDim.x == 1 ? 1 : gridDim.x - 1, bz = gridDim.x == 1 ? 0 : blockIdx.x - 1;
+    for (int64_t i = bz * kSeedThreads + tid; i < a.zero_vec; i += nz * kSeedThreads) a.zero_base[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x != 0) return;
   }
-  __device__ void emit(int64_t i, int64_t excl, int64_t) const { row_off[i] = excl; }
-  __device__ void finish(int64_t total) const { row_off[size()] = total; }
-};
+  for (int i = tid; i < (int)(sizeof(Counts) / 8); i += kSeedThreads) ((int64_t*)a.counts)[i] = 0;
+  for (int i = tid; i < (int)(sizeof(Control) / 4); i += kSeedThreads) ((unsigned*)a.ctl)[i] = 0;
+  int dup = 0;
+  for (int64_t i = tid; i < a.n; i += kSeedThreads) {
+    const int64_t v = a.seeds[i];
+    const uint32_t bit = 1u << (v & 31);
+    dup |= (atomicOr(&a.seedbits[v >> 5], bit) & bit) != 0;
+  }
+  const int any_dup = __syncthreads_or(dup);
+  int64_t n0 = a.n;
+  if (!any_dup) {
+    for (int64_t i = tid; i < a.n; i += kSeedThreads) {
+      const int64_t v = a.seeds[i];
+      a.layer0[i] = v;
+      a.seedbits[v >> 5] = 0;
+    }
+  } else {
+    for (int64_t i = tid; i < a.n; i += kSeedThreads) a.seedbits[a.seeds[i] >> 5] = 0;
+    for (uint64_t s = tid; s <= a.hash_mask; s += kSeedThreads) {
+      a.hash_keys[s] = kEmptyKey;
+      a.hash_minpos[s] = INT_MAX;
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < a.n; i += kSeedThreads) {
+      const int64_t v = a.seeds[i];
+      uint64_t slot = mix64((uint64_t)v) & a.hash_mask;
+      while (true) {
+        const int64_t old = (int64_t)atomicCAS((unsigned long long*)&a.hash_keys[slot], (unsigned long long)kEmptyKey,
+                                               (unsigned long long)v);
+        if (old == kEmptyKey || old == v) {
+          atomicMin(&a.hash_minpos[slot], (int)i);
+          break;
+        }
+        slot = (slot + 1) & a.hash_mask;
+      }
+    }
+    __syncthreads();
+    n0 = 0;
+    for (int64_t c0 = 0; c0 < a.n; c0 += kSeedThreads) {   // ordered compaction of the first occurrences
+      const int64_t i = c0 + tid;
+      int64_t keep = 0, v = 0;
+      if (i < a.n) {
+        v = a.seeds[i];
+        uint64_t slot = mix64((uint64_t)v) & a.hash_mask;
+        while (__ldcg(&a.hash_keys[slot]) != v) slot = (slot + 1) & a.hash_mask;
+        keep = __ldcg(&a.hash_minpos[slot]) == (int)i;
+      }
+      int64_t total;
+      const int64_t excl = pg::block_exclusive_scan(keep, total, sh);
+      if (keep) a.layer0[n0 + excl] = v;
+      n0 += total;
+    }
+  }
+  __syncthreads();
+  // row offsets of hop 1: exclusive scan of min(in_degree, fanout) over the seed layer, kSeedItems consecutive
+  // vertices per thread so that all of a round's indptr reads are in flight together
+  int64_t running = 0;
+  for (int64_t c0 = 0; c0 < n0; c0 += (int64_t)kSeedThreads * kSeedItems) {
+    const int64_t i0 = c0 + (int64_t)tid * kSeedItems;
+    int64_t c[kSeedItems];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kSeedItems; ++k) {
+      c[k] = 0;
+      if (i0 + k < n0) {
+        const int64_t v = a.layer0[i0 + k];
+        c[k] = min(a.indptr[v + 1] - a.indptr[v], a.fanout0);
+      }
+      s += c[k];
+    }
+    int64_t total;
+    int64_t excl = pg::block_exclusive_scan(s, total, sh) + running;
+#pragma unroll
+    for (int k = 0; k < kSeedItems; ++k) {
+      if (i0 + k < n0) a.row_off1[i0 + k] = excl;
+      excl += c[k];
+    }
+    running += total;
+  }
+  if (tid == 0) {
+    a.row_off1[n0] = running;
+    a.counts->n_layer[0] = n0;
+    a.counts->e_hop[1] = running;
+  }
+}
 
 // ------------------------------------------------------------------ per-hop: pick neighbours (one warp per frontier vertex)
 struct PickArgs {
@@ -257,35 +262,151 @@ __global__ void __launch_bounds__(kPickWarps * 32) pick_kernel(PickArgs a) {
 }
 
 // ------------------------------------------------------------------ per-hop: bitmap -> sorted unique layer + ranks
-struct BitCount {
-  const uint32_t* bitmap;
+// One kernel per hop. The vertices picked by hop h are the set bits of bitmap[h]; ascending bit order IS the layer's
+// order (sorted by parent id, Appendix A.4), so "dedup + sort" is a popcount prefix sum:
+//   phase 1  tiles of kBitsTile words, handed out by an atomic counter: per-tile (vertex count, sum of the next hop's
+//            row lengths min(in_degree, fanout)); the CTA that publishes the last tile turns the sums into exclusive
+//            tile prefixes and raises `ready`;
+//   phase 2  tiles handed out again: word_prefix[w], layer[h][rank] = vertex, row_off[h+1][rank] = edge offset.
+// CTAs that find no tile left just wait for `ready`; nothing a running CTA waits for depends on a CTA that is not
+// running yet, so the kernel needs no co-residency guarantee (and no cooperative launch).
+struct BitsArgs {
+  const uint32_t* bitmap;     // padded to a multiple of 4 words, padding zero
   int64_t nwords;
   uint32_t* word_prefix;
-  int64_t* layer;            // [cap]
+  int64_t* layer;             // [cap]
   int64_t cap;
-  __device__ int64_t size() const { return nwords; }
-  __device__ int64_t value(int64_t w) const { return __popc(bitmap[w]); }
-  __device__ void emit(int64_t w, int64_t excl, int64_t val) const {
-    word_prefix[w] = (uint32_t)excl;
-    if (!val) return;
-    uint32_t bits = bitmap[w];
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      if (excl < cap) layer[excl] = w * 32 + b;
-      ++excl;
-    }
-  }
-  __device__ void finish(int64_t) const {}
+  const int64_t* indptr;
+  int64_t fanout_next;        // row lengths of the next hop (ignored when row_off_next is null)
+  int64_t* row_off_next;      // [cap + 1] or null (last hop)
+  int64_t* tile_a;            // [ntiles] vertex counts -> exclusive prefixes
+  int64_t* tile_b;            // [ntiles] edge counts   -> exclusive prefixes
+  Counts* counts;
+  Control* ctl;
+  int h;
 };
 
-__global__ void relabel_kernel(int64_t* nb_src, const int64_t* n_edges, int64_t cap_edges,
-                               const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix) {
-  const int64_t n = min(*n_edges, cap_edges);
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t u = nb_src[e];
-    const int64_t w = u >> 5;
-    nb_src[e] = (int64_t)word_prefix[w] + __popc(bitmap[w] & ((1u << (u & 31)) - 1));
+__device__ __forceinline__ int64_t rows_of_word(const BitsArgs& a, int64_t w, uint32_t bits) {
+  int64_t s = 0;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int64_t v = w * 32 + b;
+    s += min(a.indptr[v + 1] - a.indptr[v], a.fanout_next);
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(kBitsThreads) bits_kernel(BitsArgs a) {
+  __shared__ int64_t sh[kBitsThreads / 32 + 1];
+  __shared__ unsigned s_tile;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (a.nwords + kBitsTile - 1) / kBitsTile;
+  const bool want_b = a.row_off_next != nullptr;
+  // ---- phase 1
+  while (true) {
+    if (tid == 0) s_tile = atomicAdd(&a.ctl->tile_ctr1[a.h], 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= ntiles) break;
+    const int64_t w0 = tile * kBitsTile + (int64_t)tid * 4;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (w0 < a.nwords) q = *(const uint4*)(a.bitmap + w0);
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+    int64_t na = 0, nb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      na += __popc(wd[k]);
+      if (want_b && wd[k]) nb += rows_of_word(a, w0 + k, wd[k]);
+    }
+    int64_t ta, tb = 0;
+    pg::block_exclusive_scan(na, ta, sh);
+    if (want_b) pg::block_exclusive_scan(nb, tb, sh);
+    if (tid == 0) {
+      a.tile_a[tile] = ta;
+      a.tile_b[tile] = tb;
+      __threadfence();
+      s_last = atomicAdd(&a.ctl->tiles_done[a.h], 1u) == (unsigned)(ntiles - 1);
+    }
+    __syncthreads();
+    if (s_last) {  // every tile sum is published: exclusive prefixes over the tiles, totals, release
+      __threadfence();
+      const int64_t chunk = (ntiles + kBitsThreads - 1) / kBitsThreads;
+      const int64_t lo = min((int64_t)tid * chunk, ntiles), hi = min(lo + chunk, ntiles);
+      int64_t la = 0, lb = 0;
+      for (int64_t i = lo; i < hi; ++i) {
+        la += __ldcg(a.tile_a + i);
+        lb += __ldcg(a.tile_b + i);
+      }
+      int64_t tot_a, tot_b;
+      int64_t run_a = pg::block_exclusive_scan(la, tot_a, sh);
+      int64_t run_b = pg::block_exclusive_scan(lb, tot_b, sh);
+      for (int64_t i = lo; i < hi; ++i) {
+        const int64_t xa = __ldcg(a.tile_a + i), xb = __ldcg(a.tile_b + i);
+        a.tile_a[i] = run_a;
+        a.tile_b[i] = run_b;
+        run_a += xa;
+        run_b += xb;
+      }
+      if (tid == 0) {
+        a.counts->n_layer[a.h] = tot_a;
+        if (want_b) {
+          a.counts->e_hop[a.h + 1] = tot_b;
+          a.row_off_next[min(tot_a, a.cap)] = tot_b;
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicExch(&a.ctl->ready[a.h], 1u);
+    }
+    __syncthreads();
+  }
+  // ---- wait for the tile prefixes
+  if (tid == 0) {
+    while (atomicAdd(&a.ctl->ready[a.h], 0u) == 0u) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- phase 2
+  while (true) {
+    if (tid == 0) s_tile = atomicAdd(&a.ctl->tile_ctr2[a.h], 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= ntiles) break;
+    const int64_t w0 = tile * kBitsTile + (int64_t)tid * 4;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (w0 < a.nwords) q = *(const uint4*)(a.bitmap + w0);
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+    int64_t na = 0, nb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      na += __popc(wd[k]);
+      if (want_b && wd[k]) nb += rows_of_word(a, w0 + k, wd[k]);
+    }
+    int64_t ta, tb;
+    int64_t ea = pg::block_exclusive_scan(na, ta, sh) + __ldcg(a.tile_a + tile);
+    int64_t eb = 0;
+    if (want_b) eb = pg::block_exclusive_scan(nb, tb, sh) + __ldcg(a.tile_b + tile);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (w0 + k < a.nwords) a.word_prefix[w0 + k] = (uint32_t)ea;
+      uint32_t bits = wd[k];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int64_t v = (w0 + k) * 32 + b;
+        if (ea < a.cap) {
+          a.layer[ea] = v;
+          if (want_b) {
+            a.row_off_next[ea] = eb;
+            eb += min(a.indptr[v + 1] - a.indptr[v], a.fanout_next);
+          }
+        }
+        ++ea;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -297,9 +418,13 @@ struct AssembleArgs {
   const int64_t* nb_src[PG_MAX_HOPS + 1];
   const int64_t* nb_eid[PG_MAX_HOPS + 1];
   const int64_t* row_off[PG_MAX_HOPS + 1];
+  const uint32_t* bitmap[PG_MAX_HOPS + 1];       // [hop]: the vertices hop picked
+  const uint32_t* word_prefix[PG_MAX_HOPS + 1];  // [hop]: vertices of that layer below each bitmap word
   int64_t cap_layer[PG_MAX_HOPS + 1];
   int64_t cap_nodes, cap_edges;
   pg_nodeflow_buffers out;
+  const int64_t* labels;   // optional: label table indexed by parent id
+  int64_t* seed_labels;    // optional: [n_layer[0]] labels of the seed layer, in its (deduplicated) order
 };
 
 __global__ void assemble_kernel(AssembleArgs a) {
@@ -336,6 +461,8 @@ __global__ void assemble_kernel(AssembleArgs a) {
     const int64_t base = lay_off[j], nl = lay_off[j + 1] - base;
     const int64_t* lay = a.layer[h];
     for (int64_t i = tid; i < nl; i += nth) a.out.node_mapping[base + i] = lay[i];
+    if (j == L && a.seed_labels)
+      for (int64_t i = tid; i < nl; i += nth) a.seed_labels[i] = a.labels[lay[i]];
     if (j == 0) {
       for (int64_t i = tid; i <= nl; i += nth) a.out.indptr[i] = 0;
     } else {
@@ -345,8 +472,12 @@ __global__ void assemble_kernel(AssembleArgs a) {
       for (int64_t i = tid; i < nl; i += nth) a.out.indptr[base + i + 1] = eb + ro[i + 1];
       const int64_t* src = a.nb_src[hop];
       const int64_t* eid = a.nb_eid[hop];
+      const uint32_t* __restrict__ bm = a.bitmap[hop];
+      const uint32_t* __restrict__ wp = a.word_prefix[hop];
       for (int64_t e = tid; e < ne; e += nth) {
-        a.out.indices[eb + e] = col_base + src[e];
+        // NodeFlow id of the source = its rank in the (sorted, unique) layer the hop produced
+        const int64_t u = src[e], w = u >> 5;
+        a.out.indices[eb + e] = col_base + (int64_t)wp[w] + __popc(bm[w] & ((1u << (u & 31)) - 1));
         a.out.edge_mapping[eb + e] = eid[e];
       }
     }
@@ -395,11 +526,14 @@ struct pg_sampler {
   uint64_t seed = 0;
   int64_t max_seeds = 0, cap_nodes = 0, cap_edges = 0;
   int64_t nwords = 0;
+  int64_t nwords_pad = 0;   // nwords rounded up to a multiple of 4 (uint4 loads / stores)
   // workspace (device)
-  uint32_t* bitmap = nullptr;
-  uint32_t* word_prefix = nullptr;
-  int64_t* tile_sums = nullptr;
-  unsigned* ticket = nullptr;
+  uint32_t* seedbits = nullptr;      // V-bit scratch of the seed dedup; all-zero between calls
+  uint32_t* bitmaps = nullptr;       // [L][nwords_pad]: vertices picked by hop h+1 (zeroed by every call's seed kernel)
+  uint32_t* word_prefix = nullptr;   // [L][nwords_pad]
+  int64_t* tile_a = nullptr;
+  int64_t* tile_b = nullptr;
+  Control* ctl = nullptr;
   Counts* counts = nullptr;
   int64_t* hash_keys = nullptr;
   int* hash_minpos = nullptr;
@@ -530,6 +664,7 @@ pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, u
   PG_REQUIRE(num_hops >= 1 && num_hops <= PG_MAX_HOPS, "pg_sampler_create: num_hops must be in [1, PG_MAX_HOPS]");
   PG_REQUIRE(max_seeds >= 1 && max_seeds < INT_MAX && cap_nodes >= max_seeds && cap_edges >= 1,
              "pg_sampler_create: bad capacities");
+  PG_REQUIRE(g->num_nodes < (1ll << 32), "pg_sampler_create: more than 2^32 vertices per partition are not supported");
   for (int h = 0; h < num_hops; ++h) PG_REQUIRE(fanouts[h] >= 1, "pg_sampler_create: fanout must be >= 1");
   pg::DeviceGuard guard(g->dev);
   pg_sampler* s = new pg_sampler;
@@ -539,7 +674,8 @@ pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, u
   s->max_seeds = max_seeds;
   s->cap_nodes = cap_nodes;
   s->cap_edges = cap_edges;
-  s->nwords = (g->num_nodes + 31) / 32;
+  s->nwords = std::max<int64_t>(1, (g->num_nodes + 31) / 32);
+  s->nwords_pad = (s->nwords + 3) / 4 * 4;
   int64_t max_m = 0;
   for (int h = 0; h < num_hops; ++h) {
     s->fanouts[h] = fanouts[h];
@@ -555,11 +691,13 @@ pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, u
     s->allocs.push_back(q);
     *p = (T*)q;
   };
-  alloc(&s->bitmap, (size_t)s->nwords + 1);
-  alloc(&s->word_prefix, (size_t)s->nwords + 1);
-  const int64_t max_items = std::max<int64_t>(std::max(s->nwords, cap_nodes), max_seeds);
-  alloc(&s->tile_sums, (size_t)((max_items + kTile - 1) / kTile + 1));
-  alloc(&s->ticket, 1);
+  alloc(&s->seedbits, (size_t)s->nwords_pad);
+  alloc(&s->bitmaps, (size_t)s->nwords_pad * num_hops);
+  alloc(&s->word_prefix, (size_t)s->nwords_pad * num_hops);
+  const int64_t ntiles = (s->nwords + kBitsTile - 1) / kBitsTile;
+  alloc(&s->tile_a, (size_t)ntiles);
+  alloc(&s->tile_b, (size_t)ntiles);
+  alloc(&s->ctl, 1);
   alloc(&s->counts, 1);
   uint64_t tsize = 64;
   while (tsize < (uint64_t)max_seeds * 2) tsize <<= 1;
@@ -585,7 +723,7 @@ pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, u
                   (long long)cap_edges);
     return PG_ERR_NOMEM;
   }
-  PG_CUDA(cudaMemset(s->ticket, 0, sizeof(unsigned)));
+  PG_CUDA(cudaMemset(s->seedbits, 0, (size_t)s->nwords_pad * sizeof(uint32_t)));
   *out = s;
   return PG_OK;
 }
@@ -598,7 +736,8 @@ void pg_sampler_destroy(pg_sampler* s) {
 }
 
 static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, uint32_t k0, uint32_t k1,
-                             const uint32_t* d_key, const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream);
+                             const uint32_t* d_key, const pg_nodeflow_buffers* out, int64_t* h_meta, const int64_t* d_labels,
+                             int64_t* d_seed_labels, void* stream);
 
 void pg_minibatch_key(uint64_t seed, int64_t epoch, int64_t batch, uint32_t* key) {
   minibatch_key(seed, epoch, batch, &key[0], &key[1]);
@@ -609,17 +748,20 @@ pg_status pg_sample(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, int6
   PG_REQUIRE(s != nullptr, "pg_sample: null sampler");
   uint32_t k0, k1;
   minibatch_key(s->seed, epoch, batch, &k0, &k1);
-  return sample_impl(s, d_seeds, n_seeds, k0, k1, nullptr, out, h_meta, stream);
+  return sample_impl(s, d_seeds, n_seeds, k0, k1, nullptr, out, h_meta, nullptr, nullptr, stream);
 }
 
 pg_status pg_sample_keyed(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, const uint32_t* d_key,
-                          const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream) {
+                          const pg_nodeflow_buffers* out, int64_t* h_meta, const int64_t* d_labels, int64_t* d_seed_labels,
+                          void* stream) {
   PG_REQUIRE(s != nullptr && d_key != nullptr, "pg_sample_keyed: null sampler or key");
-  return sample_impl(s, d_seeds, n_seeds, 0, 0, d_key, out, h_meta, stream);
+  PG_REQUIRE((d_labels == nullptr) == (d_seed_labels == nullptr), "pg_sample_keyed: labels in and out go together");
+  return sample_impl(s, d_seeds, n_seeds, 0, 0, d_key, out, h_meta, d_labels, d_seed_labels, stream);
 }
 
 static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_seeds, uint32_t k0, uint32_t k1,
-                             const uint32_t* d_key, const pg_nodeflow_buffers* out, int64_t* h_meta, void* stream) {
+                             const uint32_t* d_key, const pg_nodeflow_buffers* out, int64_t* h_meta, const int64_t* d_labels,
+                             int64_t* d_seed_labels, void* stream) {
   PG_REQUIRE(s && out && out->node_mapping && out->indptr && out->indices && out->edge_mapping && out->meta,
              "pg_sample: null output buffer");
   PG_REQUIRE(n_seeds >= 0 && n_seeds <= s->max_seeds, "pg_sample: n_seeds exceeds max_seeds");
@@ -630,45 +772,31 @@ static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_se
   const int dev = g->dev;
 
   pg::TimedScope timed(PG_T_SAMPLE, st);
-  PG_CUDA(cudaMemsetAsync(s->counts, 0, sizeof(Counts), st));
-  // ---- seed layer
-  if (n_seeds > 0) {
-    PG_CUDA(cudaMemsetAsync(s->hash_keys, 0xFF, (s->hash_mask + 1) * sizeof(int64_t), st));
-    PG_CUDA(cudaMemsetAsync(s->hash_minpos, 0x7F, (s->hash_mask + 1) * sizeof(int), st));
-    seed_insert_kernel<<<grid_for(n_seeds, 256, dev), 256, 0, st>>>(d_seeds, n_seeds, s->hash_keys, s->hash_minpos,
-                                                                    s->hash_mask);
-    PG_CHECK_LAUNCH();
-    SeedKeep f{d_seeds, n_seeds, s->hash_keys, s->hash_minpos, s->hash_mask, s->layer[0]};
-    const int grid = grid_for(n_seeds, kTile, dev);
-    scan_pass1<<<grid, kScanThreads, 0, st>>>(f, s->tile_sums, s->ticket, &s->counts->n_layer[0]);
-    PG_CHECK_LAUNCH();
-    scan_pass2<<<grid, kScanThreads, 0, st>>>(f, s->tile_sums);
+  // 2 + 2 * hops kernels, no memset nodes, no host synchronisation:
+  //   seed_kernel | per hop: pick_kernel, bits_kernel | assemble_kernel (relabel folded in)
+  {
+    SeedArgs sa{d_seeds, n_seeds, g->indptr, s->fanouts[0], s->seedbits, s->hash_keys, s->hash_minpos, s->hash_mask,
+                s->layer[0], s->row_off[1], s->counts, s->ctl, (uint4*)s->bitmaps, s->nwords_pad * s->L / 4};
+    const int64_t zero_ctas = std::min<int64_t>((int64_t)pg::sm_count(dev) * 2, (sa.zero_vec + kSeedThreads * 4 - 1) / (kSeedThreads * 4));
+    seed_kernel<<<(int)(1 + std::max<int64_t>(zero_ctas, 0)), kSeedThreads, 0, st>>>(sa);
     PG_CHECK_LAUNCH();
   }
-  // ---- hops
+  const int64_t ntiles = (s->nwords + kBitsTile - 1) / kBitsTile;
   for (int h = 1; h <= s->L; ++h) {
     const int64_t cap_front = s->cap_layer[h - 1];
-    PG_CUDA(cudaMemsetAsync(s->bitmap, 0, (size_t)(s->nwords + 1) * sizeof(uint32_t), st));
-    FrontCount fc{g->indptr, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->fanouts[h - 1], s->row_off[h]};
-    const int grid_f = grid_for(cap_front, kTile, dev);
-    scan_pass1<<<grid_f, kScanThreads, 0, st>>>(fc, s->tile_sums, s->ticket, &s->counts->e_hop[h]);
-    PG_CHECK_LAUNCH();
-    scan_pass2<<<grid_f, kScanThreads, 0, st>>>(fc, s->tile_sums);
-    PG_CHECK_LAUNCH();
+    uint32_t* bitmap = s->bitmaps + (size_t)(h - 1) * s->nwords_pad;
     PickArgs pa{g->indptr, g->indices, g->eids, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->row_off[h],
-                s->fanouts[h - 1], (uint32_t)h, k0, k1, d_key, s->nb_src[h], s->nb_eid[h], s->cap_edges, s->bitmap,
+                s->fanouts[h - 1], (uint32_t)h, k0, k1, d_key, s->nb_src[h], s->nb_eid[h], s->cap_edges, bitmap,
                 s->scratch, s->scratch_stride};
     const int grid_p = (int)std::min<int64_t>(s->pick_grid, std::max<int64_t>(1, (cap_front + kPickWarps - 1) / kPickWarps));
     pick_kernel<<<grid_p, kPickWarps * 32, 0, st>>>(pa);
     PG_CHECK_LAUNCH();
-    BitCount bc{s->bitmap, s->nwords, s->word_prefix, s->layer[h], s->cap_layer[h]};
-    const int grid_b = grid_for(s->nwords, kTile, dev);
-    scan_pass1<<<grid_b, kScanThreads, 0, st>>>(bc, s->tile_sums, s->ticket, &s->counts->n_layer[h]);
-    PG_CHECK_LAUNCH();
-    scan_pass2<<<grid_b, kScanThreads, 0, st>>>(bc, s->tile_sums);
-    PG_CHECK_LAUNCH();
-    relabel_kernel<<<grid_for(s->cap_edges, 256, dev), 256, 0, st>>>(s->nb_src[h], &s->counts->e_hop[h], s->cap_edges,
-                                                                     s->bitmap, s->word_prefix);
+    const bool last = h == s->L;
+    BitsArgs ba{bitmap, s->nwords, s->word_prefix + (size_t)(h - 1) * s->nwords_pad, s->layer[h], s->cap_layer[h],
+                g->indptr, last ? 0 : s->fanouts[h], last ? nullptr : s->row_off[h + 1], s->tile_a, s->tile_b,
+                s->counts, s->ctl, h};
+    const int grid_b = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev) * 4);
+    bits_kernel<<<grid_b, kBitsThreads, 0, st>>>(ba);
     PG_CHECK_LAUNCH();
   }
   // ---- assemble
@@ -680,11 +808,15 @@ static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_se
     aa.nb_src[h] = s->nb_src[h];
     aa.nb_eid[h] = s->nb_eid[h];
     aa.row_off[h] = s->row_off[h];
+    aa.bitmap[h] = (h >= 1 && h <= s->L) ? s->bitmaps + (size_t)(h - 1) * s->nwords_pad : nullptr;
+    aa.word_prefix[h] = (h >= 1 && h <= s->L) ? s->word_prefix + (size_t)(h - 1) * s->nwords_pad : nullptr;
     aa.cap_layer[h] = s->cap_layer[h];
   }
   aa.cap_nodes = s->cap_nodes;
   aa.cap_edges = s->cap_edges;
   aa.out = *out;
+  aa.labels = d_labels;
+  aa.seed_labels = d_seed_labels;
   assemble_kernel<<<grid_for(s->cap_nodes + s->cap_edges, 256, dev, 4), 256, 0, st>>>(aa);
   PG_CHECK_LAUNCH();
   if (h_meta) PG_CUDA(cudaMemcpyAsync(h_meta, out->meta, PG_META_LEN * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

@@ -30,9 +30,10 @@ import gc
 import os
 import sys
 
+import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, profiling
 from .nodeflow import NodeBatch
 from .ops import _MODES, LinearConcat, LinearCrossEntropy, linear_concat_backward, linear_concat_forward
 from .parallel import PeerAdam
@@ -115,10 +116,11 @@ class GCNTrainEngine:
         self.fi = cacher._field_names.index(self.field)
         self.F = cacher.dims[self.field]
         seeds = torch.as_tensor(train_nid, dtype=torch.int64).cpu()
-        if torch.unique(seeds).numel() != seeds.numel():
-            # labels are gathered by seed position (s.labels[i] belongs to seeds[i]); the sampler's seed layer drops
-            # duplicates (first occurrence wins), which would shift every later row against its label
-            raise ValueError("GCNTrainEngine: train_nid must not contain duplicates")
+        # The sampler's seed layer drops duplicate seeds (first occurrence wins) and the model's output rows follow the
+        # seed LAYER, so labels are gathered in that order: on the device by the sampler itself (pg_sample_keyed's
+        # d_seed_labels), on the host (host_inputs) by the same first-occurrence rule when the seed list has duplicates —
+        # the reference's own partition files do (isolated train vertices all map to sub-graph id 0, utils.py:47-51).
+        self.has_dups = bool(torch.unique(seeds).numel() != seeds.numel())
         if shuffle:                                   # once, like NeighborSampler
             seeds = seeds[torch.randperm(len(seeds))]
         self.num_batches = (len(seeds) + self.batch - 1) // self.batch
@@ -214,10 +216,9 @@ class GCNTrainEngine:
         nfb = _lib.pg_nodeflow_buffers(*[_lib.ptr(s.nf[k]) for k in
                                          ("node_mapping", "indptr", "indices", "edge_mapping", "meta")])
         key = ctypes.c_void_p(s.seeds_key.data_ptr() + 8 * self.batch)
+        lab_in, lab_out = (None, None) if self.host_inputs else (self.labels_dev, s.labels)
         _lib.check(L.pg_sample_keyed(self.sampler, _lib.ptr(s.seeds_key), n_seeds, key, ctypes.byref(nfb), _lib.ptr(s.h_meta),
-                                     _lib.stream_ptr()), "pg_sample_keyed")
-        if not self.host_inputs:
-            torch.index_select(self.labels_dev, 0, s.seeds_key[:self.batch], out=s.labels)
+                                     _lib.ptr(lab_in), _lib.ptr(lab_out), _lib.stream_ptr()), "pg_sample_keyed")
 
     def _gather_body(self, s):
         """stage B: resolve + stage the input layer, aggregate block 0; all sized on the device. The frames of layers
@@ -253,7 +254,12 @@ class GCNTrainEngine:
                 s.stage_host[:n] = self.seeds_host[lo:lo + n]
                 s.stage_host[self.batch] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
                 s.seeds_key.copy_(s.stage_host, non_blocking=True)
-                torch.index_select(self.labels_host, 0, self.seeds_host[lo:lo + n], out=s.labels_host[:n])
+                batch_seeds = self.seeds_host[lo:lo + n]
+                if self.has_dups:                            # seed-layer order = first occurrences, in order
+                    b = batch_seeds.numpy()
+                    first = np.sort(np.unique(b, return_index=True)[1])
+                    batch_seeds = torch.from_numpy(b[first])
+                torch.index_select(self.labels_host, 0, batch_seeds, out=s.labels_host[:len(batch_seeds)])
                 s.labels.copy_(s.labels_host, non_blocking=True)
             else:
                 s.seeds_key[:n].copy_(self.seeds_dev[lo:lo + n], non_blocking=True)
@@ -389,7 +395,8 @@ class GCNTrainEngine:
         C = w1.shape[0]
         _lib.check(L.pg_linear_cross_entropy(_lib.ptr(d.a2), 64, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(s.labels), n_valid, 64, C,
                                              _lib.ptr(s.loss), _lib.ptr(d.ga2), 64, _lib.ptr(w1.grad),
-                                             _lib.ptr(b1.grad if b1 is not None else None), st), "pg_linear_cross_entropy")
+                                             _lib.ptr(b1.grad if b1 is not None else None), self._meta_ptr(s, 4 + self.L), st),
+                   "pg_linear_cross_entropy")
         _lib.check(L.pg_aggregate_bwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(d.ga2), 64,
                                           _lib.ptr(ghd), 64, caps[2], n1, 64, _MODES["mean"], None, st), "pg_aggregate_bwd_dyn")
         linear_concat_backward(x, ghd, out, True, w0.grad, b0.grad if b0 is not None else None, p, self.drop_seed_hidden,
@@ -467,31 +474,36 @@ class GCNTrainEngine:
             if s.h_meta_np[0] != _lib.PG_OK:
                 raise _lib.PGError("sampler reported status %d for minibatch %d" % (int(s.h_meta_np[0]), k))
             main.wait_event(s.loaded)
-            caps, _ = self._caps_for(s)
+            caps, lay = self._caps_for(s)
             if self.size_log is not None:
                 self.size_log.append(self.layer_sizes(k % _RING))
-            full = s.n_valid == self.batch
-            if self.use_graphs and full and self._warm:
-                entry = s.compute_graphs.get(caps)
-                if entry is None:
-                    entry = s.compute_graphs[caps] = self._capture_compute(s, caps)
-                entry[0].replay()
-                self.launches += entry[1]
-            else:
-                l0 = _lib.launch_count()
-                self._compute_body(s, caps, s.n_valid)
-                self.launches += _lib.launch_count() - l0
-                self._warm = True                            # optimizer state exists after the first eager step
+            n_rows = lay[self.L]                             # seed-layer rows (< n_valid when duplicates were dropped)
+            # the fused dense stage reads the row count on the device, so its captured graph serves any batch whose SEED
+            # count is full; the autograd body slices on the host and needs the full row count as well
+            full = s.n_valid == self.batch and (self._dense_ok or n_rows == self.batch)
+            with profiling.range('gpu-compute'):
+                if self.use_graphs and full and self._warm:
+                    entry = s.compute_graphs.get(caps)
+                    if entry is None:
+                        entry = s.compute_graphs[caps] = self._capture_compute(s, caps)
+                    entry[0].replay()
+                    self.launches += entry[1]
+                else:
+                    l0 = _lib.launch_count()
+                    self._compute_body(s, caps, n_rows)
+                    self.launches += _lib.launch_count() - l0
+                    self._warm = True                            # optimizer state exists after the first eager step
             s.done.record(main)
             if self.serialize:
                 torch.cuda.synchronize(self.dev)
             self.next_compute += 1
-            if self.next_issue < end:
-                self._issue_sample(self.next_issue)
-                self.next_issue += 1
-            if self.next_gather < end:
-                self._issue_gather(self.next_gather)
-                self.next_gather += 1
+            with profiling.range('gpu-load'):                # the NEXT minibatches' sampling / cache stages
+                if self.next_issue < end:
+                    self._issue_sample(self.next_issue)
+                    self.next_issue += 1
+                if self.next_gather < end:
+                    self._issue_gather(self.next_gather)
+                    self.next_gather += 1
             loss = s.loss
             if read_loss:
                 loss = float(s.loss.item())                  # D2H read of the step's result

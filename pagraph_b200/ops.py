@@ -160,7 +160,7 @@ class LinearCrossEntropy(torch.autograd.Function):
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().pg_linear_cross_entropy(_lib.ptr(x), x.stride(0), _lib.ptr(w), _lib.ptr(bias),
                                                           _lib.ptr(labels), n, K, C, _lib.ptr(loss), _lib.ptr(gx),
-                                                          gx.stride(0), _lib.ptr(gw), _lib.ptr(gb), _lib.stream_ptr()),
+                                                          gx.stride(0), _lib.ptr(gw), _lib.ptr(gb), None, _lib.stream_ptr()),
                        "pg_linear_cross_entropy")
         ctx.save_for_backward(gx, gw, gb)
         ctx.has_bias = bias is not None

@@ -10,7 +10,7 @@ import sys
 
 import torch
 
-from . import _lib
+from . import _lib, profiling
 from .nodeflow import Frame, FrameRef
 
 _REGISTERED = {}   # data_ptr -> nbytes of host tables this process pinned with pg_host_register
@@ -262,10 +262,11 @@ class GraphCacheServer:
         """
         if self._handle is None:
             raise RuntimeError("fetch_data before init_field")
-        offsets = nodeflow._layer_offsets
-        ids = nodeflow._node_mapping.tousertensor()
-        if not ids.is_cuda:
-            ids = ids.to(self._dev)
+        with profiling.range('cache-idxload'):
+            offsets = nodeflow._layer_offsets
+            ids = nodeflow._node_mapping.tousertensor()
+            if not ids.is_cuda:
+                ids = ids.to(self._dev)
         n = offsets[nodeflow.num_layers]
         first = 0
         if self.lazy_input and nodeflow.num_layers > 1:
@@ -274,7 +275,8 @@ class GraphCacheServer:
             nodeflow._node_frames[0] = FrameRef(Frame({name: LazyCacheRows(self, name, layer0)
                                                        for name in self._field_names}))
         lo0 = offsets[first]
-        outs = self._gather(ids[lo0:n], self._field_names)
+        with profiling.range('cache-fetch'):
+            outs = self._gather(ids[lo0:n], self._field_names)
         for i in range(first, nodeflow.num_layers):
             lo, hi = offsets[i] - lo0, offsets[i + 1] - lo0
             frame = {name: out[lo:hi] for name, out in zip(self._field_names, outs)}

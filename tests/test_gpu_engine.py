@@ -258,3 +258,36 @@ def test_peer_adam_two_ranks_equals_global_batch():
         opt.step()
     want = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
     np.testing.assert_allclose(res[0], want, rtol=2e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("host_inputs", [False, True])
+@pytest.mark.parametrize("n_hidden", [16, 32])
+def test_engine_with_duplicate_train_ids_matches_eager_loop(n_hidden, host_inputs):
+    """The reference's partition files contain duplicate train ids (isolated train vertices all become sub-graph id 0,
+    PaGraph/partition/utils.py:47-51). The sampler drops duplicate seeds, so the model's rows follow the seed LAYER: the
+    engine must pair them with the labels of that layer (not of the raw seed positions) and average over its row count —
+    exactly what the eager loop does with labels[nf.layer_parent_nid(-1)]."""
+    import torch
+    from pagraph_b200.engine import GCNTrainEngine
+    from pagraph_b200.storage import GraphCacheServer
+    g, store, labels, train, V, F, classes = _world()
+    rng = np.random.default_rng(3)
+    train = np.concatenate([train[:600], np.full(90, train[0]), train[5:25], train[600:900]])   # many repeats, every batch
+    rng.shuffle(train)
+    batch, fanouts, steps = 256, [6, 4], 6
+    want, want_params = _eager_losses(g, store, labels, train, V, F, classes, 900, batch, fanouts, steps, n_hidden=n_hidden)
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(["features", "norm"])
+    model = _model(F, classes, 0.0, n_hidden)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-2, capturable=True)
+    eng = GCNTrainEngine(g, cs, model, opt, train, labels, batch, fanouts, seed=11, shuffle=False, host_inputs=host_inputs)
+    assert eng.has_dups
+    got = [eng.steps(1, read_loss=True)]
+    cs.auto_cache(g, ["features", "norm"], capability=900)
+    got += [eng.steps(1, read_loss=True) for _ in range(2)]
+    last = eng.steps(steps - 3)
+    np.testing.assert_allclose(got, want[:3], rtol=2e-4)
+    np.testing.assert_allclose(float(last), want[-1], rtol=2e-4)
+    for a, b in zip([p.detach().cpu().numpy() for p in model.parameters()], want_params):
+        np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)
+    eng.close()

@@ -204,3 +204,59 @@ def test_graph_degrees():
     np.testing.assert_array_equal(dev_g.in_degrees().numpy(), np.diff(indptr))
     host_g = DGLGraph(coo)
     np.testing.assert_array_equal(host_g.out_degrees().numpy(), np.bincount(coo.row, minlength=500))
+
+
+def test_sample_offsets_beyond_2_31():
+    """64-bit paths: CSR offsets, edge ids and one in-degree above 2^31 (configs 4/5 of BASELINE.json have nnz > 2^31).
+    Vertex 0 owns a 2^31 + 7 entry row of zeros (a 17 GB `indices` array on the device, calloc'ed — untouched — on the
+    host); every other row lives behind it, so each offset the sampler touches needs more than 32 bits, and expanding
+    vertex 0 draws positions in [0, 2^31 + 7)."""
+    import torch
+    from pagraph_b200 import _lib
+    free, _ = torch.cuda.mem_get_info()
+    big = (1 << 31) + 7
+    if free < (big + (1 << 20)) * 8 + (4 << 30):
+        pytest.skip("needs ~21 GB of free device memory")
+    rng = np.random.default_rng(11)
+    V = 2000
+    deg = rng.integers(0, 30, V)
+    deg[0] = big
+    deg[1:21] = 3                                                   # short rows (taken whole) that will name vertex 0
+    indptr = np.zeros(V + 1, np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    nnz = int(indptr[-1])
+    tail = rng.integers(0, V, nnz - big).astype(np.int64)          # neighbours of vertices 1..V-1 (vertex 0 among them)
+    tail[indptr[1:21] - big] = 0
+    try:
+        indices = np.zeros(nnz, np.int64)                             # lazily mapped zero pages on the host
+    except MemoryError:
+        pytest.skip("host cannot map a 17 GB array")
+    indices[big:] = tail
+    d_indices = torch.zeros(nnz, dtype=torch.int64, device="cuda")
+    d_indices[big:] = torch.from_numpy(tail).cuda()
+    d_indptr = torch.from_numpy(indptr).cuda()
+    L = _lib.lib()
+    gh, sh = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(L.pg_graph_create_device(_lib.ptr(d_indptr), _lib.ptr(d_indices), None, V, nnz, 0, ctypes.byref(gh)),
+               "pg_graph_create_device")
+    seeds = np.concatenate([np.arange(1, 21), rng.choice(np.arange(21, V), 280, replace=False)]).astype(np.int64)
+    fanouts = [5, 4]
+    cap_nodes, cap_edges = 300 + 1500 + 6000, 1500 + 6000
+    fan = (ctypes.c_int64 * 2)(*fanouts)
+    _lib.check(L.pg_sampler_create(gh, 2, fan, 13, 300, cap_nodes, cap_edges, ctypes.byref(sh)), "pg_sampler_create")
+    bufs = [torch.zeros(cap_nodes, dtype=torch.int64, device="cuda"), torch.zeros(cap_nodes + 1, dtype=torch.int64, device="cuda"),
+            torch.zeros(cap_edges, dtype=torch.int64, device="cuda"), torch.zeros(cap_edges, dtype=torch.int64, device="cuda"),
+            torch.zeros(_lib.PG_META_LEN, dtype=torch.int64, device="cuda")]
+    c = _lib.pg_nodeflow_buffers(*[_lib.ptr(b) for b in bufs])
+    d_seeds = torch.from_numpy(seeds).cuda()
+    try:
+        _lib.check(L.pg_sample(sh, _lib.ptr(d_seeds), len(seeds), 0, 2, ctypes.byref(c), None, _lib.stream_ptr()), "pg_sample")
+        torch.cuda.synchronize()
+        meta = bufs[4].cpu().numpy()
+        ref = oracle.sample(indptr, indices, None, seeds, fanouts, seed=13, epoch=0, batch=2)
+        _assert_same(meta, [b.cpu().numpy() for b in bufs[:4]], ref)
+        assert ref.edge_mapping.max() > (1 << 31)                     # parent edge ids = CSR positions beyond 2^31
+        assert 0 in ref.layer_parent_nid(1) and (ref.edge_mapping < big).any()   # vertex 0 was expanded by random draws
+    finally:
+        L.pg_sampler_destroy(sh)
+        L.pg_graph_destroy(gh)

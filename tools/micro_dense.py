@@ -94,7 +94,7 @@ def main():
         def run_head(i):
             _lib.check(L.pg_linear_cross_entropy(_lib.ptr(a2), 64, _lib.ptr(head.weight), _lib.ptr(head.bias), _lib.ptr(y), nb,
                                                  64, C, _lib.ptr(loss), _lib.ptr(ga), 64, _lib.ptr(gw1), _lib.ptr(gb1),
-                                                 _lib.stream_ptr()), "pg_linear_cross_entropy")
+                                                 None, _lib.stream_ptr()), "pg_linear_cross_entropy")
         res["head_us"] = round(med(run_head, a.iters), 2)
     print(json.dumps(res))
 
