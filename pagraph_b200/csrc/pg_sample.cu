@@ -43,6 +43,12 @@ struct Control {
   unsigned tiles_done[PG_MAX_HOPS + 1];  // tiles whose sums are published
   unsigned tile_ctr2[PG_MAX_HOPS + 1];   // next tile of phase 2 (emit)
   unsigned ready[PG_MAX_HOPS + 1];       // tile prefixes are final
+  unsigned front_ctr1[PG_MAX_HOPS + 1];  // the same four for front_kernel
+  unsigned front_done[PG_MAX_HOPS + 1];
+  unsigned front_ctr2[PG_MAX_HOPS + 1];
+  unsigned front_ready[PG_MAX_HOPS + 1];
+  unsigned seed_ticket;                  // CTAs of the seed kernel that have finished their slice
+  unsigned seed_dup;                     // some seed occurred twice
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -53,13 +59,14 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 }
 
 // ------------------------------------------------------------------ kernel 1 of a call: the seed layer
-// CTA 0: ordered dedup of the seeds (first occurrence wins, Appendix A.3) and the row offsets of hop 1.
-//   Duplicates are detected with a V-bit scratch bitmap (atomicOr returns the old bit): a duplicate-free batch — every
-//   training batch — is copied through; only a batch that does contain duplicates takes the exact path (open-addressing
-//   table keyed by vertex with the minimum position, then an ordered compaction). The scratch bits are cleared again
-//   through the seed list itself (work proportional to the batch, not to V).
-// CTAs 1..: zero the per-hop bitmaps for this call (one contiguous range) — the only work proportional to V, written
-//   at HBM/L2 speed while CTA 0 is busy with its latency chain.
+// Every CTA: its slice of (a) zeroing the per-hop bitmaps of this call (one contiguous range — the only work proportional
+// to V, written at HBM/L2 speed) and (b) the duplicate check of the seeds: atomicOr into a V-bit scratch bitmap returns
+// the old bit, so a batch without duplicates — every training batch of a duplicate-free train set — is recognised in one
+// parallel pass and copied through as the seed layer.
+// The CTA that finishes last (ticket) runs the serial tail: for a batch WITH duplicates the exact ordered dedup (first
+// occurrence wins, Appendix A.3: open-addressing table keyed by vertex holding the minimum position, then an ordered
+// compaction); the scratch bits are cleared again through the seed list (work proportional to the batch); the row
+// offsets of hop 1 (exclusive scan of min(in_degree, fanout) over the seed layer).
 struct SeedArgs {
   const int64_t* seeds;
   int64_t n;
@@ -77,32 +84,64 @@ struct SeedArgs {
   int64_t zero_vec;   // uint4 count
 };
 
+// row_off[i] = exclusive prefix of min(in_degree(front[i]), fanout), i < n; row_off[n] = total. One CTA; kSeedItems
+// consecutive vertices per thread so that a round's indptr reads are all in flight together. Returns the total.
+__device__ __forceinline__ int64_t cta_row_offsets(const int64_t* __restrict__ indptr, const int64_t* front, int64_t n,
+                                                   int64_t fanout, int64_t* row_off, int64_t* sh) {
+  const int tid = threadIdx.x;
+  int64_t running = 0;
+  for (int64_t c0 = 0; c0 < n; c0 += (int64_t)kSeedThreads * kSeedItems) {
+    const int64_t i0 = c0 + (int64_t)tid * kSeedItems;
+    int64_t v[kSeedItems], c[kSeedItems];
+#pragma unroll
+    for (int k = 0; k < kSeedItems; ++k) v[k] = (i0 + k < n) ? __ldcg(front + i0 + k) : -1;
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kSeedItems; ++k) {
+      c[k] = v[k] >= 0 ? min(indptr[v[k] + 1] - indptr[v[k]], fanout) : 0;
+      s += c[k];
+    }
+    int64_t total;
+    int64_t excl = pg::block_exclusive_scan(s, total, sh) + running;
+#pragma unroll
+    for (int k = 0; k < kSeedItems; ++k) {
+      if (i0 + k < n) row_off[i0 + k] = excl;
+      excl += c[k];
+    }
+    running += total;
+  }
+  if (tid == 0) row_off[n] = running;
+  return running;
+}
+
 __global__ void __launch_bounds__(kSeedThreads) seed_kernel(SeedArgs a) {
   __shared__ int64_t sh[kSeedThreads / 32 + 1];
+  __shared__ bool s_last;
   const int tid = threadIdx.x;
-  if (blockIdx.x != 0 || gridDim.x == 1) {
-    const int64_t nz = gridDim.x == 1 ? 1 : gridDim.x - 1, bz = gridDim.x == 1 ? 0 : blockIdx.x - 1;
-    for (int64_t i = bz * kSeedThreads + tid; i < a.zero_vec; i += nz * kSeedThreads) a.zero_base[i] = make_uint4(0, 0, 0, 0);
-    if (blockIdx.x != 0) return;
-  }
-  for (int i = tid; i < (int)(sizeof(Counts) / 8); i += kSeedThreads) ((int64_t*)a.counts)[i] = 0;
-  for (int i = tid; i < (int)(sizeof(Control) / 4); i += kSeedThreads) ((unsigned*)a.ctl)[i] = 0;
+  const int64_t gtid = (int64_t)blockIdx.x * kSeedThreads + tid, gth = (int64_t)gridDim.x * kSeedThreads;
+  for (int64_t i = gtid; i < a.zero_vec; i += gth) a.zero_base[i] = make_uint4(0, 0, 0, 0);
+  // duplicate check + optimistic copy (all CTAs, one seed per thread and round)
   int dup = 0;
-  for (int64_t i = tid; i < a.n; i += kSeedThreads) {
+  for (int64_t i = gtid; i < a.n; i += gth) {
     const int64_t v = a.seeds[i];
     const uint32_t bit = 1u << (v & 31);
     dup |= (atomicOr(&a.seedbits[v >> 5], bit) & bit) != 0;
+    a.layer0[i] = v;
   }
-  const int any_dup = __syncthreads_or(dup);
+  if (__syncthreads_or(dup) && tid == 0) atomicOr(&a.ctl->seed_dup, 1u);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&a.ctl->seed_ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  // ---- serial tail (one CTA)
+  __threadfence();
+  const bool any_dup = atomicAdd(&a.ctl->seed_dup, 0u) != 0;
+  for (int64_t i = tid; i < a.n; i += kSeedThreads) a.seedbits[a.seeds[i] >> 5] = 0;   // scratch bitmap back to all-zero
+  for (int i = tid; i < (int)(sizeof(Counts) / 8); i += kSeedThreads) ((int64_t*)a.counts)[i] = 0;
+  for (int i = tid; i < (int)(sizeof(Control) / 4); i += kSeedThreads) ((unsigned*)a.ctl)[i] = 0;   // incl. ticket / dup
   int64_t n0 = a.n;
-  if (!any_dup) {
-    for (int64_t i = tid; i < a.n; i += kSeedThreads) {
-      const int64_t v = a.seeds[i];
-      a.layer0[i] = v;
-      a.seedbits[v >> 5] = 0;
-    }
-  } else {
-    for (int64_t i = tid; i < a.n; i += kSeedThreads) a.seedbits[a.seeds[i] >> 5] = 0;
+  if (any_dup) {
     for (uint64_t s = tid; s <= a.hash_mask; s += kSeedThreads) {
       a.hash_keys[s] = kEmptyKey;
       a.hash_minpos[s] = INT_MAX;
@@ -139,35 +178,105 @@ __global__ void __launch_bounds__(kSeedThreads) seed_kernel(SeedArgs a) {
     }
   }
   __syncthreads();
-  // row offsets of hop 1: exclusive scan of min(in_degree, fanout) over the seed layer, kSeedItems consecutive
-  // vertices per thread so that all of a round's indptr reads are in flight together
-  int64_t running = 0;
-  for (int64_t c0 = 0; c0 < n0; c0 += (int64_t)kSeedThreads * kSeedItems) {
-    const int64_t i0 = c0 + (int64_t)tid * kSeedItems;
-    int64_t c[kSeedItems];
-    int64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kSeedItems; ++k) {
-      c[k] = 0;
-      if (i0 + k < n0) {
-        const int64_t v = a.layer0[i0 + k];
-        c[k] = min(a.indptr[v + 1] - a.indptr[v], a.fanout0);
-      }
-      s += c[k];
-    }
-    int64_t total;
-    int64_t excl = pg::block_exclusive_scan(s, total, sh) + running;
-#pragma unroll
-    for (int k = 0; k < kSeedItems; ++k) {
-      if (i0 + k < n0) a.row_off1[i0 + k] = excl;
-      excl += c[k];
-    }
-    running += total;
-  }
+  const int64_t e1 = cta_row_offsets(a.indptr, a.layer0, n0, a.fanout0, a.row_off1, sh);
   if (tid == 0) {
-    a.row_off1[n0] = running;
     a.counts->n_layer[0] = n0;
-    a.counts->e_hop[1] = running;
+    a.counts->e_hop[1] = e1;
+  }
+}
+
+// ------------------------------------------------------------------ hops >= 2: row offsets of the frontier
+// row_off[h][i] = exclusive prefix of min(in_degree(layer[h-1][i]), fanout): one kernel, tiles of the frontier handed
+// out by an atomic counter (work proportional to the frontier and balanced by frontier index, whatever the vertex ids),
+// per-tile sums -> the CTA publishing the last one turns them into tile prefixes and raises `ready` -> every CTA
+// re-derives its tiles' offsets. Same hand-off as bits_kernel below; no co-residency requirement.
+constexpr int kFrontItems = 4;
+constexpr int kFrontTile = kSeedThreads * kFrontItems;
+
+struct FrontArgs {
+  const int64_t* indptr;
+  const int64_t* front;      // layer[h-1]
+  const int64_t* n_front;    // device count
+  int64_t cap_front;
+  int64_t fanout;
+  int64_t* row_off;          // [cap_front + 1]
+  int64_t* tile_b;           // [tiles]
+  int64_t* e_hop;            // &counts->e_hop[h]
+  Control* ctl;
+  int h;
+};
+
+__global__ void __launch_bounds__(kSeedThreads) front_kernel(FrontArgs a) {
+  __shared__ int64_t sh[kSeedThreads / 32 + 1];
+  __shared__ unsigned s_tile;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int64_t n = min(*a.n_front, a.cap_front);
+  const int64_t ntiles = max((n + kFrontTile - 1) / kFrontTile, (int64_t)1);
+  for (int phase = 0; phase < 2; ++phase) {
+    unsigned* ctr = phase == 0 ? &a.ctl->front_ctr1[a.h] : &a.ctl->front_ctr2[a.h];
+    while (true) {
+      if (tid == 0) s_tile = atomicAdd(ctr, 1u);
+      __syncthreads();
+      const int64_t tile = s_tile;
+      if (tile >= ntiles) break;
+      const int64_t i0 = tile * kFrontTile + (int64_t)tid * kFrontItems;
+      int64_t v[kFrontItems], c[kFrontItems];
+#pragma unroll
+      for (int k = 0; k < kFrontItems; ++k) v[k] = (i0 + k < n) ? __ldcg(a.front + i0 + k) : -1;
+      int64_t s = 0;
+#pragma unroll
+      for (int k = 0; k < kFrontItems; ++k) {
+        c[k] = v[k] >= 0 ? min(a.indptr[v[k] + 1] - a.indptr[v[k]], a.fanout) : 0;
+        s += c[k];
+      }
+      int64_t total;
+      int64_t excl = pg::block_exclusive_scan(s, total, sh);
+      if (phase == 0) {
+        if (tid == 0) {
+          a.tile_b[tile] = total;
+          __threadfence();
+          s_last = atomicAdd(&a.ctl->front_done[a.h], 1u) == (unsigned)(ntiles - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+          __threadfence();
+          const int64_t chunk = (ntiles + kSeedThreads - 1) / kSeedThreads;
+          const int64_t lo = min((int64_t)tid * chunk, ntiles), hi = min(lo + chunk, ntiles);
+          int64_t lb = 0;
+          for (int64_t i = lo; i < hi; ++i) lb += __ldcg(a.tile_b + i);
+          int64_t tot;
+          int64_t run = pg::block_exclusive_scan(lb, tot, sh);
+          for (int64_t i = lo; i < hi; ++i) {
+            const int64_t x = __ldcg(a.tile_b + i);
+            a.tile_b[i] = run;
+            run += x;
+          }
+          if (tid == 0) {
+            *a.e_hop = tot;
+            a.row_off[n] = tot;
+          }
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) atomicExch(&a.ctl->front_ready[a.h], 1u);
+        }
+      } else {
+        excl += __ldcg(a.tile_b + tile);
+#pragma unroll
+        for (int k = 0; k < kFrontItems; ++k) {
+          if (i0 + k < n) a.row_off[i0 + k] = excl;
+          excl += c[k];
+        }
+      }
+      __syncthreads();
+    }
+    if (phase == 0) {
+      if (tid == 0) {
+        while (atomicAdd(&a.ctl->front_ready[a.h], 0u) == 0u) __nanosleep(64);
+        __threadfence();
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -264,10 +373,9 @@ __global__ void __launch_bounds__(kPickWarps * 32) pick_kernel(PickArgs a) {
 // ------------------------------------------------------------------ per-hop: bitmap -> sorted unique layer + ranks
 // One kernel per hop. The vertices picked by hop h are the set bits of bitmap[h]; ascending bit order IS the layer's
 // order (sorted by parent id, Appendix A.4), so "dedup + sort" is a popcount prefix sum:
-//   phase 1  tiles of kBitsTile words, handed out by an atomic counter: per-tile (vertex count, sum of the next hop's
-//            row lengths min(in_degree, fanout)); the CTA that publishes the last tile turns the sums into exclusive
-//            tile prefixes and raises `ready`;
-//   phase 2  tiles handed out again: word_prefix[w], layer[h][rank] = vertex, row_off[h+1][rank] = edge offset.
+//   phase 1  tiles of kBitsTile words, handed out by an atomic counter: per-tile vertex counts; the CTA that publishes
+//            the last tile turns the sums into exclusive tile prefixes and raises `ready`;
+//   phase 2  tiles handed out again: word_prefix[w] (rank of the word's first vertex) and layer[h][rank] = vertex.
 // CTAs that find no tile left just wait for `ready`; nothing a running CTA waits for depends on a CTA that is not
 // running yet, so the kernel needs no co-residency guarantee (and no cooperative launch).
 struct BitsArgs {
@@ -276,26 +384,11 @@ struct BitsArgs {
   uint32_t* word_prefix;
   int64_t* layer;             // [cap]
   int64_t cap;
-  const int64_t* indptr;
-  int64_t fanout_next;        // row lengths of the next hop (ignored when row_off_next is null)
-  int64_t* row_off_next;      // [cap + 1] or null (last hop)
   int64_t* tile_a;            // [ntiles] vertex counts -> exclusive prefixes
-  int64_t* tile_b;            // [ntiles] edge counts   -> exclusive prefixes
-  Counts* counts;
+  int64_t* n_layer;           // &counts->n_layer[h]
   Control* ctl;
   int h;
 };
-
-__device__ __forceinline__ int64_t rows_of_word(const BitsArgs& a, int64_t w, uint32_t bits) {
-  int64_t s = 0;
-  while (bits) {
-    const int b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    const int64_t v = w * 32 + b;
-    s += min(a.indptr[v + 1] - a.indptr[v], a.fanout_next);
-  }
-  return s;
-}
 
 __global__ void __launch_bounds__(kBitsThreads) bits_kernel(BitsArgs a) {
   __shared__ int64_t sh[kBitsThreads / 32 + 1];
@@ -303,110 +396,68 @@ __global__ void __launch_bounds__(kBitsThreads) bits_kernel(BitsArgs a) {
   __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int64_t ntiles = (a.nwords + kBitsTile - 1) / kBitsTile;
-  const bool want_b = a.row_off_next != nullptr;
-  // ---- phase 1
-  while (true) {
-    if (tid == 0) s_tile = atomicAdd(&a.ctl->tile_ctr1[a.h], 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= ntiles) break;
-    const int64_t w0 = tile * kBitsTile + (int64_t)tid * 4;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (w0 < a.nwords) q = *(const uint4*)(a.bitmap + w0);
-    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
-    int64_t na = 0, nb = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      na += __popc(wd[k]);
-      if (want_b && wd[k]) nb += rows_of_word(a, w0 + k, wd[k]);
-    }
-    int64_t ta, tb = 0;
-    pg::block_exclusive_scan(na, ta, sh);
-    if (want_b) pg::block_exclusive_scan(nb, tb, sh);
-    if (tid == 0) {
-      a.tile_a[tile] = ta;
-      a.tile_b[tile] = tb;
-      __threadfence();
-      s_last = atomicAdd(&a.ctl->tiles_done[a.h], 1u) == (unsigned)(ntiles - 1);
-    }
-    __syncthreads();
-    if (s_last) {  // every tile sum is published: exclusive prefixes over the tiles, totals, release
-      __threadfence();
-      const int64_t chunk = (ntiles + kBitsThreads - 1) / kBitsThreads;
-      const int64_t lo = min((int64_t)tid * chunk, ntiles), hi = min(lo + chunk, ntiles);
-      int64_t la = 0, lb = 0;
-      for (int64_t i = lo; i < hi; ++i) {
-        la += __ldcg(a.tile_a + i);
-        lb += __ldcg(a.tile_b + i);
-      }
-      int64_t tot_a, tot_b;
-      int64_t run_a = pg::block_exclusive_scan(la, tot_a, sh);
-      int64_t run_b = pg::block_exclusive_scan(lb, tot_b, sh);
-      for (int64_t i = lo; i < hi; ++i) {
-        const int64_t xa = __ldcg(a.tile_a + i), xb = __ldcg(a.tile_b + i);
-        a.tile_a[i] = run_a;
-        a.tile_b[i] = run_b;
-        run_a += xa;
-        run_b += xb;
-      }
-      if (tid == 0) {
-        a.counts->n_layer[a.h] = tot_a;
-        if (want_b) {
-          a.counts->e_hop[a.h + 1] = tot_b;
-          a.row_off_next[min(tot_a, a.cap)] = tot_b;
-        }
-      }
-      __threadfence();
+  for (int phase = 0; phase < 2; ++phase) {
+    unsigned* ctr = phase == 0 ? &a.ctl->tile_ctr1[a.h] : &a.ctl->tile_ctr2[a.h];
+    while (true) {
+      if (tid == 0) s_tile = atomicAdd(ctr, 1u);
       __syncthreads();
-      if (tid == 0) atomicExch(&a.ctl->ready[a.h], 1u);
-    }
-    __syncthreads();
-  }
-  // ---- wait for the tile prefixes
-  if (tid == 0) {
-    while (atomicAdd(&a.ctl->ready[a.h], 0u) == 0u) __nanosleep(64);
-    __threadfence();
-  }
-  __syncthreads();
-  // ---- phase 2
-  while (true) {
-    if (tid == 0) s_tile = atomicAdd(&a.ctl->tile_ctr2[a.h], 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
-    if (tile >= ntiles) break;
-    const int64_t w0 = tile * kBitsTile + (int64_t)tid * 4;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (w0 < a.nwords) q = *(const uint4*)(a.bitmap + w0);
-    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
-    int64_t na = 0, nb = 0;
+      const int64_t tile = s_tile;
+      if (tile >= ntiles) break;
+      const int64_t w0 = tile * kBitsTile + (int64_t)tid * 4;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (w0 < a.nwords) q = __ldcg((const uint4*)(a.bitmap + w0));
+      const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+      const int64_t na = __popc(wd[0]) + __popc(wd[1]) + __popc(wd[2]) + __popc(wd[3]);
+      int64_t ta;
+      int64_t ea = pg::block_exclusive_scan(na, ta, sh);
+      if (phase == 0) {
+        if (tid == 0) {
+          a.tile_a[tile] = ta;
+          __threadfence();
+          s_last = atomicAdd(&a.ctl->tiles_done[a.h], 1u) == (unsigned)(ntiles - 1);
+        }
+        __syncthreads();
+        if (s_last) {  // every tile sum is published: exclusive prefixes over the tiles, total, release
+          __threadfence();
+          const int64_t chunk = (ntiles + kBitsThreads - 1) / kBitsThreads;
+          const int64_t lo = min((int64_t)tid * chunk, ntiles), hi = min(lo + chunk, ntiles);
+          int64_t la = 0;
+          for (int64_t i = lo; i < hi; ++i) la += __ldcg(a.tile_a + i);
+          int64_t tot;
+          int64_t run = pg::block_exclusive_scan(la, tot, sh);
+          for (int64_t i = lo; i < hi; ++i) {
+            const int64_t x = __ldcg(a.tile_a + i);
+            a.tile_a[i] = run;
+            run += x;
+          }
+          if (tid == 0) *a.n_layer = tot;
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) atomicExch(&a.ctl->ready[a.h], 1u);
+        }
+      } else {
+        ea += __ldcg(a.tile_a + tile);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      na += __popc(wd[k]);
-      if (want_b && wd[k]) nb += rows_of_word(a, w0 + k, wd[k]);
-    }
-    int64_t ta, tb;
-    int64_t ea = pg::block_exclusive_scan(na, ta, sh) + __ldcg(a.tile_a + tile);
-    int64_t eb = 0;
-    if (want_b) eb = pg::block_exclusive_scan(nb, tb, sh) + __ldcg(a.tile_b + tile);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (w0 + k < a.nwords) a.word_prefix[w0 + k] = (uint32_t)ea;
-      uint32_t bits = wd[k];
-      while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int64_t v = (w0 + k) * 32 + b;
-        if (ea < a.cap) {
-          a.layer[ea] = v;
-          if (want_b) {
-            a.row_off_next[ea] = eb;
-            eb += min(a.indptr[v + 1] - a.indptr[v], a.fanout_next);
+        for (int k = 0; k < 4; ++k) {
+          if (w0 + k < a.nwords) a.word_prefix[w0 + k] = (uint32_t)ea;
+          uint32_t bits = wd[k];
+          while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (ea < a.cap) a.layer[ea] = (w0 + k) * 32 + b;
+            ++ea;
           }
         }
-        ++ea;
       }
+      __syncthreads();
     }
-    __syncthreads();
+    if (phase == 0) {
+      if (tid == 0) {
+        while (atomicAdd(&a.ctl->ready[a.h], 0u) == 0u) __nanosleep(64);
+        __threadfence();
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -696,7 +747,7 @@ pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, u
   alloc(&s->word_prefix, (size_t)s->nwords_pad * num_hops);
   const int64_t ntiles = (s->nwords + kBitsTile - 1) / kBitsTile;
   alloc(&s->tile_a, (size_t)ntiles);
-  alloc(&s->tile_b, (size_t)ntiles);
+  alloc(&s->tile_b, (size_t)((cap_nodes + kFrontTile - 1) / kFrontTile + 1));
   alloc(&s->ctl, 1);
   alloc(&s->counts, 1);
   uint64_t tsize = 64;
@@ -724,6 +775,7 @@ pg_status pg_sampler_create(pg_graph* g, int num_hops, const int64_t* fanouts, u
     return PG_ERR_NOMEM;
   }
   PG_CUDA(cudaMemset(s->seedbits, 0, (size_t)s->nwords_pad * sizeof(uint32_t)));
+  PG_CUDA(cudaMemset(s->ctl, 0, sizeof(Control)));   // every call's seed kernel leaves it zeroed for the next one
   *out = s;
   return PG_OK;
 }
@@ -772,29 +824,35 @@ static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_se
   const int dev = g->dev;
 
   pg::TimedScope timed(PG_T_SAMPLE, st);
-  // 2 + 2 * hops kernels, no memset nodes, no host synchronisation:
-  //   seed_kernel | per hop: pick_kernel, bits_kernel | assemble_kernel (relabel folded in)
+  // kernels of one call (no memset nodes, no host synchronisation):
+  //   seed_kernel | hop 1: pick_kernel, bits_kernel | hop h >= 2: front_kernel, pick_kernel, bits_kernel | assemble_kernel
   {
     SeedArgs sa{d_seeds, n_seeds, g->indptr, s->fanouts[0], s->seedbits, s->hash_keys, s->hash_minpos, s->hash_mask,
                 s->layer[0], s->row_off[1], s->counts, s->ctl, (uint4*)s->bitmaps, s->nwords_pad * s->L / 4};
-    const int64_t zero_ctas = std::min<int64_t>((int64_t)pg::sm_count(dev) * 2, (sa.zero_vec + kSeedThreads * 4 - 1) / (kSeedThreads * 4));
-    seed_kernel<<<(int)(1 + std::max<int64_t>(zero_ctas, 0)), kSeedThreads, 0, st>>>(sa);
+    const int64_t want = std::max((sa.zero_vec + kSeedThreads * 4 - 1) / (kSeedThreads * 4), (n_seeds + kSeedThreads - 1) / kSeedThreads);
+    const int grid_s = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)pg::sm_count(dev) * 2));
+    seed_kernel<<<grid_s, kSeedThreads, 0, st>>>(sa);
     PG_CHECK_LAUNCH();
   }
   const int64_t ntiles = (s->nwords + kBitsTile - 1) / kBitsTile;
   for (int h = 1; h <= s->L; ++h) {
     const int64_t cap_front = s->cap_layer[h - 1];
     uint32_t* bitmap = s->bitmaps + (size_t)(h - 1) * s->nwords_pad;
+    if (h >= 2) {
+      FrontArgs fa{g->indptr, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->fanouts[h - 1], s->row_off[h],
+                   s->tile_b, &s->counts->e_hop[h], s->ctl, h};
+      const int grid_f = (int)std::min<int64_t>((cap_front + kFrontTile - 1) / kFrontTile, (int64_t)pg::sm_count(dev) * 2);
+      front_kernel<<<std::max(grid_f, 1), kSeedThreads, 0, st>>>(fa);
+      PG_CHECK_LAUNCH();
+    }
     PickArgs pa{g->indptr, g->indices, g->eids, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->row_off[h],
                 s->fanouts[h - 1], (uint32_t)h, k0, k1, d_key, s->nb_src[h], s->nb_eid[h], s->cap_edges, bitmap,
                 s->scratch, s->scratch_stride};
     const int grid_p = (int)std::min<int64_t>(s->pick_grid, std::max<int64_t>(1, (cap_front + kPickWarps - 1) / kPickWarps));
     pick_kernel<<<grid_p, kPickWarps * 32, 0, st>>>(pa);
     PG_CHECK_LAUNCH();
-    const bool last = h == s->L;
     BitsArgs ba{bitmap, s->nwords, s->word_prefix + (size_t)(h - 1) * s->nwords_pad, s->layer[h], s->cap_layer[h],
-                g->indptr, last ? 0 : s->fanouts[h], last ? nullptr : s->row_off[h + 1], s->tile_a, s->tile_b,
-                s->counts, s->ctl, h};
+                s->tile_a, &s->counts->n_layer[h], s->ctl, h};
     const int grid_b = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev) * 4);
     bits_kernel<<<grid_b, kBitsThreads, 0, st>>>(ba);
     PG_CHECK_LAUNCH();
