@@ -101,6 +101,9 @@ def make_parser():
 
 
 if __name__ == '__main__':
+    if os.environ.get("PG_DEBUG_HANG"):        # dump every thread's stack and exit if the run takes longer than this many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PG_DEBUG_HANG"]), exit=True)
     a = make_parser().parse_args()
     if a.gpu is not None:
         os.environ['CUDA_VISIBLE_DEVICES'] = str(a.gpu)

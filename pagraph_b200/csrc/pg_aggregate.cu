@@ -13,6 +13,7 @@
 //   * no degree pass, no atomics, deterministic edge order in the forward;
 //   * backward scatters grad rows with 16-byte vector atomics (red.global.add.v4.f32).
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "pg_common.cuh"
@@ -184,36 +185,28 @@ __global__ void __launch_bounds__(kAggThreads) agg_bwd_kernel(AggBwdArgs a, int 
 }
 
 // ------------------------------------------------------------------ aggregation from row pointers (fused cache lookup)
-// TMA-staged: a warp owns a ring of DEPTH shared-memory buffers of GROUP rows each. For every task
-// (one destination row, <= GROUP of its edges) the lanes read cols -> rowptr, lane 0 arms the buffer's
-// mbarrier with the byte count and each lane pulls its source row with one cp.async.bulk (a 2400-byte
-// row = one descriptor, no registers held while in flight); the warp then sums the staged rows from
-// shared memory (conflict-free 16-byte lanes), applying the dropout mask on the fly, and re-arms the
-// buffer for task t+DEPTH. Bytes in flight per SM = warps * DEPTH * GROUP * row bytes, independent of
-// register pressure; every source row is read from HBM once per edge, every dst row written once.
+// TMA-staged: a warp owns a ring of DEPTH shared-memory buffers of GROUP rows each. For every task (one destination row,
+// <= GROUP of its edges) the lanes read cols -> rowptr, lane 0 arms the buffer's mbarrier with the byte count and each
+// lane pulls its source row with one cp.async.bulk (a 2400-byte row = one descriptor, no registers held while in
+// flight); the warp then sums the staged rows from shared memory (conflict-free 16-byte lanes), applying the dropout
+// mask on the fly, and re-arms the buffer for task t+DEPTH. Bytes in flight per SM = warps * DEPTH * GROUP * row bytes,
+// independent of register pressure; every source row is read from HBM once per edge, every dst row written once.
+//
+// Instruction diet (r2, from the ncu source view of the r1 kernel: 316 warp instructions per edge of which 85 were the
+// loads + mask + accumulate): the issuing side is the only task cursor — it leaves {count, last, row, degree} of each
+// task in a shared-memory ring slot that the consuming side reads back with one LDS.128, all in 32-bit; the dropout
+// column keys live in shared memory (under the 96-register cap the compiler re-derived the five splitmix64 keys in
+// every round); the row width is a template constant for the 600-float rows of the reference (the per-chunk `col < nvec`
+// tests become compile-time, one predicated chunk instead of five divergence regions); shared memory is addressed with
+// 32-bit shared-window addresses; the mean is one reciprocal per row and a multiply, not 4 divisions per float4.
 constexpr int kRowsMaxDepth = 4;
 constexpr int kRowsMaxGroup = 16;
 
-struct TaskCursor {  // walks (row, edge-chunk) tasks of one warp in order
-  int64_t r, s, e, off;
-  __device__ __forceinline__ void open(const pg::AggRowsArgs& a, int64_t row) {
-    r = row;
-    off = 0;
-    if (r < a.n_dst) {
-      s = a.indptr[r];
-      e = a.indptr[r + 1];
-    } else {
-      s = e = 0;
-    }
-  }
-  __device__ __forceinline__ bool valid(const pg::AggRowsArgs& a) const { return r < a.n_dst; }
-  __device__ __forceinline__ int count(int group) const { return (int)min((int64_t)group, e - s - off); }
-  __device__ __forceinline__ bool last(int group) const { return off + group >= e - s; }
-  __device__ __forceinline__ void next(const pg::AggRowsArgs& a, int group, int64_t stride) {
-    if (last(group)) open(a, r + stride);
-    else off += group;
-  }
-};
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 // acc += drop(v): the k-th 16-bit lane of h decides component k. The upper lanes are compared in place
 // (x >> 16 >= thr  <=>  x >= thr << 16), so a float4 costs 2 shifts + 4 compares + 4 predicated FMAs.
@@ -225,131 +218,156 @@ __device__ __forceinline__ void acc_drop4(float4& acc, const float4 v, uint64_t 
   if (hi >= thr_hi) acc.w = fmaf(v.w, scale, acc.w);
 }
 
-// ILP = rows consumed per round. With the row-key x column-key mask (one multiply per float4) ILP = 2 fits in 96
-// registers (512 threads x 96 = 48 k of the SM's 64 k registers, so the sampler's small CTAs on the other stream still find
-// room next to it) and is the faster choice both alone (gather stage 0.203 vs 0.225 ms at config 2) and in the pipelined
-// step (0.388 vs 0.408 ms); ILP = 1 (72 registers) stays selectable with PG_AGG_ILP=1.
-template <int W, int CH, bool DROP, int ILP>
-__global__ void __launch_bounds__(W * 32) __maxnreg__(ILP == 1 ? 80 : 96)
+// NVEC: float4 per row when known at compile time (150 for the reference's 600-float features), 0 = a.dim / 4.
+// Rows are consumed two at a time (2 * CH independent shared-memory loads in flight); 96 registers so that 16 warps
+// leave room for the sampler's small CTAs on the other stream.
+template <int W, int CH, bool DROP, int NVEC>
+__global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
     agg_rows_tma_kernel(pg::AggRowsArgs a, int group, int depth) {
-  constexpr int kRowsWarps = W;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[kRowsWarps * kRowsMaxDepth];
-  __shared__ uint64_t row_key[kRowsWarps][kRowsMaxDepth][kRowsMaxGroup];  // dropout row key of every staged row
+  __shared__ __align__(8) uint64_t bars[W * kRowsMaxDepth];
+  __shared__ uint64_t row_key[W][kRowsMaxDepth][kRowsMaxGroup];  // dropout row key of every staged row
+  __shared__ int4 task_meta[W][kRowsMaxDepth];                    // {rows staged, last task of its dst row, dst row, degree}
+  __shared__ uint64_t col_key[DROP ? CH * 32 : 1];                // dropout column keys (one per float4 column group)
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nvec = a.dim >> 2;
-  const uint32_t row_bytes = (uint32_t)a.dim * 4u;
+  const int nvec = NVEC ? NVEC : (a.dim >> 2);
+  const uint32_t row_bytes = (uint32_t)nvec * 16u;
   const uint32_t warp_smem = pg::smem_u32(smem) + (uint32_t)w * (uint32_t)(depth * group) * row_bytes;
   if (lane < depth) pg::mbar_init(pg::smem_u32(&bars[w * kRowsMaxDepth + lane]), 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
-  const int64_t warp0 = (int64_t)blockIdx.x * kRowsWarps + w, nwarps = (int64_t)gridDim.x * kRowsWarps;
+  if (DROP) {
+    for (int i = threadIdx.x; i < CH * 32; i += W * 32) col_key[i] = pg::drop_colkey((uint32_t)i);
+    __syncthreads();
+  } else {
+    __syncwarp();
+  }
+  const int warp0 = (int)(blockIdx.x * W + w), nwarps = (int)(gridDim.x * W);
   const uint64_t stepkey = DROP ? pg::drop_stepkey(a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull)) : 0ull;
-  uint64_t col_key[CH];  // dropout column keys of this lane's float4 groups
-#pragma unroll
-  for (int c = 0; c < CH; ++c) col_key[c] = DROP ? pg::drop_colkey((uint32_t)(c * 32 + lane)) : 0ull;
   const int64_t cap_dst = a.n_dst;
   if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
   a.zero_rows_to = pg::resolve_zero_rows(a.zero_rows_to, a.n_dst, cap_dst);
+  const int n_dst = (int)a.n_dst;
+  const uint32_t thr_hi = a.drop_thr << 16;
+  const float keep_scale = a.keep_scale;
+  const bool mean = a.mode == PG_AGG_MEAN;
 
-  auto issue = [&](const TaskCursor& c, int buf) {
-    const int cnt = c.count(group);
+  // ---- issuing side: the only task cursor. (ir, ipos, irem) = row being issued, absolute position of its next edge,
+  // edges left; the row after it is opened one step ahead so that its indptr reads are off the critical path.
+  int ir = warp0, irem = 0, ideg = 0;
+  int64_t ipos = 0, nxt_s = 0, nxt_e = 0;
+  auto open_next = [&](int r) {  // prefetch (s, e) of row r
+    if (r < n_dst) {
+      nxt_s = a.indptr[r];
+      nxt_e = a.indptr[r + 1];
+    }
+  };
+  open_next(ir);
+  if (ir < n_dst) {
+    ipos = nxt_s;
+    ideg = irem = (int)(nxt_e - nxt_s);
+    open_next(ir + nwarps);
+  }
+  auto issue = [&](int buf) {  // precondition: ir < n_dst
+    const int cnt = min(group, irem);
     const uint32_t bar = pg::smem_u32(&bars[w * kRowsMaxDepth + buf]);
     const float* src = nullptr;
     if (lane < cnt) {
-      const int64_t j = a.cols[c.s + c.off + lane] - a.col_base;
+      const int64_t j = a.cols[ipos + lane] - a.col_base;
       src = a.rowptr[j];
       if (DROP) row_key[w][buf][lane] = pg::drop_rowkey(stepkey, (uint64_t)j);  // one hash per fetched row, lanes in parallel
     }
-    if (lane == 0) pg::mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
+    if (lane == 0) {
+      task_meta[w][buf] = make_int4(cnt, irem <= group, ir, ideg);
+      pg::mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
+    }
     __syncwarp();
     if (lane < cnt) pg::bulk_g2s(warp_smem + (uint32_t)(buf * group + lane) * row_bytes, src, row_bytes, bar);
+    ipos += cnt;
+    irem -= cnt;
+    if (irem <= 0) {  // next destination row
+      ir += nwarps;
+      if (ir < n_dst) {
+        ipos = nxt_s;
+        ideg = irem = (int)(nxt_e - nxt_s);
+        open_next(ir + nwarps);
+      }
+    }
   };
+  int issued = 0;
+  for (; issued < depth && ir < n_dst; ++issued) issue(issued);
 
-  TaskCursor ci, cc;  // issue / consume cursors over the same task sequence
-  ci.open(a, warp0);
-  cc.open(a, warp0);
-  for (int d = 0; d < depth && ci.valid(a); ++d) {
-    issue(ci, d);
-    ci.next(a, group, nwarps);
-  }
   float4 acc[CH];
 #pragma unroll
   for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t phase_bits = 0;  // bit b = parity to wait for on buffer b
   int buf = 0;
-  while (cc.valid(a)) {
-    const int cnt = cc.count(group);
+  const uint32_t lane_off = (uint32_t)lane * 16u;
+  // consumed tasks == issued tasks: the loop ends when nothing issued is left unconsumed
+  for (int pending = issued; pending > 0;) {
     const uint32_t bar = pg::smem_u32(&bars[w * kRowsMaxDepth + buf]);
     while (!pg::mbar_try_wait(bar, (phase_bits >> buf) & 1u)) {
     }
     phase_bits ^= 1u << buf;
-    const unsigned char* base = smem + ((size_t)w * depth * group + (size_t)buf * group) * row_bytes;
-    const uint32_t thr_hi = a.drop_thr << 16;
+    const int4 meta = task_meta[w][buf];
+    const int cnt = meta.x;
+    const uint32_t base = warp_smem + (uint32_t)(buf * group) * row_bytes + lane_off;
     int k = 0;
-    if (ILP == 2) {
-      for (; k + 2 <= cnt; k += 2) {  // two staged rows per round: 2*CH independent shared-memory loads in flight
-        const float4* row0 = (const float4*)(base + (size_t)k * row_bytes);
-        const float4* row1 = (const float4*)(base + (size_t)(k + 1) * row_bytes);
-        float4 v0[CH], v1[CH];
+    for (; k + 2 <= cnt; k += 2) {  // two staged rows per round
+      const uint32_t r0 = base + (uint32_t)k * row_bytes, r1 = r0 + row_bytes;
+      float4 v0[CH], v1[CH];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int col = c * 32 + lane;
-          if (col < nvec) { v0[c] = row0[col]; v1[c] = row1[col]; }
+      for (int c = 0; c < CH; ++c)
+        if (c * 32 + lane < nvec) {
+          v0[c] = lds128(r0 + c * 512);
+          v1[c] = lds128(r1 + c * 512);
         }
-        const uint64_t j0 = DROP ? row_key[w][buf][k] : 0ull, j1 = DROP ? row_key[w][buf][k + 1] : 0ull;
+      uint64_t j0 = 0, j1 = 0;
+      if (DROP) {
+        j0 = row_key[w][buf][k];
+        j1 = row_key[w][buf][k + 1];
+      }
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int col = c * 32 + lane;
-          if (col < nvec) {
-            if (DROP) {
-              acc_drop4(acc[c], v0[c], pg::drop_mix(j0, col_key[c]), thr_hi, a.keep_scale);
-              acc_drop4(acc[c], v1[c], pg::drop_mix(j1, col_key[c]), thr_hi, a.keep_scale);
-            } else {
-              acc[c].x = (acc[c].x + v0[c].x) + v1[c].x; acc[c].y = (acc[c].y + v0[c].y) + v1[c].y;
-              acc[c].z = (acc[c].z + v0[c].z) + v1[c].z; acc[c].w = (acc[c].w + v0[c].w) + v1[c].w;
-            }
+      for (int c = 0; c < CH; ++c)
+        if (c * 32 + lane < nvec) {
+          if (DROP) {
+            const uint64_t ck = col_key[c * 32 + lane];
+            acc_drop4(acc[c], v0[c], pg::drop_mix(j0, ck), thr_hi, keep_scale);
+            acc_drop4(acc[c], v1[c], pg::drop_mix(j1, ck), thr_hi, keep_scale);
+          } else {
+            acc[c].x = (acc[c].x + v0[c].x) + v1[c].x; acc[c].y = (acc[c].y + v0[c].y) + v1[c].y;
+            acc[c].z = (acc[c].z + v0[c].z) + v1[c].z; acc[c].w = (acc[c].w + v0[c].w) + v1[c].w;
           }
         }
-      }
     }
-    for (; k < cnt; ++k) {
-      const float4* row = (const float4*)(base + (size_t)k * row_bytes);
-      const uint64_t j = DROP ? row_key[w][buf][k] : 0ull;
+    if (k < cnt) {
+      const uint32_t r0 = base + (uint32_t)k * row_bytes;
+      const uint64_t j0 = DROP ? row_key[w][buf][k] : 0ull;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int col = c * 32 + lane;
-        if (col < nvec) {
-          const float4 v = row[col];
+      for (int c = 0; c < CH; ++c)
+        if (c * 32 + lane < nvec) {
+          const float4 v = lds128(r0 + c * 512);
           if (DROP) {
-            acc_drop4(acc[c], v, pg::drop_mix(j, col_key[c]), thr_hi, a.keep_scale);
+            acc_drop4(acc[c], v, pg::drop_mix(j0, col_key[c * 32 + lane]), thr_hi, keep_scale);
           } else {
             acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
           }
         }
-      }
     }
-    if (cc.last(group)) {  // row complete: scale, write once, reset
-      const float deg = (float)max(cc.e - cc.s, (int64_t)1);
-      const float nrm = a.norm ? a.norm[cc.r] : 1.0f;
-      float4* out = (float4*)(a.dst + cc.r * a.dst_stride);
+    if (meta.y) {  // row complete: scale, write once, reset
+      float sc = mean ? 1.0f / (float)max(meta.w, 1) : 1.0f;
+      if (a.norm) sc *= a.norm[meta.z];
+      float4* out = (float4*)(a.dst + (int64_t)meta.z * a.dst_stride);
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const int col = c * 32 + lane;
-        if (col < nvec) {
-          float4 v = acc[c];
-          if (a.mode == PG_AGG_MEAN) { v.x /= deg; v.y /= deg; v.z /= deg; v.w /= deg; }
-          if (a.norm) { v.x *= nrm; v.y *= nrm; v.z *= nrm; v.w *= nrm; }
-          out[col] = v;
-        }
+        if (c * 32 + lane < nvec) out[c * 32 + lane] = make_float4(acc[c].x * sc, acc[c].y * sc, acc[c].z * sc, acc[c].w * sc);
         acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    cc.next(a, group, nwarps);
-    __syncwarp();  // every lane is done reading this buffer
-    if (ci.valid(a)) {
-      issue(ci, buf);
-      ci.next(a, group, nwarps);
+    --pending;
+    __syncwarp();  // every lane is done reading this buffer (and its meta / row keys)
+    if (ir < n_dst) {
+      issue(buf);
+      ++pending;
     }
     buf = (buf + 1 == depth) ? 0 : buf + 1;
   }
@@ -404,10 +422,12 @@ pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, 
   const int group = std::min(kRowsMaxGroup, slots / depth);
   const size_t smem = (size_t)W * depth * group * row_bytes;
   const bool drop = a.drop_thr != 0;
-  const char* env_i = getenv("PG_AGG_ILP");
-  const int ilp = env_i ? atoi(env_i) : 2;
-  auto kern = ilp == 1 ? (drop ? agg_rows_tma_kernel<W, CH, true, 1> : agg_rows_tma_kernel<W, CH, false, 1>)
-                       : (drop ? agg_rows_tma_kernel<W, CH, true, 2> : agg_rows_tma_kernel<W, CH, false, 2>);
+  // the reference's 600-float rows get the compile-time width (CH == 5 covers 129..160 float4)
+  constexpr int kRefVec = 150;
+  const bool ref_width = CH == 5 && a.dim == 4 * kRefVec && !getenv("PG_AGG_GENERIC");
+  auto kern = ref_width ? (drop ? agg_rows_tma_kernel<W, CH, true, (CH == 5 ? kRefVec : 0)>
+                                : agg_rows_tma_kernel<W, CH, false, (CH == 5 ? kRefVec : 0)>)
+                        : (drop ? agg_rows_tma_kernel<W, CH, true, 0> : agg_rows_tma_kernel<W, CH, false, 0>);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t rows = std::max(a.n_dst, a.zero_rows_to);   // a negative zero_rows_to is bounded by the capacity n_dst
   const int64_t need = std::max<int64_t>(1, (rows + W - 1) / W);
@@ -448,8 +468,9 @@ void launch_fwd(const AggArgs& a, int dev, cudaStream_t st) {
 namespace pg {
 pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st) {
   const int nvec = a.dim / 4;
+  // the TMA kernel keeps row indices in 32 bits (a NodeFlow layer / a row block of the server-side fold)
   const bool tma_ok = (a.dim % 4 == 0) && (a.dst_stride % 4 == 0) && ((uintptr_t)a.dst % 16 == 0) && nvec <= 8 * 32 &&
-                      !getenv("PG_AGG_NO_TMA");
+                      std::max(a.n_dst, a.zero_rows_to) < (int64_t)INT32_MAX - (1 << 24) && !getenv("PG_AGG_NO_TMA");
   if (tma_ok) {
     pg_status s = PG_ERR_INVALID;
     if (nvec <= 32) s = launch_rows_tma<1>(a, dev, st);

@@ -115,6 +115,10 @@ pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st);
 pg_status linear_ce_mma(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias, const int64_t* d_labels,
                         int64_t n, int32_t in_dim, int32_t n_classes, float* d_loss, float* d_grad_a, int64_t ga_stride,
                         float* d_grad_weight, float* d_grad_bias, const int64_t* d_lo, cudaStream_t st);
+// tcgen05 / TMEM / TMA forward of the first NodeUpdate (pg_dense_umma.cu); PG_ERR_INVALID = not eligible, nothing launched
+pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float* d_weight, const float* d_bias, int64_t n,
+                                 int32_t K, int concat, float* d_out, int64_t out_stride, float* d_out_drop, int64_t od_stride,
+                                 float dropout_p, uint64_t dropout_seed, const int64_t* d_step, int dev, cudaStream_t st);
 // fp32-pipe dW kernel of pg_dense.cu (A/B baseline of the tensor-core kernel in pg_dense_mma.cu); outputs pre-zeroed
 pg_status linear_concat_bwd_simt(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
                                  const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int concat,

@@ -925,6 +925,14 @@ pg_status pg_linear_concat_fwd(const float* d_x, int64_t x_stride, const float* 
   PG_CUDA(cudaGetDevice(&dev));
   cudaStream_t st = (cudaStream_t)stream;
   pg::TimedScope timed(PG_T_DENSE_FWD, st);
+  {  // tcgen05 path (pg_dense_umma.cu) whenever the layout allows TMA boxes; PG_FWD_UMMA=0 keeps the mma.sync kernel
+    const char* env_u = getenv("PG_FWD_UMMA");
+    if (!(env_u && atoi(env_u) == 0)) {
+      const pg_status s = pg::linear_concat_fwd_umma(d_x, x_stride, d_weight, d_bias, n, in_dim, concat, d_out, out_stride,
+                                                     d_out_drop, od_stride, dropout_p, dropout_seed, d_step, dev, st);
+      if (s != PG_ERR_INVALID) return s;
+    }
+  }
   const size_t smem = 2 * (size_t)kOut * fwd_wstride(in_dim) * sizeof(uint32_t);
   const DropArgs drop = make_drop(d_out_drop ? dropout_p : 0.f, dropout_seed, d_step);
   auto launch = [&](auto kern, int warps, int rows_per_warp) -> pg_status {

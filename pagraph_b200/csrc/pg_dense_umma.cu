@@ -1,0 +1,360 @@
+// pg_dense_umma.cu — the first NodeUpdate's forward product on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Reference: PaGraph/model/gcn_nssc.py:14-24 (z = Linear(x); out = cat(z, relu z)) and :66-67 (dropout ahead of the next
+// block_compute). x [n, K] is the aggregated input block (K = 600: 85 MB per minibatch at config 2), W [32, K].
+//
+// fp32-level accuracy on a TF32 tensor core = error-compensated product (3xTF32): x = x_hi + x_lo, W = W_hi + W_lo with the
+// hi parts being what `kind::tf32` keeps of a 32-bit container (it ignores the low 13 mantissa bits), and
+//     z = x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T   (fp32 accumulate in TMEM; the x_lo W_lo term is 2^-22 relative).
+//
+// One CTA per SM, 128-row tiles, K walked in chunks of 32 columns (one 128-byte swizzle row):
+//   warp 0      TMA producer: per chunk one [128 x 32] box of x and one [32 x 32] box of W (SWIZZLE_128B, OOB -> 0) into
+//               a kStages-deep shared-memory ring
+//   warps 8-11  transform, one tile row per thread: reads its 32 floats of x from the ring (swizzle-aware, conflict-free),
+//               splits them and writes x_hi / x_lo into TENSOR MEMORY (tcgen05.st) — the A operand of the MMAs is read
+//               from TMEM, not from shared memory: an SS-mode M = 128 tf32 MMA would fetch 4 KB of A per instruction and
+//               run at the shared-memory port's 128 B/clk (~32 clk) instead of the tensor core's 16 clk; it also splits
+//               the chunk's W box in place next to it (W_lo plane)
+//   warp 1      MMA issuer (one thread): 4 k-steps x 3 terms of tcgen05.mma.cta_group::1.kind::tf32 (M 128, N 32, K 8) per
+//               chunk, A from TMEM, B = W_hi / W_lo from shared memory; tcgen05.commit releases the ring slot
+//   warps 4-7   epilogue, one output row per thread: tcgen05.ld of the 32 accumulator columns, + bias, relu, concat,
+//               dropout mask (pg_common.cuh drop_hash contract), 16-byte stores; double-buffered accumulators
+// Roofline: the kernel streams x once (HBM floor 13.5 us at config 2); tensor time per tile 19 x 12 x 16 clk = 1.9 us,
+// shared-memory traffic per chunk ~56 KB (TMA fill 20 KB, transform read 20 KB + W_lo 4 KB, B operand 12 KB) = 440 clk.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "pg_common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;       // rows per tile (UMMA M)
+constexpr int kN = 32;             // outputs (UMMA N)
+constexpr int kChunk = 32;         // K per stage: 32 floats = 128 bytes = one swizzle row
+constexpr int kStages = 6;
+constexpr int kUmmaK = 8;          // K per tcgen05.mma for 32-bit operands
+constexpr int kThreads = 12 * 32;
+constexpr uint32_t kXBytes = kBlockM * kChunk * 4;            // 16 KB
+constexpr uint32_t kWBytes = kN * kChunk * 4;                 // 4 KB
+constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;       // x, w_hi, w_lo = 24 KB
+constexpr uint32_t kAccCols = 2 * kN;                         // 2 accumulator stages
+constexpr uint32_t kTmemCols = 512;                           // 64 accumulator + kStages * 64 operand columns (power of 2)
+static_assert(kAccCols + kStages * 2 * kChunk <= kTmemCols, "TMEM budget");
+
+using pg::smem_u32;
+using pg::mbar_init;
+using pg::mbar_expect_tx;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+// K-major SWIZZLE_128B operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart, tile base 1024-byte aligned):
+// cute::UMMA::SmemDescriptor with version 1, layout_type 2, LBO 1, SBO 64 (both in 16-byte units)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)64 << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), K-major both, N >> 3 at 17, M >> 4 at 24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives when all prior MMAs of this thread are done
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t tf32_lo(uint32_t bits) {  // x - (what kind::tf32 keeps of x)
+  return __float_as_uint(__uint_as_float(bits) - __uint_as_float(bits & 0xFFFFE000u));
+}
+
+struct UmmaDrop {
+  uint32_t thr;        // drop when the 16-bit hash lane < thr (0 = no dropout)
+  float scale;         // 1 / (1 - p)
+  uint64_t seed;
+  const int64_t* step; // optional device counter added to the seed
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+    linear_concat_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                                  const float* __restrict__ bias, int64_t n, int K, int concat, float* __restrict__ out,
+                                  int64_t out_stride, float* __restrict__ out_drop, int64_t od_stride, UmmaDrop drop) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[3 * kStages + 4];   // full[s], ready[s], empty[s], tmem_full[2], tmem_empty[2]
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ uint64_t colkey_sh[16];
+  __shared__ float bias_sh[kN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  auto full = [&](int s) { return smem_u32(&bars[s]); };
+  auto ready = [&](int s) { return smem_u32(&bars[kStages + s]); };
+  auto empty = [&](int s) { return smem_u32(&bars[2 * kStages + s]); };
+  auto tfull = [&](int a) { return smem_u32(&bars[3 * kStages + a]); };
+  auto tempty = [&](int a) { return smem_u32(&bars[3 * kStages + 2 + a]); };
+  const int nchunks = (K + kChunk - 1) / kChunk;
+  const int64_t ntiles = (n + kBlockM - 1) / kBlockM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full(s), 1);         // the producer's arrive.expect_tx; the TMA completes the transaction bytes
+      mbar_init(ready(s), 128);      // every transform thread
+      mbar_init(empty(s), 1);        // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull(a), 1);        // tcgen05.commit after the tile's last MMA
+      mbar_init(tempty(a), 128);     // every epilogue thread
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 16) colkey_sh[threadIdx.x] = pg::drop_colkey((uint32_t)threadIdx.x);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kN) bias_sh[threadIdx.x - 32] = bias ? bias[threadIdx.x - 32] : 0.f;
+  if (warp == 1) {                   // TMEM: allocated and later freed by the same warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+  const uint32_t tmem_opnd = tmem_base + kAccCols;    // operand stages behind the two accumulators
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int s = it % kStages;
+          mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);             // a fresh barrier passes the wait for parity 1
+          const uint32_t st = smem_base + s * kStageBytes;
+          mbar_expect_tx(full(s), kXBytes + kWBytes);
+          tma_load_2d(st, &tm_x, c * kChunk, (int)(tile * kBlockM), full(s));       // x (OOB rows / cols -> 0)
+          tma_load_2d(st + kXBytes, &tm_w, c * kChunk, 0, full(s));                 // W chunk
+        }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        const int a = tl & 1;
+        mbar_wait(tempty(a), ((tl >> 1) & 1) ^ 1);                   // epilogue has drained this accumulator stage
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem_base + a * kN;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int s = it % kStages;
+          mbar_wait(ready(s), (it / kStages) & 1);                   // x_hi / x_lo in TMEM, W_lo in shared memory
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_base + s * kStageBytes;
+          const uint32_t a_hi = tmem_opnd + s * 2 * kChunk, a_lo = a_hi + kChunk;
+          const uint64_t b_hi = umma_desc_k_sw128(st + kXBytes), b_lo = umma_desc_k_sw128(st + kXBytes + kWBytes);
+#pragma unroll
+          for (int k = 0; k < kChunk / kUmmaK; ++k) {
+            const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
+            umma_tf32_ts(d, a_lo + k * kUmmaK, b_hi + adv, (c | k) != 0);   // small terms first
+            umma_tf32_ts(d, a_hi + k * kUmmaK, b_lo + adv, 1);
+            umma_tf32_ts(d, a_hi + k * kUmmaK, b_hi + adv, 1);
+          }
+          umma_commit(empty(s));                                     // ring slot + TMEM operand stage reusable
+        }
+        umma_commit(tfull(a));                                       // accumulator complete
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================================================== transform: split x into TMEM, W_lo in place
+    const int q = warp & 3;                                          // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;                                   // tile row owned by this thread
+    const int tt = threadIdx.x - 8 * 32;                             // 0 .. 127
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int c = 0; c < nchunks; ++c, ++it) {
+        const int s = it % kStages;
+        mbar_wait(full(s), (it / kStages) & 1);
+        const uint32_t st = smem_base + s * kStageBytes;
+        // row `row` of the box: 8 x 16 bytes, logical unit u stored at unit u ^ (row & 7) (SWIZZLE_128B)
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t addr = st + (uint32_t)row * 128u + (uint32_t)((u ^ (row & 7)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(hi[4 * u]), "=r"(hi[4 * u + 1]), "=r"(hi[4 * u + 2]), "=r"(hi[4 * u + 3])
+                       : "r"(addr));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lo[j] = tf32_lo(hi[j]);
+        const uint32_t ta = tmem_opnd + ((uint32_t)(q * 32) << 16) + s * 2 * kChunk;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + kChunk, lo);
+        // W box: elementwise, so the swizzled placement does not matter — same offset in the lo plane
+#pragma unroll
+        for (int h = 0; h < (int)(kWBytes / 16 / 128); ++h) {
+          const uint32_t off = (uint32_t)(h * 128 + tt) * 16;
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(st + kXBytes + off));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(st + kXBytes + kWBytes + off), "r"(tf32_lo(w0)),
+                       "r"(tf32_lo(w1)), "r"(tf32_lo(w2)), "r"(tf32_lo(w3))
+                       : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(ready(s));
+      }
+  } else if (warp >= 4) {
+    // ================================================================== epilogue: one output row per thread
+    const int q = warp & 3;
+    const uint64_t stepkey = drop.thr ? pg::drop_stepkey(drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull)) : 0ull;
+    const uint32_t thr_hi = drop.thr << 16;
+    uint32_t tl = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      const int a = tl & 1;
+      mbar_wait(tfull(a), (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * kN, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tempty(a));                                        // the MMA warp may overwrite this accumulator stage
+      const int64_t grow = tile * kBlockM + q * 32 + lane;
+      if (grow < n) {
+        float* orow = out + grow * out_stride;
+        float* drow = out_drop ? out_drop + grow * od_stride : nullptr;
+        const uint64_t rk = drow ? pg::drop_rowkey(stepkey, (uint64_t)grow) : 0ull;
+        auto masked = [&](float4 v, int g) {   // dropout of the 4 columns of group g under the drop_hash contract
+          const uint64_t h = pg::drop_mix(rk, colkey_sh[g]);
+          const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
+          v.x = (hl << 16) >= thr_hi ? v.x * drop.scale : 0.f;
+          v.y = hl >= thr_hi ? v.y * drop.scale : 0.f;
+          v.z = (hh << 16) >= thr_hi ? v.z * drop.scale : 0.f;
+          v.w = hh >= thr_hi ? v.w * drop.scale : 0.f;
+          return v;
+        };
+#pragma unroll
+        for (int j = 0; j < kN; j += 4) {
+          const float4 z = make_float4(__uint_as_float(r[j]) + bias_sh[j], __uint_as_float(r[j + 1]) + bias_sh[j + 1],
+                                       __uint_as_float(r[j + 2]) + bias_sh[j + 2], __uint_as_float(r[j + 3]) + bias_sh[j + 3]);
+          const float4 p = make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f));
+          if (concat) {
+            *(float4*)(orow + j) = z;
+            *(float4*)(orow + kN + j) = p;
+            if (drow) {
+              *(float4*)(drow + j) = masked(z, j >> 2);
+              *(float4*)(drow + kN + j) = masked(p, (kN + j) >> 2);
+            }
+          } else {
+            *(float4*)(orow + j) = p;
+            if (drow) *(float4*)(drow + j) = masked(p, j >> 2);
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(EncodeTiledFn enc, CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
+             uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};                        // innermost first
+  cuuint64_t strides[1] = {row_stride_floats * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return (int)enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace
+
+namespace pg {
+
+// PG_ERR_INVALID = not eligible (layout / driver entry point), nothing launched: the caller uses the mma.sync kernel.
+pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float* d_weight, const float* d_bias, int64_t n,
+                                 int32_t K, int concat, float* d_out, int64_t out_stride, float* d_out_drop, int64_t od_stride,
+                                 float dropout_p, uint64_t dropout_seed, const int64_t* d_step, int dev, cudaStream_t st) {
+  const bool ok = K % 4 == 0 && x_stride % 4 == 0 && out_stride % 4 == 0 && (!d_out_drop || od_stride % 4 == 0) &&
+                  (((uintptr_t)d_x | (uintptr_t)d_weight | (uintptr_t)d_out | (uintptr_t)d_out_drop) & 15) == 0 &&
+                  n < (int64_t)1 << 31;
+  if (!ok) return PG_ERR_INVALID;
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      cudaGetLastError();
+      return PG_ERR_INVALID;
+    }
+    enc = (EncodeTiledFn)fn;
+  }
+  CUtensorMap tm_x, tm_w;
+  if (make_map(enc, &tm_x, d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, kBlockM)) return PG_ERR_INVALID;
+  if (make_map(enc, &tm_w, d_weight, kN, (uint64_t)K, (uint64_t)K, kN)) return PG_ERR_INVALID;
+  const size_t smem = (size_t)kStages * kStageBytes + 1024;
+  PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (n + kBlockM - 1) / kBlockM;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev));
+  UmmaDrop drop;
+  drop.thr = (d_out_drop && dropout_p > 0.f) ? (uint32_t)(dropout_p * 65536.0f + 0.5f) : 0u;
+  drop.scale = drop.thr ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  drop.seed = dropout_seed;
+  drop.step = d_step;
+  linear_concat_fwd_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_w, d_bias, n, K, concat, d_out, out_stride,
+                                                             d_out_drop, od_stride, drop);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+}  // namespace pg

@@ -277,8 +277,8 @@ def test_training_learns_and_eval_entry_reports_accuracy(tmp_path):
                                  "--keep-store"] if engine == "graph" else
                                 [sys.executable, os.path.join(ROOT, "examples", "eval.py"), "--dataset", ds, "--gpu", "0",
                                  "--feat-size", str(Fdim), "--start", "0", "--end", "6", "--interval", "5", "--ckpt", ck],
-                                env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
-            assert ev.returncode == 0, ev.stdout[-2000:] + ev.stderr[-2000:]
+                                env=dict(env, PG_DEBUG_HANG="150"), cwd=ROOT, capture_output=True, text=True, timeout=300)
+            assert ev.returncode == 0, ev.stdout[-2000:] + ev.stderr[-3000:]
             lines = [ln for ln in ev.stdout.splitlines() if "Test Accuracy" in ln]
             assert len(lines) == 2, ev.stdout
             accs[engine] = [float(ln.split()[-1]) for ln in lines]

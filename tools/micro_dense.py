@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--n", type=int, default=36864)
     ap.add_argument("--F", type=int, default=600)
-    ap.add_argument("--fwd-variants", default="0,1,5")
+    ap.add_argument("--fwd-variants", default="0,u", help="mma.sync template variants 0/1/5, u = the tcgen05 kernel")
     ap.add_argument("--only", default="")
     ap.add_argument("--p", type=float, default=0.2)
     a = ap.parse_args()
@@ -53,7 +53,8 @@ def main():
     ref = None
     if a.only in ("", "fwd"):
         for v in a.fwd_variants.split(","):
-            os.environ["PG_FWD_VARIANT"] = v
+            os.environ["PG_FWD_UMMA"] = "1" if v == "u" else "0"
+            os.environ["PG_FWD_VARIANT"] = "0" if v == "u" else v
             t = med(lambda i: linear_concat_forward(xs[i % 3], W, b, True, out=out, out_drop=od, dropout_p=a.p, seed=5, step=step),
                     a.iters)
             linear_concat_forward(xs[0], W, b, True, out=out, out_drop=od, dropout_p=a.p, seed=5, step=step)
@@ -61,9 +62,14 @@ def main():
                 ref = out.clone()
                 z = torch.nn.functional.linear(xs[0].double(), W.double(), b.double())
                 res["fwd_max_err_vs_fp64"] = float((out[:, :32].double() - z).abs().max())
+            zz = torch.nn.functional.linear(xs[0].double(), W.double(), b.double())
+            res["fwd_variant_%s_max_err_vs_fp64" % v] = float((out[:, :32].double() - zz).abs().max())
+            keep = od != 0
+            res["fwd_variant_%s_drop_ok" % v] = bool(torch.equal(od[keep], (out * (1.0 / (1.0 - a.p)))[keep])) if a.p > 0 else None
             res["fwd_variant_%s_us" % v] = round(t, 2)
             res["fwd_variant_%s_maxdiff" % v] = float((out - ref).abs().max())
         os.environ.pop("PG_FWD_VARIANT", None)
+        os.environ.pop("PG_FWD_UMMA", None)
         tl = med(lambda i: torch.nn.functional.linear(xs[i % 3], W, b), a.iters)
         res["cublas_fp32_linear_us"] = round(tl, 2)
     if a.only in ("", "bwd"):

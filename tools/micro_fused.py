@@ -30,7 +30,9 @@ def timeit(fn, nfs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--sweep", default="2:200,3:200,2:120,4:200,1:200")
+    ap.add_argument("--sweep", default="2:200,3:200,2:120,4:200,1:200", help="depth:smem_kb[:warps],...")
+    ap.add_argument("--modes", default="hbm20,vtx20")
+    ap.add_argument("--quick", action="store_true", help="only the fused_only sweep")
     a = ap.parse_args()
     sys.argv = [sys.argv[0]]
     args = bench.parse_args()
@@ -45,6 +47,8 @@ def main():
     nfs = [sampler.sample_batch(k) for k in range(a.iters)]
     out = {}
     for mode, cap in (("hbm20", args.vnum), ("vtx20", args.vnum // 5)):
+        if mode not in a.modes.split(","):
+            continue
         cs = GraphCacheServer(wl.store, args.vnum, torch.arange(args.vnum), 0)
         cs.init_field(["features", "norm"])
         cs.auto_cache(wl.g, ["features", "norm"], capability=cap)
@@ -69,15 +73,24 @@ def main():
                                        dropout_p=p, seed=7)
 
         res = {}
-        timeit(unfused, nfs[:3])
-        res["unfused_fetch+dropout+agg_ms"] = timeit(unfused, nfs)
+        if not a.quick:
+            timeit(unfused, nfs[:3])
+            res["unfused_fetch+dropout+agg_ms"] = timeit(unfused, nfs)
         for sw in a.sweep.split(","):
-            depth, kb = sw.split(":")
+            depth, kb, *rest = sw.split(":")
             os.environ["PG_AGG_DEPTH"], os.environ["PG_AGG_SMEM"] = depth, str(int(kb) * 1024)
+            if rest:
+                os.environ["PG_AGG_WARPS"] = rest[0]
+            tag = "depth%s_smem%sk%s" % (depth, kb, "_w" + rest[0] if rest else "")
             timeit(fused_only, nfs[:3])
-            res["fused_only_depth%s_smem%sk_ms" % (depth, kb)] = timeit(fused_only, nfs)
-            res["fused_only_nodrop_depth%s_smem%sk_ms" % (depth, kb)] = timeit(lambda nf: fused_only(nf, 0.0), nfs)
-        os.environ.pop("PG_AGG_DEPTH"), os.environ.pop("PG_AGG_SMEM")
+            res["fused_only_%s_ms" % tag] = timeit(fused_only, nfs)
+            res["fused_only_nodrop_%s_ms" % tag] = timeit(lambda nf: fused_only(nf, 0.0), nfs)
+        os.environ.pop("PG_AGG_DEPTH"), os.environ.pop("PG_AGG_SMEM"), os.environ.pop("PG_AGG_WARPS", None)
+        if a.quick:
+            lo, bo = nfs[0]._layer_offsets, nfs[0]._block_offsets
+            res["n0,n1,E0"] = [lo[1] - lo[0], lo[2] - lo[1], bo[1] - bo[0]]
+            out[mode] = res
+            continue
         res["fused+fetch_other_layers_ms"] = timeit(fused, nfs)
         os.environ["PG_AGG_NO_TMA"] = "1"
         timeit(fused_only, nfs[:2])
