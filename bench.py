@@ -43,16 +43,21 @@ def parse_args():
     p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--vnum", type=int, default=10_000_000)
-    p.add_argument("--nnz", type=int, default=100_000_000)
-    p.add_argument("--feat-size", type=int, default=600)
-    p.add_argument("--n-classes", type=int, default=60)
-    p.add_argument("--n-hidden", type=int, default=32)
+    p.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                   help="BASELINE.json configs[N-1]; 2 (the one the metric is quoted on) is the default and the headline")
+    p.add_argument("--scale", type=float, default=1.0, help="shrink a config's graph (vertices and edges) by this factor; "
+                                                            "recorded in config.workload — a scaled run is not the config")
+    p.add_argument("--vnum", type=int, default=None)
+    p.add_argument("--nnz", type=int, default=None)
+    p.add_argument("--feat-size", type=int, default=None)
+    p.add_argument("--n-classes", type=int, default=None)
+    p.add_argument("--n-hidden", type=int, default=None)
     p.add_argument("--batch-size", type=int, default=6000)
-    p.add_argument("--fanout", default="25,10", help="per hop, index 0 expands the seeds")
+    p.add_argument("--fanout", default=None, help="per hop, index 0 expands the seeds")
     p.add_argument("--dropout", type=float, default=0.2)
     p.add_argument("--lr", type=float, default=3e-2)
-    p.add_argument("--modes", default="hbm20,vtx20", help="cache modes to run; the first is the headline")
+    p.add_argument("--modes", default=None, help="cache modes to run; the first is the headline (default hbmNN,vtxNN with NN "
+                                                 "the config's cache percentage)")
     p.add_argument("--path", default="engine", choices=["engine", "fused", "eager"],
                    help="engine: GCNTrainEngine — two-stream CUDA-graph pipeline over the fused kernels (default); "
                         "fused: the eager Python loop with the input layer aggregated straight from the cache "
@@ -64,7 +69,44 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-parity-gate", action="store_true", help="skip the oracle check of one minibatch before timing")
     p.add_argument("--seed", type=int, default=1)
-    return p.parse_args()
+    return apply_config(p.parse_args())
+
+
+# BASELINE.json `configs`, made concrete. model: gcn = examples/profile/pa_gcn.py, gcn-pre = the same with
+# --preprocess (num_hops = n_layers, features folded by the server), sage = examples/profile/pa_gs.py (n_hidden 16).
+# partition: hash = hash.py over the train ids (config 1/2: the 2-hop closure of any share is the whole graph, so every
+# rank walks the full graph); dg = dg.py assignment + get_sub_graph closure per rank (in-process, on the GPU).
+CONFIGS = {
+    1: dict(tag="Reddit-shaped", vnum=232_965, nnz=114_615_892, feat=602, classes=41, model="gcn", hidden=32, fanout="2,2",
+            partition="hash", parts=1, rmat=(0.25, 0.25, 0.25), cache_frac=0.2),
+    2: dict(tag="R-MAT", vnum=10_000_000, nnz=100_000_000, feat=600, classes=60, model="gcn", hidden=32, fanout="25,10",
+            partition="hash", parts=0, rmat=(0.45, 0.22, 0.22), cache_frac=0.2),
+    3: dict(tag="R-MAT", vnum=10_000_000, nnz=100_000_000, feat=600, classes=60, model="sage", hidden=16, fanout="25,10",
+            partition="dg", parts=4, rmat=(0.45, 0.22, 0.22), cache_frac=0.2),
+    4: dict(tag="R-MAT", vnum=50_000_000, nnz=500_000_000, feat=600, classes=60, model="gcn-pre", hidden=32, fanout="25",
+            partition="dg", parts=8, rmat=(0.45, 0.22, 0.22), cache_frac=0.4),
+    5: dict(tag="papers100M-shaped", vnum=111_000_000, nnz=1_600_000_000, feat=128, classes=172, model="sage", hidden=16,
+            fanout="15,10,5", partition="dg", parts=8, rmat=(0.45, 0.22, 0.22), cache_frac=0.2, n_layers=2),
+}
+
+
+def apply_config(args):
+    c = CONFIGS[args.config]
+    args.model, args.partition, args.parts, args.rmat = c["model"], c["partition"], c["parts"], c["rmat"]
+    args.cache_frac, args.n_layers, args.tag = c["cache_frac"], c.get("n_layers", 1), c["tag"]
+    if args.vnum is None:
+        args.vnum = max(1000, int(c["vnum"] * args.scale))
+    if args.nnz is None:
+        args.nnz = max(2000, int(c["nnz"] * args.scale) // 2 * 2)
+    args.feat_size = c["feat"] if args.feat_size is None else args.feat_size
+    args.n_classes = c["classes"] if args.n_classes is None else args.n_classes
+    args.n_hidden = c["hidden"] if args.n_hidden is None else args.n_hidden
+    args.fanout = c["fanout"] if args.fanout is None else args.fanout
+    args.fields = ["features"] if args.model == "sage" else ["features", "norm"]
+    pct = int(round(args.cache_frac * 100))
+    if args.modes is None:
+        args.modes = "hbm%d,vtx%d" % (pct, pct)
+    return args
 
 
 # ------------------------------------------------------------------------------------ helpers
@@ -145,10 +187,13 @@ def agg_bytes(n_src, n_dst, e, d):
 
 # ------------------------------------------------------------------------------------ workload
 class Workload:
-    """BASELINE.json configs[1] made concrete: synthetic R-MAT graph, U[0,1) features,
-    norm = 1/in_degree, random labels, 65 % train split, hash partition of the train ids over ranks.
-    At this density the 2-hop in-neighbour closure of any 1/N share of the train vertices is the whole
-    graph, so every rank's partition graph is the full graph and nid_map is the identity."""
+    """BASELINE.json configs[args.config - 1] made concrete: synthetic R-MAT graph, U[0,1) features,
+    norm = 1/in_degree, random labels, 65 % train split. Partition per rank:
+      hash  hash.py split of the train ids; at these densities the 2-hop in-neighbour closure of any 1/N share of the train
+            vertices is the whole graph, so every rank's partition graph is the full graph and nid_map is the identity;
+      dg    dg.py assignment (pg_partition_dg, rank 0, host) into `parts` partitions + the get_sub_graph closure of THIS
+            rank's partition on the GPU: the rank walks its own relabelled sub-graph and nid_map = sub -> full id.
+    Features live in ONE pinned host table indexed by full id (the reference's shared-memory store)."""
 
     def __init__(self, args, rank, world, dev):
         from pagraph_b200 import DGLGraph, data
@@ -156,50 +201,129 @@ class Workload:
         from pagraph_b200.parallel import hash_split
         self.args, self.rank, self.world, self.dev = args, rank, world, dev
         V, Fdim = args.vnum, args.feat_size
+        self.setup = {}
         t0 = time.time()
-        self.indptr, self.indices = data.rmat_in_csr_cuda(V, args.nnz, seed=args.seed, device=dev)
+        a_, b_, c_ = args.rmat
+        self.indptr, self.indices = data.rmat_in_csr_cuda(V, args.nnz, seed=args.seed, device=dev, a=a_, b=b_, c=c_)
         self.g = DGLGraph.from_in_csr(self.indptr, self.indices)
-        self.t_graph = time.time() - t0
+        self.setup["graph_s"] = round(time.time() - t0, 2)
         t0 = time.time()
         name = "bench%d" % os.getpid() if world == 1 else "bench_w%s" % os.environ.get("MASTER_PORT", "0")
         self.server = None
+        norm = None
         if world == 1:
             self.store = gs.LocalGraphStore(name=name)
-            feat, norm = self.store.alloc_field("features", V, Fdim), self.store.alloc_field("norm", V, 1)
+            feat = self.store.alloc_field("features", V, Fdim)
+            norm = self.store.alloc_field("norm", V, 1) if "norm" in args.fields else None
         elif rank == 0:
             self.server = gs.create_graph_store_server(None, name, "shared_mem", world)
-            feat, norm = self.server.alloc_field("features", V, Fdim), self.server.alloc_field("norm", V, 1)
+            feat = self.server.alloc_field("features", V, Fdim)
+            norm = self.server.alloc_field("norm", V, 1) if "norm" in args.fields else None
         if rank == 0:
             gen = torch.Generator(device=dev)
             gen.manual_seed(2)
             chunk = 1 << 18
-            for lo in range(0, V, chunk):
-                hi = min(V, lo + chunk)
-                feat[lo:hi].copy_(torch.rand((hi - lo, Fdim), device=dev, generator=gen))
             deg = (self.indptr[1:] - self.indptr[:-1]).float()
-            norm.copy_((1.0 / deg).unsqueeze(1))          # inf where in-degree is 0 (pa_server.py:43)
+            if args.model == "gcn-pre":
+                # server-side --preprocess fold (server/pa_server.py:45-52): features' = (1/in_degree) * sum over in-edges,
+                # through pg_aggregate_fwd in row blocks over the whole graph
+                from pagraph_b200 import ops
+                tp = time.time()
+                raw = torch.empty((V, Fdim), dtype=torch.float32, device=dev)
+                for lo in range(0, V, chunk):
+                    hi = min(V, lo + chunk)
+                    raw[lo:hi] = torch.rand((hi - lo, Fdim), device=dev, generator=gen)
+                nrm = 1.0 / deg
+                for lo in range(0, V, 1 << 20):
+                    hi = min(V, lo + (1 << 20))
+                    feat[lo:hi].copy_(ops.aggregate_forward(self.indptr[lo:hi + 1], self.indices, 0, raw, hi - lo, "sum",
+                                                            norm=nrm[lo:hi]))
+                del raw
+                torch.cuda.synchronize()
+                self.setup["preprocess_fold_s"] = round(time.time() - tp, 2)
+            else:
+                for lo in range(0, V, chunk):
+                    hi = min(V, lo + chunk)
+                    feat[lo:hi].copy_(torch.rand((hi - lo, Fdim), device=dev, generator=gen))
+            if norm is not None:
+                norm.copy_((1.0 / deg).unsqueeze(1))          # inf where in-degree is 0 (pa_server.py:43)
             torch.cuda.synchronize()
             if self.server is not None:
                 self.server.commit()
         if world > 1:
             dist.barrier()
-            self.store = gs.SharedMemoryStoreClient(name, expect_fields=["features", "norm"])
-        self.t_store = time.time() - t0
+            self.store = gs.SharedMemoryStoreClient(name, expect_fields=list(args.fields))
+        self.setup["store_s"] = round(time.time() - t0, 2)
         gen = torch.Generator(device=dev)
         gen.manual_seed(3)
         self.labels_dev = torch.randint(0, args.n_classes, (V,), device=dev, generator=gen)
-        self.labels_cpu = self.labels_dev.cpu()
         gen.manual_seed(4)
         perm = torch.randperm(V, device=dev, generator=gen)
         train = torch.sort(perm[:int(V * 0.65)]).values.cpu().numpy()
-        self.train_nid = np.sort(hash_split(train, world, seed=5)[rank])
+        del perm
         self.fanouts = [int(x) for x in args.fanout.split(",")]
-        self.R = 4 * (Fdim + 1)
+        self.R = 4 * sum(Fdim if f == "features" else 1 for f in args.fields)
+        self.nid_map = None
+        if args.partition == "hash":
+            parts = args.parts or world
+            self.train_nid = np.sort(hash_split(train, parts, seed=5)[rank % parts])
+            self.setup["partition"] = {"kind": "hash", "parts": parts, "vertices": int(V), "edges": int(args.nnz),
+                                       "train": int(len(self.train_nid))}
+        else:
+            self._partition_dg(train)
+        self.labels_cpu = self.labels_dev.cpu()
+        self.V_p = self.g.number_of_nodes()
+
+    def _partition_dg(self, train):
+        """dg assignment on rank 0 (host code, scoring over 1-hop in-neighbourhoods: the reference's 2-hop scoring is
+        quadratic in hub degrees), broadcast, then this rank's closure on its own GPU."""
+        import ctypes
+        from pagraph_b200 import DGLGraph, _lib
+        from pagraph_b200.partition.utils import get_sub_graph_device
+        args, dev, V = self.args, self.dev, self.args.vnum
+        P = args.parts
+        belongs = torch.empty(V, dtype=torch.int8)
+        t0 = time.time()
+        if self.rank == 0:
+            indptr, indices = self.host_graph()
+            member = np.empty((P, V), dtype=np.uint8)
+            tr = np.ascontiguousarray(train, np.int64)
+            b = belongs.numpy()
+            _lib.check(_lib.lib().pg_partition_dg(indptr.ctypes.data, indices.ctypes.data, V, tr.ctypes.data, len(tr), P, 1,
+                                                  b.ctypes.data, member.ctypes.data), "pg_partition_dg")
+            del member
+        t_dg = time.time() - t0
+        if self.world > 1:
+            bd = belongs.to(dev)
+            dist.broadcast(bd, src=0)
+            belongs = bd.cpu()
+        mine = np.nonzero(belongs.numpy() == (self.rank % P))[0].astype(np.int64)
+        t0 = time.time()
+        hops = len(self.fanouts)
+        ip, ix, sub2full, subtrain = get_sub_graph_device(self.g, mine, hops)
+        torch.cuda.synchronize()
+        t_cl = time.time() - t0
+        self.indptr, self.indices, self._host_graph = ip, ix, None
+        self.g = DGLGraph.from_in_csr(ip, ix)                # the rank's own relabelled partition graph
+        self.nid_map = sub2full
+        self.labels_dev = self.labels_dev[sub2full]          # labels by sub-graph id (pa_gcn.py:38-41)
+        self.train_nid = np.sort(subtrain.cpu().numpy())
+        torch.cuda.empty_cache()
+        self.setup["partition"] = {"kind": "dg", "parts": P, "dg_assign_s": round(t_dg, 2), "closure_s": round(t_cl, 2),
+                                   "vertices": int(ip.numel() - 1), "edges": int(ix.numel()), "train": int(len(self.train_nid)),
+                                   "scoring_hops": 1, "closure_hops": hops}
 
     def host_graph(self):
         if getattr(self, "_host_graph", None) is None:
             self._host_graph = (self.indptr.cpu().numpy(), self.indices.cpu().numpy())
         return self._host_graph
+
+    def host_rows(self, name, local_ids):
+        """rows of field `name` for local (partition) ids, from the host table (the parity gate's reference)"""
+        ids = torch.as_tensor(local_ids, dtype=torch.int64)
+        if self.nid_map is not None:
+            ids = self.nid_map.cpu()[ids]
+        return self.store.ndata[name][ids]
 
     def close(self):
         if self.world > 1:
@@ -210,33 +334,41 @@ class Workload:
 
 
 class Trainer:
-    """The trainer of examples/profile/pa_gcn.py:27-113 on the rebuilt path."""
+    """The trainer of examples/profile/pa_gcn.py:27-113 (pa_gs.py for GraphSAGE) on the rebuilt path."""
 
     def __init__(self, wl, mode, host_inputs):
         from pagraph_b200.model.gcn_nssc import GCNSampling
+        from pagraph_b200.model.graphsage_nssc import GraphSageSampling
         from pagraph_b200.parallel import FlatGradAllReduce
         from pagraph_b200.sampling import NeighborSampler
         from pagraph_b200.storage import GraphCacheServer
         a = wl.args
         self.wl, self.mode, self.host_inputs = wl, mode, host_inputs
         dev = wl.dev
-        V = a.vnum
-        self.cacher = GraphCacheServer(wl.store, V, torch.arange(V, dtype=torch.int64), dev.index)
-        self.cacher.init_field(["features", "norm"])
+        V = wl.V_p
+        nid_map = wl.nid_map if wl.nid_map is not None else torch.arange(V, dtype=torch.int64)
+        self.cacher = GraphCacheServer(wl.store, V, nid_map, dev.index)
+        self.cacher.init_field(list(a.fields))
         self.cacher.log = True
         self.cacher.lazy_input = (a.path == "fused")
         torch.manual_seed(wl.rank)                                            # pa_gcn.py:23
-        self.model = GCNSampling(a.feat_size, a.n_hidden, a.n_classes, 1, F.relu, a.dropout, False).cuda(dev)
+        if a.model == "sage":
+            self.model = GraphSageSampling(a.feat_size, a.n_hidden, a.n_classes, a.n_layers, F.relu, a.dropout, 'mean').cuda(dev)
+        else:
+            self.model = GCNSampling(a.feat_size, a.n_hidden, a.n_classes, a.n_layers, F.relu, a.dropout,
+                                     a.model == "gcn-pre").cuda(dev)
         self.sync = FlatGradAllReduce(self.model)
         self.opt = torch.optim.Adam(self.sync.flat_parameters(), lr=a.lr, weight_decay=0, capturable=(a.path == "engine"),
                                     fused=True)
         self.loss_fcn = torch.nn.CrossEntropyLoss()
         self.engine = None
         if a.path == "engine":
-            from pagraph_b200.engine import GCNTrainEngine
-            self.engine = GCNTrainEngine(wl.g, self.cacher, self.model, self.opt, wl.train_nid,
-                                         wl.labels_cpu if host_inputs else wl.labels_dev, a.batch_size, wl.fanouts,
-                                         sync=self.sync, seed=a.seed, shuffle=True, host_inputs=host_inputs)
+            from pagraph_b200.engine import make_train_engine
+            self.engine = make_train_engine(wl.g, self.cacher, self.model, self.opt, wl.train_nid,
+                                            wl.labels_cpu if host_inputs else wl.labels_dev, a.batch_size, wl.fanouts,
+                                            sync=self.sync, seed=a.seed, shuffle=True, host_inputs=host_inputs)
+        elif a.model != "gcn":
+            raise SystemExit("--path %s drives the GCN model only; configs 3-5 need --path engine" % a.path)
         self.sampler = NeighborSampler(wl.g, a.batch_size, wl.fanouts, neighbor_type='in', shuffle=True,
                                        num_workers=16, num_hops=len(wl.fanouts),
                                        seed_nodes=torch.from_numpy(wl.train_nid), prefetch=True, seed=a.seed,
@@ -248,8 +380,10 @@ class Trainer:
         # step 1 cold, then fill the cache (pa_gcn.py:99-100)
         self.run(1, record=False)
         total = torch.cuda.get_device_properties(dev).total_memory
-        cap = int(0.2 * total / (4 * self.cacher.total_dim)) if mode == "hbm20" else V // 5
-        self.cacher.auto_cache(wl.g, ["features", "norm"], capability=cap)
+        # hbmNN: capacity = NN % of the HBM bytes (BASELINE.json's literal wording); vtxNN: NN % of the partition's vertices
+        frac = a.cache_frac
+        cap = int(frac * total / (4 * self.cacher.total_dim)) if mode.startswith("hbm") else int(V * frac)
+        self.cacher.auto_cache(wl.g, list(a.fields), capability=cap)
         self.cacher.get_miss_rate()
 
     def run(self, count, record, read_loss=False):
@@ -337,18 +471,25 @@ def kernel_report(tr, reg, hbm_peak, pcie_peak):
     against the algorithmic bytes of SURVEY.md §8d."""
     from pagraph_b200 import _lib
     wl = tr.wl
-    R, Fdim, H2 = wl.R, wl.args.feat_size, 2 * wl.args.n_hidden
+    a = wl.args
+    R, Fdim, H2 = wl.R, a.feat_size, 2 * a.n_hidden
+    L = len(wl.fanouts)
     by = {}
     for slot, ms in reg["recs"]:
         by.setdefault(slot, []).append(ms)
     steps = len(tr.sizes)
     N = sum(lo[-1] for lo, _ in tr.sizes)
-    n0 = sum(lo[1] - lo[0] for lo, _ in tr.sizes)
     M = reg["misses"]
     fused = _lib.T_FUSED in by
     if not by:
         return {}, N, M
     out = {}
+
+    def n_(lo, l):
+        return lo[l + 1] - lo[l]
+
+    def e_(bo, i):
+        return bo[i + 1] - bo[i]
 
     def add(name, slot_ms, nbytes, peak, peak_name):
         if not slot_ms:
@@ -359,32 +500,58 @@ def kernel_report(tr, reg, hbm_peak, pcie_peak):
 
     add("sample(all kernels of one pg_sample)", by.get(_lib.T_SAMPLE), sum(sampling_bytes(lo, bo) for lo, bo in tr.sizes),
         hbm_peak, "hbm")
-    add("split_kernel/resolve_kernel", by.get(_lib.T_SPLIT), 25 * N, hbm_peak, "hbm")
-    n_hit_rows = (N - n0 if fused else N) - (M * (N - n0) // max(N, 1) if fused else M)   # rows gathered from the HBM cache
-    add("gather_hit(rows_ldg_kernel)", by.get(_lib.T_GATHER_HIT), 2 * R * n_hit_rows + ID_BYTES * n_hit_rows, hbm_peak, "hbm")
+    # rows the step looked up in the cache: gcn / gcn-pre the input layer, sage layers 0..L-1 (sources) + 1..L (self rows)
+    if a.model == "sage":
+        looked = sum(lo[L] + (lo[-1] - lo[1]) for lo, _ in tr.sizes)
+    elif tr.engine is not None or fused:
+        looked = sum(n_(lo, 0) for lo, _ in tr.sizes)
+    else:
+        looked = N
+    add("split_kernel/resolve_kernel", by.get(_lib.T_SPLIT), 25 * looked, hbm_peak, "hbm")
+    if a.model == "sage":
+        rows_g = sum(lo[-1] - lo[1] for lo, _ in tr.sizes)
+    else:
+        rows_g = 0 if (tr.engine is not None) else (N - sum(n_(lo, 0) for lo, _ in tr.sizes) if fused else N)
+    miss_share = M / max(looked, 1)
+    add("gather_hit(rows_ldg_kernel)", by.get(_lib.T_GATHER_HIT), (2 * R + ID_BYTES) * rows_g * (1 - miss_share), hbm_peak, "hbm")
     add("gather_miss(rows_bulk_kernel)", by.get(_lib.T_GATHER_MISS), 4 * Fdim * M, pcie_peak, "pcie")
-    b0 = sum(agg_bytes(lo[1] - lo[0], lo[2] - lo[1], bo[1] - bo[0], Fdim) for lo, bo in tr.sizes)
-    b1 = sum(agg_bytes(lo[2] - lo[1], lo[3] - lo[2], bo[2] - bo[1], H2) for lo, bo in tr.sizes)
     fw = by.get(_lib.T_AGG_FWD, [])
-    if fused:
-        add("cache_aggregate_block0(agg_rows_tma_kernel,D=%d)" % Fdim, by.get(_lib.T_FUSED), b0 + 8 * n0, hbm_peak, "hbm")
-        add("agg_fwd_block1(D=%d)" % H2, fw, b1, hbm_peak, "hbm")
-    elif len(fw) == 2 * steps:
-        add("agg_fwd_block0(D=%d)" % Fdim, fw[0::2], b0, hbm_peak, "hbm")
-        add("agg_fwd_block1(D=%d)" % H2, fw[1::2], b1, hbm_peak, "hbm")
-    add("agg_bwd_block1(D=%d)" % H2, by.get(_lib.T_AGG_BWD), b1, hbm_peak, "hbm")
-    # dense stage (the engine's fused path): x [n_1, F] streamed once per direction; out / out_drop / grad rows are H2 wide
-    n1 = sum(lo[2] - lo[1] for lo, _ in tr.sizes)
-    nb = sum(lo[3] - lo[2] for lo, _ in tr.sizes)
-    drop = 1 if wl.args.dropout > 0 else 0
-    wbytes = 4 * steps * (Fdim + 1) * wl.args.n_hidden
-    add("node_update_fwd(linear_concat_fwd_kernel,3xTF32)", by.get(_lib.T_DENSE_FWD),
+    if a.model == "sage":       # L fused launches per step at width F; the 2*hidden-wide blocks behind them
+        bF = sum(sum(agg_bytes(n_(lo, i), n_(lo, i + 1), e_(bo, i), Fdim) + 8 * n_(lo, i) for i in range(L)) for lo, bo in tr.sizes)
+        add("cache_aggregate_blocks0..%d(agg_rows_tma_kernel,D=%d)" % (L - 1, Fdim), by.get(_lib.T_FUSED), bF, hbm_peak, "hbm")
+        bh = sum(sum(agg_bytes(n_(lo, i), n_(lo, i + 1), e_(bo, i), H2) for i in range(1, L)) for lo, bo in tr.sizes)
+        add("agg_fwd_hidden_blocks(D=%d)" % H2, fw, bh, hbm_peak, "hbm")
+        add("agg_bwd_hidden_blocks(D=%d)" % H2, by.get(_lib.T_AGG_BWD), bh, hbm_peak, "hbm")
+    elif a.model == "gcn-pre":  # the fused launch is the cache gather (+ dropout) of the input layer; one 64-wide block
+        bg = sum((2 * 4 * Fdim + 8 + 16) * n_(lo, 0) for lo, _ in tr.sizes)
+        add("cache_gather_dropout_layer0(agg_rows_tma_kernel,D=%d)" % Fdim, by.get(_lib.T_FUSED), bg, hbm_peak, "hbm")
+        b1 = sum(agg_bytes(n_(lo, 0), n_(lo, 1), e_(bo, 0), H2) for lo, bo in tr.sizes)
+        add("agg_fwd_block0(D=%d)" % H2, fw, b1, hbm_peak, "hbm")
+        add("agg_bwd_block0(D=%d)" % H2, by.get(_lib.T_AGG_BWD), b1, hbm_peak, "hbm")
+    else:
+        b0 = sum(agg_bytes(n_(lo, 0), n_(lo, 1), e_(bo, 0), Fdim) for lo, bo in tr.sizes)
+        b1 = sum(agg_bytes(n_(lo, 1), n_(lo, 2), e_(bo, 1), H2) for lo, bo in tr.sizes)
+        n0 = sum(n_(lo, 0) for lo, _ in tr.sizes)
+        if fused:
+            add("cache_aggregate_block0(agg_rows_tma_kernel,D=%d)" % Fdim, by.get(_lib.T_FUSED), b0 + 8 * n0, hbm_peak, "hbm")
+            add("agg_fwd_block1(D=%d)" % H2, fw, b1, hbm_peak, "hbm")
+        elif len(fw) == 2 * steps:
+            add("agg_fwd_block0(D=%d)" % Fdim, fw[0::2], b0, hbm_peak, "hbm")
+            add("agg_fwd_block1(D=%d)" % H2, fw[1::2], b1, hbm_peak, "hbm")
+        add("agg_bwd_block1(D=%d)" % H2, by.get(_lib.T_AGG_BWD), b1, hbm_peak, "hbm")
+    # dense stage (the engines' fused path): x [n_x, F] streamed once per direction; out / out_drop / grad rows are H2 wide
+    xl = 0 if a.model == "gcn-pre" else 1
+    n1 = sum(n_(lo, xl) for lo, _ in tr.sizes)
+    nb = sum(n_(lo, L) for lo, _ in tr.sizes)
+    drop = 1 if (a.dropout > 0 and a.model == "gcn") else 0
+    wbytes = 4 * steps * (Fdim + 1) * a.n_hidden
+    add("node_update_fwd(linear_concat_fwd_umma_kernel,tcgen05 3xTF32)", by.get(_lib.T_DENSE_FWD),
         4 * n1 * (Fdim + H2 * (1 + drop)) + wbytes, hbm_peak, "hbm")
-    add("node_update_bwd(linear_concat_dw_kernel,3xTF32)", by.get(_lib.T_DENSE_BWD), 4 * n1 * (Fdim + 2 * H2) + wbytes,
+    add("node_update_bwd(linear_concat_dw2_kernel,3xTF32)", by.get(_lib.T_DENSE_BWD), 4 * n1 * (Fdim + 2 * H2) + wbytes,
         hbm_peak, "hbm")
-    add("head+loss(linear_ce_kernel)", by.get(_lib.T_HEAD), 4 * nb * 2 * H2 + 8 * nb + 8 * steps * (H2 + 1) * wl.args.n_classes,
+    add("head+loss(linear_ce_mma_kernel)", by.get(_lib.T_HEAD), 4 * nb * 2 * H2 + 8 * nb + 8 * steps * (H2 + 1) * a.n_classes,
         hbm_peak, "hbm")
-    nparam = (Fdim + 1) * wl.args.n_hidden + (H2 + 1) * wl.args.n_classes
+    nparam = sum(p.numel() for p in tr.model.parameters())
     add("allreduce+adam(allreduce_adam_kernel)", by.get(_lib.T_OPT), 4 * 7 * nparam * steps, hbm_peak, "hbm")
     return out, N, M
 
@@ -511,8 +678,8 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
                  launches=reg["launches"], loss=reg["loss"], clocks=reg["clocks"], kernels=kern,
                  full_cached=tr.cacher.full_cached, cached_rows=tr.cacher.cached_num, parity_gate=gate,
                  replicas_identical=replicas,
-                 layer_sizes=[int(np.mean([lo[i + 1] - lo[i] for lo, _ in tr.sizes])) for i in range(3)],
-                 block_edges=[int(np.mean([bo[i + 1] - bo[i] for _, bo in tr.sizes])) for i in range(2)])
+                 layer_sizes=[int(np.mean([lo[i + 1] - lo[i] for lo, _ in tr.sizes])) for i in range(len(wl.fanouts) + 1)],
+                 block_edges=[int(np.mean([bo[i + 1] - bo[i] for _, bo in tr.sizes])) for i in range(len(wl.fanouts))])
         if host_inputs:
             b = args.batch_size * ID_BYTES
             r["h2d_bytes_per_step"] = int(2 * b + 4 * args.feat_size * M / steps)   # seeds + labels + missed input rows over PCIe
@@ -541,18 +708,61 @@ class CpuAgg(torch.autograd.Function):
         return torch.from_numpy(oracle.aggregate_bwd(ip, cols, base, g.contiguous().numpy(), ctx.n_src, "mean")), None, None
 
 
+def _cpu_model(args):
+    """torch-CPU modules of the config's model (parameter shapes of PaGraph/model/gcn_nssc.py / graphsage_nssc.py)"""
+    Fd, H, C, nl = args.feat_size, args.n_hidden, args.n_classes, args.n_layers
+    torch.manual_seed(0)
+    if args.model == "sage":
+        dims = [(Fd, H)] + [(H, H)] * (nl - 1) + [(2 * H, C)]
+        mods = [(torch.nn.Linear(i, o), torch.nn.Linear(i, o)) for i, o in dims]          # (fc_self, fc_neigh) per NodeUpdate
+        params = [p for pair in mods for m in pair for p in m.parameters()]
+    else:
+        mods = [torch.nn.Linear(Fd, H)] + [torch.nn.Linear(H, H) for _ in range(nl - 1)] + [torch.nn.Linear(2 * H, C)]
+        params = [p for m in mods for p in m.parameters()]
+    return mods, params
+
+
+def _cpu_forward(args, mods, nf, frames, threads):
+    """forward of the config's model on one OracleNodeFlow with the oracle's CPU aggregation (fp32, `threads` threads)"""
+    L, nl = nf.num_layers - 1, args.n_layers
+
+    def act(z, last_hidden):
+        return torch.cat((z, F.relu(z)), 1) if last_hidden else F.relu(z)
+    feats = [torch.from_numpy(fr["features"]) for fr in frames]
+    if args.model == "gcn":
+        h = feats[0]
+        for i, lin in enumerate(mods):
+            h = lin(CpuAgg.apply(h, nf.block(i), threads))
+            if i < len(mods) - 1:
+                h = act(h, i == nl - 1)
+        return h
+    if args.model == "gcn-pre":
+        h = act(mods[0](feats[0]), nl == 1)
+        for i, lin in enumerate(mods[1:]):
+            h = lin(CpuAgg.apply(h, nf.block(i), threads))
+            if i < len(mods) - 2:
+                h = act(h, i == nl - 2)
+        return h
+    h = {l: feats[l] for l in range(L + 1)}                 # sage: NodeUpdate `lid` is applied to every remaining block
+    for lid, (fc_self, fc_neigh) in enumerate(mods):
+        new = {}
+        for i in range(lid, L):
+            z = fc_self(h[i + 1]) + fc_neigh(CpuAgg.apply(h[i], nf.block(i), threads))
+            new[i + 1] = z if lid == len(mods) - 1 else act(z, lid == nl - 1)
+        h = new
+    return h[L]
+
+
 def cpu_path(args, indptr, indices, tables, seeds, n_batches, threads, first_batch=0):
     """The reference path restated on the CPU (oracle/): DGL-style sampling (OpenMP over batches, one
-    thread each), storage.py's host gather of every layer's rows for both fields (all rows come from
+    thread each), storage.py's host gather of every layer's rows for every field (all rows come from
     the host table — the reference's miss path, storage.py:117-129 — and no H2D copy is charged),
-    float64 mean aggregation and the GCN forward/backward/Adam on torch-CPU. Returns seconds."""
+    fp32 mean aggregation and the model's forward/backward/Adam on torch-CPU. Returns seconds."""
     import oracle
     fan = [int(x) for x in args.fanout.split(",")]
     V = len(indptr) - 1
-    torch.manual_seed(0)
-    lin1 = torch.nn.Linear(args.feat_size, args.n_hidden)
-    lin2 = torch.nn.Linear(2 * args.n_hidden, args.n_classes)
-    opt = torch.optim.Adam(list(lin1.parameters()) + list(lin2.parameters()), lr=args.lr)
+    mods, params = _cpu_model(args)
+    opt = torch.optim.Adam(params, lr=args.lr)
     labels = torch.randint(0, args.n_classes, (V,))
     flag = np.zeros(V, np.uint8)
     ident = np.zeros(1, np.int64)
@@ -576,14 +786,9 @@ def cpu_path(args, indptr, indices, tables, seeds, n_batches, threads, first_bat
                     fr[name] = _cpu_fetch(oracle, ids, flag, ident, tab, threads)
                 frames.append(fr)
             t2 = time.perf_counter()
-            h = torch.from_numpy(frames[0]["features"])
             # dropout mask generation is left out of the CPU arm: torch-CPU bernoulli is single-threaded
             # (0.6 s per minibatch here) and would dominate; leaving it out favours the CPU arm.
-            a0 = CpuAgg.apply(h, nf.block(0), threads)
-            z = lin1(a0)
-            z = torch.cat((z, F.relu(z)), 1)
-            a1 = CpuAgg.apply(z, nf.block(1), threads)
-            pred = lin2(a1)
+            pred = _cpu_forward(args, mods, nf, frames, threads)
             loss = F.cross_entropy(pred, labels[torch.from_numpy(nf.layer_parent_nid(-1))])
             opt.zero_grad()
             loss.backward()
@@ -630,9 +835,12 @@ def host_threads():
 
 
 def workload_name(args):
-    return ("R-MAT %.3gM vtx/%.3gM edges f%d, GCN-2L h%d c%d, fanout %s, batch %d"
-            % (args.vnum / 1e6, args.nnz / 1e6, args.feat_size, args.n_hidden, args.n_classes,
-               args.fanout.replace(",", "/"), args.batch_size))
+    model = {"gcn": "GCN-2L", "gcn-pre": "GCN-2L --preprocess", "sage": "GraphSAGE-%dL" % (args.n_layers + 1)}[args.model]
+    part = "hash" if args.partition == "hash" else "dg/%d" % args.parts
+    scale = "" if args.scale == 1.0 else " scale=%g" % args.scale
+    return ("cfg%d %s %.3gM vtx/%.3gM edges f%d, %s h%d c%d, fanout %s, batch %d, %s%s"
+            % (args.config, args.tag, args.vnum / 1e6, args.nnz / 1e6, args.feat_size, model, args.n_hidden, args.n_classes,
+               args.fanout.replace(",", "/"), args.batch_size, part, scale))
 
 
 
@@ -662,13 +870,13 @@ def parity_gate(wl, tr, batch_idx=3):
     outs = c._gather(ids, c._field_names)
     ids_cpu = torch.from_numpy(ref.node_mapping)
     for name, got in zip(c._field_names, outs):
-        want = wl.store.ndata[name][ids_cpu]
+        want = wl.host_rows(name, ids_cpu)
         if not torch.equal(got.cpu().view(torch.int32), want.view(torch.int32)):
             raise SystemExit("parity gate: fetched rows of %r differ from the host table" % name)
     bi, bc, bb, n_dst, n_src = nf.block_csr(0)
     got = ops.cache_aggregate(c, "features", nf.layer_parent_nid_dev(0), bi, bc, bb, n_src, n_dst, "mean").cpu().numpy()
     ip, cols, base = ref.block(0)
-    feats0 = wl.store.ndata["features"][torch.from_numpy(ref.layer_parent_nid(0))].numpy()
+    feats0 = wl.host_rows("features", torch.from_numpy(ref.layer_parent_nid(0))).numpy()
     want = oracle.aggregate(ip, cols, base, feats0, "mean", threads=host_threads())
     err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
     if not err <= 1e-5:
@@ -711,7 +919,7 @@ def compact_line(d):
         "steps": d["steps"], "warmup": d["warmup"], "ms_per_step": _r(d["ms_per_step"]), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": d["config"]["workload"][:120], "cache_mode": d["config"]["cache_mode"],
-                   "path": d["config"]["path"], "l2": "inputs>L2 (24GB table, new batch/step)"},
+                   "path": d["config"]["path"], "l2": "inputs>L2 (feature table, new batch/step)"},
         "e2e": {"value": _r(e["value"], 6), "unit": "minibatches/s", "h2d_bytes_per_step": e["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": e["d2h_bytes_per_step"]},
         "gpu_launches": d["gpu_launches"],
@@ -724,15 +932,15 @@ def compact_line(d):
         "gather_gbs": _r(d.get("gather_gbs"), 4), "hit_rate": _r(d.get("hit_rate"), 4),
         "parity_gate": d.get("parity_gate"), "replicas_identical": d.get("replicas_identical"),
     }
-    v20 = d.get("vtx20")
-    if v20:
-        line["vtx20"] = {k: _r(v20.get(k), 4) for k in ("value", "e2e", "gather_gbs", "hit_rate", "miss_frac_pcie")}
+    vkey = next((k for k in d if k.startswith("vtx") and isinstance(d[k], dict)), None)
+    if vkey:
+        line[vkey] = {k: _r(d[vkey].get(k), 4) for k in ("value", "e2e", "gather_gbs", "hit_rate", "miss_frac_pcie")}
     out = json.dumps(line, separators=(",", ":"))
     # never let the line grow past what the driver keeps: shorten the free-text strings first, then drop the optional tail
     for shrink in (lambda: line["cpu_baseline"] and line["cpu_baseline"].update(sample=line["cpu_baseline"]["sample"][:48]),
                    lambda: line["roofline"].update(kernel=line["roofline"]["kernel"][:32]),
                    lambda: line["config"].update(l2="inputs>L2"),
-                   lambda: line.pop("vtx20", None), lambda: line.pop("gather_gbs", None)):
+                   lambda: line.pop(vkey, None), lambda: line.pop("gather_gbs", None)):
         if len(out) < 1150:
             break
         shrink()
@@ -763,7 +971,8 @@ def main_reference(args):
     threads = host_threads()
     if torch.cuda.is_available():            # data generation only (setup, untimed) — same graph as our arm
         dev = torch.device("cuda", 0)
-        ip, ix = data.rmat_in_csr_cuda(args.vnum, args.nnz, seed=args.seed, device=dev)
+        a_, b_, c_ = args.rmat
+        ip, ix = data.rmat_in_csr_cuda(args.vnum, args.nnz, seed=args.seed, device=dev, a=a_, b=b_, c=c_)
         indptr, indices = ip.cpu().numpy(), ix.cpu().numpy()
         feat = torch.empty((args.vnum, args.feat_size), dtype=torch.float32)
         gen = torch.Generator(device=dev)
@@ -785,10 +994,13 @@ def main_reference(args):
         norm = torch.from_numpy(1.0 / np.maximum(np.diff(indptr), 1).astype(np.float32)).unsqueeze(1)
         train = np.sort(np.random.default_rng(4).permutation(args.vnum)[:int(args.vnum * 0.65)])
     from pagraph_b200.parallel import hash_split
-    seeds = np.sort(hash_split(train, max(args.gpus, 1), seed=5)[0])
+    # the CPU arm walks the full graph with a 1/parts hash share of the train ids (for the dg configs too: the partition
+    # only decides which seeds a rank owns, and a dg partition's closure is nearly the whole graph at these densities)
+    seeds = np.sort(hash_split(train, max(args.parts or args.gpus, 1), seed=5)[0])
     torch.manual_seed(0)
     seeds = np.ascontiguousarray(seeds[torch.randperm(len(seeds)).numpy()])
     tables = {"features": feat, "norm": norm}
+    tables = {f: tables[f] for f in args.fields}
     torch.set_num_threads(threads)
     cpu_path(args, indptr, indices, tables, seeds, args.warmup, threads, first_batch=0)
     t, stage = cpu_path(args, indptr, indices, tables, seeds, args.steps, threads, first_batch=args.warmup)
@@ -838,7 +1050,10 @@ def main_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         indptr, indices = wl.host_graph()
-        tables = {"features": wl.store.ndata["features"], "norm": wl.store.ndata["norm"]}
+        tables = {f: wl.store.ndata[f] for f in args.fields}
+        if wl.nid_map is not None:       # the CPU arm walks the same partition graph; its rows come through nid_map
+            nm = wl.nid_map.cpu()
+            tables = {f: t[nm] for f, t in tables.items()}
         torch.manual_seed(0)
         seeds = np.ascontiguousarray(wl.train_nid[torch.randperm(len(wl.train_nid)).numpy()])
         torch.set_num_threads(threads)
@@ -864,13 +1079,15 @@ def main_ours(args):
     except Exception:
         pass
     detail = {
-        "metric": "minibatches/sec (sample + cache fetch + GCN train step) + feature-gather GB/s",
+        "metric": "minibatches/sec (sample + cache fetch + train step) + feature-gather GB/s",
         "value": v["minibatches_per_s"], "unit": "minibatches/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "cache_mode": modes[0], "path": args.path,
-                   "cache": "hbm20 = capacity 20% of HBM bytes (>= the 24 GB table -> full_cached, headline); "
-                            "vtx20 = top-20%-out-degree vertices cached (real hit/miss split)",
+                   "cache": "hbmNN = capacity NN% of the HBM bytes (BASELINE.json's wording; >= the feature table -> "
+                            "full_cached, headline); vtxNN = top-NN%-out-degree vertices of the partition cached (real "
+                            "hit/miss split)",
+                   "setup": wl.setup,
                    "dropout": args.dropout, "optimizer": "Adam lr %g" % args.lr,
                    "l2": "inputs larger than L2 (24 GB feature table, new random minibatch every step); no flush",
                    "kernel_timing": ("pg_timing_* CUDA-event pairs on the launching stream; with --path engine the timed region "
@@ -899,10 +1116,11 @@ def main_ours(args):
         "variants": {m: results[m] for m in modes},
         "setup_s": round(t_setup, 1),
     }
-    if "vtx20" in results and modes[0] != "vtx20":
-        x = results["vtx20"]
+    vmode = next((m for m in modes[1:] if m.startswith("vtx")), None)
+    if vmode:
+        x = results[vmode]
         g = x["value"]["gather"] or {}
-        detail["vtx20"] = {"value": x["value"]["minibatches_per_s"], "e2e": x["e2e"]["minibatches_per_s"],
+        detail[vmode] = {"value": x["value"]["minibatches_per_s"], "e2e": x["e2e"]["minibatches_per_s"],
                            "gather_gbs": g.get("gather_gbs"), "hit_rate": g.get("hit_rate"),
                            "miss_frac_pcie": (g.get("miss") or {}).get("frac")}
     detail["detail_file"] = write_detail(detail, world)

@@ -70,7 +70,7 @@ def trainer(rank, world_size, args, backend='nccl'):
     optimizer = torch.optim.Adam(sync.flat_parameters(), lr=args.lr, weight_decay=args.weight_decay)
 
     fanout = [int(x) for x in str(args.num_neighbors).split(',')]
-    if args.engine == 'graph' and not args.preprocess:
+    if args.engine == 'graph':
         return train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fanout, num_hops, embed_names, remote_g)
     fanout = fanout[0] if len(fanout) == 1 else fanout
     sampler = NeighborSampler(g, args.batch_size, fanout, neighbor_type='in', shuffle=True,
@@ -115,23 +115,24 @@ def trainer(rank, world_size, args, backend='nccl'):
     dist.destroy_process_group()
 
 
-def save_checkpoint(args, model, epoch, rank):
-    """`--ckpt DIR` (extension): rank 0 saves the parameters after every epoch as DIR/gcn-nssc_{epoch}, the file name
+def save_checkpoint(args, model, epoch, rank, arch='gcn-nssc'):
+    """`--ckpt DIR` (extension): rank 0 saves the parameters after every epoch as DIR/{arch}_{epoch}, the file name
     examples/eval.py loads (the reference's eval.py:28-32 expects them; nothing in its tree writes them)."""
     if args.ckpt and rank == 0:
         os.makedirs(args.ckpt, exist_ok=True)
         torch.save({k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
-                   os.path.join(args.ckpt, 'gcn-nssc_{}'.format(epoch)))
+                   os.path.join(args.ckpt, '{}_{}'.format(arch, epoch)))
 
 
-def train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fanout, num_hops, embed_names, remote_g):
+def train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fanout, num_hops, embed_names, remote_g,
+                      arch='gcn-nssc'):
     """Same loop on pagraph_b200.engine.GCNTrainEngine: the minibatch work is two CUDA-graph replays (load + compute)."""
-    from pagraph_b200.engine import GCNTrainEngine
+    from pagraph_b200.engine import make_train_engine
     from pagraph_b200.parallel import equalised_num_batches
     optimizer = torch.optim.Adam(sync.flat_parameters(), lr=args.lr, weight_decay=args.weight_decay, capturable=True, fused=True)
     fanouts = fanout * num_hops if len(fanout) == 1 else fanout
-    engine = GCNTrainEngine(g, cacher, model, optimizer, train_nid, labels, args.batch_size, fanouts, sync=sync, seed=args.seed,
-                            shuffle=True)
+    engine = make_train_engine(g, cacher, model, optimizer, train_nid, labels, args.batch_size, fanouts, sync=sync,
+                               seed=args.seed, shuffle=True)       # GCN / GCN --preprocess / GraphSAGE pipelines
     steps_per_epoch = equalised_num_batches(engine.num_batches)
     epoch_dur = []
     tic = time.time()
@@ -153,10 +154,11 @@ def train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fan
             epoch_dur.append(time.time() - epoch_start_time)
             print('Epoch average time: {:.4f}'.format(np.mean(np.array(epoch_dur[2:])) if len(epoch_dur) > 2
                                                       else epoch_dur[-1]))
-        save_checkpoint(args, model, epoch, rank)
+        save_checkpoint(args, model, epoch, rank, arch)
     print('Total Time: {:.4f}s'.format(time.time() - tic))
     engine.close()
-    remote_g.destroy()
+    if not args.keep_store:
+        remote_g.destroy()
     dist.destroy_process_group()
 
 

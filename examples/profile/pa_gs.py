@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, HERE)
 
-from pa_gcn import init_process, make_parser  # noqa: E402  (shared with the GCN entry)
+from pa_gcn import init_process, make_parser, save_checkpoint, train_with_engine  # noqa: E402  (shared with the GCN entry)
 from pagraph_b200 import DGLGraph  # noqa: E402
 from pagraph_b200 import data, graph_store, storage  # noqa: E402
 from pagraph_b200.model.graphsage_nssc import GraphSageSampling  # noqa: E402
@@ -59,6 +59,9 @@ def trainer(rank, world_size, args, backend='nccl'):
     optimizer = torch.optim.Adam(sync.flat_parameters(), lr=args.lr, weight_decay=args.weight_decay)
 
     fanout = [int(x) for x in str(args.num_neighbors).split(',')]
+    if args.engine == 'graph' and not args.preprocess:       # SageTrainEngine: the same loop as a CUDA-graph pipeline
+        return train_with_engine(rank, args, g, cacher, model, sync, labels, train_nid, fanout, num_hops, embed_names,
+                                 remote_g, arch='gs-nssc')
     fanout = fanout[0] if len(fanout) == 1 else fanout
     sampler = NeighborSampler(g, args.batch_size, fanout, neighbor_type='in', shuffle=True,
                               num_workers=args.num_workers, num_hops=num_hops, seed_nodes=train_nid,
@@ -92,6 +95,7 @@ def trainer(rank, world_size, args, backend='nccl'):
                                                       else epoch_dur[-1]))
         if cacher.log:
             print('Epoch average miss rate: {:.4f}'.format(cacher.get_miss_rate()))
+        save_checkpoint(args, model, epoch, rank, 'gs-nssc')
     print('Total Time: {:.4f}s'.format(time.time() - tic))
     if not args.keep_store:
         remote_g.destroy()
@@ -101,7 +105,7 @@ def trainer(rank, world_size, args, backend='nccl'):
 if __name__ == '__main__':
     parser = make_parser()
     parser.description = 'GraphSAGE'
-    parser.set_defaults(n_hidden=16, engine='eager')       # pa_gs.py:134; the CUDA-graph engine drives the GCN model only
+    parser.set_defaults(n_hidden=16)                        # pa_gs.py:134
     args = parser.parse_args()
     if args.remote_sample:
         raise SystemExit("--remote-sample (server-side CPU sampling, parallel/dataloader.py) has no role when the "

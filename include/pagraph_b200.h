@@ -147,9 +147,11 @@ pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, fl
                          uint8_t* d_hit_mask, int64_t* d_counts, int mode, void* stream);
 /* Same for the id range [*d_begin, *d_end) of d_ids_base, the range living on the device (e.g. two entries of a
  * NodeFlow's meta block): nothing about the minibatch's size is needed on the host, so the call can be captured in a
- * CUDA graph and replayed. `cap` bounds the row count (output capacity, grid sizing). */
+ * CUDA graph and replayed. `cap` bounds the row count (output capacity, grid sizing). d_ws: optional caller-owned
+ * workspace int64[2 + 4 * cap] (hit / miss lists) — one per captured call site, so that nothing a replayed graph
+ * addresses is shared with calls on other streams; NULL = the handle's shared workspace. */
 pg_status pg_cache_fetch_dyn(pg_cache* c, const int64_t* d_ids_base, const int64_t* d_begin, const int64_t* d_end,
-                             int64_t cap, float* const* d_out, int64_t* d_counts, int mode, void* stream);
+                             int64_t cap, float* const* d_out, int64_t* d_counts, int mode, int64_t* d_ws, void* stream);
 /* ---------------------------------------------------------------- aggregation (replaces nf.block_compute(i, fn.copy_src,
  * fn.sum|fn.mean, ...), PaGraph/model/gcn_nssc.py:71-74, graphsage_nssc.py:98-106; and, run over
  * the full graph with mode=PG_AGG_SUM + norm, the server-side --preprocess fold, server/pa_server.py:45-52).

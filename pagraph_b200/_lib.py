@@ -69,7 +69,7 @@ SIGNATURES = {
     "pg_aggregate_rows": (ctypes.c_int, [c_vp, ctypes.POINTER(pg_block), ctypes.c_int32, c_vp, ctypes.c_int64, ctypes.c_int,
                                          c_vp, ctypes.c_float, ctypes.c_uint64, c_vp, ctypes.c_int64, c_vp]),
     "pg_cache_fetch_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp,
-                                          ctypes.c_int, c_vp]),
+                                          ctypes.c_int, c_vp, c_vp]),
     "pg_minibatch_key": (None, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint32)]),
     "pg_sample_keyed": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.POINTER(pg_nodeflow_buffers), c_vp,
                                        c_vp, c_vp, c_vp]),

@@ -446,7 +446,10 @@ pg_status launch_rows_tma(const pg::AggRowsArgs& a, int dev, cudaStream_t st) {
   const char* env_d = getenv("PG_AGG_DEPTH");
   const char* env_w = getenv("PG_AGG_WARPS");
   const int depth = env_d ? atoi(env_d) : 0;
-  const int warps = env_w ? atoi(env_w) : 16;
+  // measured at config 2 (tools/micro_fused.py, resolve + kernel, us): 16 warps x (depth 2 x group 2) 154, 12 x (2 x 3) 152,
+  // 8 x (2 x 5) 150, 8 x (3 x 3) 173: after the instruction diet the kernel is latency-bound on the row fetches, so fewer
+  // warps with more rows per task win — and 8 warps x 88 registers leave 2/3 of the register file to the other streams
+  const int warps = env_w ? atoi(env_w) : 8;
   pg_status s = PG_ERR_INVALID;
   if (warps >= 16) s = launch_rows_tma_w<16, CH>(a, dev, st, budget, depth);
   if (s == PG_ERR_INVALID && warps >= 12) s = launch_rows_tma_w<12, CH>(a, dev, st, budget, depth);

@@ -339,11 +339,31 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
     }
     enc = (EncodeTiledFn)fn;
   }
-  CUtensorMap tm_x, tm_w;
-  if (make_map(enc, &tm_x, d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, kBlockM)) return PG_ERR_INVALID;
-  if (make_map(enc, &tm_w, d_weight, kN, (uint64_t)K, (uint64_t)K, kN)) return PG_ERR_INVALID;
+  // tensor maps of the most recent (pointer, shape) pairs: the training loop calls with the same persistent buffers
+  // every step, so the driver encode (a few microseconds of host time each) is paid once
+  struct MapEntry { const float* base; uint64_t rows, cols, stride; uint32_t box; CUtensorMap map; };
+  static MapEntry cache[8];
+  static int next_slot = 0;
+  auto get_map = [&](const float* base, uint64_t rows, uint64_t cols, uint64_t stride, uint32_t box) -> const CUtensorMap* {
+    for (MapEntry& e : cache)
+      if (e.base == base && e.rows == rows && e.cols == cols && e.stride == stride && e.box == box) return &e.map;
+    MapEntry& e = cache[next_slot];
+    next_slot = (next_slot + 1) % 8;
+    e.base = nullptr;
+    if (make_map(enc, &e.map, base, rows, cols, stride, box)) return nullptr;
+    e.base = base; e.rows = rows; e.cols = cols; e.stride = stride; e.box = box;
+    return &e.map;
+  };
+  const CUtensorMap* pm_x = get_map(d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, kBlockM);
+  const CUtensorMap* pm_w = get_map(d_weight, kN, (uint64_t)K, (uint64_t)K, kN);
+  if (!pm_x || !pm_w) return PG_ERR_INVALID;
+  const CUtensorMap tm_x = *pm_x, tm_w = *pm_w;
   const size_t smem = (size_t)kStages * kStageBytes + 1024;
-  PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   const int64_t ntiles = (n + kBlockM - 1) / kBlockM;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev));
   UmmaDrop drop;

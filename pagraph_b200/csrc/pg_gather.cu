@@ -486,22 +486,22 @@ pg_status pg_cache_fetch_host(pg_cache* c, const int64_t* d_nids, int64_t n, flo
 
 static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out,
                                   uint8_t* d_hit_mask, int64_t* d_counts, int mode, const int64_t* d_begin,
-                                  const int64_t* d_end, void* stream);
+                                  const int64_t* d_end, int64_t* d_ws, void* stream);
 
 pg_status pg_cache_fetch(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out, uint8_t* d_hit_mask,
                          int64_t* d_counts, int mode, void* stream) {
-  return cache_fetch_impl(c, d_parent_ids, n, d_out, d_hit_mask, d_counts, mode, nullptr, nullptr, stream);
+  return cache_fetch_impl(c, d_parent_ids, n, d_out, d_hit_mask, d_counts, mode, nullptr, nullptr, nullptr, stream);
 }
 
 pg_status pg_cache_fetch_dyn(pg_cache* c, const int64_t* d_ids_base, const int64_t* d_begin, const int64_t* d_end,
-                             int64_t cap, float* const* d_out, int64_t* d_counts, int mode, void* stream) {
+                             int64_t cap, float* const* d_out, int64_t* d_counts, int mode, int64_t* d_ws, void* stream) {
   PG_REQUIRE(d_begin && d_end, "pg_cache_fetch_dyn: null range");
-  return cache_fetch_impl(c, d_ids_base, cap, d_out, nullptr, d_counts, mode, d_begin, d_end, stream);
+  return cache_fetch_impl(c, d_ids_base, cap, d_out, nullptr, d_counts, mode, d_begin, d_end, d_ws, stream);
 }
 
 static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int64_t n, float* const* d_out,
                                   uint8_t* d_hit_mask, int64_t* d_counts, int mode, const int64_t* d_begin,
-                                  const int64_t* d_end, void* stream) {
+                                  const int64_t* d_end, int64_t* d_ws, void* stream) {
   PG_REQUIRE(c && d_out && (d_parent_ids || n == 0) && n >= 0, "pg_cache_fetch: bad arguments");
   PG_REQUIRE(mode >= 0 && mode <= 2, "pg_cache_fetch: mode must be 0, 1 or 2");
   if (n == 0) return PG_OK;
@@ -524,14 +524,26 @@ static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int6
     return launch_rows(c, c->cache_tables, cache_strides, d_out, nullptr, d_parent_ids, nullptr, n, false, st, 0, -1,
                        d_begin, d_end);
   }
-  pg_status s = ensure_ws(c, n);
-  if (s != PG_OK) return s;
+  // hit / miss lists and their counters: the caller's workspace (int64[2 + 4 n]: a pipeline replaying captured graphs
+  // owns one per call site) or the handle's shared one
+  pg_status s = PG_OK;
+  int64_t *hit_pos, *hit_row, *miss_pos, *miss_row;
+  unsigned long long* list_counts;
+  if (d_ws) {
+    list_counts = (unsigned long long*)d_ws;
+    hit_pos = d_ws + 2; hit_row = hit_pos + n; miss_pos = hit_row + n; miss_row = miss_pos + n;
+  } else {
+    s = ensure_ws(c, n);
+    if (s != PG_OK) return s;
+    list_counts = c->list_counts;
+    hit_pos = c->hit_pos; hit_row = c->hit_row; miss_pos = c->miss_pos; miss_row = c->miss_row;
+  }
   {
     pg::TimedScope ts(PG_T_SPLIT, st);
-    PG_CUDA(cudaMemsetAsync(c->list_counts, 0, 16, st));
+    PG_CUDA(cudaMemsetAsync(list_counts, 0, 16, st));
     const int grid = (int)std::min<int64_t>((n + kSplitThreads - 1) / kSplitThreads, (int64_t)sms * 8);
-    split_kernel<<<grid, kSplitThreads, 0, st>>>(d_parent_ids, n, c->flag, c->l2c, c->nid_map, c->hit_pos, c->hit_row,
-                                                 c->miss_pos, c->miss_row, c->list_counts, d_hit_mask,
+    split_kernel<<<grid, kSplitThreads, 0, st>>>(d_parent_ids, n, c->flag, c->l2c, c->nid_map, hit_pos, hit_row,
+                                                 miss_pos, miss_row, list_counts, d_hit_mask,
                                                  (unsigned long long*)d_counts, d_begin, d_end);
     PG_CHECK_LAUNCH();
   }
@@ -541,14 +553,14 @@ static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int6
   PG_CUDA(cudaStreamWaitEvent(c->miss_stream, c->ev_split, 0));
   {
     pg::TimedScope ts(PG_T_GATHER_MISS, c->miss_stream);
-    s = launch_rows(c, c->host_dev, host_strides, d_out, c->miss_pos, c->miss_row, c->list_counts + 1, n, mode == 2,
+    s = launch_rows(c, c->host_dev, host_strides, d_out, miss_pos, miss_row, list_counts + 1, n, mode == 2,
                     c->miss_stream);
   }
   if (s != PG_OK) return s;
   PG_CUDA(cudaEventRecord(c->ev_miss_done, c->miss_stream));
   if (c->cached_rows > 0) {
     pg::TimedScope ts(PG_T_GATHER_HIT, st);
-    s = launch_rows(c, c->cache_tables, cache_strides, d_out, c->hit_pos, c->hit_row, c->list_counts, n, false, st);
+    s = launch_rows(c, c->cache_tables, cache_strides, d_out, hit_pos, hit_row, list_counts, n, false, st);
     if (s != PG_OK) return s;
   }
   PG_CUDA(cudaStreamWaitEvent(st, c->ev_miss_done, 0));

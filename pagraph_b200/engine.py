@@ -88,6 +88,8 @@ def _capture_guard():
 
 
 class GCNTrainEngine:
+    _first_dense_layer = 1       # lowest NodeFlow layer whose rows enter a dense (padded-shape) kernel
+
     def __init__(self, g, cacher, model, optimizer, train_nid, labels, batch_size, fanouts, sync=None, seed=0,
                  shuffle=True, host_inputs=False, stage_rows=131072, use_graphs=True, loss_fcn=None):
         """
@@ -99,15 +101,12 @@ class GCNTrainEngine:
                     host_inputs — then seeds and labels of every minibatch are copied from pinned host memory)
         sync:       pagraph_b200.parallel.FlatGradAllReduce or None
         """
-        if getattr(model, "preprocess", False):
-            raise NotImplementedError("GCNTrainEngine drives the non-preprocess model (input block fused from the cache)")
         self.g, self.cacher, self.model, self.opt, self.sync = g, cacher, model, optimizer, sync
         self.dev = cacher._dev
         self.batch = int(batch_size)
         self.fanouts = [int(f) for f in fanouts]
         self.L = len(self.fanouts)
-        if len(model.layers) != self.L:
-            raise ValueError("model has %d blocks but %d hops are sampled" % (len(model.layers), self.L))
+        self._check_model(model)
         self.seed = int(seed)
         self.host_inputs = bool(host_inputs)
         self.use_graphs = bool(use_graphs)
@@ -180,6 +179,22 @@ class GCNTrainEngine:
         self._cache_state = None
         self._warm = False
 
+    # ------------------------------------------------------------------ model-specific hooks (overridden by the siblings below)
+    def _check_model(self, model):
+        if getattr(model, "preprocess", False):
+            raise NotImplementedError("GCNTrainEngine drives the non-preprocess model (input block fused from the cache); "
+                                      "use GCNPreprocessTrainEngine")
+        if len(model.layers) != self.L:
+            raise ValueError("model has %d blocks but %d hops are sampled" % (len(model.layers), self.L))
+
+    def _cap_nf(self, l):
+        """worst-case size of NodeFlow layer l (0 = inputs .. L = seeds)"""
+        return self.cap_layer[self.L - l]
+
+    def _capb(self, l):
+        """padded (bucketed) row capacity of the dense buffers of NodeFlow layer l"""
+        return self.batch if l == self.L else -(-self._cap_nf(l) // _BUCKET) * _BUCKET
+
     # ------------------------------------------------------------------ buffers
     def _make_slot(self):
         s, dev = _Slot(), self.dev
@@ -193,11 +208,7 @@ class GCNTrainEngine:
                     meta=torch.zeros(_lib.PG_META_LEN, **i64))
         s.h_meta = torch.zeros(_lib.PG_META_LEN, dtype=torch.int64).pin_memory()
         s.h_meta_np = s.h_meta.numpy()
-        s.rowptr = torch.zeros(self.cap_n0, **i64)
-        s.stage = torch.empty((max(self.stage_rows, 1), self.F), dtype=torch.float32, device=dev)
-        s.ws = torch.zeros(2 + max(self.stage_rows, 1), **i64)              # this slot's miss list (pg_cache_resolve d_ws)
-        cap1 = -(-self.cap_layer[-2] // _BUCKET) * _BUCKET
-        s.agg = torch.empty((cap1, self.F), dtype=torch.float32, device=dev)       # block-0 aggregate, padded rows zeroed
+        self._make_slot_buffers(s)
         s.loss = torch.zeros((), dtype=torch.float32, device=dev)
         s.sampled, s.loaded, s.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         s.sample_graph, s.sample_kernels = None, 0
@@ -205,6 +216,18 @@ class GCNTrainEngine:
         s.compute_graphs = {}
         s.n_valid = self.batch
         return s
+
+    def _make_slot_buffers(self, s):
+        """model-specific device buffers of one ring slot (row pointers, miss staging, aggregates)"""
+        dev = self.dev
+        s.rowptr = torch.zeros(self.cap_n0, dtype=torch.int64, device=dev)
+        self._make_stage(s, self.stage_rows)
+        s.agg = torch.empty((self._capb(1), self.F), dtype=torch.float32, device=dev)   # block-0 aggregate, padded rows zeroed
+
+    def _make_stage(self, s, stage_rows):
+        """miss staging rows + miss list of the slot's pg_cache_resolve call(s); re-made when the cache state changes"""
+        s.stage = torch.empty((max(stage_rows, 1), self.F), dtype=torch.float32, device=self.dev)
+        s.ws = torch.zeros(2 + max(stage_rows, 1), dtype=torch.int64, device=self.dev)   # pg_cache_resolve d_ws
 
     def _meta_ptr(self, s, idx):
         return ctypes.c_void_p(s.nf["meta"].data_ptr() + 8 * idx)
@@ -327,6 +350,10 @@ class GCNTrainEngine:
                 h = layer(NodeBatch({"h": h}))["activation"]
         if loss is None:
             loss = self.loss_fcn(h[:n_valid], s.labels[:n_valid])
+        self._backward_and_step(s, loss)
+
+    def _backward_and_step(self, s, loss):
+        """zero_grad -> backward -> gradient all-reduce -> optimizer step (pa_gcn.py:94-97), then the loss into the slot"""
         if self.sync is not None:
             self.sync.zero_grad()
         else:
@@ -347,19 +374,30 @@ class GCNTrainEngine:
     # the parameters' .grad (the flat all-reduce bucket): tensor-core NodeUpdate forward (+ bias, relu, concat, dropout),
     # block-1 aggregation, head + loss forward/backward, aggregation backward, tensor-core dW/db (+ dropout', relu',
     # concat split), all-reduce + Adam. No autograd graph, no elementwise library kernels.
+    def _fused_spec(self):
+        """What the fused dense stage works on: the first linear (F -> 32) with its activation flags, the classifier head,
+        the NodeFlow layer whose rows are its input x (held in s.agg), the block aggregated at width 64 behind it and
+        whether dropout follows the first layer. None = this model shape has no fused stage."""
+        m = self.model
+        if self.L != 2 or len(m.layers) != 2:
+            return None
+        l0 = m.layers[0]
+        return dict(lin=l0.linear, act=l0.activation, concat=l0.concat and not l0.test, head=m.layers[1], xl=1, blk=1,
+                    drop_hidden=True)
+
     def _dense_fusable(self):
         m = self.model
-        if os.environ.get("PG_ENGINE_FUSED_DENSE", "1") == "0" or self.L != 2 or len(m.layers) != 2:
+        spec = self._fused_spec() if os.environ.get("PG_ENGINE_FUSED_DENSE", "1") != "0" else None
+        if spec is None:
             return False
-        l0, l1 = m.layers[0], m.layers[1]
-        relu = l0.activation is torch.relu or l0.activation is torch.nn.functional.relu
-        w0, w1 = l0.linear.weight, l1.linear.weight
+        relu = spec["act"] is torch.relu or spec["act"] is torch.nn.functional.relu
+        w0, w1 = spec["lin"].weight, spec["head"].linear.weight
         agg = self.slots[0].agg
-        ok = (relu and l0.concat and not l0.test and w0.shape == (32, self.F) and w1.shape[1] == 64
+        ok = (relu and spec["concat"] and w0.shape == (32, self.F) and w1.shape[1] == 64
               and LinearConcat.supported(agg, w0) and w0.is_contiguous() and w1.is_contiguous()
               and (w0.grad is None or w0.grad.data_ptr() % 16 == 0)
               and all(p.requires_grad for p in m.parameters())
-              and self._head_fusable(l1, torch.empty((1, 64), dtype=torch.float32, device=self.dev)))
+              and self._head_fusable(spec["head"], torch.empty((1, 64), dtype=torch.float32, device=self.dev)))
         return bool(ok)
 
     def _dense_buffers(self):
@@ -367,10 +405,10 @@ class GCNTrainEngine:
             d, dev = _Slot(), self.dev
             cap1 = self.slots[0].agg.shape[0]
             f32 = dict(dtype=torch.float32, device=dev)
-            d.out = torch.zeros((cap1, 64), **f32)          # cat(z, relu z) of layer 0 (pre-dropout)
-            d.hd = torch.zeros((cap1, 64), **f32)           # dropout(out): source rows of block 1
+            d.out = torch.zeros((cap1, 64), **f32)          # cat(z, relu z) of the first layer (pre-dropout)
+            d.hd = torch.zeros((cap1, 64), **f32)           # dropout(out): source rows of the 64-wide block
             d.ghd = torch.zeros((cap1, 64), **f32)          # d loss / d hd
-            d.a2 = torch.zeros((self.batch, 64), **f32)     # block-1 aggregate: input of the head
+            d.a2 = torch.zeros((self.batch, 64), **f32)     # 64-wide aggregate: input of the head
             d.ga2 = torch.zeros((self.batch, 64), **f32)
             for p in self.model.parameters():               # no sync object: plain .grad tensors the kernels overwrite
                 if p.grad is None:
@@ -380,25 +418,25 @@ class GCNTrainEngine:
 
     def _compute_body_fused(self, s, caps, n_valid):
         L, m, d = _lib.lib(), self.model, self._dense_buffers()
-        l0, l1 = m.layers[0], m.layers[1]
+        spec = self._fused_spec()
         nf, st = s.nf, _lib.stream_ptr()
-        n1 = caps[1]
-        p = float(m.dropout.p) if (m.dropout is not None and m.training) else 0.0
+        n1, blk = caps[spec["xl"]], spec["blk"]
+        p = float(m.dropout.p) if (spec["drop_hidden"] and m.dropout is not None and m.training) else 0.0
         x, out, hd, ghd = s.agg[:n1], d.out[:n1], d.hd[:n1], d.ghd[:n1]
-        w0, b0, w1, b1 = l0.linear.weight, l0.linear.bias, l1.linear.weight, l1.linear.bias
+        w0, b0, w1, b1 = spec["lin"].weight, spec["lin"].bias, spec["head"].linear.weight, spec["head"].linear.bias
         linear_concat_forward(x, w0, b0, True, out=out, out_drop=hd, dropout_p=p, seed=self.drop_seed_hidden,
                               step=self.step_counter)
         h = hd if p > 0 else out
-        lo = self._meta_ptr(s, 4 + 1)
+        lo = self._meta_ptr(s, 4 + blk)
         _lib.check(L.pg_aggregate_fwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(h), 64,
-                                          _lib.ptr(d.a2), 64, caps[2], 64, _MODES["mean"], None, st), "pg_aggregate_fwd_dyn")
+                                          _lib.ptr(d.a2), 64, caps[blk + 1], 64, _MODES["mean"], None, st), "pg_aggregate_fwd_dyn")
         C = w1.shape[0]
         _lib.check(L.pg_linear_cross_entropy(_lib.ptr(d.a2), 64, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(s.labels), n_valid, 64, C,
                                              _lib.ptr(s.loss), _lib.ptr(d.ga2), 64, _lib.ptr(w1.grad),
                                              _lib.ptr(b1.grad if b1 is not None else None), self._meta_ptr(s, 4 + self.L), st),
                    "pg_linear_cross_entropy")
         _lib.check(L.pg_aggregate_bwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(d.ga2), 64,
-                                          _lib.ptr(ghd), 64, caps[2], n1, 64, _MODES["mean"], None, st), "pg_aggregate_bwd_dyn")
+                                          _lib.ptr(ghd), 64, caps[blk + 1], n1, 64, _MODES["mean"], None, st), "pg_aggregate_bwd_dyn")
         linear_concat_backward(x, ghd, out, True, w0.grad, b0.grad if b0 is not None else None, p, self.drop_seed_hidden,
                                self.step_counter)
         if self.fused_opt is not None:                       # gradient all-reduce + Adam: one kernel over NVLink peer memory
@@ -420,8 +458,8 @@ class GCNTrainEngine:
         meta = s.h_meta_np
         lay = [int(meta[4 + j + 1] - meta[4 + j]) for j in range(self.L + 1)]       # NodeFlow layer sizes
         caps = [0] * (self.L + 1)
-        for j in range(1, self.L):
-            caps[j] = min(-(-max(lay[j], 1) // _BUCKET) * _BUCKET, self.cap_layer[self.L - j])
+        for j in range(self._first_dense_layer, self.L):
+            caps[j] = min(-(-max(lay[j], 1) // _BUCKET) * _BUCKET, self._capb(j))
         caps[self.L] = self.batch
         return tuple(caps), lay
 
@@ -444,8 +482,7 @@ class GCNTrainEngine:
             for s in self.slots:
                 s.sample_graph, s.gather_graph, s.compute_graphs = None, None, {}
                 if new_stage != self.stage_rows:
-                    s.stage = torch.empty((max(new_stage, 1), self.F), dtype=torch.float32, device=self.dev)
-                    s.ws = torch.zeros(2 + max(new_stage, 1), dtype=torch.int64, device=self.dev)
+                    self._make_stage(s, new_stage)
             self.stage_rows = new_stage
             self.pool = None
 
@@ -531,3 +568,154 @@ class GCNTrainEngine:
             self.close()
         except Exception:
             pass
+
+
+class GCNPreprocessTrainEngine(GCNTrainEngine):
+    """The `--preprocess` GCN (PaGraph/model/gcn_nssc.py:80-100: the server has already folded the first aggregation into
+    the features, server/pa_server.py:45-52) on the same three-stream CUDA-graph pipeline. num_hops = n_layers, so the
+    default model is ONE block:
+        h = dropout(features[layer 0]);  h = cat(z, relu z), z = linear(h);  mean over block 0 at width 64;  head + loss.
+    Gather stage: pg_cache_resolve of the input layer + the fused row kernel over an IDENTITY block (one edge per row), i.e.
+    a cache gather with the dropout mask applied on the fly, written once in padded shape. Compute stage: the same fused
+    dense kernels as GCNTrainEngine (tcgen05 forward, dW, head + loss, all-reduce + Adam) with the 64-wide aggregation
+    behind the first linear instead of a 600-wide one in front of it; other shapes run through autograd."""
+    _first_dense_layer = 0
+
+    def _check_model(self, model):
+        if not getattr(model, "preprocess", False):
+            raise ValueError("GCNPreprocessTrainEngine drives GCNSampling(preprocess=True)")
+        if len(model.layers) != self.L:
+            raise ValueError("model has %d blocks but %d hops are sampled" % (len(model.layers), self.L))
+
+    def _make_slot_buffers(self, s):
+        dev = self.dev
+        s.rowptr = torch.zeros(self.cap_n0, dtype=torch.int64, device=dev)
+        self._make_stage(s, self.stage_rows)
+        s.agg = torch.empty((self._capb(0), self.F), dtype=torch.float32, device=dev)   # dropout(features[layer 0]), padded
+        s.idlo = torch.zeros(3, dtype=torch.int64, device=dev)                          # extents of the identity block
+        if not hasattr(self, "_ident"):
+            self._ident = torch.arange(self.cap_n0 + 1, dtype=torch.int64, device=dev)  # indptr and cols of the identity block
+
+    def _gather_body(self, s):
+        L, c = _lib.lib(), self.cacher
+        st = _lib.stream_ptr()
+        counts = c._counts if (c.log and not c.full_cached) else None
+        blk = _lib.pg_block(_lib.ptr(s.nf["node_mapping"]), _lib.ptr(s.nf["indptr"]), _lib.ptr(s.nf["indices"]), 0,
+                            self.cap_n0, s.agg.shape[0], self._meta_ptr(s, 4))
+        _lib.check(L.pg_cache_resolve(c._handle, self.fi, ctypes.byref(blk), _lib.ptr(s.rowptr), _lib.ptr(s.stage),
+                                      self.stage_rows, _lib.ptr(counts), _lib.ptr(s.ws), st), "pg_cache_resolve")
+        s.idlo[2:3].copy_(s.nf["meta"][5:6], non_blocking=True)      # [0, 0, n_0]: row r of the block has the one edge r
+        ident = _lib.pg_block(None, _lib.ptr(self._ident), _lib.ptr(self._ident), 0, self.cap_n0, s.agg.shape[0], _lib.ptr(s.idlo))
+        m = self.model
+        p = m.dropout.p if (m.dropout is not None and m.training) else 0.0
+        _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptr), ctypes.byref(ident), self.F, _lib.ptr(s.agg), s.agg.stride(0),
+                                       _MODES["sum"], None, float(p), self.drop_seed, _lib.ptr(self.load_counter), -_BUCKET,
+                                       st), "pg_aggregate_rows")
+        self.load_counter.add_(1)
+
+    def _fused_spec(self):
+        m = self.model
+        if self.L != 1 or len(m.layers) != 1 or m.n_layers != 1:
+            return None
+        return dict(lin=m.linear, act=m.activation, concat=True, head=m.layers[0], xl=0, blk=0, drop_hidden=False)
+
+    def _compute_body(self, s, caps, n_valid):
+        if self._dense_ok:
+            return self._compute_body_fused(s, caps, n_valid)
+        m, nf = self.model, s.nf
+        h = m.linear(s.agg[:caps[0]])                        # the dropout is already in s.agg
+        h = torch.cat((h, m.activation(h)), dim=1) if m.n_layers == 1 else m.activation(h)
+        for i, layer in enumerate(m.layers):
+            h = _BlockAggregateDyn.apply(h, nf["indptr"], nf["indices"], nf["meta"], i, caps[i + 1], "mean")
+            h = layer(NodeBatch({"h": h}))["activation"]
+        self._backward_and_step(s, self.loss_fcn(h[:n_valid], s.labels[:n_valid]))
+
+
+class SageTrainEngine(GCNTrainEngine):
+    """GraphSAGE with mean (or 'gcn' = sum) aggregation — PaGraph/model/graphsage_nssc.py:74-134, trained by
+    examples/profile/pa_gs.py:75-100 — on the three-stream CUDA-graph pipeline. With L hops the first NodeUpdate is applied
+    to every block (graphsage_nssc.py:96-97), so a minibatch needs, at feature width F,
+        neigh_{i+1} = reduce over block i of dropout(features[layer i])      for i = 0 .. L-1   (L aggregations), and
+        features[layer l] themselves (the fc_self input)                     for l = 1 .. L.
+    Gather stage (HBM / PCIe bound, ours): per block one pg_cache_resolve + the fused cache-lookup + dropout + aggregation
+    kernel — the F-wide source rows are never materialised — and per layer l >= 1 one pg_cache_fetch_dyn. Compute stage:
+    the model's own NodeUpdate modules (fc_self + fc_neigh, 16 hidden units: library GEMMs over [n_l, F] x [F, 16]) with
+    the 2 * n_hidden-wide aggregations on pg_aggregate_fwd_dyn / bwd_dyn, captured per padded-shape bucket."""
+
+    def _check_model(self, model):
+        if getattr(model, "preprocess", False):
+            raise NotImplementedError("SageTrainEngine drives GraphSageSampling(preprocess=False)")
+        if model.aggregator_type not in ("mean", "gcn"):
+            raise KeyError("aggregator %r is not on the rebuilt hot path" % model.aggregator_type)
+        if len(model.layers) != self.L:
+            raise ValueError("model has %d NodeUpdate layers but %d hops are sampled" % (len(model.layers), self.L))
+        self.mode = "mean" if model.aggregator_type == "mean" else "sum"
+
+    def _make_slot_buffers(self, s):
+        dev, F = self.dev, self.F
+        i64 = dict(dtype=torch.int64, device=dev)
+        s.rowptrs = [torch.zeros(self._cap_nf(i), **i64) for i in range(self.L)]
+        self._make_stage(s, self.stage_rows)
+        s.neigh = {i + 1: torch.zeros((self._capb(i + 1), F), dtype=torch.float32, device=dev) for i in range(self.L)}
+        s.feat = {l: torch.zeros((self._capb(l), F), dtype=torch.float32, device=dev) for l in range(1, self.L + 1)}
+        s.fetch_ws = {l: torch.zeros(2 + 4 * self._cap_nf(l), **i64) for l in range(1, self.L + 1)}
+        s.agg = s.neigh[1]                                   # what the base class sizes its (unused) dense buffers by
+
+    def _make_stage(self, s, stage_rows):
+        rows = [min(stage_rows, self._cap_nf(i)) for i in range(self.L)]
+        s.stages = [torch.empty((max(r, 1), self.F), dtype=torch.float32, device=self.dev) for r in rows]
+        s.stage_rows = rows
+        s.wss = [torch.zeros(2 + max(r, 1), dtype=torch.int64, device=self.dev) for r in rows]
+
+    def _fused_spec(self):
+        return None
+
+    def _gather_body(self, s):
+        L, c = _lib.lib(), self.cacher
+        st = _lib.stream_ptr()
+        counts = c._counts if (c.log and not c.full_cached) else None
+        m = self.model
+        p = float(m.dropout.p) if m.training else 0.0
+        nm, ip, ix = (_lib.ptr(s.nf[k]) for k in ("node_mapping", "indptr", "indices"))
+        for i in range(self.L):                              # neigh_{i+1}: block i reduced straight from the cache
+            dst = s.neigh[i + 1]
+            blk = _lib.pg_block(nm, ip, ix, 0, self._cap_nf(i), dst.shape[0], self._meta_ptr(s, 4 + i))
+            _lib.check(L.pg_cache_resolve(c._handle, self.fi, ctypes.byref(blk), _lib.ptr(s.rowptrs[i]), _lib.ptr(s.stages[i]),
+                                          s.stage_rows[i], _lib.ptr(counts), _lib.ptr(s.wss[i]), st), "pg_cache_resolve")
+            _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptrs[i]), ctypes.byref(blk), self.F, _lib.ptr(dst), dst.stride(0),
+                                           _MODES[self.mode], None, p, (self.drop_seed + 0x632BE59BD9B4E019 * i) & (2 ** 64 - 1),
+                                           _lib.ptr(self.load_counter), -_BUCKET, st), "pg_aggregate_rows")
+        for l in range(1, self.L + 1):                       # fc_self inputs: the layers' own rows
+            outs = (ctypes.c_void_p * 1)(s.feat[l].data_ptr())
+            _lib.check(L.pg_cache_fetch_dyn(c._handle, nm, self._meta_ptr(s, 4 + l), self._meta_ptr(s, 4 + l + 1),
+                                            self._cap_nf(l) if l < self.L else self.batch, outs, _lib.ptr(counts), 0,
+                                            _lib.ptr(s.fetch_ws[l]), st), "pg_cache_fetch_dyn")
+        self.load_counter.add_(1)
+
+    def _compute_body(self, s, caps, n_valid):
+        m, nf = self.model, s.nf
+        h = {l: s.feat[l][:caps[l]] for l in range(1, self.L + 1)}
+        layer0 = m.layers[0]
+        h = {i + 1: layer0(NodeBatch({"h": h[i + 1], "neigh": s.neigh[i + 1][:caps[i + 1]]}))["activation"]
+             for i in range(self.L)}
+        for lid in range(1, len(m.layers)):
+            layer, new = m.layers[lid], {}
+            for i in range(lid, self.L):
+                hd = m.dropout(h[i])
+                neigh = _BlockAggregateDyn.apply(hd, nf["indptr"], nf["indices"], nf["meta"], i, caps[i + 1], self.mode)
+                new[i + 1] = layer(NodeBatch({"h": h[i + 1], "neigh": neigh}))["activation"]
+            h = new
+        self._backward_and_step(s, self.loss_fcn(h[self.L][:n_valid], s.labels[:n_valid]))
+
+
+def make_train_engine(g, cacher, model, optimizer, train_nid, labels, batch_size, fanouts, **kw):
+    """The pipeline engine for `model`: GCNSampling -> GCNTrainEngine / GCNPreprocessTrainEngine, GraphSageSampling ->
+    SageTrainEngine."""
+    from .model.graphsage_nssc import GraphSageSampling
+    if isinstance(model, GraphSageSampling):
+        cls = SageTrainEngine
+    elif getattr(model, "preprocess", False):
+        cls = GCNPreprocessTrainEngine
+    else:
+        cls = GCNTrainEngine
+    return cls(g, cacher, model, optimizer, train_nid, labels, batch_size, fanouts, **kw)

@@ -12,7 +12,9 @@ import torch
 from ..sampling import NeighborSampler
 
 
-def get_sub_graph(dgl_g, train_nid, num_hops):
+def _closure_edges(dgl_g, train_nid, num_hops):
+    """ONE full-fanout NeighborSampler batch over all of `train_nid` (utils.py:11-18): the union of its block edges is the
+    `num_hops`-hop in-neighbour closure. Returns (full_srcs, full_dsts, seed parent ids) on the GPU."""
     train_nid = np.asarray(train_nid, dtype=np.int64)
     nfs = []
     for nf in NeighborSampler(dgl_g, len(train_nid), dgl_g.number_of_nodes(), neighbor_type='in', shuffle=False,
@@ -30,15 +32,45 @@ def get_sub_graph(dgl_g, train_nid, num_hops):
         dst = torch.repeat_interleave(torch.arange(lo, hi, device=dev), deg, output_size=ee - eb)
         full_src.append(node_map[nf._indices[eb:ee]])
         full_dst.append(node_map[dst])
-    full_srcs, full_dsts = torch.cat(full_src), torch.cat(full_dst)
-    # mappings (utils.py:32-37)
+    return torch.cat(full_src), torch.cat(full_dst), nf.layer_parent_nid_dev(-1)
+
+
+def _relabel(full_srcs, full_dsts, tnid):
+    """utils.py:32-51 on the GPU: sorted sub->full map, unique (src, dst) pairs in sub-graph ids (CSR order), train ids."""
+    dev = full_srcs.device
     sub2full = torch.unique(torch.cat((full_srcs, full_dsts)))
     full2sub = torch.zeros(int(sub2full.max().item()) + 1, dtype=torch.int64, device=dev)
     full2sub[sub2full] = torch.arange(sub2full.numel(), device=dev)
-    sub_srcs, sub_dsts = full2sub[full_srcs], full2sub[full_dsts]
     vnum = sub2full.numel()
+    key = torch.unique(full2sub[full_srcs] * vnum + full2sub[full_dsts])       # duplicate edges merged, row-major order
+    # train nid (utils.py:46-51, including the clamp of out-of-range ids and the id-0 fate of isolated train vertices)
+    valid_t_max, valid_t_min = sub2full.max(), tnid.min()
+    tnid = torch.where(tnid <= valid_t_max, tnid, valid_t_min)
+    subtrainid = full2sub[torch.unique(tnid)]
+    return sub2full, key, vnum, subtrainid
+
+
+def get_sub_graph_device(dgl_g, train_nid, num_hops):
+    """get_sub_graph without leaving the GPU, for a trainer that partitions in-process: (in_indptr, in_indices,
+    sub2full, subtrainid) as CUDA tensors — the in-CSR (row v = sources of u -> v, ascending) a GPU sampler walks, i.e.
+    what `DGLGraph(subadj)` builds from the `subadj_{r}.npz` this partition would be saved as."""
+    full_srcs, full_dsts, tnid = _closure_edges(dgl_g, train_nid, num_hops)
+    sub2full, key, vnum, subtrainid = _relabel(full_srcs, full_dsts, tnid)
+    del full_srcs, full_dsts
+    src, dst = key // vnum, key % vnum
+    del key
+    order = torch.sort(dst * vnum + src).values                                 # by destination, then ascending source
+    in_indices = order % vnum
+    counts = torch.bincount(order // vnum, minlength=vnum)
+    in_indptr = torch.zeros(vnum + 1, dtype=torch.int64, device=src.device)
+    torch.cumsum(counts, 0, out=in_indptr[1:])
+    return in_indptr, in_indices.contiguous(), sub2full, subtrainid
+
+
+def get_sub_graph(dgl_g, train_nid, num_hops):
+    full_srcs, full_dsts, tnid = _closure_edges(dgl_g, train_nid, num_hops)
+    sub2full, key, vnum, subtrainid = _relabel(full_srcs, full_dsts, tnid)
     # CSR with duplicate edges merged and unit weights (utils.py:40-44)
-    key = torch.unique(sub_srcs * vnum + sub_dsts)
     rows, cols = (key // vnum).cpu().numpy(), (key % vnum).cpu().numpy()
     indptr = np.zeros(vnum + 1, dtype=np.int64)
     np.cumsum(np.bincount(rows, minlength=vnum), out=indptr[1:])
@@ -46,12 +78,4 @@ def get_sub_graph(dgl_g, train_nid, num_hops):
     csr_adj = spsp.csr_matrix((np.ones(len(cols), dtype=np.uint8), cols.astype(idx_dtype), indptr.astype(idx_dtype)),
                               shape=(vnum, vnum))
     print('vertex#: {} edge#: {}'.format(vnum, len(cols)))
-    sub2full_np = sub2full.cpu().numpy()
-    full2sub_np = full2sub.cpu().numpy()
-    # train nid (utils.py:46-51, including the clamp of out-of-range ids)
-    tnid = nf.layer_parent_nid(-1).numpy()
-    valid_t_max = np.max(sub2full_np)
-    valid_t_min = np.min(tnid)
-    tnid = np.where(tnid <= valid_t_max, tnid, valid_t_min)
-    subtrainid = full2sub_np[np.unique(tnid)]
-    return csr_adj, sub2full_np, subtrainid
+    return csr_adj, sub2full.cpu().numpy(), subtrainid.cpu().numpy()

@@ -13,6 +13,7 @@ import bench  # noqa: E402
 def _canned():
     class A:
         vnum, nnz, feat_size, n_hidden, n_classes, fanout, batch_size = 10_000_000, 100_000_000, 600, 32, 60, "25,10", 6000
+        config, tag, model, n_layers, partition, parts, scale = 2, "R-MAT", "gcn", 1, "hash", 0, 1.0
     kern = {"x" * 70: {"launches": 40, "avg_ms": 0.1773910, "achieved_gbs": 4213.123456789, "frac": 0.6430123456}}
     return {
         "value": 2725.123456789, "n_gpus": 8, "steps": 200, "warmup": 10, "ms_per_step": 0.36696123456,
@@ -64,6 +65,21 @@ def test_compact_line_worst_case_strings_still_fit():
     c["config"]["workload"] = "w" * 300
     line = bench.compact_line(c)
     assert len(line) < 1150 and json.loads(line)["value"] > 0
+
+
+def test_every_config_resolves_and_names_itself():
+    import sys
+    for cfg in (1, 2, 3, 4, 5):
+        old = sys.argv
+        sys.argv = ["bench.py", "--config", str(cfg)]
+        try:
+            a = bench.parse_args()
+        finally:
+            sys.argv = old
+        assert a.model in ("gcn", "gcn-pre", "sage") and len(a.fanout.split(",")) == (a.n_layers if a.model == "gcn-pre" else a.n_layers + 1)
+        name = bench.workload_name(a)
+        assert name.startswith("cfg%d " % cfg) and len(name) <= 120, name
+        assert a.modes.split(",")[0].startswith("hbm") and a.modes.split(",")[1].startswith("vtx")
 
 
 def test_compact_line_without_optional_parts():

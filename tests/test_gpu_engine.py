@@ -291,3 +291,95 @@ def test_engine_with_duplicate_train_ids_matches_eager_loop(n_hidden, host_input
     for a, b in zip([p.detach().cpu().numpy() for p in model.parameters()], want_params):
         np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)
     eng.close()
+
+
+def _eager_loop(model, g, store, labels, train, V, fields, cap, batch, fanouts, steps):
+    """the reference's op-by-op loop (examples/profile/pa_gcn.py / pa_gs.py:86-97) on the drop-in classes"""
+    import torch
+    from pagraph_b200.sampling import NeighborSampler
+    from pagraph_b200.storage import GraphCacheServer
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(fields)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-2)
+    sampler = NeighborSampler(g, batch, fanouts, num_hops=len(fanouts), seed_nodes=torch.from_numpy(train), seed=11)
+    lab = labels.cuda()
+    losses = []
+    for k, nf in enumerate(sampler.batches(0, steps)):
+        cs.fetch_data(nf)
+        loss = torch.nn.functional.cross_entropy(model(nf), lab[nf.layer_parent_nid_dev(-1)])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        if k == 0 and cap is not None:
+            cs.auto_cache(g, fields, capability=cap)
+    return losses, [p.detach().cpu().numpy() for p in model.parameters()]
+
+
+def _run_engine(cls, model, g, store, labels, train, V, fields, cap, batch, fanouts, steps, use_graphs, **kw):
+    import torch
+    from pagraph_b200.storage import GraphCacheServer
+    cs = GraphCacheServer(store, V, torch.arange(V), 0)
+    cs.init_field(fields)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-2, capturable=use_graphs)
+    eng = cls(g, cs, model, opt, train, labels, batch, fanouts, seed=11, shuffle=False, use_graphs=use_graphs, stage_rows=300, **kw)
+    got = [eng.steps(1, read_loss=True)]
+    if cap is not None:
+        cs.auto_cache(g, fields, capability=cap)
+    got += [eng.steps(1, read_loss=True) for _ in range(2)]
+    last = eng.steps(steps - 3)
+    params = [p.detach().cpu().numpy() for p in model.parameters()]
+    return got, float(last), params, eng
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+@pytest.mark.parametrize("cap", [None, 900, 10 ** 9])
+def test_sage_engine_matches_eager_loop(cap, use_graphs):
+    """GraphSAGE-mean (PaGraph/model/graphsage_nssc.py:74-134, trainer examples/profile/pa_gs.py): three aggregations per
+    step, two of them 600 wide and fused with the cache lookup in the engine — same losses and parameters as the eager loop."""
+    import torch
+    from pagraph_b200.engine import SageTrainEngine, make_train_engine
+    from pagraph_b200.model.graphsage_nssc import GraphSageSampling
+    g, store, labels, train, V, F, classes = _world()
+    batch, fanouts, steps = 256, [6, 4], 7
+
+    def model():
+        torch.manual_seed(0)
+        return GraphSageSampling(F, 16, classes, 1, torch.relu, 0.0, 'mean').cuda()
+    want, want_params = _eager_loop(model(), g, store, labels, train, V, ["features"], cap, batch, fanouts, steps)
+    m = model()
+    got, last, params, eng = _run_engine(SageTrainEngine, m, g, store, labels, train, V, ["features"], cap, batch, fanouts, steps,
+                                         use_graphs)
+    assert isinstance(make_train_engine(g, eng.cacher, m, eng.opt, train, labels, batch, fanouts, use_graphs=False), SageTrainEngine)
+    np.testing.assert_allclose(got, want[:3], rtol=2e-4)
+    np.testing.assert_allclose(last, want[-1], rtol=2e-4)
+    for a, b in zip(params, want_params):
+        np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)
+    eng.close()
+
+
+@pytest.mark.parametrize("n_hidden", [16, 32])          # 32 = the fused dense stage, 16 = the autograd body
+@pytest.mark.parametrize("use_graphs", [False, True])
+@pytest.mark.parametrize("cap", [None, 900, 10 ** 9])
+def test_gcn_preprocess_engine_matches_eager_loop(cap, use_graphs, n_hidden):
+    """GCN --preprocess (PaGraph/model/gcn_nssc.py:80-100; num_hops = n_layers = 1): linear on the dropped-out input rows,
+    one 64-wide block aggregation, head — engine (cache gather fused with the dropout mask, fused dense kernels) vs eager."""
+    import torch
+    from pagraph_b200.engine import GCNPreprocessTrainEngine
+    from pagraph_b200.model.gcn_nssc import GCNSampling
+    g, store, labels, train, V, F, classes = _world()
+    batch, fanouts, steps = 256, [6], 7
+
+    def model():
+        torch.manual_seed(0)
+        return GCNSampling(F, n_hidden, classes, 1, torch.relu, 0.0, True).cuda()
+    fields = ["features", "norm"]
+    want, want_params = _eager_loop(model(), g, store, labels, train, V, fields, cap, batch, fanouts, steps)
+    got, last, params, eng = _run_engine(GCNPreprocessTrainEngine, model(), g, store, labels, train, V, fields, cap, batch,
+                                         fanouts, steps, use_graphs)
+    assert eng._dense_ok == (n_hidden == 32)
+    np.testing.assert_allclose(got, want[:3], rtol=2e-4)
+    np.testing.assert_allclose(last, want[-1], rtol=2e-4)
+    for a, b in zip(params, want_params):
+        np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)
+    eng.close()

@@ -173,6 +173,14 @@ def test_get_sub_graph_is_the_in_neighbour_closure(hops):
     assert subadj.dtype == np.uint8 and (subadj.data == 1).all()
     present = train[np.isin(train, verts)]                  # train vertices that have or feed an edge of the closure
     assert set(present.tolist()) <= set(sub2full[subtrain].tolist())
+    # the in-process variant (no host round trip): the in-CSR DGLGraph(subadj) would build, sub2full, train ids
+    from pagraph_b200.partition.utils import get_sub_graph_device
+    ip, ix, s2f, st = get_sub_graph_device(g, train, hops)
+    ref_g = DGLGraph(subadj, readonly=True)
+    np.testing.assert_array_equal(ip.cpu().numpy(), ref_g.indptr)
+    np.testing.assert_array_equal(ix.cpu().numpy(), ref_g.indices)
+    np.testing.assert_array_equal(s2f.cpu().numpy(), sub2full)
+    np.testing.assert_array_equal(st.cpu().numpy(), subtrain)
 
 
 def test_entry_scripts_end_to_end(tmp_path):
