@@ -160,6 +160,21 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop_ev.set()
 
+    def sample_now(self):
+        """one sample taken by the caller (the driver's default run times ~6 ms: the polling thread may miss it)"""
+        if not self.ok:
+            return
+        try:
+            nv = self.nv
+            mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            try:
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append((time.perf_counter(), mhz, reasons, nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+        except Exception:
+            pass
+
     def summary(self, t0, t1):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
@@ -383,8 +398,12 @@ class Trainer:
         # hbmNN: capacity = NN % of the HBM bytes (BASELINE.json's literal wording); vtxNN: NN % of the partition's vertices
         frac = a.cache_frac
         cap = int(frac * total / (4 * self.cacher.total_dim)) if mode.startswith("hbm") else int(V * frac)
-        self.cacher.auto_cache(wl.g, list(a.fields), capability=cap)
+        if mode.startswith("peer"):          # peerNN: vtxNN's capacity per rank, pooled over NVLink
+            self.cacher.auto_cache_peers(wl.g, list(a.fields), capability=cap)
+        else:
+            self.cacher.auto_cache(wl.g, list(a.fields), capability=cap)
         self.cacher.get_miss_rate()
+        self.cacher.peer_hits()
 
     def run(self, count, record, read_loss=False):
         """`count` consecutive training steps. Returns the last loss (host float if read_loss)."""
@@ -431,6 +450,7 @@ def timed_region(tr, steps, read_loss, clock, world):
         dist.barrier()
     torch.cuda.synchronize()
     tr.cacher.get_miss_rate() if tr.cacher.try_num else None
+    tr.cacher.peer_hits()
     _lib.timing_drain()
     _lib.timing_enable(True)
     launches0 = _lib.launch_count()
@@ -440,6 +460,8 @@ def timed_region(tr, steps, read_loss, clock, world):
     ev0.record()
     loss = tr.run(steps, record=True, read_loss=read_loss)
     ev1.record()
+    if clock is not None:
+        clock.sample_now()                   # the GPU is still draining the enqueued steps: a sample under load
     torch.cuda.synchronize()
     w1 = time.perf_counter()
     _lib.timing_enable(False)
@@ -461,7 +483,7 @@ def timed_region(tr, steps, read_loss, clock, world):
     recs = _lib.timing_drain()
     tries, misses = tr.cacher.try_num, tr.cacher.miss_num
     tr.cacher.get_miss_rate() if tries else None
-    return dict(ms=ms, wall_ms=wall_ms, launches=launches, recs=recs, tries=tries, misses=misses,
+    return dict(ms=ms, wall_ms=wall_ms, launches=launches, recs=recs, tries=tries, misses=misses, peer_hits=tr.cacher.peer_hits(),
                 loss=float(loss), clocks=clock.summary(w0, w1) if clock else None,
                 fetch_ms=sum(a.elapsed_time(b) for a, b in tr.fetch_events))
 
@@ -677,6 +699,9 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
                  fetch_ms_per_step=reg["fetch_ms"] / steps, gather=gather,
                  launches=reg["launches"], loss=reg["loss"], clocks=reg["clocks"], kernels=kern,
                  full_cached=tr.cacher.full_cached, cached_rows=tr.cacher.cached_num, parity_gate=gate,
+                 peer_tier=getattr(tr.cacher, "peer_tier", None), peer_rows_per_step=reg["peer_hits"] / steps,
+                 nvlink_bytes_per_step=4 * args.feat_size * reg["peer_hits"] / steps,
+                 pcie_bytes_per_step=4 * args.feat_size * reg["misses"] / steps,
                  replicas_identical=replicas,
                  layer_sizes=[int(np.mean([lo[i + 1] - lo[i] for lo, _ in tr.sizes])) for i in range(len(wl.fanouts) + 1)],
                  block_edges=[int(np.mean([bo[i + 1] - bo[i] for _, bo in tr.sizes])) for i in range(len(wl.fanouts))])
@@ -935,12 +960,15 @@ def compact_line(d):
     vkey = next((k for k in d if k.startswith("vtx") and isinstance(d[k], dict)), None)
     if vkey:
         line[vkey] = {k: _r(d[vkey].get(k), 4) for k in ("value", "e2e", "gather_gbs", "hit_rate", "miss_frac_pcie")}
+    pkey = next((k for k in d if k.startswith("peer") and isinstance(d[k], dict)), None)
+    if pkey:
+        line[pkey] = {k: _r(d[pkey].get(k), 4) for k in ("value", "e2e", "nvlink_mb_per_step", "pcie_mb_per_step")}
     out = json.dumps(line, separators=(",", ":"))
     # never let the line grow past what the driver keeps: shorten the free-text strings first, then drop the optional tail
     for shrink in (lambda: line["cpu_baseline"] and line["cpu_baseline"].update(sample=line["cpu_baseline"]["sample"][:48]),
                    lambda: line["roofline"].update(kernel=line["roofline"]["kernel"][:32]),
                    lambda: line["config"].update(l2="inputs>L2"),
-                   lambda: line.pop(vkey, None), lambda: line.pop("gather_gbs", None)):
+                   lambda: line.pop(pkey, None), lambda: line.pop(vkey, None), lambda: line.pop("gather_gbs", None)):
         if len(out) < 1150:
             break
         shrink()
@@ -948,10 +976,11 @@ def compact_line(d):
     return out
 
 
-def write_detail(detail, n):
+def write_detail(detail, n, config=2):
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        path = os.path.join(ROOT, "gpurun_out", "bench_detail_n%d.json" % n)
+        name = "bench_detail_n%d.json" % n if config == 2 else "bench_detail_cfg%d_n%d.json" % (config, n)
+        path = os.path.join(ROOT, "gpurun_out", name)
         with open(path, "w") as f:
             json.dump(detail, f, indent=1)
         return os.path.relpath(path, ROOT)
@@ -1123,7 +1152,13 @@ def main_ours(args):
         detail[vmode] = {"value": x["value"]["minibatches_per_s"], "e2e": x["e2e"]["minibatches_per_s"],
                            "gather_gbs": g.get("gather_gbs"), "hit_rate": g.get("hit_rate"),
                            "miss_frac_pcie": (g.get("miss") or {}).get("frac")}
-    detail["detail_file"] = write_detail(detail, world)
+    pmode = next((m for m in modes[1:] if m.startswith("peer")), None)
+    if pmode:
+        x = results[pmode]
+        detail[pmode] = {"value": x["value"]["minibatches_per_s"], "e2e": x["e2e"]["minibatches_per_s"],
+                         "nvlink_mb_per_step": x["value"]["nvlink_bytes_per_step"] / 1e6,
+                         "pcie_mb_per_step": x["value"]["pcie_bytes_per_step"] / 1e6, "hit_rate": x["value"]["hit_rate"]}
+    detail["detail_file"] = write_detail(detail, world, args.config)
     sys.stdout.flush()
     print(compact_line(detail), flush=True)
 

@@ -209,6 +209,26 @@ typedef struct {
  * handle's shared workspace (grown on demand; replaced buffers stay allocated until pg_cache_destroy). */
 pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const float** d_rowptr, float* d_stage,
                            int64_t stage_rows, int64_t* d_counts, int64_t* d_ws, void* stream);
+/* Peer-GPU cache tier over NVLink (optional; not in the reference — extends the lookup of storage.py:157-204): the ranks of
+ * one node shard the hottest rows between them. With the vertices in one agreed caching order (d_pos[t] = position of local
+ * id t, < 0 = never cached), positions [0, c_local) are replicated in every rank's table and position c_local + j lives on
+ * rank j % world at row c_local + j / world (j < world * c_shard). d_peer_tables[r]: rank r's cache table of `field`
+ * ([c_local + c_shard, dim] fp32, a CUDA-IPC mapping for r != rank). pg_cache_resolve then points a row that is not in the
+ * local table at the owner's HBM before falling back to the pinned host row; flag / l2c keep describing the LOCAL table, so
+ * pg_cache_fetch is unchanged (it reads non-local rows from the host). d_peer_hits: optional device counter. world <= 1
+ * switches the tier off. */
+/* Fill the cache tables straight from full-graph row ids (no local-id bookkeeping): table row i <- host_table[d_full_rows[i]]
+ * for every field, and install the tables (cached_rows = n). flag / l2c are left to the caller — a peer-tier owner also
+ * holds rows of vertices its own partition never names. */
+pg_status pg_cache_fill_rows(pg_cache* c, const int64_t* d_full_rows, int64_t n, float* const* d_cache_tables, void* stream);
+/* Peer-visible device buffers for those tables: cudaMalloc + CUDA-IPC handle (PG_IPC_HANDLE_BYTES), opened by the other
+ * ranks of the node with lazy peer access. */
+pg_status pg_peer_alloc(size_t bytes, int dev, void** d_out, unsigned char* handle_out);
+pg_status pg_peer_open(const unsigned char* handle, int dev, void** d_out);
+pg_status pg_peer_close(void* d_ptr, int dev);
+pg_status pg_peer_free(void* d_ptr, int dev);
+pg_status pg_cache_set_peers(pg_cache* c, int field, int world, int rank, const float* const* d_peer_tables,
+                             const int32_t* d_pos, int64_t c_local, int64_t c_shard, int64_t* d_peer_hits);
 pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, int32_t dim, float* d_dst,
                             int64_t dst_stride, int mode, const float* d_norm, float dropout_p, uint64_t dropout_seed,
                             const int64_t* d_step, int64_t zero_rows_to, void* stream);

@@ -66,6 +66,13 @@ SIGNATURES = {
                                       ctypes.c_int, c_vp]),
     "pg_cache_resolve": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(pg_block), c_vp, c_vp, ctypes.c_int64, c_vp,
                                         c_vp, c_vp]),
+    "pg_cache_fill_rows": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp]),
+    "pg_peer_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(c_vp), c_vp]),
+    "pg_peer_open": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "pg_peer_close": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "pg_peer_free": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "pg_cache_set_peers": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp), c_vp,
+                                          ctypes.c_int64, ctypes.c_int64, c_vp]),
     "pg_aggregate_rows": (ctypes.c_int, [c_vp, ctypes.POINTER(pg_block), ctypes.c_int32, c_vp, ctypes.c_int64, ctypes.c_int,
                                          c_vp, ctypes.c_float, ctypes.c_uint64, c_vp, ctypes.c_int64, c_vp]),
     "pg_cache_fetch_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp,

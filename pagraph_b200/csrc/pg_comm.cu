@@ -178,6 +178,50 @@ void pg_peer_group_destroy(pg_peer_group* g) {
   delete g;
 }
 
+/* ---- plain peer-visible device buffers (the peer-GPU cache tier's tables) */
+pg_status pg_peer_alloc(size_t bytes, int dev, void** d_out, unsigned char* handle_out) {
+  PG_REQUIRE(d_out && handle_out && bytes > 0, "pg_peer_alloc: bad arguments");
+  pg::DeviceGuard guard(dev);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    pg::set_error("pg_peer_alloc: out of device memory (%zu bytes)", bytes);
+    return PG_ERR_NOMEM;
+  }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+    pg::set_error("pg_peer_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(p);
+    return PG_ERR_CUDA;
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *d_out = p;
+  return PG_OK;
+}
+
+pg_status pg_peer_open(const unsigned char* handle, int dev, void** d_out) {
+  PG_REQUIRE(handle && d_out, "pg_peer_open: bad arguments");
+  pg::DeviceGuard guard(dev);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  PG_CUDA(cudaIpcOpenMemHandle(d_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return PG_OK;
+}
+
+pg_status pg_peer_close(void* d_ptr, int dev) {
+  if (!d_ptr) return PG_OK;
+  pg::DeviceGuard guard(dev);
+  PG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return PG_OK;
+}
+
+pg_status pg_peer_free(void* d_ptr, int dev) {
+  if (!d_ptr) return PG_OK;
+  pg::DeviceGuard guard(dev);
+  PG_CUDA(cudaFree(d_ptr));
+  return PG_OK;
+}
+
 pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
                             const float* d_step, const int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
                             float weight_decay, void* stream) {

@@ -354,10 +354,13 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
     e.base = base; e.rows = rows; e.cols = cols; e.stride = stride; e.box = box;
     return &e.map;
   };
-  const CUtensorMap* pm_x = get_map(d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, kBlockM);
-  const CUtensorMap* pm_w = get_map(d_weight, kN, (uint64_t)K, (uint64_t)K, kN);
-  if (!pm_x || !pm_w) return PG_ERR_INVALID;
-  const CUtensorMap tm_x = *pm_x, tm_w = *pm_w;
+  // each map is copied out before the next lookup: an insertion may recycle the slot a previous lookup returned
+  const CUtensorMap* pm = get_map(d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, kBlockM);
+  if (!pm) return PG_ERR_INVALID;
+  const CUtensorMap tm_x = *pm;
+  pm = get_map(d_weight, kN, (uint64_t)K, (uint64_t)K, kN);
+  if (!pm) return PG_ERR_INVALID;
+  const CUtensorMap tm_w = *pm;
   const size_t smem = (size_t)kStages * kStageBytes + 1024;
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {

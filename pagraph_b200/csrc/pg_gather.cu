@@ -118,6 +118,20 @@ split_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __restri
   if (user_counts && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&user_counts[0], (unsigned long long)n);
 }
 
+// ------------------------------------------------------------------ peer-GPU cache tier (extends storage.py:157-204)
+// The ranks of one node shard the hottest rows between them instead of each holding the same ones: with the vertices in
+// one agreed caching order (position k = pos[t]), the first c_local rows are replicated in every rank's table, the next
+// world * c_shard are dealt round-robin — position c_local + j lives on rank j % world at row c_local + j / world. A row
+// that is not in this rank's HBM is read from the owner's HBM over NVLink (the peer tables are CUDA-IPC mappings) before
+// the pinned host table over PCIe is considered.
+struct PeerTier {
+  int world = 0, rank = 0;
+  const float* table[PG_MAX_RANKS] = {nullptr};  // every rank's cache table of the field (table[rank] = the local one)
+  const int32_t* pos = nullptr;                  // [node_num] caching position of local id t, < 0 = never cached
+  int64_t c_local = 0, c_shard = 0;
+  unsigned long long* peer_hits = nullptr;       // optional device counter of rows resolved to a peer
+};
+
 // ------------------------------------------------------------------ resolve (fused path): node -> row pointer
 // rowptr[j] = start of the feature row of NodeFlow node j: inside the HBM cache table when flag[t_j], else inside
 // the miss staging buffer at a freshly allocated slot (the slot's host row goes to miss_row[] for the fetch).
@@ -126,7 +140,7 @@ resolve_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __rest
                const int64_t* __restrict__ l2c, const int64_t* __restrict__ nid_map, int is_full, const float* cache,
                int64_t cache_stride, float* stage, int64_t stage_stride, int64_t stage_rows, const float* host,
                int64_t host_stride, const float** rowptr, int64_t* miss_row, unsigned long long* list_counts,
-               unsigned long long* user_counts, const int64_t* lo) {
+               unsigned long long* user_counts, const int64_t* lo, PeerTier peer) {
   __shared__ int warp_miss[kSplitThreads / 32];
   __shared__ unsigned long long base_miss;
   if (lo) {  // device-resident extents: ids is the NodeFlow-wide node_mapping, n a capacity
@@ -144,7 +158,16 @@ resolve_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __rest
     if (valid) {
       t = ids[j];
       hit = is_full || flag[t] != 0;
-      if (hit) rowptr[j] = cache + (is_full ? t : l2c[t]) * cache_stride;
+      if (hit) {
+        rowptr[j] = cache + (is_full ? t : l2c[t]) * cache_stride;
+      } else if (peer.world > 1) {  // another rank's shard? (this rank's own shard rows carry flag[t])
+        const int64_t k = peer.pos[t] - peer.c_local;
+        if (k >= 0 && k < peer.c_shard * peer.world) {
+          rowptr[j] = peer.table[k % peer.world] + (peer.c_local + k / peer.world) * cache_stride;
+          hit = true;
+          if (peer.peer_hits) atomicAdd(peer.peer_hits, 1ull);
+        }
+      }
     }
     if (is_full) continue;
     const unsigned mb = __ballot_sync(kFullMask, valid && !hit);
@@ -315,6 +338,7 @@ struct pg_cache {
   int64_t stage_floats = 0;
   // buffers replaced by a larger workspace: kept until destroy, because a captured CUDA graph may still address them
   std::vector<void*> retired;
+  PeerTier peer[PG_MAX_FIELDS];   // optional peer-GPU tier per field (pg_cache_set_peers)
 };
 
 static pg_status ensure_ws(pg_cache* c, int64_t n) {
@@ -466,6 +490,22 @@ pg_status pg_cache_fill(pg_cache* c, const int64_t* d_nids, int64_t n, int is_fu
   for (int f = 0; f < c->nfields; ++f) strides[f] = c->fields[f].host_stride;
   return launch_rows(c, c->host_dev, strides, c->cache_tables, nullptr, c->miss_row, nullptr, n,
                      env_int("PG_MISS_MODE", 2) == 2, st);
+}
+
+pg_status pg_cache_fill_rows(pg_cache* c, const int64_t* d_full_rows, int64_t n, float* const* d_cache_tables, void* stream) {
+  PG_REQUIRE(c && d_cache_tables && (d_full_rows || n == 0) && n >= 0, "pg_cache_fill_rows: bad arguments");
+  pg::DeviceGuard guard(c->dev);
+  for (int f = 0; f < c->nfields; ++f) {
+    PG_REQUIRE(d_cache_tables[f] != nullptr || n == 0, "pg_cache_fill_rows: null cache table");
+    c->cache_tables[f] = d_cache_tables[f];
+  }
+  c->cached_rows = n;
+  c->is_full = false;
+  if (n == 0) return PG_OK;
+  int64_t strides[PG_MAX_FIELDS];
+  for (int f = 0; f < c->nfields; ++f) strides[f] = c->fields[f].host_stride;
+  return launch_rows(c, c->host_dev, strides, c->cache_tables, nullptr, d_full_rows, nullptr, n,
+                     env_int("PG_MISS_MODE", 2) == 2, (cudaStream_t)stream);
 }
 
 pg_status pg_cache_fetch_host(pg_cache* c, const int64_t* d_nids, int64_t n, float* const* d_out, void* stream) {
@@ -629,7 +669,7 @@ pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const fl
     resolve_kernel<<<grid, kSplitThreads, 0, st>>>(blk->parent_ids, n_src, c->flag, c->l2c, c->nid_map, full ? 1 : 0,
                                                   c->cache_tables[field], dim, d_stage, dim, stage_rows, c->host_dev[field],
                                                   c->fields[field].host_stride, d_rowptr, miss_row, list_counts,
-                                                  (unsigned long long*)d_counts, blk->d_layer_offsets);
+                                                  (unsigned long long*)d_counts, blk->d_layer_offsets, c->peer[field]);
     PG_CHECK_LAUNCH();
   }
   if (!full && stage_rows > 0) {  // missed rows: pinned host table -> staging rows, slot order (TMA bulk copies over PCIe)
@@ -641,6 +681,27 @@ pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const fl
                               env_int("PG_MISS_MODE", 2) == 2, st, field, 1);
     if (s != PG_OK) return s;
   }
+  return PG_OK;
+}
+
+pg_status pg_cache_set_peers(pg_cache* c, int field, int world, int rank, const float* const* d_peer_tables,
+                             const int32_t* d_pos, int64_t c_local, int64_t c_shard, int64_t* d_peer_hits) {
+  PG_REQUIRE(c && field >= 0 && field < c->nfields, "pg_cache_set_peers: no such field");
+  if (world <= 1) {  // tier off
+    c->peer[field] = PeerTier();
+    return PG_OK;
+  }
+  PG_REQUIRE(world <= PG_MAX_RANKS && rank >= 0 && rank < world && d_peer_tables && d_pos && c_local >= 0 && c_shard >= 0,
+             "pg_cache_set_peers: bad arguments");
+  PG_REQUIRE(!c->is_full, "pg_cache_set_peers: the local cache already holds every row");
+  PeerTier p;
+  p.world = world; p.rank = rank; p.pos = d_pos; p.c_local = c_local; p.c_shard = c_shard;
+  p.peer_hits = (unsigned long long*)d_peer_hits;
+  for (int r = 0; r < world; ++r) {
+    PG_REQUIRE(d_peer_tables[r] != nullptr, "pg_cache_set_peers: null peer table");
+    p.table[r] = d_peer_tables[r];
+  }
+  c->peer[field] = p;
   return PG_OK;
 }
 

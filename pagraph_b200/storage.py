@@ -28,6 +28,18 @@ def _ensure_device_visible(t):
     _REGISTERED[key] = nbytes
 
 
+class _DevicePtr:
+    """raw device allocation exposed through __cuda_array_interface__ so that torch can view it"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _tensor_from_ptr(ptr, shape, dev):
+    with torch.cuda.device(dev):
+        return torch.as_tensor(_DevicePtr(ptr, shape), device=dev)
+
+
 class LazyCacheRows:
     """Stand-in for the not-yet-gathered rows of one field of one NodeFlow layer (`lazy_input`).
 
@@ -199,6 +211,119 @@ class GraphCacheServer:
             sort_nid = torch.sort(out_degrees, descending=True, stable=True).indices
             self._fill(sort_nid[:max(self.capability, 0)].contiguous(), is_full=False)
 
+    # ---- peer-GPU cache tier (extension): the ranks of one node shard the hot rows over NVLink
+    def auto_cache_peers(self, dgl_g, embed_names, capability=None, group=None, local_rows=None):
+        """auto_cache for `world` ranks that pool their HBM (collective: every rank of `group` calls it).
+
+        Each rank still holds `capability` rows (same memory as auto_cache), but not the same ones: with all vertices of the
+        job ranked once by out-degree (full-graph ids, max over the ranks' partition graphs; ties by id), the first
+        `local_rows` are replicated on every rank and the next world * (capability - local_rows) are dealt round-robin. A row
+        another rank owns is then read from that rank's HBM over NVLink by the fused lookup (pg_cache_resolve /
+        GCNTrainEngine), before the pinned host table over PCIe is considered. `local_rows` defaults to the largest value
+        for which the pooled caches still cover every vertex (0 if they cannot). gpu_flag / localid2cacheid keep describing
+        the LOCAL table, so fetch_data stays correct (it reads rows it does not hold from the host)."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self._field_names != list(embed_names):
+            self._make_handle(embed_names)
+            self.total_dim = sum(self._table(n).size(1) for n in embed_names)
+            for n in embed_names:
+                self.dims[n] = self._table(n).size(1)
+        if capability is None:
+            total_mem = torch.cuda.get_device_properties(self.gpuid).total_memory
+            available = (total_mem - torch.cuda.max_memory_allocated(self.gpuid) - torch.cuda.max_memory_reserved(self.gpuid)
+                         - 1024 * 1024 * 1024)
+            capability = int(available / (self.total_dim * 4))
+        cap_t = torch.tensor([int(capability), int(self.nid_map.max().item()) + 1], dtype=torch.int64, device=self._dev)
+        if world > 1:
+            lo = cap_t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(cap_t, op=dist.ReduceOp.MAX, group=group)
+            cap_t[0] = lo[0]
+        C, v_full = int(cap_t[0].item()), int(cap_t[1].item())
+        if world == 1 or C >= self.node_num:
+            return self.auto_cache(dgl_g, embed_names, capability=C)
+        rank = dist.get_rank(group)
+        self.capability = C
+        # one caching order for the whole job, in full-graph ids
+        deg_full = torch.zeros(v_full, dtype=torch.int64, device=self._dev)
+        deg_full[self.nid_map] = dgl_g.out_degrees().to(self._dev)
+        dist.all_reduce(deg_full, op=dist.ReduceOp.MAX, group=group)
+        order_full = torch.sort(deg_full, descending=True, stable=True).indices
+        del deg_full
+        if local_rows is None:
+            local_rows = max(0, (world * C - v_full) // (world - 1))
+        c_local = int(min(max(local_rows, 0), C))
+        c_shard = C - c_local
+        mine = torch.cat((order_full[:c_local], order_full[c_local + rank:c_local + world * c_shard:world]))   # full ids, row order
+        n_rows = mine.numel()
+        # peer-visible tables (cudaMalloc + CUDA IPC), wrapped as torch tensors for the public gpu_fix_cache attribute
+        L = _lib.lib()
+        self._peer_alloc, self._peer_open = [], []
+        ptrs, handles = [], []
+        for name in self._field_names:
+            p, h = ctypes.c_void_p(), (ctypes.c_ubyte * _lib.PG_IPC_HANDLE_BYTES)()
+            _lib.check(L.pg_peer_alloc(max(C, 1) * self.dims[name] * 4, self.gpuid, ctypes.byref(p), h), "pg_peer_alloc")
+            self._peer_alloc.append(p)
+            ptrs.append(p)
+            handles.append(bytes(h))
+            self.gpu_fix_cache[name] = _tensor_from_ptr(p.value, (C, self.dims[name]), self._dev)
+        with torch.cuda.device(self._dev):
+            _lib.check(L.pg_cache_fill_rows(self._handle, _lib.ptr(mine), n_rows, (ctypes.c_void_p * len(ptrs))(*[p.value for p in ptrs]),
+                                            _lib.stream_ptr()), "pg_cache_fill_rows")
+        # local bookkeeping (storage.py:145,153) for the rows of MY table that my partition names
+        full2local = torch.full((v_full,), -1, dtype=torch.int64, device=self._dev)
+        full2local[self.nid_map] = torch.arange(self.node_num, device=self._dev)
+        loc = full2local[mine]
+        has = loc >= 0
+        self.localid2cacheid[loc[has]] = torch.arange(n_rows, device=self._dev)[has]
+        self.gpu_flag[loc[has]] = True
+        self.cached_num = int(has.sum().item())
+        self.full_cached = False
+        pos_full = torch.empty(v_full, dtype=torch.int32, device=self._dev)
+        pos_full[order_full] = torch.arange(v_full, dtype=torch.int32, device=self._dev)
+        self._peer_pos = pos_full[self.nid_map].contiguous()
+        del pos_full, full2local, order_full
+        self._peer_hits = torch.zeros(1, dtype=torch.int64, device=self._dev)
+        torch.cuda.synchronize(self._dev)
+        # exchange the IPC handles and map the peers' tables
+        allh = [None] * world
+        dist.all_gather_object(allh, handles, group=group)
+        for fi, name in enumerate(self._field_names):
+            tabs = (ctypes.c_void_p * world)()
+            for r in range(world):
+                if r == rank:
+                    tabs[r] = ptrs[fi].value
+                else:
+                    q = ctypes.c_void_p()
+                    _lib.check(L.pg_peer_open(allh[r][fi], self.gpuid, ctypes.byref(q)), "pg_peer_open")
+                    self._peer_open.append(q)
+                    tabs[r] = q.value
+            _lib.check(L.pg_cache_set_peers(self._handle, fi, world, rank, tabs, _lib.ptr(self._peer_pos), c_local, c_shard,
+                                            _lib.ptr(self._peer_hits)), "pg_cache_set_peers")
+        dist.barrier(group=group)       # every table is filled and mapped before anyone reads a peer's rows
+        self.peer_tier = dict(world=world, rank=rank, local_rows=c_local, shard_rows=c_shard, covered=c_local + world * c_shard,
+                              vertices=v_full)
+        print('peer cache tier: {} replicated + {} sharded rows per rank over {} ranks ({:.1f}% of {} vertices pooled)'.format(
+            c_local, c_shard, world, 100.0 * min(c_local + world * c_shard, v_full) / v_full, v_full), file=sys.stderr)
+
+    def peer_hits(self, reset=True):
+        """rows the fused lookup resolved to another rank's HBM since the last reset (0 without a peer tier)"""
+        if getattr(self, "_peer_hits", None) is None:
+            return 0
+        n = int(self._peer_hits.item())
+        if reset:
+            self._peer_hits.zero_()
+        return n
+
+    def _release_peers(self):
+        L = _lib.lib()
+        for q in getattr(self, "_peer_open", []):
+            L.pg_peer_close(q, self.gpuid)
+        for p in getattr(self, "_peer_alloc", []):
+            L.pg_peer_free(p, self.gpuid)
+        self._peer_open, self._peer_alloc = [], []
+
     def _fill(self, nids, is_full):
         """cache_fix_data with the rows pulled from the pinned host table by the GPU itself."""
         rows = nids.size(0)
@@ -322,5 +447,7 @@ class GraphCacheServer:
         try:
             if self._handle is not None:
                 _lib.lib().pg_cache_destroy(self._handle)
+                self._handle = None
+            self._release_peers()
         except Exception:
             pass
