@@ -383,5 +383,8 @@ def test_gcn_preprocess_engine_matches_eager_loop(cap, use_graphs, n_hidden):
     # value carries the amplified difference between the 3xTF32 kernels and cuBLAS fp32
     np.testing.assert_allclose(last, want[-1], rtol=5e-3)
     for a, b in zip(params, want_params):
-        np.testing.assert_allclose(a, b, rtol=1e-2, atol=1e-3)
+        # Adam moves every weight by ~lr per step whatever the gradient's size: a weight whose gradient is noise-level
+        # can differ by a few lr-sized steps between two fp32 summation orders
+        assert np.mean(np.abs(a - b) > 1e-3 + 1e-2 * np.abs(b)) < 1e-3
+        np.testing.assert_allclose(a, b, rtol=1e-2, atol=3e-2)
     eng.close()
