@@ -119,6 +119,9 @@ pg_status linear_ce_mma(const float* d_a, int64_t a_stride, const float* d_weigh
 pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float* d_weight, const float* d_bias, int64_t n,
                                  int32_t K, int concat, float* d_out, int64_t out_stride, float* d_out_drop, int64_t od_stride,
                                  float dropout_p, uint64_t dropout_seed, const int64_t* d_step, int dev, cudaStream_t st);
+pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float* d_gout, int64_t g_stride, const float* d_y,
+                                int64_t y_stride, int64_t n, int32_t K, int concat, float dropout_p, uint64_t dropout_seed,
+                                const int64_t* d_step, float* d_gw, float* d_gb, int dev, cudaStream_t st);
 // fp32-pipe dW kernel of pg_dense.cu (A/B baseline of the tensor-core kernel in pg_dense_mma.cu); outputs pre-zeroed
 pg_status linear_concat_bwd_simt(const float* d_x, int64_t x_stride, const float* d_grad_out, int64_t g_stride,
                                  const float* d_out, int64_t out_stride, int64_t n, int32_t in_dim, int concat,

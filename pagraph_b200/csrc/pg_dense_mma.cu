@@ -971,6 +971,14 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
   PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)kOut * in_dim * sizeof(float), st));
   if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, kOut * sizeof(float), st));
   if (n == 0) return PG_OK;
+  {  // tcgen05 path (pg_dense_umma.cu: x^T from tensor memory); PG_DW_UMMA=0 keeps the mma.sync kernel
+    const char* env_u = getenv("PG_DW_UMMA");
+    if (!(env_u && atoi(env_u) == 0)) {
+      const pg_status s = pg::linear_concat_dw_umma(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim, concat,
+                                                    dropout_p, dropout_seed, d_step, d_grad_weight, d_grad_bias, dev, st);
+      if (s != PG_ERR_INVALID) return s;
+    }
+  }
   const char* simt = getenv("PG_DENSE_SIMT");
   if (simt && atoi(simt) && dropout_p == 0.f)
     return pg::linear_concat_bwd_simt(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim, concat, d_grad_weight,

@@ -404,3 +404,326 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
 }
 
 }  // namespace pg
+
+// =====================================================================================================================
+// Backward of the first NodeUpdate on tcgen05:  dW [32, K] = gz^T x,  db [32] = sum_r gz,  gz [n, 32] = the gradient of z
+// recovered from grad_out and out (dropout', relu' and the concat split folded in — same definition as
+// linear_concat_dw2_kernel in pg_dense_mma.cu).
+//
+// The reduction runs over ROWS, so the tensor-core operands are the transposes of what HBM holds:
+//     D_fb [128 features x 32]  +=  A_fb [128 features x 8 rows] * B [32 outputs x 8 rows]^T ,   fb = 0 .. ceil(K / 128) - 1.
+//   * A = x^T lives in TENSOR MEMORY: lane = feature, column = row. The transform threads (one feature lane each) read
+//     the TMA-staged [32 rows x 128 features] boxes column-wise — for a fixed row the 32 lanes of a warp touch 32
+//     consecutive words, conflict-free — so the transposition costs nothing; x_hi / x_lo go to TMEM with tcgen05.st.
+//   * B = gz^T is built by the same threads straight into the canonical K-major SWIZZLE_128B layout ([32 outputs] rows of
+//     128 bytes = 32 rows of the minibatch), hi and lo planes.
+//   * 3xTF32 as in the forward (A_lo B_hi + A_hi B_lo + A_hi B_hi), fp32 accumulators in TMEM: ceil(K/128) x 32 columns.
+// One CTA per SM walks 32-row super-chunks (stride gridDim); at the end the accumulators go through shared memory and
+// are added to dW with 16-byte vector reductions (red.global.add.v4.f32), db with scalar ones.
+// TMEM: 160 accumulator columns + 2 operand stages x (5 blocks x 2 planes x 16 rows) = 480 of 512.
+namespace {
+
+constexpr int kDwRows = 32;                       // rows per super-chunk (one 128-byte swizzle row of gz^T)
+constexpr int kDwHalf = 16;                       // rows per TMEM operand stage
+constexpr int kDwFB = 5;                          // feature blocks of 128 (K <= 640)
+constexpr int kDwXStages = 2;                     // x ring (super-chunks)
+constexpr uint32_t kDwBoxBytes = kDwRows * 128 * 4;                    // [32 rows x 128 features] = 16 KB
+constexpr uint32_t kDwXStageBytes = kDwFB * kDwBoxBytes;               // 80 KB
+constexpr uint32_t kDwBBytes = kN * kDwRows * 4;                       // one gz^T plane = 4 KB
+constexpr uint32_t kDwSmemBytes = kDwXStages * kDwXStageBytes + 2 * 2 * kDwBBytes;   // 160 KB + 16 KB
+constexpr uint32_t kDwAccCols = kDwFB * kN;                            // 160
+constexpr uint32_t kDwOpStageCols = kDwFB * 2 * kDwHalf;               // 160
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    linear_concat_dw_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ gout, int64_t g_stride,
+                                 const float* __restrict__ y, int64_t y_stride, int64_t n, int K, int concat, UmmaDrop drop,
+                                 float* __restrict__ dW, float* __restrict__ db) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // xfull[2], xempty[2] (x ring) | ready[2], opfree[2] (TMEM operand stages) | bfree[2] (gz^T buffers) | done
+  __shared__ __align__(8) uint64_t bars[2 * kDwXStages + 4 + 2 + 1];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ uint64_t colkey_sh[16];
+  __shared__ float db_sh[kN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + kDwXStages * kDwXStageBytes;     // [buf][plane] gz^T tiles, 1024-byte aligned
+  auto xfull = [&](int s) { return smem_u32(&bars[s]); };
+  auto xempty = [&](int s) { return smem_u32(&bars[kDwXStages + s]); };
+  auto ready = [&](int h) { return smem_u32(&bars[2 * kDwXStages + h]); };
+  auto opfree = [&](int h) { return smem_u32(&bars[2 * kDwXStages + 2 + h]); };
+  auto bfree = [&](int b) { return smem_u32(&bars[2 * kDwXStages + 4 + b]); };
+  const uint32_t done = smem_u32(&bars[2 * kDwXStages + 6]);
+  const int nfb = (K + 127) / 128;
+  const int64_t nsc = (n + kDwRows - 1) / kDwRows;                      // super-chunks
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDwXStages; ++s) {
+      mbar_init(xfull(s), 1);
+      mbar_init(xempty(s), 128);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(ready(h), 128);
+      mbar_init(opfree(h), 1);
+      mbar_init(bfree(h), 1);
+    }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 16) colkey_sh[threadIdx.x] = pg::drop_colkey((uint32_t)threadIdx.x);
+  if (threadIdx.x < kN) db_sh[threadIdx.x] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+  const uint32_t tmem_opnd = tmem_base + kDwAccCols;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer: x super-chunks
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t sc = blockIdx.x; sc < nsc; sc += gridDim.x, ++it) {
+        const int s = it % kDwXStages;
+        mbar_wait(xempty(s), ((it / kDwXStages) & 1) ^ 1);
+        mbar_expect_tx(xfull(s), (uint32_t)nfb * kDwBoxBytes);
+        for (int fb = 0; fb < nfb; ++fb)
+          tma_load_2d(smem_base + s * kDwXStageBytes + fb * kDwBoxBytes, &tm_x, fb * 128, (int)(sc * kDwRows), xfull(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t sc = blockIdx.x; sc < nsc; sc += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint64_t b_hi = umma_desc_k_sw128(b_base + b * 2 * kDwBBytes), b_lo = umma_desc_k_sw128(b_base + b * 2 * kDwBBytes + kDwBBytes);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(ready(h), it & 1);                               // x^T half in TMEM, gz^T tile in shared memory
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int fb = 0; fb < nfb; ++fb) {
+            const uint32_t d = tmem_base + fb * kN;
+            const uint32_t a_hi = tmem_opnd + h * kDwOpStageCols + fb * 2 * kDwHalf, a_lo = a_hi + kDwHalf;
+#pragma unroll
+            for (int ks = 0; ks < kDwHalf / kUmmaK; ++ks) {
+              const uint64_t adv = (uint64_t)(((h * kDwHalf + ks * kUmmaK) * 4) >> 4);   // rows h*16 + ks*8 .. inside the 128-byte row
+              const uint32_t acc = (it | (uint32_t)h | (uint32_t)ks) != 0;
+              umma_tf32_ts(d, a_lo + ks * kUmmaK, b_hi + adv, acc);
+              umma_tf32_ts(d, a_hi + ks * kUmmaK, b_lo + adv, 1);
+              umma_tf32_ts(d, a_hi + ks * kUmmaK, b_hi + adv, 1);
+            }
+          }
+          umma_commit(opfree(h));                                    // TMEM operand stage h reusable
+        }
+        umma_commit(bfree(b));                                       // gz^T buffer b reusable
+      }
+      umma_commit(done);
+    }
+  } else if (warp >= 8) {
+    // ================================================================== transform: x^T -> TMEM, gz^T -> shared memory
+    const int q = warp & 3;
+    const int tt = threadIdx.x - 8 * 32;                             // 0 .. 127 = feature lane inside a block
+    const uint64_t stepkey = drop.thr ? pg::drop_stepkey(drop.seed + (drop.step ? (uint64_t)*drop.step : 0ull)) : 0ull;
+    const uint32_t thr_hi = drop.thr << 16;
+    const int gr = tt >> 2, gj0 = (tt & 3) * 8;                      // gz: row gr of the super-chunk, outputs gj0 .. gj0 + 7
+    float dbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t it = 0;
+    for (int64_t sc = blockIdx.x; sc < nsc; sc += gridDim.x, ++it) {
+      const int s = it % kDwXStages, b = it & 1;
+      // ---- gz of this thread's (row, 8 outputs): global loads first, they fly while x lands
+      const int64_t r = sc * kDwRows + gr;
+      float gzv[8];
+      {
+        float4 ga[2], gb[2], gy[2];
+        ga[0] = ga[1] = gb[0] = gb[1] = gy[0] = gy[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n) {
+          const float* grow = gout + r * g_stride;
+          const float* yrow = y + r * y_stride;
+          ga[0] = __ldg((const float4*)(grow + gj0));
+          ga[1] = __ldg((const float4*)(grow + gj0 + 4));
+          if (concat) {
+            gb[0] = __ldg((const float4*)(grow + kN + gj0));
+            gb[1] = __ldg((const float4*)(grow + kN + gj0 + 4));
+            gy[0] = __ldg((const float4*)(yrow + kN + gj0));
+            gy[1] = __ldg((const float4*)(yrow + kN + gj0 + 4));
+          } else {
+            gy[0] = __ldg((const float4*)(yrow + gj0));
+            gy[1] = __ldg((const float4*)(yrow + gj0 + 4));
+          }
+        }
+        const uint64_t rk = drop.thr ? pg::drop_rowkey(stepkey, (uint64_t)r) : 0ull;
+        auto factor4 = [&](int g, float (&f)[4]) {                   // keep-scale of the 4 columns of group g
+          const uint64_t h = pg::drop_mix(rk, colkey_sh[g]);
+          const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
+          f[0] = (hl << 16) >= thr_hi ? drop.scale : 0.f;
+          f[1] = hl >= thr_hi ? drop.scale : 0.f;
+          f[2] = (hh << 16) >= thr_hi ? drop.scale : 0.f;
+          f[3] = hh >= thr_hi ? drop.scale : 0.f;
+        };
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const float av[4] = {ga[half].x, ga[half].y, ga[half].z, ga[half].w};
+          const float bv[4] = {gb[half].x, gb[half].y, gb[half].z, gb[half].w};
+          const float yv[4] = {gy[half].x, gy[half].y, gy[half].z, gy[half].w};
+          float fa[4] = {1.f, 1.f, 1.f, 1.f}, fb_[4] = {1.f, 1.f, 1.f, 1.f};
+          if (drop.thr) {
+            factor4((gj0 >> 2) + half, fa);
+            if (concat) factor4(8 + (gj0 >> 2) + half, fb_);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v;
+            if (concat) v = av[e] * fa[e] + (yv[e] > 0.f ? bv[e] * fb_[e] : 0.f);
+            else v = yv[e] > 0.f ? av[e] * fa[e] : 0.f;
+            gzv[half * 4 + e] = v;
+            dbv[half * 4 + e] += v;
+          }
+        }
+      }
+      // ---- gz^T tile: output j is a 128-byte row, minibatch row gr the element inside it (SWIZZLE_128B K-major)
+      mbar_wait(bfree(b), ((it >> 1) & 1) ^ 1);
+      {
+        const uint32_t bh = b_base + b * 2 * kDwBBytes, bl = bh + kDwBBytes;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = gj0 + e;
+          const uint32_t off = (uint32_t)j * 128u + (uint32_t)(((gr >> 2) ^ (j & 7)) << 4) + (uint32_t)(gr & 3) * 4u;
+          const uint32_t bits = __float_as_uint(gzv[e]);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(bh + off), "r"(bits) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(bl + off), "r"(tf32_lo(bits)) : "memory");
+        }
+      }
+      // ---- x^T: feature lane tt of every block, 16 rows per TMEM operand stage
+      mbar_wait(xfull(s), (it / kDwXStages) & 1);
+      const uint32_t sx = smem_base + s * kDwXStageBytes + (uint32_t)tt * 4u;
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(opfree(h), (it & 1) ^ 1);                          // the MMAs of the previous super-chunk's half h are done
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int fb = 0; fb < nfb; ++fb) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int rr = 0; rr < kDwHalf; ++rr)
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hi[rr]) : "r"(sx + fb * kDwBoxBytes + (uint32_t)(h * kDwHalf + rr) * 512u));
+#pragma unroll
+          for (int rr = 0; rr < kDwHalf; ++rr) lo[rr] = tf32_lo(hi[rr]);
+          const uint32_t ta = tmem_opnd + ((uint32_t)(q * 32) << 16) + h * kDwOpStageCols + fb * 2 * kDwHalf;
+          tmem_st16(ta, hi);
+          tmem_st16(ta + kDwHalf, lo);
+        }
+        if (h == 1) mbar_arrive(xempty(s));                          // every load of this stage has been consumed (lo[])
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the gz^T stores -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(ready(h));
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (dbv[e] != 0.f) atomicAdd(&db_sh[gj0 + e], dbv[e]);
+  }
+  // ---- epilogue: accumulators -> shared memory (transposed) -> 16-byte vector reductions into dW
+  __syncthreads();                                                    // db_sh complete; producers / transform have issued everything
+  if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    mbar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stage = (float*)(smem + (smem_base - smem_u32(smem)));     // [32 outputs][nfb * 128 + 4] floats, reuses the x ring
+    const int pitch = nfb * 128 + 4;
+    for (int fb = 0; fb < nfb; ++fb) {
+      uint32_t rg[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + fb * kN, rg);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int f = fb * 128 + q * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < kN; ++j) stage[j * pitch + f] = __uint_as_float(rg[j]);   // lanes -> consecutive words
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int t = threadIdx.x - 4 * 32;
+    const int kvec = K >> 2;
+    for (int i = t; i < kN * kvec; i += 128) {
+      const int j = i / kvec, c = (i % kvec) << 2;
+      const float4 v = *(const float4*)(stage + j * pitch + c);
+      atomicAdd((float4*)(dW + (size_t)j * K + c), v);
+    }
+    if (db && t < kN) atomicAdd(db + t, db_sh[t]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+}
+
+int make_map_plain(EncodeTiledFn enc, CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
+                   uint32_t box_cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_floats * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return (int)enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace
+
+namespace pg {
+
+// dW / db must be zeroed by the caller. PG_ERR_INVALID = not eligible, nothing launched.
+pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float* d_gout, int64_t g_stride, const float* d_y,
+                                int64_t y_stride, int64_t n, int32_t K, int concat, float dropout_p, uint64_t dropout_seed,
+                                const int64_t* d_step, float* d_gw, float* d_gb, int dev, cudaStream_t st) {
+  const bool ok = K % 4 == 0 && K <= 128 * kDwFB && x_stride % 4 == 0 && g_stride % 4 == 0 && y_stride % 4 == 0 &&
+                  (((uintptr_t)d_x | (uintptr_t)d_gout | (uintptr_t)d_y | (uintptr_t)d_gw) & 15) == 0 && n < (int64_t)1 << 31;
+  if (!ok) return PG_ERR_INVALID;
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      cudaGetLastError();
+      return PG_ERR_INVALID;
+    }
+    enc = (EncodeTiledFn)fn;
+  }
+  struct MapEntry { const float* base; uint64_t rows, cols, stride; CUtensorMap map; };
+  static MapEntry cache[8];
+  static int next_slot = 0;
+  const CUtensorMap* pm = nullptr;
+  for (MapEntry& e : cache)
+    if (e.base == d_x && e.rows == (uint64_t)n && e.cols == (uint64_t)K && e.stride == (uint64_t)x_stride) pm = &e.map;
+  if (!pm) {
+    MapEntry& e = cache[next_slot];
+    next_slot = (next_slot + 1) % 8;
+    e.base = nullptr;
+    if (make_map_plain(enc, &e.map, d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, 128, kDwRows)) return PG_ERR_INVALID;
+    e.base = d_x; e.rows = (uint64_t)n; e.cols = (uint64_t)K; e.stride = (uint64_t)x_stride;
+    pm = &e.map;
+  }
+  const CUtensorMap tm_x = *pm;
+  const size_t smem = (size_t)kDwSmemBytes + 1024;
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  UmmaDrop drop;
+  drop.thr = dropout_p > 0.f ? (uint32_t)(dropout_p * 65536.0f + 0.5f) : 0u;
+  drop.scale = drop.thr ? 1.0f / (1.0f - dropout_p) : 1.0f;
+  drop.seed = dropout_seed;
+  drop.step = d_step;
+  const int64_t nsc = (n + kDwRows - 1) / kDwRows;
+  const int grid = (int)std::min<int64_t>(nsc, (int64_t)pg::sm_count(dev));
+  linear_concat_dw_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, d_gout, g_stride, d_y, y_stride, n, K, concat, drop, d_gw, d_gb);
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+}  // namespace pg

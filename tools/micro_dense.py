@@ -77,12 +77,22 @@ def main():
         gw = torch.empty(32, F, device="cuda")
         gb = torch.empty(32, device="cuda")
         linear_concat_forward(xs[0], W, b, True, out=out)
-        for simt in ("0", "1"):
-            os.environ["PG_DENSE_SIMT"] = simt
-            p = 0.0 if simt == "1" else a.p
+        gz_ref = None
+        for name, env in (("umma_3xtf32", {"PG_DW_UMMA": "1"}), ("mma_3xtf32", {"PG_DW_UMMA": "0"}),
+                          ("simt_ffma2", {"PG_DW_UMMA": "0", "PG_DENSE_SIMT": "1"})):
+            os.environ.update(env)
+            p = 0.0 if name == "simt_ffma2" else a.p
             t = med(lambda i: linear_concat_backward(xs[i % 3], g, out, True, gw, gb, p, 5, step), a.iters)
-            res["bwd_%s_us" % ("simt_ffma2" if simt == "1" else "mma_3xtf32")] = round(t, 2)
-        os.environ.pop("PG_DENSE_SIMT", None)
+            res["bwd_%s_us" % name] = round(t, 2)
+            linear_concat_forward(xs[0], W, b, True, out=out, out_drop=od, dropout_p=p, seed=5, step=step)
+            linear_concat_backward(xs[0], g, out, True, gw, gb, p, 5, step)
+            keep = (od != 0) if p > 0 else torch.ones_like(od, dtype=torch.bool)
+            gm = g.double() * keep * (1.0 / (1.0 - p))
+            gz64 = gm[:, :32] + gm[:, 32:] * (out[:, 32:] > 0)
+            res["bwd_%s_dw_rel_err" % name] = float((gw.double() - gz64.t() @ xs[0].double()).abs().max() / (gz64.t() @ xs[0].double()).abs().max())
+            res["bwd_%s_db_rel_err" % name] = float((gb.double() - gz64.sum(0)).abs().max() / gz64.sum(0).abs().max())
+            for k in env:
+                os.environ.pop(k, None)
         linear_concat_backward(xs[0], g, out, True, gw, gb, 0.0, 5, step)
         pos = out[:, 32:] > 0
         gz = g[:, :32].double() + g[:, 32:].double() * pos
