@@ -8,9 +8,8 @@
 //     z = x_lo W_hi^T + x_hi W_lo^T + x_hi W_hi^T   (fp32 accumulate in TMEM; the x_lo W_lo term is 2^-22 relative).
 //
 // One CTA per SM, 128-row tiles, K walked in chunks of 32 columns (one 128-byte swizzle row):
-//   warp 0      TMA producer of x: per chunk one [128 x 32] box (SWIZZLE_128B, OOB -> 0) into a 10-deep ring whose slots
-//               recycle as soon as the transform has read them (160 KB of x in flight per SM: HBM latency under load)
-//   warp 2      TMA producer of W: per chunk one [32 x 32] box into a 6-deep ring that lives until the chunk's MMAs are done
+//   warp 0      TMA producer: per chunk one [128 x 32] box of x and one [32 x 32] box of W (SWIZZLE_128B, OOB -> 0) into
+//               a kStages-deep shared-memory ring
 //   warps 8-11  transform, one tile row per thread: reads its 32 floats of x from the ring (swizzle-aware, conflict-free),
 //               splits them and writes x_hi / x_lo into TENSOR MEMORY (tcgen05.st) — the A operand of the MMAs is read
 //               from TMEM, not from shared memory: an SS-mode M = 128 tf32 MMA would fetch 4 KB of A per instruction and
@@ -34,14 +33,12 @@ namespace {
 constexpr int kBlockM = 128;       // rows per tile (UMMA M)
 constexpr int kN = 32;             // outputs (UMMA N)
 constexpr int kChunk = 32;         // K per stage: 32 floats = 128 bytes = one swizzle row
-constexpr int kXStages = 10;       // x ring: a slot is free again as soon as the transform has read it into TMEM
-constexpr int kStages = 6;         // W ring = TMEM operand stages: held until the chunk's MMAs have completed
+constexpr int kStages = 6;
 constexpr int kUmmaK = 8;          // K per tcgen05.mma for 32-bit operands
 constexpr int kThreads = 12 * 32;
 constexpr uint32_t kXBytes = kBlockM * kChunk * 4;            // 16 KB
 constexpr uint32_t kWBytes = kN * kChunk * 4;                 // 4 KB
-constexpr uint32_t kWStageBytes = 2 * kWBytes;                // w_hi, w_lo = 8 KB
-constexpr uint32_t kSmemBytes = kXStages * kXBytes + kStages * kWStageBytes;   // 160 + 48 KB
+constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;       // x, w_hi, w_lo = 24 KB
 constexpr uint32_t kAccCols = 2 * kN;                         // 2 accumulator stages
 constexpr uint32_t kTmemCols = 512;                           // 64 accumulator + kStages * 64 operand columns (power of 2)
 static_assert(kAccCols + kStages * 2 * kChunk <= kTmemCols, "TMEM budget");
@@ -131,8 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                   const float* __restrict__ bias, int64_t n, int K, int concat, float* __restrict__ out,
                                   int64_t out_stride, float* __restrict__ out_drop, int64_t od_stride, UmmaDrop drop) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // wfull[s], ready[s], empty[s] (W / TMEM-operand ring), tmem_full[2], tmem_empty[2], xfull[x], xempty[x] (x ring)
-  __shared__ __align__(8) uint64_t bars[3 * kStages + 4 + 2 * kXStages];
+  __shared__ __align__(8) uint64_t bars[3 * kStages + 4];   // full[s], ready[s], empty[s], tmem_full[2], tmem_empty[2]
   __shared__ uint32_t tmem_base_sh;
   __shared__ uint64_t colkey_sh[16];
   __shared__ float bias_sh[kN];
@@ -143,9 +139,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   auto empty = [&](int s) { return smem_u32(&bars[2 * kStages + s]); };
   auto tfull = [&](int a) { return smem_u32(&bars[3 * kStages + a]); };
   auto tempty = [&](int a) { return smem_u32(&bars[3 * kStages + 2 + a]); };
-  auto xfull = [&](int x) { return smem_u32(&bars[3 * kStages + 4 + x]); };
-  auto xempty = [&](int x) { return smem_u32(&bars[3 * kStages + 4 + kXStages + x]); };
-  const uint32_t w_base = smem_base + kXStages * kXBytes;
   const int nchunks = (K + kChunk - 1) / kChunk;
   const int64_t ntiles = (n + kBlockM - 1) / kBlockM;
 
@@ -158,10 +151,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull(a), 1);        // tcgen05.commit after the tile's last MMA
       mbar_init(tempty(a), 128);     // every epilogue thread
-    }
-    for (int x = 0; x < kXStages; ++x) {
-      mbar_init(xfull(x), 1);
-      mbar_init(xempty(x), 128);     // every transform thread has its row in registers
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,27 +167,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_opnd = tmem_base + kAccCols;    // operand stages behind the two accumulators
 
   if (warp == 0) {
-    // ================================================================== TMA producer: x
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int c = 0; c < nchunks; ++c, ++it) {
-          const int x = it % kXStages;
-          mbar_wait(xempty(x), ((it / kXStages) & 1) ^ 1);           // a fresh barrier passes the wait for parity 1
-          mbar_expect_tx(xfull(x), kXBytes);
-          tma_load_2d(smem_base + x * kXBytes, &tm_x, c * kChunk, (int)(tile * kBlockM), xfull(x));   // OOB rows / cols -> 0
-        }
-    }
-  } else if (warp == 2) {
-    // ================================================================== TMA producer: W chunks
+    // ================================================================== TMA producer
     if (lane == 0) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         for (int c = 0; c < nchunks; ++c, ++it) {
           const int s = it % kStages;
-          mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);             // the MMAs that read this W / TMEM stage are done
-          mbar_expect_tx(full(s), kWBytes);
-          tma_load_2d(w_base + s * kWStageBytes, &tm_w, c * kChunk, 0, full(s));
+          mbar_wait(empty(s), ((it / kStages) & 1) ^ 1);             // a fresh barrier passes the wait for parity 1
+          const uint32_t st = smem_base + s * kStageBytes;
+          mbar_expect_tx(full(s), kXBytes + kWBytes);
+          tma_load_2d(st, &tm_x, c * kChunk, (int)(tile * kBlockM), full(s));       // x (OOB rows / cols -> 0)
+          tma_load_2d(st + kXBytes, &tm_w, c * kChunk, 0, full(s));                 // W chunk
         }
     }
   } else if (warp == 1) {
@@ -214,9 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int s = it % kStages;
           mbar_wait(ready(s), (it / kStages) & 1);                   // x_hi / x_lo in TMEM, W_lo in shared memory
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t st = w_base + s * kWStageBytes;
+          const uint32_t st = smem_base + s * kStageBytes;
           const uint32_t a_hi = tmem_opnd + s * 2 * kChunk, a_lo = a_hi + kChunk;
-          const uint64_t b_hi = umma_desc_k_sw128(st), b_lo = umma_desc_k_sw128(st + kWBytes);
+          const uint64_t b_hi = umma_desc_k_sw128(st + kXBytes), b_lo = umma_desc_k_sw128(st + kXBytes + kWBytes);
 #pragma unroll
           for (int k = 0; k < kChunk / kUmmaK; ++k) {
             const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
@@ -237,22 +216,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
       for (int c = 0; c < nchunks; ++c, ++it) {
-        const int s = it % kStages, x = it % kXStages;
-        mbar_wait(xfull(x), (it / kXStages) & 1);
-        const uint32_t sx = smem_base + x * kXBytes, st = w_base + s * kWStageBytes;
+        const int s = it % kStages;
+        mbar_wait(full(s), (it / kStages) & 1);
+        const uint32_t st = smem_base + s * kStageBytes;
         // row `row` of the box: 8 x 16 bytes, logical unit u stored at unit u ^ (row & 7) (SWIZZLE_128B)
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const uint32_t addr = sx + (uint32_t)row * 128u + (uint32_t)((u ^ (row & 7)) << 4);
+          const uint32_t addr = st + (uint32_t)row * 128u + (uint32_t)((u ^ (row & 7)) << 4);
           asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                        : "=r"(hi[4 * u]), "=r"(hi[4 * u + 1]), "=r"(hi[4 * u + 2]), "=r"(hi[4 * u + 3])
                        : "r"(addr));
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) lo[j] = tf32_lo(hi[j]);
-        mbar_arrive(xempty(x));                                      // the row is in registers (lo[] consumed every load)
-        mbar_wait(full(s), (it / kStages) & 1);                      // W chunk landed; its TMEM operand stage is free
         const uint32_t ta = tmem_opnd + ((uint32_t)(q * 32) << 16) + s * 2 * kChunk;
         tmem_st32(ta, hi);
         tmem_st32(ta + kChunk, lo);
@@ -261,8 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int h = 0; h < (int)(kWBytes / 16 / 128); ++h) {
           const uint32_t off = (uint32_t)(h * 128 + tt) * 16;
           uint32_t w0, w1, w2, w3;
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(st + off));
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(st + kWBytes + off), "r"(tf32_lo(w0)),
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(st + kXBytes + off));
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(st + kXBytes + kWBytes + off), "r"(tf32_lo(w0)),
                        "r"(tf32_lo(w1)), "r"(tf32_lo(w2)), "r"(tf32_lo(w3))
                        : "memory");
         }
@@ -367,8 +344,10 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
   struct MapEntry { const float* base; uint64_t rows, cols, stride; uint32_t box; CUtensorMap map; };
   static MapEntry cache[8];
   static int next_slot = 0;
+  static const bool no_cache = getenv("PG_UMMA_NOCACHE") != nullptr;
   auto get_map = [&](const float* base, uint64_t rows, uint64_t cols, uint64_t stride, uint32_t box) -> const CUtensorMap* {
-    for (MapEntry& e : cache)
+    if (!no_cache)
+      for (MapEntry& e : cache)
       if (e.base == base && e.rows == rows && e.cols == cols && e.stride == stride && e.box == box) return &e.map;
     MapEntry& e = cache[next_slot];
     next_slot = (next_slot + 1) % 8;
@@ -384,7 +363,7 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
   pm = get_map(d_weight, kN, (uint64_t)K, (uint64_t)K, kN);
   if (!pm) return PG_ERR_INVALID;
   const CUtensorMap tm_w = *pm;
-  const size_t smem = (size_t)kSmemBytes + 1024;
+  const size_t smem = (size_t)kStages * kStageBytes + 1024;
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -537,30 +516,36 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t thr_hi = drop.thr << 16;
     const int gr = tt >> 2, gj0 = (tt & 3) * 8;                      // gz: row gr of the super-chunk, outputs gj0 .. gj0 + 7
     float dbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // raw operands of gz for one (row, 8 outputs): loaded one super-chunk ahead so that the global-load latency is
+    // hidden behind the x^T fill of the current one
+    float4 ga[2], gb[2], gy[2];
+    auto load_g = [&](int64_t sc) {
+      const int64_t r = sc * kDwRows + gr;
+      ga[0] = ga[1] = gb[0] = gb[1] = gy[0] = gy[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sc < nsc && r < n) {
+        const float* grow = gout + r * g_stride;
+        const float* yrow = y + r * y_stride;
+        ga[0] = __ldg((const float4*)(grow + gj0));
+        ga[1] = __ldg((const float4*)(grow + gj0 + 4));
+        if (concat) {
+          gb[0] = __ldg((const float4*)(grow + kN + gj0));
+          gb[1] = __ldg((const float4*)(grow + kN + gj0 + 4));
+          gy[0] = __ldg((const float4*)(yrow + kN + gj0));
+          gy[1] = __ldg((const float4*)(yrow + kN + gj0 + 4));
+        } else {
+          gy[0] = __ldg((const float4*)(yrow + gj0));
+          gy[1] = __ldg((const float4*)(yrow + gj0 + 4));
+        }
+      }
+    };
+    load_g(blockIdx.x);
     uint32_t it = 0;
     for (int64_t sc = blockIdx.x; sc < nsc; sc += gridDim.x, ++it) {
       const int s = it % kDwXStages, b = it & 1;
-      // ---- gz of this thread's (row, 8 outputs): global loads first, they fly while x lands
+      // ---- gz of this thread's (row, 8 outputs)
       const int64_t r = sc * kDwRows + gr;
       float gzv[8];
       {
-        float4 ga[2], gb[2], gy[2];
-        ga[0] = ga[1] = gb[0] = gb[1] = gy[0] = gy[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < n) {
-          const float* grow = gout + r * g_stride;
-          const float* yrow = y + r * y_stride;
-          ga[0] = __ldg((const float4*)(grow + gj0));
-          ga[1] = __ldg((const float4*)(grow + gj0 + 4));
-          if (concat) {
-            gb[0] = __ldg((const float4*)(grow + kN + gj0));
-            gb[1] = __ldg((const float4*)(grow + kN + gj0 + 4));
-            gy[0] = __ldg((const float4*)(yrow + kN + gj0));
-            gy[1] = __ldg((const float4*)(yrow + kN + gj0 + 4));
-          } else {
-            gy[0] = __ldg((const float4*)(yrow + gj0));
-            gy[1] = __ldg((const float4*)(yrow + gj0 + 4));
-          }
-        }
         const uint64_t rk = drop.thr ? pg::drop_rowkey(stepkey, (uint64_t)r) : 0ull;
         auto factor4 = [&](int g, float (&f)[4]) {                   // keep-scale of the 4 columns of group g
           const uint64_t h = pg::drop_mix(rk, colkey_sh[g]);
@@ -590,6 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
+      load_g(sc + gridDim.x);                                          // next super-chunk's operands, in flight from here on
       // ---- gz^T tile: output j is a 128-byte row, minibatch row gr the element inside it (SWIZZLE_128B K-major)
       mbar_wait(bfree(b), ((it >> 1) & 1) ^ 1);
       {
