@@ -267,23 +267,25 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
     ideg = irem = (int)(nxt_e - nxt_s);
     open_next(ir + nwarps);
   }
-  auto issue = [&](int buf) {  // precondition: ir < n_dst
-    const int cnt = min(group, irem);
-    const uint32_t bar = pg::smem_u32(&bars[w * kRowsMaxDepth + buf]);
-    const float* src = nullptr;
-    if (lane < cnt) {
+  // The task about to be issued is PREPARED one step ahead: its cols -> rowptr loads (two dependent global loads, the
+  // longest stall of the r2a kernel in the ncu source view) fly while the warp consumes a staged buffer.
+  const float* psrc = nullptr;   // this lane's source row of the prepared task (lane < pcnt)
+  uint64_t pkey = 0;             // its dropout row key
+  int pcnt = 0;
+  int4 pmeta = make_int4(0, 0, 0, 0);
+  bool phave = false;
+  auto prepare = [&]() {  // reads the cursor, loads the prepared task's operands, advances the cursor
+    phave = ir < n_dst;
+    if (!phave) return;
+    pcnt = min(group, irem);
+    pmeta = make_int4(pcnt, irem <= group, ir, ideg);
+    if (lane < pcnt) {
       const int64_t j = a.cols[ipos + lane] - a.col_base;
-      src = a.rowptr[j];
-      if (DROP) row_key[w][buf][lane] = pg::drop_rowkey(stepkey, (uint64_t)j);  // one hash per fetched row, lanes in parallel
+      psrc = a.rowptr[j];
+      if (DROP) pkey = pg::drop_rowkey(stepkey, (uint64_t)j);  // one hash per fetched row, lanes in parallel
     }
-    if (lane == 0) {
-      task_meta[w][buf] = make_int4(cnt, irem <= group, ir, ideg);
-      pg::mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
-    }
-    __syncwarp();
-    if (lane < cnt) pg::bulk_g2s(warp_smem + (uint32_t)(buf * group + lane) * row_bytes, src, row_bytes, bar);
-    ipos += cnt;
-    irem -= cnt;
+    ipos += pcnt;
+    irem -= pcnt;
     if (irem <= 0) {  // next destination row
       ir += nwarps;
       if (ir < n_dst) {
@@ -293,8 +295,20 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
       }
     }
   };
+  auto issue = [&](int buf) {  // precondition: phave
+    const uint32_t bar = pg::smem_u32(&bars[w * kRowsMaxDepth + buf]);
+    if (DROP && lane < pcnt) row_key[w][buf][lane] = pkey;
+    if (lane == 0) {
+      task_meta[w][buf] = pmeta;
+      pg::mbar_expect_tx(bar, (uint32_t)pcnt * row_bytes);
+    }
+    __syncwarp();
+    if (lane < pcnt) pg::bulk_g2s(warp_smem + (uint32_t)(buf * group + lane) * row_bytes, psrc, row_bytes, bar);
+    prepare();
+  };
+  prepare();
   int issued = 0;
-  for (; issued < depth && ir < n_dst; ++issued) issue(issued);
+  for (; issued < depth && phave; ++issued) issue(issued);
 
   float4 acc[CH];
 #pragma unroll
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
     }
     --pending;
     __syncwarp();  // every lane is done reading this buffer (and its meta / row keys)
-    if (ir < n_dst) {
+    if (phave) {
       issue(buf);
       ++pending;
     }
