@@ -569,10 +569,16 @@ def kernel_report(tr, reg, hbm_peak, pcie_peak):
     wbytes = 4 * steps * (Fdim + 1) * a.n_hidden
     add("node_update_fwd(linear_concat_fwd_umma_kernel,tcgen05 3xTF32)", by.get(_lib.T_DENSE_FWD),
         4 * n1 * (Fdim + H2 * (1 + drop)) + wbytes, hbm_peak, "hbm")
-    add("node_update_bwd(linear_concat_dw2_kernel,3xTF32)", by.get(_lib.T_DENSE_BWD), 4 * n1 * (Fdim + 2 * H2) + wbytes,
-        hbm_peak, "hbm")
-    add("head+loss(linear_ce_mma_kernel)", by.get(_lib.T_HEAD), 4 * nb * 2 * H2 + 8 * nb + 8 * steps * (H2 + 1) * a.n_classes,
-        hbm_peak, "hbm")
+    add("node_update_bwd(linear_concat_dw_umma_kernel,tcgen05 3xTF32)", by.get(_lib.T_DENSE_BWD),
+        4 * n1 * (Fdim + 2 * H2) + wbytes, hbm_peak, "hbm")
+    head_bytes = 4 * nb * 2 * H2 + 8 * nb + 8 * steps * (H2 + 1) * a.n_classes
+    if tr.engine is not None and tr.engine._dense_ok and tr.engine._block_head:
+        # the 64-wide block, the head, the loss and their backward in one kernel: block read + gradient scatter + head
+        bl = sum(agg_bytes(n_(lo, L - 1), n_(lo, L), e_(bo, L - 1), H2) for lo, bo in tr.sizes)
+        add("block%d+head+loss fwd/bwd(linear_ce_mma_kernel<BLOCK>)" % (L - 1), by.get(_lib.T_HEAD), 2 * bl + head_bytes,
+            hbm_peak, "hbm")
+    else:
+        add("head+loss(linear_ce_mma_kernel)", by.get(_lib.T_HEAD), head_bytes, hbm_peak, "hbm")
     nparam = sum(p.numel() for p in tr.model.parameters())
     add("allreduce+adam(allreduce_adam_kernel)", by.get(_lib.T_OPT), 4 * 7 * nparam * steps, hbm_peak, "hbm")
     return out, N, M

@@ -267,6 +267,22 @@ pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride, const floa
                                   float* d_grad_a, int64_t ga_stride, float* d_grad_weight, float* d_grad_bias,
                                   const int64_t* d_lo, void* stream);
 
+/* The last NodeFlow block, the classifier head and the loss as ONE kernel, forward and backward (the last
+ * nf.block_compute(i, fn.copy_src, fn.mean) feeding the last NodeUpdate, gcn_nssc.py:71-74 + :48, then CrossEntropyLoss,
+ * pa_gcn.py:62,93-94, and their backward):
+ *   a = reduce over the block of d_src rows;  loss = CE(a W^T + b, labels);
+ *   d_grad_src [cap_src, in_dim] = d loss / d src (overwritten), d_grad_weight, d_grad_bias (overwritten).
+ * Same results as pg_aggregate_fwd_dyn -> pg_linear_cross_entropy -> pg_aggregate_bwd_dyn without the two latency-bound
+ * launches and the [n, in_dim] round trips of a and its gradient. The block is given like the _dyn calls: NodeFlow-wide
+ * indptr base, cols, d_layer_offsets = &meta[4 + block] (device: source-layer, destination-layer and end offsets);
+ * cap_dst / cap_src = row capacities. labels are indexed by destination row. in_dim (% 4 == 0), n_classes <= 64,
+ * 16-byte aligned rows. */
+pg_status pg_block_linear_cross_entropy(const int64_t* d_indptr_base, const int64_t* d_cols, const int64_t* d_layer_offsets,
+                                        const float* d_src, int64_t src_stride, int64_t cap_dst, int64_t cap_src, int mode,
+                                        const float* d_weight, const float* d_bias, const int64_t* d_labels, int32_t in_dim,
+                                        int32_t n_classes, float* d_loss, float* d_grad_src, int64_t gsrc_stride,
+                                        float* d_grad_weight, float* d_grad_bias, void* stream);
+
 /* ---------------------------------------------------------------- gradient all-reduce fused with the optimizer step
  * Replaces DistributedDataParallel's all-reduce of the flat gradient followed by Adam (examples/profile/pa_gcn.py:65,96-97)
  * with ONE kernel over NVLink peer memory: every CTA pushes its slice of the gradient into every peer's receive area
@@ -314,6 +330,9 @@ enum {
 };
 pg_status pg_timing_enable(int enabled);
 pg_status pg_timing_drain(int32_t* slots, float* ms, int64_t cap, int64_t* n_out);
+/* Same drain as a timeline: begin_ms[i] / end_ms[i] = when record i's bracket opened / closed on its stream, relative to
+ * the first record of the drain (records of different streams are comparable). SYNC. */
+pg_status pg_timing_drain_timeline(int32_t* slots, float* begin_ms, float* end_ms, int64_t cap, int64_t* n_out);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 int64_t pg_launch_count(void);
 

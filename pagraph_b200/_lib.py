@@ -99,6 +99,9 @@ SIGNATURES = {
                                             c_vp, c_vp, c_vp, c_vp]),
     "pg_linear_cross_entropy": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32,
                                                ctypes.c_int32, c_vp, c_vp, ctypes.c_int64, c_vp, c_vp, c_vp, c_vp]),
+    "pg_block_linear_cross_entropy": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                     ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_int32, ctypes.c_int32, c_vp,
+                                                     c_vp, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "pg_peer_group_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(c_vp),
                                             c_vp]),
     "pg_peer_group_connect": (ctypes.c_int, [c_vp, c_vp]),
@@ -112,6 +115,9 @@ SIGNATURES = {
     "pg_timing_enable": (ctypes.c_int, [ctypes.c_int]),
     "pg_timing_drain": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float),
                                        ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
+    "pg_timing_drain_timeline": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float),
+                                                ctypes.POINTER(ctypes.c_float), ctypes.c_int64,
+                                                ctypes.POINTER(ctypes.c_int64)]),
     "pg_launch_count": (ctypes.c_int64, []),
     "pg_dropout_keep_mask": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, c_vp]),
 }
@@ -175,6 +181,16 @@ def timing_drain(cap=1 << 16):
     n = ctypes.c_int64()
     check(lib().pg_timing_drain(slots, ms, cap, ctypes.byref(n)), "pg_timing_drain")
     return [(slots[i], ms[i]) for i in range(n.value)]
+
+
+def timing_drain_timeline(cap=1 << 16):
+    """[(slot, begin_ms, end_ms)] of every timed launch since the previous drain, relative to the first. Synchronises."""
+    slots = (ctypes.c_int32 * cap)()
+    t0 = (ctypes.c_float * cap)()
+    t1 = (ctypes.c_float * cap)()
+    n = ctypes.c_int64()
+    check(lib().pg_timing_drain_timeline(slots, t0, t1, cap, ctypes.byref(n)), "pg_timing_drain_timeline")
+    return [(slots[i], t0[i], t1[i]) for i in range(n.value)]
 
 
 def launch_count():

@@ -235,14 +235,15 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
   const uint32_t warp_smem = pg::smem_u32(smem) + (uint32_t)w * (uint32_t)(depth * group) * row_bytes;
   if (lane < depth) pg::mbar_init(pg::smem_u32(&bars[w * kRowsMaxDepth + lane]), 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __shared__ uint64_t stepkey_s;   // dropout step key (read once per task: not worth two registers)
   if (DROP) {
     for (int i = threadIdx.x; i < CH * 32; i += W * 32) col_key[i] = pg::drop_colkey((uint32_t)i);
+    if (threadIdx.x == 0) stepkey_s = pg::drop_stepkey(a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull));
     __syncthreads();
   } else {
     __syncwarp();
   }
   const int warp0 = (int)(blockIdx.x * W + w), nwarps = (int)(gridDim.x * W);
-  const uint64_t stepkey = DROP ? pg::drop_stepkey(a.drop_seed + (a.drop_step ? (uint64_t)*a.drop_step : 0ull)) : 0ull;
   const int64_t cap_dst = a.n_dst;
   if (a.lo) pg::apply_extents(a.lo, a.indptr, a.col_base, a.n_dst);
   a.zero_rows_to = pg::resolve_zero_rows(a.zero_rows_to, a.n_dst, cap_dst);
@@ -267,25 +268,26 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
     ideg = irem = (int)(nxt_e - nxt_s);
     open_next(ir + nwarps);
   }
-  // The task about to be issued is PREPARED one step ahead: its cols -> rowptr loads (two dependent global loads, the
-  // longest stall of the r2a kernel in the ncu source view) fly while the warp consumes a staged buffer.
-  const float* psrc = nullptr;   // this lane's source row of the prepared task (lane < pcnt)
+  // The task to be issued is PREPARED two steps ahead, one dependent load per step: step t reads the column ids of task
+  // t + 2 (`fetch`: the cursor advances here) and turns the ids of task t + 1 into row pointers + dropout row keys
+  // (`resolve`). Each of the two global loads of the cols -> rowptr chain — the longest stall of the r2a kernel in the
+  // ncu source view — then has a whole task period to land instead of both sharing one, which is what lets short tasks
+  // (small GROUP, i.e. a small shared-memory footprint that leaves room for the dense stage's CTAs) keep up.
+  int qj = 0;                    // fetched task: this lane's source index (lane < qmeta.x)
+  int3 qmeta = make_int3(0, 0, 0);   // {rows | last-task-of-its-row << 8, dst row, degree}
+  bool qhave = false;
+  const float* psrc = nullptr;   // resolved task: this lane's source row (lane < pmeta.x)
   uint64_t pkey = 0;             // its dropout row key
-  int pcnt = 0;
-  int4 pmeta = make_int4(0, 0, 0, 0);
+  int3 pmeta = make_int3(0, 0, 0);
   bool phave = false;
-  auto prepare = [&]() {  // reads the cursor, loads the prepared task's operands, advances the cursor
-    phave = ir < n_dst;
-    if (!phave) return;
-    pcnt = min(group, irem);
-    pmeta = make_int4(pcnt, irem <= group, ir, ideg);
-    if (lane < pcnt) {
-      const int64_t j = a.cols[ipos + lane] - a.col_base;
-      psrc = a.rowptr[j];
-      if (DROP) pkey = pg::drop_rowkey(stepkey, (uint64_t)j);  // one hash per fetched row, lanes in parallel
-    }
-    ipos += pcnt;
-    irem -= pcnt;
+  auto fetch = [&]() {  // reads the cursor, loads the task's column ids, advances the cursor
+    qhave = ir < n_dst;
+    if (!qhave) return;
+    const int cnt = min(group, irem);
+    qmeta = make_int3(cnt | (irem <= group ? 256 : 0), ir, ideg);
+    if (lane < cnt) qj = (int)(a.cols[ipos + lane] - a.col_base);
+    ipos += cnt;
+    irem -= cnt;
     if (irem <= 0) {  // next destination row
       ir += nwarps;
       if (ir < n_dst) {
@@ -295,18 +297,30 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
       }
     }
   };
+  auto resolve = [&]() {  // fetched -> resolved
+    phave = qhave;
+    pmeta = qmeta;
+    if (qhave && lane < (qmeta.x & 255)) {
+      psrc = a.rowptr[qj];
+      if (DROP) pkey = pg::drop_rowkey(stepkey_s, (uint64_t)qj);  // one hash per fetched row, lanes in parallel
+    }
+  };
   auto issue = [&](int buf) {  // precondition: phave
     const uint32_t bar = pg::smem_u32(&bars[w * kRowsMaxDepth + buf]);
+    const int pcnt = pmeta.x & 255;
     if (DROP && lane < pcnt) row_key[w][buf][lane] = pkey;
     if (lane == 0) {
-      task_meta[w][buf] = pmeta;
+      task_meta[w][buf] = make_int4(pcnt, pmeta.x >> 8, pmeta.y, pmeta.z);
       pg::mbar_expect_tx(bar, (uint32_t)pcnt * row_bytes);
     }
     __syncwarp();
     if (lane < pcnt) pg::bulk_g2s(warp_smem + (uint32_t)(buf * group + lane) * row_bytes, psrc, row_bytes, bar);
-    prepare();
+    resolve();
+    fetch();
   };
-  prepare();
+  fetch();
+  resolve();
+  fetch();
   int issued = 0;
   for (; issued < depth && phave; ++issued) issue(issued);
 
@@ -443,6 +457,7 @@ pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, 
                                 : agg_rows_tma_kernel<W, CH, false, (CH == 5 ? kRefVec : 0)>)
                         : (drop ? agg_rows_tma_kernel<W, CH, true, 0> : agg_rows_tma_kernel<W, CH, false, 0>);
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int64_t rows = std::max(a.n_dst, a.zero_rows_to);   // a negative zero_rows_to is bounded by the capacity n_dst
   const int64_t need = std::max<int64_t>(1, (rows + W - 1) / W);
   const int grid = (int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev));
@@ -477,6 +492,7 @@ void launch_fwd(const AggArgs& a, int dev, cudaStream_t st) {
   constexpr int rows_per_block = (kAggThreads / 32) * (32 / LANES);
   const int64_t need = std::max<int64_t>(1, (a.n_dst + rows_per_block - 1) / rows_per_block);
   const int grid = (int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev) * 16);
+  pg::prefer_max_smem_k(agg_fwd_vec4<LANES, CH>);
   agg_fwd_vec4<LANES, CH><<<grid, kAggThreads, 0, st>>>(a);
 }
 
@@ -500,6 +516,7 @@ pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st) {
   }
   const int64_t rows = std::max(a.n_dst, a.zero_rows_to);
   const int64_t need = std::max<int64_t>(1, (rows + kAggThreads / 32 - 1) / (kAggThreads / 32));
+  pg::prefer_max_smem_k(agg_rows_ldg_kernel);
   agg_rows_ldg_kernel<<<(int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev) * 16), kAggThreads, 0, st>>>(a);
   PG_CHECK_LAUNCH();
   return PG_OK;
@@ -552,6 +569,7 @@ static pg_status aggregate_fwd_impl(const int64_t* d_indptr, const int64_t* d_co
     else launch_fwd<32, 5>(a, dev, st);  // 600 floats = 150 float4: one pass; wider rows loop in passes of 160
   } else {
     const int64_t need = std::max<int64_t>(1, (n_dst + kAggThreads / 32 - 1) / (kAggThreads / 32));
+    pg::prefer_max_smem_k(agg_fwd_scalar);
     agg_fwd_scalar<<<(int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev) * 16), kAggThreads, 0, st>>>(a);
   }
   PG_CHECK_LAUNCH();
@@ -601,6 +619,7 @@ static pg_status aggregate_bwd_impl(const int64_t* d_indptr, const int64_t* d_co
   const int vec4 = (dim % 4 == 0) && (gdst_stride % 4 == 0) && (gsrc_stride % 4 == 0) &&
                    (((uintptr_t)d_grad_dst | (uintptr_t)d_grad_src) % 16 == 0);
   const int64_t need = std::max<int64_t>(1, (n_dst + kAggThreads / 32 - 1) / (kAggThreads / 32));
+  pg::prefer_max_smem_k(agg_bwd_kernel);
   agg_bwd_kernel<<<(int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev) * 16), kAggThreads, 0, st>>>(a, vec4);
   PG_CHECK_LAUNCH();
   return PG_OK;

@@ -231,6 +231,7 @@ pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, flo
   pg::DeviceGuard guard(g->dev);
   AdamArgs ad{d_param, d_grad, d_exp_avg, d_exp_avg_sq, d_step, lr, beta1, beta2, eps, weight_decay};
   pg::TimedScope timed(PG_T_OPT, (cudaStream_t)stream);
+  pg::prefer_max_smem_k(allreduce_adam_kernel);
   allreduce_adam_kernel<<<g->ctas, kCommThreads, 0, (cudaStream_t)stream>>>(g->args, ad, d_step_id);
   PG_CHECK_LAUNCH();
   return PG_OK;

@@ -49,6 +49,17 @@ struct DeviceGuard {
 
 int sm_count(int dev);
 
+// One shared-memory carve-out for every kernel of the library. An SM cannot hold CTAs of kernels that were configured
+// with different L1 / shared-memory splits: with the default (driver-chosen) preference the sampler's small kernels ran
+// under a small-shared split, and the aggregation kernel of the NEXT minibatch (192 KB of shared memory, maximum split)
+// had to wait for every such CTA on an SM to drain before it could start there — and vice versa for the classifier head
+// (95 KB) beside it. Measured (tools/engine_breakdown.py): the sample chain replayed beside the gather graph slowed the
+// gather stage from 0.158 to 0.222 ms and the two streams ended in lock-step. Every launch site therefore asks for the
+// maximum shared-memory split once per kernel. Cached per function pointer; safe under stream capture (not a stream op).
+void prefer_max_smem(const void* kernel);
+template <class K>
+inline void prefer_max_smem_k(K kernel) { prefer_max_smem((const void*)kernel); }
+
 // Live per-launch timing (pg_timing_* in the header): a TimedScope brackets the launches of one
 // kernel class with a CUDA-event pair on the launching stream when timing is enabled; it costs
 // nothing otherwise.
@@ -115,6 +126,10 @@ pg_status launch_agg_rows(const AggRowsArgs& a, int dev, cudaStream_t st);
 pg_status linear_ce_mma(const float* d_a, int64_t a_stride, const float* d_weight, const float* d_bias, const int64_t* d_labels,
                         int64_t n, int32_t in_dim, int32_t n_classes, float* d_loss, float* d_grad_a, int64_t ga_stride,
                         float* d_grad_weight, float* d_grad_bias, const int64_t* d_lo, cudaStream_t st);
+pg_status block_linear_ce_mma(const int64_t* d_indptr_base, const int64_t* d_cols, const int64_t* d_lo3, const float* d_src,
+                              int64_t src_stride, int64_t cap_dst, int mode, const float* d_weight, const float* d_bias,
+                              const int64_t* d_labels, int32_t in_dim, int32_t n_classes, float* d_loss, float* d_grad_src,
+                              int64_t gsrc_stride, float* d_grad_weight, float* d_grad_bias, cudaStream_t st);
 // tcgen05 / TMEM / TMA forward of the first NodeUpdate (pg_dense_umma.cu); PG_ERR_INVALID = not eligible, nothing launched
 pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float* d_weight, const float* d_bias, int64_t n,
                                  int32_t K, int concat, float* d_out, int64_t out_stride, float* d_out_drop, int64_t od_stride,

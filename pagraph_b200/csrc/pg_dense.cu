@@ -168,6 +168,7 @@ pg_status linear_concat_bwd_simt(const float* d_x, int64_t x_stride, const float
   auto launch = [&](auto kern, int kt) -> pg_status {
     const size_t smem = 2 * (size_t)kt * in_dim * sizeof(float);
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (n + kt - 1) / kt), (int64_t)pg::sm_count(dev));
     kern<<<grid, kBwdThreads, smem, st>>>(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim, concat,
                                           d_grad_weight, d_grad_bias);
@@ -325,9 +326,48 @@ extern "C" pg_status pg_linear_cross_entropy(const float* d_a, int64_t a_stride,
   const int grid = (int)std::min<int64_t>((n + kHeadWarps - 1) / kHeadWarps, (int64_t)pg::sm_count(dev));
   const size_t smem = ((size_t)kHeadMaxK * (kHeadMaxC + 1) + 2 * (size_t)kHeadMaxK * kHeadMaxC) * sizeof(float);
   PG_CUDA(cudaFuncSetAttribute(linear_ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PG_CUDA(cudaFuncSetAttribute(linear_ce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   linear_ce_kernel<<<grid, kHeadWarps * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
                                                      1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight, d_grad_bias,
                                                      d_lo);
   PG_CHECK_LAUNCH();
   return PG_OK;
+}
+
+// The last NodeFlow block + the classifier head + CrossEntropyLoss, forward and backward, as ONE kernel:
+//   a = reduce(block, src);  loss = CE(a W^T + b, labels);  grad_src = reduce^T(d loss / d a);  grad_weight, grad_bias.
+// Replaces pg_aggregate_fwd_dyn -> pg_linear_cross_entropy -> pg_aggregate_bwd_dyn (three latency-bound launches and
+// the [n, in_dim] round trips of a and grad_a between them). Layouts that rule out 16-byte accesses are rejected (the
+// caller then issues the three calls).
+extern "C" pg_status pg_block_linear_cross_entropy(const int64_t* d_indptr_base, const int64_t* d_cols,
+                                                   const int64_t* d_layer_offsets, const float* d_src, int64_t src_stride,
+                                                   int64_t cap_dst, int64_t cap_src, int mode, const float* d_weight,
+                                                   const float* d_bias, const int64_t* d_labels, int32_t in_dim,
+                                                   int32_t n_classes, float* d_loss, float* d_grad_src, int64_t gsrc_stride,
+                                                   float* d_grad_weight, float* d_grad_bias, void* stream) {
+  PG_REQUIRE(d_indptr_base && d_cols && d_layer_offsets && d_src && d_weight && d_labels && d_loss && d_grad_src &&
+                 d_grad_weight && cap_dst >= 0 && cap_src >= 0,
+             "pg_block_linear_cross_entropy: bad arguments");
+  PG_REQUIRE(mode == PG_AGG_SUM || mode == PG_AGG_MEAN, "pg_block_linear_cross_entropy: mode must be PG_AGG_SUM or PG_AGG_MEAN");
+  PG_REQUIRE(in_dim >= 1 && in_dim <= kHeadMaxK && n_classes >= 1 && n_classes <= kHeadMaxC,
+             "pg_block_linear_cross_entropy: in_dim and n_classes must be <= 64");
+  PG_REQUIRE(src_stride >= in_dim && gsrc_stride >= in_dim, "pg_block_linear_cross_entropy: stride smaller than in_dim");
+  const bool ok = in_dim % 4 == 0 && src_stride % 4 == 0 && gsrc_stride % 4 == 0 &&
+                  (((uintptr_t)d_src | (uintptr_t)d_weight | (uintptr_t)d_grad_src | (uintptr_t)d_grad_weight) & 15) == 0;
+  PG_REQUIRE(ok, "pg_block_linear_cross_entropy: in_dim and strides must be multiples of 4 with 16-byte aligned buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  pg::TimedScope timed(PG_T_HEAD, st);
+  PG_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(float), st));
+  PG_CUDA(cudaMemsetAsync(d_grad_weight, 0, (size_t)n_classes * in_dim * sizeof(float), st));
+  if (d_grad_bias) PG_CUDA(cudaMemsetAsync(d_grad_bias, 0, (size_t)n_classes * sizeof(float), st));
+  if (cap_src > 0) {
+    if (gsrc_stride == in_dim) {
+      PG_CUDA(cudaMemsetAsync(d_grad_src, 0, (size_t)cap_src * in_dim * sizeof(float), st));
+    } else {
+      PG_CUDA(cudaMemset2DAsync(d_grad_src, (size_t)gsrc_stride * 4, 0, (size_t)in_dim * 4, (size_t)cap_src, st));
+    }
+  }
+  if (cap_dst == 0) return PG_OK;
+  return pg::block_linear_ce_mma(d_indptr_base, d_cols, d_layer_offsets, d_src, src_stride, cap_dst, mode, d_weight, d_bias,
+                                 d_labels, in_dim, n_classes, d_loss, d_grad_src, gsrc_stride, d_grad_weight, d_grad_bias, st);
 }

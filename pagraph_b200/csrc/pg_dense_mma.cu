@@ -617,13 +617,36 @@ constexpr int kHeadWS = 84;   // row stride (words) of the W planes: conflict-fr
 constexpr int kHeadGS = 66;   // ... of the G planes (8-byte loads, 4 rows x 8 class groups per half-warp)
 constexpr int kHeadAS = 72;   // ... of the staged a tile (16-byte loads, 4 rows x 2 column groups per quarter-warp)
 
+//
+// BLOCK = true fuses the NodeFlow block in front of the head and its backward into the same kernel (the last
+// block_compute of gcn_nssc.py:71-74 feeding the last NodeUpdate): row r of `a` is then not loaded but REDUCED from
+// the block's source rows (a = src rows, copy_src + sum / mean over indptr / cols, sequential edge order like
+// agg_fwd_vec4), and grad_a is not stored but SCATTERED back over the same edges into grad_src (pre-zeroed; vector
+// reductions like agg_bwd_kernel). lo3 = device-resident NodeFlow offsets {source layer, destination layer, end}.
+struct HeadBlock {
+  const int64_t* indptr;   // NodeFlow-wide indptr base
+  const int64_t* cols;
+  const int64_t* lo3;
+  int mean;
+  float* grad_src;
+  int64_t gsrc_stride;
+};
+
+template <bool BLOCK>
 __global__ void __launch_bounds__(kHeadWarpsM * 32)
     linear_ce_mma_kernel(const float* __restrict__ a, int64_t a_stride, const float* __restrict__ W,
                          const float* __restrict__ bias, const int64_t* __restrict__ labels, int64_t n, int K, int C,
                          float inv_n, float* loss, float* grad_a, int64_t ga_stride, float* dW, float* db,
-                         const int64_t* __restrict__ lo) {
+                         const int64_t* __restrict__ lo, HeadBlock blk) {
   extern __shared__ __align__(16) uint32_t hsm[];
-  if (lo) {  // device-resident row count: n is a capacity
+  int64_t col_base = 0;
+  if (BLOCK) {
+    const int64_t l0 = blk.lo3[0], l1 = blk.lo3[1], l2 = blk.lo3[2];
+    blk.indptr += l1;
+    col_base = l0;
+    n = min(n, l2 - l1);
+    inv_n = 1.0f / (float)max(n, (int64_t)1);
+  } else if (lo) {  // device-resident row count: n is a capacity
     n = min(n, lo[1] - lo[0]);
     inv_n = 1.0f / (float)max(n, (int64_t)1);
   }
@@ -652,11 +675,73 @@ __global__ void __launch_bounds__(kHeadWarpsM * 32)
   const int64_t ra = r0 + g, rb = r0 + g + 8;
   const bool va = ra < n, vb = rb < n;
   float4 xa[4], xb[4];
+  int64_t ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0;   // BLOCK: edge ranges of rows ra, rb
+  // BLOCK: the quad (lanes 4 g .. 4 g + 3) keeps the first 12 source indices of each of its two rows in registers —
+  // lane t holds edges t, t + 4, t + 8 — for the reduction here and the scatter of the backward; longer rows (not
+  // produced by the reference's fanouts) take the remaining edges from memory.
+  constexpr int kHeadEdgeRegs = 3;
+  int ca[kHeadEdgeRegs], cb[kHeadEdgeRegs];
+  if (BLOCK) {
+    if (va) { ea0 = blk.indptr[ra]; ea1 = blk.indptr[ra + 1]; }
+    if (vb) { eb0 = blk.indptr[rb]; eb1 = blk.indptr[rb + 1]; }
+#pragma unroll
+    for (int i = 0; i < kHeadEdgeRegs; ++i) {
+      const int64_t ja = ea0 + 4 * i + t, jb = eb0 + 4 * i + t;
+      ca[i] = ja < ea1 ? (int)(blk.cols[ja] - col_base) : 0;
+      cb[i] = jb < eb1 ? (int)(blk.cols[jb] - col_base) : 0;
+    }
+    // lane t holds columns 16 c + 4 t (c = 0..3) of the quad's rows; edges are summed in order (like agg_fwd_vec4)
+    auto reduce_row = [&](int64_t e0, int64_t e1, const int(&cr)[kHeadEdgeRegs], float4(&x)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int deg = (int)min(e1 - e0, (int64_t)(4 * kHeadEdgeRegs));
+#pragma unroll
+      for (int i = 0; i < kHeadEdgeRegs; ++i) {
+        float4 v[4][4];
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {   // four source rows in flight
+          const int src_row = __shfl_sync(pg::kFullMask, cr[i], (lane & ~3) | tt);
+          const float* p = a + (int64_t)src_row * a_stride;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = 16 * c + 4 * t;
+            v[tt][c] = (4 * i + tt < deg && col < K) ? __ldg((const float4*)(p + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt)
+          if (4 * i + tt < deg) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { x[c].x += v[tt][c].x; x[c].y += v[tt][c].y; x[c].z += v[tt][c].z; x[c].w += v[tt][c].w; }
+          }
+      }
+      for (int64_t j = e0 + 4 * kHeadEdgeRegs; j < e1; ++j) {
+        const float* p = a + (blk.cols[j] - col_base) * a_stride;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = 16 * c + 4 * t;
+          if (col < K) {
+            const float4 v = __ldg((const float4*)(p + col));
+            x[c].x += v.x; x[c].y += v.y; x[c].z += v.z; x[c].w += v.w;
+          }
+        }
+      }
+      if (blk.mean) {
+        const float dg = (float)max(e1 - e0, (int64_t)1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { x[c].x /= dg; x[c].y /= dg; x[c].z /= dg; x[c].w /= dg; }
+      }
+    };
+    reduce_row(ea0, ea1, ca, xa);
+    reduce_row(eb0, eb1, cb, xb);
+  }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int col = 16 * c + 4 * t;
-    xa[c] = (va && col < K) ? __ldg((const float4*)(a + ra * a_stride + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    xb[c] = (vb && col < K) ? __ldg((const float4*)(a + rb * a_stride + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!BLOCK) {
+      xa[c] = (va && col < K) ? __ldg((const float4*)(a + ra * a_stride + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[c] = (vb && col < K) ? __ldg((const float4*)(a + rb * a_stride + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     *(float4*)(a_s + (w * 16 + g) * kHeadAS + col) = xa[c];
     *(float4*)(a_s + (w * 16 + g + 8) * kHeadAS + col) = xb[c];
   }
@@ -817,16 +902,62 @@ __global__ void __launch_bounds__(kHeadWarpsM * 32)
           mma_tf32(acc2[4 * h + i], av[0], av[1], av[2], av[3], x0, x1);
         }
   }
+  if (BLOCK) {
+    // backward of the block: row r's gradient (/ degree for mean) added to every source row of r
+    const float sa_ = (blk.mean && ea1 > ea0) ? (float)(ea1 - ea0) : 1.0f;   // divided, like agg_bwd_kernel
+    const float sb_ = (blk.mean && eb1 > eb0) ? (float)(eb1 - eb0) : 1.0f;
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+    for (int half = 0; half < 2; ++half) {
+      const int64_t e0 = half ? eb0 : ea0, e1 = half ? eb1 : ea1;
+      const float sc = half ? sb_ : sa_;
+      float4 gv[2][2];   // [h][qq]: this lane's 4 x 4 columns of the row's gradient
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t r = (q < 2) ? ra : rb;
-      const int col = 32 * h + 8 * t + 4 * (q & 1);
-      if (r < n && col < K)
-        *(float4*)(grad_a + r * ga_stride + col) =
-            make_float4(acc2[4 * h][q], acc2[4 * h + 1][q], acc2[4 * h + 2][q], acc2[4 * h + 3][q]);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int q = 2 * half + qq;
+          gv[h][qq] = make_float4(acc2[4 * h][q] / sc, acc2[4 * h + 1][q] / sc, acc2[4 * h + 2][q] / sc, acc2[4 * h + 3][q] / sc);
+        }
+      const int deg = (int)min(e1 - e0, (int64_t)(4 * kHeadEdgeRegs));
+#pragma unroll
+      for (int i = 0; i < kHeadEdgeRegs; ++i)
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+          const int src_row = __shfl_sync(pg::kFullMask, half ? cb[i] : ca[i], (lane & ~3) | tt);
+          if (4 * i + tt < deg) {
+            float* dst = blk.grad_src + (int64_t)src_row * blk.gsrc_stride;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int qq = 0; qq < 2; ++qq) {
+                const int col = 32 * h + 8 * t + 4 * qq;
+                if (col < K) atomicAdd((float4*)(dst + col), gv[h][qq]);
+              }
+          }
+        }
+      for (int64_t j = e0 + 4 * kHeadEdgeRegs; j < e1; ++j) {
+        float* dst = blk.grad_src + (blk.cols[j] - col_base) * blk.gsrc_stride;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            const int col = 32 * h + 8 * t + 4 * qq;
+            if (col < K) atomicAdd((float4*)(dst + col), gv[h][qq]);
+          }
+      }
     }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t r = (q < 2) ? ra : rb;
+        const int col = 32 * h + 8 * t + 4 * (q & 1);
+        if (r < n && col < K)
+          *(float4*)(grad_a + r * ga_stride + col) =
+              make_float4(acc2[4 * h][q], acc2[4 * h + 1][q], acc2[4 * h + 2][q], acc2[4 * h + 3][q]);
+      }
+  }
   __syncthreads();
   // ---- phase 3: dW[16 w + .][.] += G^T a over the CTA's 64 rows (8 k-steps of 8 rows)
   float acc3[8][4];
@@ -893,11 +1024,33 @@ pg_status linear_ce_mma(const float* d_a, int64_t a_stride, const float* d_weigh
                   (((uintptr_t)d_a | (uintptr_t)d_weight | (uintptr_t)d_grad_a | (uintptr_t)d_grad_weight) & 15) == 0;
   if (!ok) return PG_ERR_INVALID;
   const size_t smem = (2 * 64 * (size_t)kHeadWS + 2 * 64 * (size_t)kHeadGS + 64 * (size_t)kHeadAS) * sizeof(uint32_t);
-  PG_CUDA(cudaFuncSetAttribute(linear_ce_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PG_CUDA(cudaFuncSetAttribute(linear_ce_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PG_CUDA(cudaFuncSetAttribute(linear_ce_mma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int grid = (int)((n + 16 * kHeadWarpsM - 1) / (16 * kHeadWarpsM));
-  linear_ce_mma_kernel<<<grid, kHeadWarpsM * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim, n_classes,
-                                                             1.0f / (float)n, d_loss, d_grad_a, ga_stride, d_grad_weight,
-                                                             d_grad_bias, d_lo);
+  linear_ce_mma_kernel<false><<<grid, kHeadWarpsM * 32, smem, st>>>(d_a, a_stride, d_weight, d_bias, d_labels, n, in_dim,
+                                                                    n_classes, 1.0f / (float)n, d_loss, d_grad_a, ga_stride,
+                                                                    d_grad_weight, d_grad_bias, d_lo, HeadBlock{});
+  PG_CHECK_LAUNCH();
+  return PG_OK;
+}
+
+// Block + head + loss, forward and backward, in one kernel (linear_ce_mma_kernel<true>). grad_src must be zeroed by the
+// caller. PG_ERR_INVALID = layout not eligible, nothing launched.
+pg_status block_linear_ce_mma(const int64_t* d_indptr_base, const int64_t* d_cols, const int64_t* d_lo3, const float* d_src,
+                              int64_t src_stride, int64_t cap_dst, int mode, const float* d_weight, const float* d_bias,
+                              const int64_t* d_labels, int32_t in_dim, int32_t n_classes, float* d_loss, float* d_grad_src,
+                              int64_t gsrc_stride, float* d_grad_weight, float* d_grad_bias, cudaStream_t st) {
+  const bool ok = in_dim % 4 == 0 && in_dim <= 64 && n_classes <= 64 && src_stride % 4 == 0 && gsrc_stride % 4 == 0 &&
+                  (((uintptr_t)d_src | (uintptr_t)d_weight | (uintptr_t)d_grad_src | (uintptr_t)d_grad_weight) & 15) == 0;
+  if (!ok) return PG_ERR_INVALID;
+  const size_t smem = (2 * 64 * (size_t)kHeadWS + 2 * 64 * (size_t)kHeadGS + 64 * (size_t)kHeadAS) * sizeof(uint32_t);
+  PG_CUDA(cudaFuncSetAttribute(linear_ce_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PG_CUDA(cudaFuncSetAttribute(linear_ce_mma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const int grid = (int)((cap_dst + 16 * kHeadWarpsM - 1) / (16 * kHeadWarpsM));
+  HeadBlock blk{d_indptr_base, d_cols, d_lo3, mode == PG_AGG_MEAN ? 1 : 0, d_grad_src, gsrc_stride};
+  linear_ce_mma_kernel<true><<<grid, kHeadWarpsM * 32, smem, st>>>(d_src, src_stride, d_weight, d_bias, d_labels, cap_dst,
+                                                                   in_dim, n_classes, 1.0f, d_loss, nullptr, 0,
+                                                                   d_grad_weight, d_grad_bias, nullptr, blk);
   PG_CHECK_LAUNCH();
   return PG_OK;
 }
@@ -937,6 +1090,7 @@ pg_status pg_linear_concat_fwd(const float* d_x, int64_t x_stride, const float* 
   const DropArgs drop = make_drop(d_out_drop ? dropout_p : 0.f, dropout_seed, d_step);
   auto launch = [&](auto kern, int warps, int rows_per_warp) -> pg_status {
     PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t ntiles = (n + warps * rows_per_warp - 1) / (warps * rows_per_warp);
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev));
     kern<<<grid, warps * 32, smem, st>>>(d_x, x_stride, d_weight, d_bias, n, in_dim, concat, d_out, out_stride, d_out_drop,
@@ -986,6 +1140,7 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
   const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)pg::sm_count(dev));
   const DropArgs drop = make_drop(dropout_p, dropout_seed, d_step);
   auto launch = [&](auto kern, int warps) -> pg_status {
+    pg::prefer_max_smem_k(kern);
     kern<<<grid, warps * 32, 0, st>>>(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim, concat, drop,
                                       d_grad_weight, d_grad_bias);
     PG_CHECK_LAUNCH();
@@ -996,6 +1151,7 @@ pg_status pg_linear_concat_bwd(const float* d_x, int64_t x_stride, const float* 
     const int warps = (in_dim + 31) / 32;
     const size_t smem = 2 * (size_t)kDw2Super * kGzStride * sizeof(uint32_t);
     PG_CUDA(cudaFuncSetAttribute(linear_concat_dw2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     linear_concat_dw2_kernel<<<grid, warps * 32, smem, st>>>(d_x, x_stride, d_grad_out, g_stride, d_out, out_stride, n, in_dim,
                                                              concat, drop, d_grad_weight, d_grad_bias);
     PG_CHECK_LAUNCH();

@@ -367,6 +367,7 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int64_t ntiles = (n + kBlockM - 1) / kBlockM;
@@ -698,6 +699,7 @@ pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float*
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PG_CUDA(cudaFuncSetAttribute(linear_concat_dw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   UmmaDrop drop;

@@ -392,6 +392,7 @@ static pg_status launch_rows(pg_cache* c, const float* const* src, const int64_t
       a.stages = stages;
       const size_t smem = (size_t)kBulkWarps * stages * stage;
       PG_CUDA(cudaFuncSetAttribute(rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PG_CUDA(cudaFuncSetAttribute(rows_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       const int64_t need = std::max<int64_t>(1, (n + kBulkWarps * stages - 1) / (kBulkWarps * stages));
       const int grid = (int)std::min<int64_t>(need, (int64_t)sms * env_int("PG_BULK_CTAS_PER_SM", 2));
       rows_bulk_kernel<<<grid, kBulkWarps * 32, smem, st>>>(a);
@@ -401,6 +402,7 @@ static pg_status launch_rows(pg_cache* c, const float* const* src, const int64_t
   }
   const int64_t need = std::max<int64_t>(1, (n + kRowWarps - 1) / kRowWarps);
   const int grid = (int)std::min<int64_t>(need, (int64_t)sms * 8);
+  pg::prefer_max_smem_k(rows_ldg_kernel);
   rows_ldg_kernel<<<grid, kRowWarps * 32, 0, st>>>(a);
   PG_CHECK_LAUNCH();
   return PG_OK;
@@ -582,6 +584,7 @@ static pg_status cache_fetch_impl(pg_cache* c, const int64_t* d_parent_ids, int6
     pg::TimedScope ts(PG_T_SPLIT, st);
     PG_CUDA(cudaMemsetAsync(list_counts, 0, 16, st));
     const int grid = (int)std::min<int64_t>((n + kSplitThreads - 1) / kSplitThreads, (int64_t)sms * 8);
+    pg::prefer_max_smem_k(split_kernel);
     split_kernel<<<grid, kSplitThreads, 0, st>>>(d_parent_ids, n, c->flag, c->l2c, c->nid_map, hit_pos, hit_row,
                                                  miss_pos, miss_row, list_counts, d_hit_mask,
                                                  (unsigned long long*)d_counts, d_begin, d_end);
@@ -666,6 +669,7 @@ pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const fl
     pg::TimedScope timed(PG_T_SPLIT, st);
     if (!full) PG_CUDA(cudaMemsetAsync(list_counts, 0, 16, st));
     const int grid = (int)std::min<int64_t>((n_src + kSplitThreads - 1) / kSplitThreads, (int64_t)pg::sm_count(c->dev) * 8);
+    pg::prefer_max_smem_k(resolve_kernel);
     resolve_kernel<<<grid, kSplitThreads, 0, st>>>(blk->parent_ids, n_src, c->flag, c->l2c, c->nid_map, full ? 1 : 0,
                                                   c->cache_tables[field], dim, d_stage, dim, stage_rows, c->host_dev[field],
                                                   c->fields[field].host_stride, d_rowptr, miss_row, list_counts,

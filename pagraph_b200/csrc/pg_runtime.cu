@@ -35,6 +35,17 @@ int sm_count(int dev) {
   return n;
 }
 
+void prefer_max_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::vector<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  for (const void* k : done)
+    if (k == kernel) return;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+    cudaGetLastError();   // a preference, not a requirement
+  done.push_back(kernel);
+}
+
 // ------------------------------------------------------------------ live timing
 struct TimingRec {
   int slot;
@@ -100,6 +111,29 @@ pg_status pg_timing_drain(int32_t* slots, float* ms, int64_t cap, int64_t* n_out
     }
     pg::g_free_events.emplace_back(r.a, r.b);
   }
+  cudaGetLastError();
+  pg::g_recs.clear();
+  *n_out = n;
+  return PG_OK;
+}
+
+pg_status pg_timing_drain_timeline(int32_t* slots, float* begin_ms, float* end_ms, int64_t cap, int64_t* n_out) {
+  PG_REQUIRE(n_out != nullptr && cap >= 0 && (cap == 0 || (slots && begin_ms && end_ms)), "pg_timing_drain_timeline: bad arguments");
+  std::lock_guard<std::mutex> lk(pg::g_timing_mu);
+  int64_t n = 0;
+  cudaEvent_t base = nullptr;
+  for (const pg::TimingRec& r : pg::g_recs) {
+    if (!base && cudaEventSynchronize(r.a) == cudaSuccess) base = r.a;
+    float t0 = 0.f, t1 = 0.f;
+    if (base && cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t0, base, r.a) == cudaSuccess &&
+        cudaEventElapsedTime(&t1, base, r.b) == cudaSuccess && n < cap) {
+      slots[n] = r.slot;
+      begin_ms[n] = t0;
+      end_ms[n] = t1;
+      ++n;
+    }
+  }
+  for (const pg::TimingRec& r : pg::g_recs) pg::g_free_events.emplace_back(r.a, r.b);
   cudaGetLastError();
   pg::g_recs.clear();
   *n_out = n;

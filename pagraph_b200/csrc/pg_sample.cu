@@ -824,6 +824,11 @@ static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_se
   const int dev = g->dev;
 
   pg::TimedScope timed(PG_T_SAMPLE, st);
+  // measurement aid (tools/engine_breakdown.py interference runs): launch only the first PG_SAMPLE_KERNELS kernels of the
+  // chain — the outputs are then incomplete, never set outside a timing experiment
+  const char* dbg_env = getenv("PG_SAMPLE_KERNELS");
+  const int dbg_limit = dbg_env ? atoi(dbg_env) : 1 << 30;
+  int dbg_n = 0;
   // kernels of one call (no memset nodes, no host synchronisation):
   //   seed_kernel | hop 1: pick_kernel, bits_kernel | hop h >= 2: front_kernel, pick_kernel, bits_kernel | assemble_kernel
   {
@@ -831,7 +836,8 @@ static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_se
                 s->layer[0], s->row_off[1], s->counts, s->ctl, (uint4*)s->bitmaps, s->nwords_pad * s->L / 4};
     const int64_t want = std::max((sa.zero_vec + kSeedThreads * 4 - 1) / (kSeedThreads * 4), (n_seeds + kSeedThreads - 1) / kSeedThreads);
     const int grid_s = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)pg::sm_count(dev) * 2));
-    seed_kernel<<<grid_s, kSeedThreads, 0, st>>>(sa);
+    pg::prefer_max_smem_k(seed_kernel);
+    if (dbg_n++ < dbg_limit) seed_kernel<<<grid_s, kSeedThreads, 0, st>>>(sa);
     PG_CHECK_LAUNCH();
   }
   const int64_t ntiles = (s->nwords + kBitsTile - 1) / kBitsTile;
@@ -842,19 +848,22 @@ static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_se
       FrontArgs fa{g->indptr, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->fanouts[h - 1], s->row_off[h],
                    s->tile_b, &s->counts->e_hop[h], s->ctl, h};
       const int grid_f = (int)std::min<int64_t>((cap_front + kFrontTile - 1) / kFrontTile, (int64_t)pg::sm_count(dev) * 2);
-      front_kernel<<<std::max(grid_f, 1), kSeedThreads, 0, st>>>(fa);
+      pg::prefer_max_smem_k(front_kernel);
+      if (dbg_n++ < dbg_limit) front_kernel<<<std::max(grid_f, 1), kSeedThreads, 0, st>>>(fa);
       PG_CHECK_LAUNCH();
     }
     PickArgs pa{g->indptr, g->indices, g->eids, s->layer[h - 1], &s->counts->n_layer[h - 1], cap_front, s->row_off[h],
                 s->fanouts[h - 1], (uint32_t)h, k0, k1, d_key, s->nb_src[h], s->nb_eid[h], s->cap_edges, bitmap,
                 s->scratch, s->scratch_stride};
     const int grid_p = (int)std::min<int64_t>(s->pick_grid, std::max<int64_t>(1, (cap_front + kPickWarps - 1) / kPickWarps));
-    pick_kernel<<<grid_p, kPickWarps * 32, 0, st>>>(pa);
+    pg::prefer_max_smem_k(pick_kernel);
+    if (dbg_n++ < dbg_limit) pick_kernel<<<grid_p, kPickWarps * 32, 0, st>>>(pa);
     PG_CHECK_LAUNCH();
     BitsArgs ba{bitmap, s->nwords, s->word_prefix + (size_t)(h - 1) * s->nwords_pad, s->layer[h], s->cap_layer[h],
                 s->tile_a, &s->counts->n_layer[h], s->ctl, h};
     const int grid_b = (int)std::min<int64_t>(ntiles, (int64_t)pg::sm_count(dev) * 4);
-    bits_kernel<<<grid_b, kBitsThreads, 0, st>>>(ba);
+    pg::prefer_max_smem_k(bits_kernel);
+    if (dbg_n++ < dbg_limit) bits_kernel<<<grid_b, kBitsThreads, 0, st>>>(ba);
     PG_CHECK_LAUNCH();
   }
   // ---- assemble
@@ -875,7 +884,8 @@ static pg_status sample_impl(pg_sampler* s, const int64_t* d_seeds, int64_t n_se
   aa.out = *out;
   aa.labels = d_labels;
   aa.seed_labels = d_seed_labels;
-  assemble_kernel<<<grid_for(s->cap_nodes + s->cap_edges, 256, dev, 4), 256, 0, st>>>(aa);
+  pg::prefer_max_smem_k(assemble_kernel);
+  if (dbg_n++ < dbg_limit) assemble_kernel<<<grid_for(s->cap_nodes + s->cap_edges, 256, dev, 4), 256, 0, st>>>(aa);
   PG_CHECK_LAUNCH();
   if (h_meta) PG_CUDA(cudaMemcpyAsync(h_meta, out->meta, PG_META_LEN * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   return PG_OK;

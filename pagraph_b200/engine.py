@@ -29,6 +29,7 @@ import ctypes
 import gc
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -38,7 +39,8 @@ from .nodeflow import NodeBatch
 from .ops import _MODES, LinearConcat, LinearCrossEntropy, linear_concat_backward, linear_concat_forward
 from .parallel import PeerAdam
 
-_RING = 4          # ring slots: sampling runs 2 minibatches ahead of compute, gathering 1
+_RING = 4          # ring slots: compute k | gather k+1 | sampling k+2 .. k+_AHEAD
+_AHEAD = 1 + max(1, int(os.environ.get("PG_ENGINE_SAMPLERS", "2")))   # sampling runs this many minibatches ahead of compute
 _BUCKET = 4096     # padded-shape granularity of the dense layers
 
 
@@ -128,7 +130,13 @@ class GCNTrainEngine:
         with torch.cuda.device(self.dev):
             # the load stage is a chain of small latency-bound kernels: high priority lets them slip in between the
             # compute stage's full-GPU kernels instead of queueing behind them
-            self.side = torch.cuda.Stream(device=self.dev, priority=-1)     # stream A: sampling
+            # stream(s) A: sampling. Sampling a minibatch is a dependent chain of small kernels whose time is memory
+            # LATENCY (it doubles while the HBM-bound stages run beside it), and minibatches are sampled independently
+            # of each other (draws are keyed by (epoch, batch, vertex)): with two sampler states on two streams the
+            # chains of consecutive minibatches overlap, so the stage's throughput doubles at the same latency.
+            self.n_samplers = _AHEAD - 1
+            self.sides = [torch.cuda.Stream(device=self.dev, priority=-1) for _ in range(self.n_samplers)]
+            self.side = self.sides[0]
             self.gather = torch.cuda.Stream(device=self.dev)                # stream B: fetch / resolve / aggregate
             if self.host_inputs:
                 self.seeds_host = seeds.pin_memory()
@@ -150,16 +158,21 @@ class GCNTrainEngine:
             self.cap_rest = sum(self.cap_layer[:-1])                  # NodeFlow layers 1..L
             self._stage_rows_req = int(stage_rows)
             self.stage_rows = 0 if cacher.full_cached else int(min(stage_rows, self.cap_n0))
-            h = ctypes.c_void_p()
             fan = (ctypes.c_int64 * self.L)(*self.fanouts)
-            _lib.check(L.pg_sampler_create(g.handle(self.dev.index), self.L, fan, self.seed, self.batch, self.cap_nodes,
-                                           self.cap_edges, ctypes.byref(h)), "pg_sampler_create")
-            self.sampler = h
+            self.samplers = []                                 # one sampler state (bitmaps, frontier lists) per stream A
+            for _ in range(self.n_samplers):
+                h = ctypes.c_void_p()
+                _lib.check(L.pg_sampler_create(g.handle(self.dev.index), self.L, fan, self.seed, self.batch, self.cap_nodes,
+                                               self.cap_edges, ctypes.byref(h)), "pg_sampler_create")
+                self.samplers.append(h)
+            self.sampler = self.samplers[0]
             self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # optimizer steps taken
             self.load_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)   # minibatches loaded: keys the fused dropout mask
             self.drop_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             self.drop_seed_hidden = int(torch.randint(0, 2 ** 62, (1,)).item())
             self.slots = [self._make_slot() for _ in range(_RING)]
+            for j, sl in enumerate(self.slots):               # _RING is a multiple of the sampler count: a slot keeps its
+                sl.sampler, sl.side = self.samplers[j % self.n_samplers], self.sides[j % self.n_samplers]   # sampler
         self.fused_opt = None
         if sync is not None and os.environ.get("PG_ENGINE_FUSED_OPT", "1") != "0" and PeerAdam.supported(sync, optimizer):
             try:                                            # PeerAdam agrees on the outcome across ranks before it returns
@@ -169,12 +182,16 @@ class GCNTrainEngine:
                       file=sys.stderr)
         self.serialize = False       # True: every stage runs alone (host sync after each) — per-kernel timing passes
         self._dense_ok = False
+        self._block_head = os.environ.get("PG_ENGINE_BLOCK_HEAD", "0") != "0"   # block + head + loss as one kernel
+        self._split = False          # compute stage issued in two halves around the next minibatch's input aggregation
         self.dense = None            # buffers of the fused dense stage (_compute_body_fused), made on first use
         self.pool = None
         self.next_issue = 0          # global minibatch index of the next stage A to issue
         self.next_gather = 0         # ... of the next stage B
         self.next_compute = 0
         self.launches = 0            # kernels launched / replayed by this engine (bench.py's gpu_launches)
+        self.trace = None            # set to [] to record a per-stage GPU timeline (timing events around every stage)
+        self.host_prof = None        # set to {} to accumulate the host's blocked time in steps() (tools/engine_breakdown.py)
         self.size_log = None         # set to [] to record (layer offsets, block offsets) of every computed minibatch
         self._cache_state = None
         self._warm = False
@@ -210,7 +227,7 @@ class GCNTrainEngine:
         s.h_meta_np = s.h_meta.numpy()
         self._make_slot_buffers(s)
         s.loss = torch.zeros((), dtype=torch.float32, device=dev)
-        s.sampled, s.loaded, s.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        s.sampled, s.loaded, s.done, s.fwd_done = (torch.cuda.Event() for _ in range(4))
         s.sample_graph, s.sample_kernels = None, 0
         s.gather_graph, s.gather_kernels = None, 0
         s.compute_graphs = {}
@@ -240,7 +257,7 @@ class GCNTrainEngine:
                                          ("node_mapping", "indptr", "indices", "edge_mapping", "meta")])
         key = ctypes.c_void_p(s.seeds_key.data_ptr() + 8 * self.batch)
         lab_in, lab_out = (None, None) if self.host_inputs else (self.labels_dev, s.labels)
-        _lib.check(L.pg_sample_keyed(self.sampler, _lib.ptr(s.seeds_key), n_seeds, key, ctypes.byref(nfb), _lib.ptr(s.h_meta),
+        _lib.check(L.pg_sample_keyed(s.sampler, _lib.ptr(s.seeds_key), n_seeds, key, ctypes.byref(nfb), _lib.ptr(s.h_meta),
                                      _lib.ptr(lab_in), _lib.ptr(lab_out), _lib.stream_ptr()), "pg_sample_keyed")
 
     def _gather_body(self, s):
@@ -271,8 +288,9 @@ class GCNTrainEngine:
         _lib.lib().pg_minibatch_key(self.seed, epoch, b, key)
         keyword = key[0] | (key[1] << 32)
         s.n_valid, s.k = n, k
-        self.side.wait_event(s.done)                         # the slot's previous minibatch has been consumed
-        with torch.cuda.stream(self.side):
+        side = s.side
+        side.wait_event(s.done)                         # the slot's previous minibatch has been consumed
+        with torch.cuda.stream(side):
             if self.host_inputs:                             # this minibatch's inputs: pinned host -> device
                 s.stage_host[:n] = self.seeds_host[lo:lo + n]
                 s.stage_host[self.batch] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
@@ -288,24 +306,36 @@ class GCNTrainEngine:
                 s.seeds_key[:n].copy_(self.seeds_dev[lo:lo + n], non_blocking=True)
                 s.stage_host[0] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
                 s.seeds_key[self.batch:].copy_(s.stage_host[:1], non_blocking=True)
+            self._mark("sample+", k, side)
             if self.use_graphs and n == self.batch:
                 if s.sample_graph is None:
-                    s.sample_graph, s.sample_kernels = self._capture(self.side, lambda: self._sample_body(s, self.batch))
+                    s.sample_graph, s.sample_kernels = self._capture(side, lambda: self._sample_body(s, self.batch))
                 s.sample_graph.replay()
                 self.launches += s.sample_kernels
             else:
                 l0 = _lib.launch_count()
                 self._sample_body(s, n)
                 self.launches += _lib.launch_count() - l0
-            s.sampled.record(self.side)
+            s.sampled.record(side)
+            self._mark("sample-", k, side)
         if self.serialize:
             torch.cuda.synchronize(self.dev)
 
-    def _issue_gather(self, k):
-        """Enqueue stage B of global minibatch k (after its stage A)."""
+    def _mark(self, stage, k, stream):
+        """stage timeline (tools/engine_breakdown.py): a timing event on `stream`, kept with (stage, minibatch)"""
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self.trace.append((stage, k, e))
+
+    def _issue_gather(self, k, after=None):
+        """Enqueue stage B of global minibatch k (after its stage A, and after the event `after` if given)."""
         s = self.slots[k % _RING]
         self.gather.wait_event(s.sampled)
+        if after is not None:
+            self.gather.wait_event(after)
         with torch.cuda.stream(self.gather):
+            self._mark("gather+", k, self.gather)
             if self.use_graphs:
                 if s.gather_graph is None:
                     s.gather_graph, s.gather_kernels = self._capture(self.gather, lambda: self._gather_body(s))
@@ -316,6 +346,7 @@ class GCNTrainEngine:
                 self._gather_body(s)
                 self.launches += _lib.launch_count() - l0
             s.loaded.record(self.gather)
+            self._mark("gather-", k, self.gather)
         if self.serialize:
             torch.cuda.synchronize(self.dev)
 
@@ -329,10 +360,11 @@ class GCNTrainEngine:
         return g, _lib.launch_count() - l0
 
     # ------------------------------------------------------------------ compute stage (main stream)
-    def _compute_body(self, s, caps, n_valid):
-        """caps[j]: padded row count of NodeFlow layer j (j = 1..L; caps[L] = batch)."""
+    def _compute_body(self, s, caps, n_valid, part=None):
+        """caps[j]: padded row count of NodeFlow layer j (j = 1..L; caps[L] = batch). `part` (0 / 1) selects one half of
+        the fused dense stage when the step is scheduled around the input aggregation (_split)."""
         if self._dense_ok:
-            return self._compute_body_fused(s, caps, n_valid)
+            return self._compute_body_fused(s, caps, n_valid, part)
         L, m = _lib.lib(), self.model
         nf = s.nf
         agg = s.agg[:caps[1]]                                 # aggregated by the load stage; rows >= n_1 are zero
@@ -416,7 +448,8 @@ class GCNTrainEngine:
             self.dense = d
         return self.dense
 
-    def _compute_body_fused(self, s, caps, n_valid):
+    def _compute_body_fused(self, s, caps, n_valid, part=None):
+        """part: None = the whole stage; 0 = the first NodeUpdate forward only; 1 = everything after it"""
         L, m, d = _lib.lib(), self.model, self._dense_buffers()
         spec = self._fused_spec()
         nf, st = s.nf, _lib.stream_ptr()
@@ -424,19 +457,30 @@ class GCNTrainEngine:
         p = float(m.dropout.p) if (spec["drop_hidden"] and m.dropout is not None and m.training) else 0.0
         x, out, hd, ghd = s.agg[:n1], d.out[:n1], d.hd[:n1], d.ghd[:n1]
         w0, b0, w1, b1 = spec["lin"].weight, spec["lin"].bias, spec["head"].linear.weight, spec["head"].linear.bias
-        linear_concat_forward(x, w0, b0, True, out=out, out_drop=hd, dropout_p=p, seed=self.drop_seed_hidden,
-                              step=self.step_counter)
+        if part in (None, 0):
+            linear_concat_forward(x, w0, b0, True, out=out, out_drop=hd, dropout_p=p, seed=self.drop_seed_hidden,
+                                  step=self.step_counter)
+        if part == 0:
+            return
         h = hd if p > 0 else out
         lo = self._meta_ptr(s, 4 + blk)
-        _lib.check(L.pg_aggregate_fwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(h), 64,
-                                          _lib.ptr(d.a2), 64, caps[blk + 1], 64, _MODES["mean"], None, st), "pg_aggregate_fwd_dyn")
         C = w1.shape[0]
-        _lib.check(L.pg_linear_cross_entropy(_lib.ptr(d.a2), 64, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(s.labels), n_valid, 64, C,
-                                             _lib.ptr(s.loss), _lib.ptr(d.ga2), 64, _lib.ptr(w1.grad),
-                                             _lib.ptr(b1.grad if b1 is not None else None), self._meta_ptr(s, 4 + self.L), st),
-                   "pg_linear_cross_entropy")
-        _lib.check(L.pg_aggregate_bwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(d.ga2), 64,
-                                          _lib.ptr(ghd), 64, caps[blk + 1], n1, 64, _MODES["mean"], None, st), "pg_aggregate_bwd_dyn")
+        if self._block_head:
+            # the 64-wide block, the classifier head, the loss and their backward: one kernel
+            _lib.check(L.pg_block_linear_cross_entropy(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(h), 64,
+                                                       caps[blk + 1], n1, _MODES["mean"], _lib.ptr(w1), _lib.ptr(b1),
+                                                       _lib.ptr(s.labels), 64, C, _lib.ptr(s.loss), _lib.ptr(ghd), 64,
+                                                       _lib.ptr(w1.grad), _lib.ptr(b1.grad if b1 is not None else None), st),
+                       "pg_block_linear_cross_entropy")
+        else:
+            _lib.check(L.pg_aggregate_fwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(h), 64,
+                                              _lib.ptr(d.a2), 64, caps[blk + 1], 64, _MODES["mean"], None, st), "pg_aggregate_fwd_dyn")
+            _lib.check(L.pg_linear_cross_entropy(_lib.ptr(d.a2), 64, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(s.labels), n_valid, 64, C,
+                                                 _lib.ptr(s.loss), _lib.ptr(d.ga2), 64, _lib.ptr(w1.grad),
+                                                 _lib.ptr(b1.grad if b1 is not None else None), self._meta_ptr(s, 4 + self.L), st),
+                       "pg_linear_cross_entropy")
+            _lib.check(L.pg_aggregate_bwd_dyn(_lib.ptr(nf["indptr"]), _lib.ptr(nf["indices"]), lo, _lib.ptr(d.ga2), 64,
+                                              _lib.ptr(ghd), 64, caps[blk + 1], n1, 64, _MODES["mean"], None, st), "pg_aggregate_bwd_dyn")
         linear_concat_backward(x, ghd, out, True, w0.grad, b0.grad if b0 is not None else None, p, self.drop_seed_hidden,
                                self.step_counter)
         if self.fused_opt is not None:                       # gradient all-reduce + Adam: one kernel over NVLink peer memory
@@ -464,13 +508,16 @@ class GCNTrainEngine:
         return tuple(caps), lay
 
     def _capture_compute(self, s, caps):
-        g = torch.cuda.CUDAGraph()
-        l0 = _lib.launch_count()
-        with _capture_guard(), torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
-            self._compute_body(s, caps, self.batch)
-        if self.pool is None:
-            self.pool = g.pool()
-        return g, _lib.launch_count() - l0
+        """[graph, ...] of the compute stage (one graph, or the two halves of the split schedule) and its kernel count"""
+        graphs, l0 = [], _lib.launch_count()
+        for part in ((0, 1) if self._split else (None,)):
+            g = torch.cuda.CUDAGraph()
+            with _capture_guard(), torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                self._compute_body(s, caps, self.batch, part)
+            if self.pool is None:
+                self.pool = g.pool()
+            graphs.append(g)
+        return graphs, _lib.launch_count() - l0
 
     # ------------------------------------------------------------------ public loop
     def _check_cache_state(self):
@@ -493,11 +540,17 @@ class GCNTrainEngine:
         self._dense_ok = self._dense_fusable()               # decided (and buffers made) outside any stream capture
         if self._dense_ok:
             self._dense_buffers()
+        split = self._dense_ok and not self.serialize and os.environ.get("PG_ENGINE_SPLIT", "0") != "0"
+        if split != self._split:                             # the compute graphs were captured for the other schedule
+            torch.cuda.synchronize(self.dev)
+            for sl in self.slots:
+                sl.compute_graphs = {}
+            self._split = split
         main = torch.cuda.current_stream(self.dev)
         end = self.next_compute + count
         self.next_gather = max(self.next_gather, self.next_compute)
         self.next_issue = max(self.next_issue, self.next_gather)
-        while self.next_issue < min(end, self.next_compute + 2):       # prologue: A runs 2 ahead, B 1 ahead
+        while self.next_issue < min(end, self.next_compute + _AHEAD):   # prologue: A runs _AHEAD ahead, B 1 ahead
             self._issue_sample(self.next_issue)
             self.next_issue += 1
         while self.next_gather < min(end, self.next_compute + 1):
@@ -507,7 +560,13 @@ class GCNTrainEngine:
         while self.next_compute < end:
             k = self.next_compute
             s = self.slots[k % _RING]
-            s.sampled.synchronize()                          # sampling is 2 minibatches ahead: normally no wait
+            if self.host_prof is not None:                   # host time blocked on the GPU vs. spent issuing work
+                t0 = time.perf_counter()
+                s.sampled.synchronize()
+                self.host_prof["wait_s"] = self.host_prof.get("wait_s", 0.0) + time.perf_counter() - t0
+                self.host_prof["steps"] = self.host_prof.get("steps", 0) + 1
+            else:
+                s.sampled.synchronize()                      # sampling is >= 2 minibatches ahead: normally no wait
             if s.h_meta_np[0] != _lib.PG_OK:
                 raise _lib.PGError("sampler reported status %d for minibatch %d" % (int(s.h_meta_np[0]), k))
             main.wait_event(s.loaded)
@@ -518,19 +577,38 @@ class GCNTrainEngine:
             # the fused dense stage reads the row count on the device, so its captured graph serves any batch whose SEED
             # count is full; the autograd body slices on the host and needs the full row count as well
             full = s.n_valid == self.batch and (self._dense_ok or n_rows == self.batch)
-            with profiling.range('gpu-compute'):
-                if self.use_graphs and full and self._warm:
-                    entry = s.compute_graphs.get(caps)
-                    if entry is None:
-                        entry = s.compute_graphs[caps] = self._capture_compute(s, caps)
-                    entry[0].replay()
-                    self.launches += entry[1]
-                else:
-                    l0 = _lib.launch_count()
-                    self._compute_body(s, caps, n_rows)
-                    self.launches += _lib.launch_count() - l0
-                    self._warm = True                            # optimizer state exists after the first eager step
+            self._mark("compute+", k, main)
+            parts = (0, 1) if self._split else (None,)
+            graphs = None
+            if self.use_graphs and full and self._warm:
+                entry = s.compute_graphs.get(caps)
+                if entry is None:
+                    entry = s.compute_graphs[caps] = self._capture_compute(s, caps)
+                graphs = entry[0]
+                self.launches += entry[1]
+            l0 = _lib.launch_count()
+            for i, part in enumerate(parts):
+                with profiling.range('gpu-compute'):
+                    if graphs is not None:
+                        graphs[i].replay()
+                    else:
+                        self._compute_body(s, caps, n_rows, part)
+                if part == 0:
+                    # Split schedule: the input aggregation of the NEXT minibatch (every SM's shared memory, HBM-bound)
+                    # and the two tensor-core kernels of this one (NodeUpdate forward, dW: one CTA per SM each) cannot
+                    # share an SM, so left to the hardware they interleave badly. Ordered explicitly, the aggregation
+                    # starts when the forward ends and runs beside the small latency-bound kernels between forward
+                    # and dW (64-wide aggregation, head + loss, its backward); dW follows when it drains.
+                    s.fwd_done.record(main)
+                    if self.next_gather < end:
+                        with profiling.range('gpu-load'):
+                            self._issue_gather(self.next_gather, after=s.fwd_done)
+                        self.next_gather += 1
+            if graphs is None:
+                self.launches += _lib.launch_count() - l0
+                self._warm = True                                # optimizer state exists after the first eager step
             s.done.record(main)
+            self._mark("compute-", k, main)
             if self.serialize:
                 torch.cuda.synchronize(self.dev)
             self.next_compute += 1
@@ -538,7 +616,7 @@ class GCNTrainEngine:
                 if self.next_issue < end:
                     self._issue_sample(self.next_issue)
                     self.next_issue += 1
-                if self.next_gather < end:
+                if self.next_gather < min(end, self.next_compute + 1):
                     self._issue_gather(self.next_gather)
                     self.next_gather += 1
             loss = s.loss
@@ -556,9 +634,9 @@ class GCNTrainEngine:
         torch.cuda.synchronize(self.dev)
         for s in self.slots:
             s.sample_graph, s.gather_graph, s.compute_graphs = None, None, {}
-        if self.sampler is not None:
-            _lib.lib().pg_sampler_destroy(self.sampler)
-            self.sampler = None
+        for h in getattr(self, "samplers", []):
+            _lib.lib().pg_sampler_destroy(h)
+        self.samplers, self.sampler = [], None
         if self.fused_opt is not None:
             self.fused_opt.close()
             self.fused_opt = None
@@ -619,9 +697,9 @@ class GCNPreprocessTrainEngine(GCNTrainEngine):
             return None
         return dict(lin=m.linear, act=m.activation, concat=True, head=m.layers[0], xl=0, blk=0, drop_hidden=False)
 
-    def _compute_body(self, s, caps, n_valid):
+    def _compute_body(self, s, caps, n_valid, part=None):
         if self._dense_ok:
-            return self._compute_body_fused(s, caps, n_valid)
+            return self._compute_body_fused(s, caps, n_valid, part)
         m, nf = self.model, s.nf
         h = m.linear(s.agg[:caps[0]])                        # the dropout is already in s.agg
         h = torch.cat((h, m.activation(h)), dim=1) if m.n_layers == 1 else m.activation(h)
@@ -692,7 +770,7 @@ class SageTrainEngine(GCNTrainEngine):
                                             _lib.ptr(s.fetch_ws[l]), st), "pg_cache_fetch_dyn")
         self.load_counter.add_(1)
 
-    def _compute_body(self, s, caps, n_valid):
+    def _compute_body(self, s, caps, n_valid, part=None):
         m, nf = self.model, s.nf
         h = {l: s.feat[l][:caps[l]] for l in range(1, self.L + 1)}
         layer0 = m.layers[0]

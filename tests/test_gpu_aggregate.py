@@ -227,3 +227,55 @@ def test_linear_cross_entropy_matches_torch(n, K, C):
     torch.testing.assert_close(loss.double(), ref, rtol=1e-5, atol=1e-6)
     for a, b in zip(got, (x64.grad, w64.grad, b64.grad)):
         torch.testing.assert_close(a.double(), b, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["mean", "sum"])
+@pytest.mark.parametrize("n_dst,n_src,K,C", [(6000, 35000, 64, 60), (130, 400, 64, 41), (64, 64, 32, 7), (1, 5, 64, 60)])
+def test_block_linear_cross_entropy_matches_torch(n_dst, n_src, K, C, mode):
+    """pg_block_linear_cross_entropy (block + head + loss, forward and backward, one kernel) through the raw C-ABI against
+    float64 torch: a = reduce(block, src); CE(a W^T + b); gradients wrt src, W, b. The block sits inside a larger
+    NodeFlow (non-zero layer offsets, read from the device), with zero-degree rows and row capacities above the sizes."""
+    import ctypes
+
+    import torch
+    from pagraph_b200 import _lib
+    rng = np.random.default_rng(n_dst + n_src + K + C)
+    pre = 37                                                     # a layer in front of the source layer
+    deg = rng.integers(0, 11, n_dst)
+    if n_dst > 1:
+        deg[rng.integers(0, n_dst, max(1, n_dst // 10))] = 0
+    else:
+        deg[:] = 3
+    indptr_blk = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    cols_blk = rng.integers(0, n_src, int(indptr_blk[-1])).astype(np.int64) + pre      # NodeFlow-wide source ids
+    # NodeFlow-wide indptr: rows [0, pre + n_src) have no in-edges here, rows of the destination layer follow
+    indptr = np.concatenate([np.zeros(pre + n_src, np.int64), indptr_blk])
+    lo = torch.tensor([pre, pre + n_src, pre + n_src + n_dst], dtype=torch.int64, device="cuda")
+    cap_dst, cap_src = n_dst + 50, n_src + 100
+    src = torch.randn(cap_src, K, device="cuda")
+    lin = torch.nn.Linear(K, C).cuda()
+    y = torch.randint(0, C, (cap_dst,), device="cuda")
+    d_indptr, d_cols = torch.from_numpy(indptr).cuda(), torch.from_numpy(cols_blk).cuda()
+    loss = torch.full((1,), 7.0, device="cuda")
+    gsrc = torch.full((cap_src, K), 3.0, device="cuda")
+    gw, gb = torch.full((C, K), 5.0, device="cuda"), torch.full((C,), 5.0, device="cuda")
+    L = _lib.lib()
+    w = lin.weight.detach().contiguous()
+    _lib.check(L.pg_block_linear_cross_entropy(_lib.ptr(d_indptr), _lib.ptr(d_cols), _lib.ptr(lo), _lib.ptr(src), K, cap_dst,
+                                               cap_src, 1 if mode == "mean" else 0, _lib.ptr(w), _lib.ptr(lin.bias.detach()),
+                                               _lib.ptr(y), K, C, _lib.ptr(loss), _lib.ptr(gsrc), K, _lib.ptr(gw), _lib.ptr(gb),
+                                               _lib.stream_ptr()), "pg_block_linear_cross_entropy")
+    torch.cuda.synchronize()
+    src64 = src.double().requires_grad_(True)
+    w64, b64 = w.double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
+    rows = torch.from_numpy(np.repeat(np.arange(n_dst), deg)).cuda()
+    a = torch.zeros(n_dst, K, dtype=torch.float64, device="cuda").index_add(0, rows, src64[d_cols - pre])
+    if mode == "mean":
+        a = a / torch.from_numpy(np.maximum(deg, 1)).cuda().double()[:, None]
+    ref = torch.nn.functional.cross_entropy(torch.nn.functional.linear(a, w64, b64), y[:n_dst])
+    ref.backward()
+    torch.testing.assert_close(loss[0].double(), ref, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gsrc.double(), src64.grad, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gw.double(), w64.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(gb.double(), b64.grad, rtol=1e-4, atol=1e-6)
