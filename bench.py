@@ -3,9 +3,12 @@
 
 One "step" = one training minibatch of examples/profile/pa_gcn.py:86-97 on BASELINE.json configs[1]
 (R-MAT 10 M vertices / 100 M edges, feat 600, 2-layer GCN, fanout 25/10, batch 6000):
-    sample (pg_sample) -> cache fetch of every NodeFlow layer (pg_cache_fetch) -> labels ->
-    GCN forward (pg_aggregate_fwd x2 + cuBLAS linears) -> loss -> backward (pg_aggregate_bwd) ->
-    gradient all-reduce (N>1) -> Adam step.
+    sample (pg_sample_keyed, 7 kernels) -> input layer straight from the cache (pg_cache_resolve + the fused
+    lookup + dropout + block-0 mean kernel) -> first NodeUpdate on tcgen05 (pg_linear_concat_fwd) -> block-1 mean
+    (pg_aggregate_fwd_dyn) -> classifier head + CrossEntropyLoss forward/backward (pg_linear_cross_entropy) ->
+    pg_aggregate_bwd_dyn -> dW/db on tcgen05 (pg_linear_concat_bwd) -> gradient all-reduce + Adam in one kernel
+    (pg_allreduce_adam).  --path engine (default) replays this as three CUDA graphs on three streams; --path eager is
+    the reference's op sequence (fetch_data of every layer, torch dropout, block_compute, autograd).
 Nothing is skipped or cached between steps; every step samples a new minibatch.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]        # our arm (torchrun for N>1)

@@ -19,7 +19,7 @@
 //   * aggregation (dgl block_compute copy_src + sum/mean, call sites PaGraph/model/gcn_nssc.py:71-74)
 //     is restated in float64, sequential edge order.
 //
-// RNG contract (shared with pagraph_b200/csrc/pg_rng.cuh)
+// RNG contract (shared with pagraph_b200/csrc/pg_common.cuh: philox4x32_10, draw_pos)
 //   mbkey    = philox4x32_10(ctr=(epoch_lo, epoch_hi, batch_lo, batch_hi), key=(seed_lo, seed_hi))[0..1]
 //   draw(v, hop, t, deg) = mulhi64(w0 | w1<<32, deg),  (w0..w3) = philox4x32_10(ctr=(v_lo, v_hi, hop, t), key=mbkey)
 //   (range reduction bias < deg * 2^-64). hop = 1 for the expansion of the seeds.
@@ -319,15 +319,28 @@ void pgo_aggregate_f32(const int64_t* indptr, const int64_t* cols, int64_t col_b
 // Backward of the above: grad_src[u] += grad_dst[v] * scale(v) over block edges (float64 accumulate).
 void pgo_aggregate_bwd(const int64_t* indptr, const int64_t* cols, int64_t col_base, const float* grad_dst,
                        int64_t n_dst, int64_t n_src, int64_t dim, int mode, float* grad_src) {
+  // Column-parallel: every thread owns a slice of the feature columns and walks the edges in the same sequential order,
+  // so the float64 sums do not depend on the thread count.
   std::vector<double> acc((size_t)(n_src * dim), 0.0);
-  for (int64_t r = 0; r < n_dst; ++r) {
-    const int64_t s = indptr[r], e = indptr[r + 1];
-    const double scale = (mode == 1) ? 1.0 / (double)std::max<int64_t>(e - s, 1) : 1.0;
-    for (int64_t j = s; j < e; ++j) {
-      double* a = acc.data() + (cols[j] - col_base) * dim;
-      for (int64_t d = 0; d < dim; ++d) a[d] += (double)grad_dst[r * dim + d] * scale;
-    }
+#pragma omp parallel
+  {
+#ifdef _OPENMP
+    const int64_t nt = omp_get_num_threads(), tid = omp_get_thread_num();
+#else
+    const int64_t nt = 1, tid = 0;
+#endif
+    const int64_t d0 = dim * tid / nt, d1 = dim * (tid + 1) / nt;
+    if (d0 < d1)
+      for (int64_t r = 0; r < n_dst; ++r) {
+        const int64_t s = indptr[r], e = indptr[r + 1];
+        const double scale = (mode == 1) ? 1.0 / (double)std::max<int64_t>(e - s, 1) : 1.0;
+        for (int64_t j = s; j < e; ++j) {
+          double* a = acc.data() + (cols[j] - col_base) * dim;
+          for (int64_t d = d0; d < d1; ++d) a[d] += (double)grad_dst[r * dim + d] * scale;
+        }
+      }
   }
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n_src * dim; ++i) grad_src[i] = (float)acc[(size_t)i];
 }
 
