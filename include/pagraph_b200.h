@@ -229,6 +229,13 @@ pg_status pg_peer_close(void* d_ptr, int dev);
 pg_status pg_peer_free(void* d_ptr, int dev);
 pg_status pg_cache_set_peers(pg_cache* c, int field, int world, int rank, const float* const* d_peer_tables,
                              const int32_t* d_pos, int64_t c_local, int64_t c_shard, int64_t* d_peer_hits);
+/* Reuse hint for the fused path (optional; no reference counterpart — the reference's gather has no notion of L2): d_hot is a
+ * caller-owned uint8[node_num], non-zero for the local ids whose rows are worth keeping in the L2 cache — the highest
+ * out-degree vertices recur as sources within a minibatch and from one minibatch to the next (auto_cache ranks by the same
+ * out-degree, storage.py:98-101). pg_cache_resolve then sets bit 0 of the row pointers of those rows (rows are 16-byte
+ * aligned); pg_aggregate_rows fetches a tagged row with the L2 evict_last priority and the others with evict_first, and
+ * masks the bit off. Results are unchanged; NULL switches the hint off. */
+pg_status pg_cache_set_hot(pg_cache* c, const uint8_t* d_hot);
 pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, int32_t dim, float* d_dst,
                             int64_t dst_stride, int mode, const float* d_norm, float dropout_p, uint64_t dropout_seed,
                             const int64_t* d_step, int64_t zero_rows_to, void* stream);

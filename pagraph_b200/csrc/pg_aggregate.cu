@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
   // (`resolve`). Each of the two global loads of the cols -> rowptr chain — the longest stall of the r2a kernel in the
   // ncu source view — then has a whole task period to land instead of both sharing one, which is what lets short tasks
   // (small GROUP, i.e. a small shared-memory footprint that leaves room for the dense stage's CTAs) keep up.
+  const uint64_t pol_hot = a.hints ? pg::l2_policy_evict_last() : pg::l2_policy_evict_normal();
+  const uint64_t pol_cold = a.hints ? pg::l2_policy_evict_first() : pol_hot;
   int qj = 0;                    // fetched task: this lane's source index (lane < qmeta.x)
   int3 qmeta = make_int3(0, 0, 0);   // {rows | last-task-of-its-row << 8, dst row, degree}
   bool qhave = false;
@@ -314,7 +316,13 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
       pg::mbar_expect_tx(bar, (uint32_t)pcnt * row_bytes);
     }
     __syncwarp();
-    if (lane < pcnt) pg::bulk_g2s(warp_smem + (uint32_t)(buf * group + lane) * row_bytes, psrc, row_bytes, bar);
+    if (lane < pcnt) {
+      // bit 0 of a row pointer = hot row (kept in L2: hub vertices recur within and across minibatches); the read-once
+      // rest streams through with evict_first so that it does not push the hot rows (or the output rows) out
+      const uintptr_t ps = (uintptr_t)psrc;
+      pg::bulk_g2s_hint(warp_smem + (uint32_t)(buf * group + lane) * row_bytes, (const void*)(ps & ~(uintptr_t)1), row_bytes, bar,
+                        (ps & 1) ? pol_hot : pol_cold);
+    }
     resolve();
     fetch();
   };
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_rows_ldg_kernel(pg::AggRowsAr
       float acc = 0.f;
       for (int64_t q = s; q < e; ++q) {
         const int64_t j = a.cols[q] - a.col_base;
-        float v = __ldg(a.rowptr[j] + col);
+        float v = __ldg((const float*)((uintptr_t)a.rowptr[j] & ~(uintptr_t)1) + col);
         if (a.drop_thr) {
           const uint64_t h = pg::drop_hash(seed, (uint64_t)j, (uint32_t)(col >> 2));
           v = ((uint32_t)((h >> (16 * (col & 3))) & 0xffff) < a.drop_thr) ? 0.f : v * a.keep_scale;

@@ -3,17 +3,20 @@
 // Reference: the only cross-GPU traffic of the trainer is DistributedDataParallel's all-reduce of the 23 k gradient
 // floats (92 KB), followed by optimizer.step() (examples/profile/pa_gcn.py:65,96-97). At that size the collective is pure
 // latency: NCCL costs ~40-50 us per step inside the captured compute graph, plus a division and the optimizer kernel.
-// Here one kernel does all of it:
-//   push    every CTA owns one slice of the flat gradient; it stores the slice into every peer's receive area over NVLink
-//           (peer pointers from CUDA IPC), fences at system scope and raises a per-slice flag on the peer;
-//   reduce  the same CTA spins (acquire, system scope) on its own flags until every peer's slice for this step has
-//           landed, sums the slices in rank order (every rank computes the same bits), divides by the world size;
-//   update  and applies Adam to its slice of the parameters / moments in place.
-// No grid-wide or host synchronisation: a slice is independent end to end. Receive areas are double-buffered by step
-// parity: a rank can run at most one step ahead of the slowest peer (it needs that peer's push to finish its own
-// reduce), so a buffer is never overwritten before it has been consumed. With world == 1 the kernel is just the
-// optimizer step. The flag values are the (monotonic) step number, so nothing is ever reset and the launch can be
-// captured in a CUDA graph; the step number is read from device memory.
+// Here one kernel does all of it, and every THREAD is independent end to end (no fence, no barrier, no separate flag):
+//   push    a thread owns pairs of gradient floats; it stores each pair into every peer's receive area over NVLink
+//           (peer pointers from CUDA IPC) as ONE 16-byte line {g0, step, g1, step}: the data carries its own flag, so a
+//           line that reads back with both step words equal to this step's number is complete (8-byte halves are
+//           written atomically) — the protocol NCCL calls LL. One NVLink store latency, no system-scope fence, no
+//           second round trip for a flag;
+//   reduce  the same thread polls the W-1 lines of its pairs in its own receive area until they carry this step's
+//           number, sums them in rank order (every rank computes the same bits), divides by the world size;
+//   update  and applies Adam to its elements of the parameters / moments in place.
+// Receive areas are double-buffered by step parity: a rank can run at most one step ahead of the slowest peer (it needs
+// that peer's push of step s+1 to finish its own step s+1, and the peer pushes s+1 only after its step-s kernel has
+// consumed the step-s lines), so a line is never overwritten before it has been read. Step numbers are monotonic (>= 1,
+// the areas start zeroed), so nothing is ever reset and the launch can be captured in a CUDA graph; the step number is
+// read from device memory. With world == 1 the kernel is just the optimizer step.
 #include <algorithm>
 #include <cstring>
 
@@ -21,13 +24,13 @@
 
 namespace {
 
-constexpr int kCommThreads = 256;
-constexpr int kCommMaxCtas = 64;
+constexpr int kCommThreads = 128;
+constexpr int kCommMaxCtas = 148;
+constexpr int kCommPairs = 2;   // pairs per thread in flight between the push and the poll
 
 struct PeerArgs {
   int world, rank;
-  float* recv[PG_MAX_RANKS];            // recv[p]: base of rank p's receive area [2][world][n_pad] (mapped here)
-  unsigned long long* flags[PG_MAX_RANKS];  // flags[p]: base of rank p's flags [2][world][kCommMaxCtas]
+  uint4* recv[PG_MAX_RANKS];   // recv[p]: base of rank p's receive area [2][world][n_pad / 2] lines (mapped here)
   int64_t n, n_pad;
 };
 
@@ -40,62 +43,84 @@ struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_line(uint4* p, uint32_t a, uint32_t b, uint32_t flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(flag), "r"(b), "r"(flag) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float ld_cg(const float* p) {   // bypass L1: the line was written by a peer
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+__device__ __forceinline__ uint4 ld_line(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 
+__device__ __forceinline__ void adam_one(const AdamArgs& ad, int64_t i, float g, float step_size, float bc2_sqrt) {
+  ad.grad[i] = g;                                   // the averaged gradient stays visible to the caller
+  float p = ad.param[i];
+  if (ad.weight_decay != 0.f) g += ad.weight_decay * p;
+  const float m = ad.exp_avg[i] + (g - ad.exp_avg[i]) * (1.0f - ad.beta1);
+  const float v = ad.exp_avg_sq[i] * ad.beta2 + g * g * (1.0f - ad.beta2);
+  ad.exp_avg[i] = m;
+  ad.exp_avg_sq[i] = v;
+  ad.param[i] = p - step_size * m / (sqrtf(v) / bc2_sqrt + ad.eps);
+}
+
 __global__ void __launch_bounds__(kCommThreads) allreduce_adam_kernel(PeerArgs pa, AdamArgs ad, const int64_t* step_id_ptr) {
-  const int64_t per = (pa.n + gridDim.x - 1) / gridDim.x;
-  const int64_t lo = (int64_t)blockIdx.x * per, hi = min(pa.n, lo + per);
   const unsigned long long step_id = (unsigned long long)*step_id_ptr;
+  const uint32_t flag = (uint32_t)step_id;
   const int parity = (int)(step_id & 1);
   const int W = pa.world, me = pa.rank;
-  if (W > 1) {
-    // ---- push my slice to every peer's receive area [parity][me]
-    for (int p = 0; p < W; ++p) {
-      if (p == me) continue;
-      float* dst = pa.recv[p] + ((size_t)parity * W + me) * pa.n_pad;
-      for (int64_t i = lo + threadIdx.x; i < hi; i += kCommThreads) dst[i] = ad.grad[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < W && threadIdx.x != me)
-      st_release_sys(pa.flags[threadIdx.x] + ((size_t)parity * W + me) * kCommMaxCtas + blockIdx.x, step_id);
-    // ---- wait for every peer's slice of this step
-    if (threadIdx.x < W && threadIdx.x != me) {
-      const unsigned long long* f = pa.flags[me] + ((size_t)parity * W + threadIdx.x) * kCommMaxCtas + blockIdx.x;
-      while (ld_acquire_sys(f) < step_id) {
-      }
-    }
-    __syncthreads();
-  }
-  // ---- reduce in rank order + Adam
+  const int64_t lines = pa.n_pad / 2;                      // one line = two gradient floats
   const float step = *ad.step;
   const float bc1 = 1.0f - powf(ad.beta1, step), bc2 = 1.0f - powf(ad.beta2, step);
   const float step_size = ad.lr / bc1, bc2_sqrt = sqrtf(bc2), inv_w = 1.0f / (float)W;
-  const float* mine = pa.recv[me];
-  for (int64_t i = lo + threadIdx.x; i < hi; i += kCommThreads) {
-    float g = 0.f;
-    for (int r = 0; r < W; ++r) g += (r == me) ? ad.grad[i] : ld_cg(mine + ((size_t)parity * W + r) * pa.n_pad + i);
-    g *= inv_w;
-    ad.grad[i] = g;                                   // the averaged gradient stays visible to the caller
-    float p = ad.param[i];
-    if (ad.weight_decay != 0.f) g += ad.weight_decay * p;
-    const float m = ad.exp_avg[i] + (g - ad.exp_avg[i]) * (1.0f - ad.beta1);
-    const float v = ad.exp_avg_sq[i] * ad.beta2 + g * g * (1.0f - ad.beta2);
-    ad.exp_avg[i] = m;
-    ad.exp_avg_sq[i] = v;
-    ad.param[i] = p - step_size * m / (sqrtf(v) / bc2_sqrt + ad.eps);
+  const int64_t nth = (int64_t)gridDim.x * kCommThreads;
+  for (int64_t j0 = (int64_t)blockIdx.x * kCommThreads + threadIdx.x; j0 < lines; j0 += nth * kCommPairs) {
+    float g0[kCommPairs], g1[kCommPairs];
+#pragma unroll
+    for (int k = 0; k < kCommPairs; ++k) {
+      const int64_t j = j0 + k * nth, i = 2 * j;
+      g0[k] = (j < lines && i < pa.n) ? ad.grad[i] : 0.f;
+      g1[k] = (j < lines && i + 1 < pa.n) ? ad.grad[i + 1] : 0.f;
+    }
+    if (W > 1) {
+      // ---- push my lines to every peer's receive area [parity][me], nearest-higher rank first (spreads the links)
+#pragma unroll
+      for (int k = 0; k < kCommPairs; ++k) {
+        const int64_t j = j0 + k * nth;
+        if (j >= lines) continue;
+        for (int d = 1; d < W; ++d) {
+          const int p = (me + d) % W;
+          st_line(pa.recv[p] + ((size_t)parity * W + me) * lines + j, __float_as_uint(g0[k]), __float_as_uint(g1[k]), flag);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kCommPairs; ++k) {
+      const int64_t j = j0 + k * nth, i = 2 * j;
+      if (j >= lines) continue;
+      float s0 = 0.f, s1 = 0.f;
+      if (W > 1) {
+        // ---- poll the peers' lines of this step, sum in rank order
+        const uint4* mine = pa.recv[me] + (size_t)parity * W * lines + j;
+        for (int r = 0; r < W; ++r) {
+          if (r == me) {
+            s0 += g0[k];
+            s1 += g1[k];
+            continue;
+          }
+          uint4 v = ld_line(mine + (size_t)r * lines);
+          while (v.y != flag || v.w != flag) v = ld_line(mine + (size_t)r * lines);
+          s0 += __uint_as_float(v.x);
+          s1 += __uint_as_float(v.z);
+        }
+        s0 *= inv_w;
+        s1 *= inv_w;
+      } else {
+        s0 = g0[k];
+        s1 = g1[k];
+      }
+      if (i < pa.n) adam_one(ad, i, s0, step_size, bc2_sqrt);
+      if (i + 1 < pa.n) adam_one(ad, i + 1, s1, step_size, bc2_sqrt);
+    }
   }
 }
 
@@ -109,11 +134,7 @@ struct pg_peer_group {
   size_t region_bytes = 0;
 };
 
-static size_t region_layout(int world, int64_t n_pad, size_t* flags_off) {
-  const size_t recv_bytes = (size_t)2 * world * n_pad * sizeof(float);
-  *flags_off = (recv_bytes + 255) / 256 * 256;
-  return *flags_off + (size_t)2 * world * kCommMaxCtas * sizeof(unsigned long long);
-}
+static size_t region_bytes_for(int world, int64_t n_pad) { return (size_t)2 * world * (n_pad / 2) * sizeof(uint4); }
 
 extern "C" {
 
@@ -128,9 +149,9 @@ pg_status pg_peer_group_create(int world, int rank, int64_t n, int dev, pg_peer_
   g->args.rank = rank;
   g->args.n = n;
   g->args.n_pad = (n + 63) / 64 * 64;
-  g->ctas = (int)std::min<int64_t>(kCommMaxCtas, std::max<int64_t>(1, (n + 511) / 512));  // 2 elements per thread
-  size_t flags_off = 0;
-  g->region_bytes = region_layout(world, g->args.n_pad, &flags_off);
+  const int64_t per_cta = (int64_t)2 * kCommPairs * kCommThreads;   // gradient floats per CTA and pass
+  g->ctas = (int)std::min<int64_t>(kCommMaxCtas, std::max<int64_t>(1, (g->args.n_pad + per_cta - 1) / per_cta));
+  g->region_bytes = region_bytes_for(world, g->args.n_pad);
   if (cudaMalloc(&g->local, g->region_bytes) != cudaSuccess) {
     cudaGetLastError();
     delete g;
@@ -138,8 +159,7 @@ pg_status pg_peer_group_create(int world, int rank, int64_t n, int dev, pg_peer_
     return PG_ERR_NOMEM;
   }
   PG_CUDA(cudaMemset(g->local, 0, g->region_bytes));
-  g->args.recv[rank] = (float*)g->local;
-  g->args.flags[rank] = (unsigned long long*)((char*)g->local + flags_off);
+  g->args.recv[rank] = (uint4*)g->local;
   cudaIpcMemHandle_t h;
   memset(&h, 0, sizeof(h));
   if (world > 1) PG_CUDA(cudaIpcGetMemHandle(&h, g->local));
@@ -152,8 +172,6 @@ pg_status pg_peer_group_create(int world, int rank, int64_t n, int dev, pg_peer_
 pg_status pg_peer_group_connect(pg_peer_group* g, const unsigned char* handles /* [world][PG_IPC_HANDLE_BYTES] */) {
   PG_REQUIRE(g && handles, "pg_peer_group_connect: bad arguments");
   pg::DeviceGuard guard(g->dev);
-  size_t flags_off = 0;
-  region_layout(g->args.world, g->args.n_pad, &flags_off);
   for (int p = 0; p < g->args.world; ++p) {
     if (p == g->args.rank) continue;
     cudaIpcMemHandle_t h;
@@ -161,8 +179,7 @@ pg_status pg_peer_group_connect(pg_peer_group* g, const unsigned char* handles /
     void* ptr = nullptr;
     PG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     g->opened[p] = ptr;
-    g->args.recv[p] = (float*)ptr;
-    g->args.flags[p] = (unsigned long long*)((char*)ptr + flags_off);
+    g->args.recv[p] = (uint4*)ptr;
   }
   return PG_OK;
 }

@@ -86,7 +86,8 @@ struct AggRowsArgs {
   const int64_t* indptr;
   const int64_t* cols;
   int64_t col_base;
-  const float* const* rowptr;  // [n_src] start of every source row (16-byte aligned for the TMA kernel)
+  const float* const* rowptr;  // [n_src] start of every source row (16-byte aligned for the TMA kernel); bit 0 set =
+                               // "hot" row (pg_cache_set_hot): fetched with the L2 evict_last priority
   float* dst;
   int64_t dst_stride;
   int64_t n_dst;
@@ -103,6 +104,8 @@ struct AggRowsArgs {
   const int64_t* lo;           // optional device-resident extents (see pg_block.d_layer_offsets): indptr/n_dst/col_base
                                // are then NodeFlow-wide base / capacity / ignored, and the kernel derives the block's
                                // own from the device (apply_extents)
+  int hints;                   // 1: source rows are fetched with L2 eviction priorities (hot rows evict_last, the
+                               // read-once stream evict_first); 0: default priority for every row
 };
 
 // Device-resident block extents: lo[0..2] = NodeFlow layer offsets of the block's source layer, its destination layer
@@ -224,6 +227,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// The same copy with an L2 eviction-priority hint (createpolicy): rows that will be read again soon are kept
+// (evict_last) while the stream of read-once rows leaves first (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {

@@ -140,7 +140,7 @@ resolve_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __rest
                const int64_t* __restrict__ l2c, const int64_t* __restrict__ nid_map, int is_full, const float* cache,
                int64_t cache_stride, float* stage, int64_t stage_stride, int64_t stage_rows, const float* host,
                int64_t host_stride, const float** rowptr, int64_t* miss_row, unsigned long long* list_counts,
-               unsigned long long* user_counts, const int64_t* lo, PeerTier peer) {
+               unsigned long long* user_counts, const int64_t* lo, PeerTier peer, const uint8_t* __restrict__ hot) {
   __shared__ int warp_miss[kSplitThreads / 32];
   __shared__ unsigned long long base_miss;
   if (lo) {  // device-resident extents: ids is the NodeFlow-wide node_mapping, n a capacity
@@ -159,7 +159,9 @@ resolve_kernel(const int64_t* __restrict__ ids, int64_t n, const uint8_t* __rest
       t = ids[j];
       hit = is_full || flag[t] != 0;
       if (hit) {
-        rowptr[j] = cache + (is_full ? t : l2c[t]) * cache_stride;
+        // bit 0 of the pointer carries the reuse hint of the row to the row-fetching kernel (rows are 16-byte aligned)
+        const uintptr_t tag = hot ? (uintptr_t)(hot[t] & 1) : 0;
+        rowptr[j] = (const float*)((uintptr_t)(cache + (is_full ? t : l2c[t]) * cache_stride) | tag);
       } else if (peer.world > 1) {  // another rank's shard? (this rank's own shard rows carry flag[t])
         const int64_t k = peer.pos[t] - peer.c_local;
         if (k >= 0 && k < peer.c_shard * peer.world) {
@@ -339,6 +341,7 @@ struct pg_cache {
   // buffers replaced by a larger workspace: kept until destroy, because a captured CUDA graph may still address them
   std::vector<void*> retired;
   PeerTier peer[PG_MAX_FIELDS];   // optional peer-GPU tier per field (pg_cache_set_peers)
+  const uint8_t* hot = nullptr;   // optional [node_num] reuse hint (pg_cache_set_hot), caller-owned
 };
 
 static pg_status ensure_ws(pg_cache* c, int64_t n) {
@@ -673,7 +676,7 @@ pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const fl
     resolve_kernel<<<grid, kSplitThreads, 0, st>>>(blk->parent_ids, n_src, c->flag, c->l2c, c->nid_map, full ? 1 : 0,
                                                   c->cache_tables[field], dim, d_stage, dim, stage_rows, c->host_dev[field],
                                                   c->fields[field].host_stride, d_rowptr, miss_row, list_counts,
-                                                  (unsigned long long*)d_counts, blk->d_layer_offsets, c->peer[field]);
+                                                  (unsigned long long*)d_counts, blk->d_layer_offsets, c->peer[field], c->hot);
     PG_CHECK_LAUNCH();
   }
   if (!full && stage_rows > 0) {  // missed rows: pinned host table -> staging rows, slot order (TMA bulk copies over PCIe)
@@ -685,6 +688,12 @@ pg_status pg_cache_resolve(pg_cache* c, int field, const pg_block* blk, const fl
                               env_int("PG_MISS_MODE", 2) == 2, st, field, 1);
     if (s != PG_OK) return s;
   }
+  return PG_OK;
+}
+
+pg_status pg_cache_set_hot(pg_cache* c, const uint8_t* d_hot) {
+  PG_REQUIRE(c, "pg_cache_set_hot: null cache");
+  c->hot = d_hot;
   return PG_OK;
 }
 
@@ -729,6 +738,7 @@ pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, i
   a.keep_scale = 1.0f / (1.0f - dropout_p);
   a.drop_seed = dropout_seed; a.drop_step = d_step;
   a.lo = blk->d_layer_offsets;
+  a.hints = env_int("PG_AGG_L2HINT", 1) != 0;
   pg::TimedScope timed(PG_T_FUSED, st);
   return pg::launch_agg_rows(a, dev, st);
 }

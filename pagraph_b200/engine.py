@@ -227,6 +227,8 @@ class GCNTrainEngine:
         s.h_meta_np = s.h_meta.numpy()
         self._make_slot_buffers(s)
         s.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        s.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()   # read_loss: every step's loss lands here
+        s.loss_ready = torch.cuda.Event()
         s.sampled, s.loaded, s.done, s.fwd_done = (torch.cuda.Event() for _ in range(4))
         s.sample_graph, s.sample_kernels = None, 0
         s.gather_graph, s.gather_kernels = None, 0
@@ -535,7 +537,9 @@ class GCNTrainEngine:
 
     def steps(self, count, read_loss=False):
         """Run `count` training minibatches (continuing from the previous call, wrapping over epochs). Returns the
-        last loss (a CUDA scalar, or a float when read_loss — then every step's loss is read back)."""
+        last loss: a CUDA scalar, or a float when read_loss — then EVERY step's loss is copied to pinned host memory
+        behind its compute stage and read by the host (kept in `self.losses`). The host reads step k's loss after it
+        has enqueued step k + 1, so the read never drains the pipeline; the call returns once the last one is in."""
         self._check_cache_state()
         self._dense_ok = self._dense_fusable()               # decided (and buffers made) outside any stream capture
         if self._dense_ok:
@@ -556,7 +560,9 @@ class GCNTrainEngine:
         while self.next_gather < min(end, self.next_compute + 1):
             self._issue_gather(self.next_gather)
             self.next_gather += 1
-        loss = None
+        loss, pending = None, None
+        if read_loss:
+            self.losses = []
         while self.next_compute < end:
             k = self.next_compute
             s = self.slots[k % _RING]
@@ -608,6 +614,9 @@ class GCNTrainEngine:
                 self.launches += _lib.launch_count() - l0
                 self._warm = True                                # optimizer state exists after the first eager step
             s.done.record(main)
+            if read_loss:                                    # D2H copy of the step's result, behind its compute stage
+                s.loss_host.copy_(s.loss, non_blocking=True)
+                s.loss_ready.record(main)
             self._mark("compute-", k, main)
             if self.serialize:
                 torch.cuda.synchronize(self.dev)
@@ -621,7 +630,14 @@ class GCNTrainEngine:
                     self.next_gather += 1
             loss = s.loss
             if read_loss:
-                loss = float(s.loss.item())                  # D2H read of the step's result
+                if pending is not None:                      # the previous step's loss: its successor is already enqueued
+                    pending.loss_ready.synchronize()
+                    self.losses.append(float(pending.loss_host))
+                pending = s
+        if pending is not None:
+            pending.loss_ready.synchronize()
+            self.losses.append(float(pending.loss_host))
+            loss = self.losses[-1]
         return loss
 
     def layer_sizes(self, k_slot):

@@ -6,6 +6,7 @@ missed rows straight from the pinned host table, for all NodeFlow layers in one 
 synchronisation (the reference: ~10 torch kernels and >= 3 syncs per layer, CPU gather of misses).
 """
 import ctypes
+import os
 import sys
 
 import torch
@@ -205,11 +206,32 @@ class GraphCacheServer:
             print('cache the full graph...', file=sys.stderr)
             nids = torch.arange(self.node_num, device=self._dev)
             self._fill(nids, is_full=True)
+            self._mark_hot(dgl_g, None)
         else:
             print('cache the part of graph... caching percentage: {:.4f}'.format(self.capability / self.node_num), file=sys.stderr)
             out_degrees = dgl_g.out_degrees().to(self._dev)
             sort_nid = torch.sort(out_degrees, descending=True, stable=True).indices
             self._fill(sort_nid[:max(self.capability, 0)].contiguous(), is_full=False)
+            self._mark_hot(dgl_g, sort_nid[:max(self.capability, 0)])
+
+    def _mark_hot(self, dgl_g, cached_by_rank):
+        """L2 reuse hint for the fused lookup + aggregation (pg_cache_set_hot; no reference counterpart): the cached rows
+        with the highest out-degree — the ranking auto_cache itself uses, storage.py:98-101 — recur as sources within a
+        minibatch and across minibatches, so about PG_CACHE_HOT_MB (default 40) of them are fetched with the L2
+        evict_last priority while the read-once rows stream through. Results do not depend on it."""
+        budget = float(os.environ.get("PG_CACHE_HOT_MB", "40")) * 1e6
+        k = int(min(budget // max(self.total_dim * 4, 1), self.node_num if cached_by_rank is None else len(cached_by_rank)))
+        if getattr(self, "_hot", None) is None:              # one buffer per cacher: captured graphs keep its address
+            self._hot = torch.zeros(self.node_num, dtype=torch.uint8, device=self._dev)
+        else:
+            self._hot.zero_()
+        if k > 0:
+            if cached_by_rank is None:
+                top = torch.topk(dgl_g.out_degrees().to(self._dev), k, sorted=False).indices
+            else:
+                top = cached_by_rank[:k]
+            self._hot[top] = 1
+        _lib.check(_lib.lib().pg_cache_set_hot(self._handle, _lib.ptr(self._hot)), "pg_cache_set_hot")
 
     # ---- peer-GPU cache tier (extension, SURVEY §8 f3): the ranks of one node shard the hot rows over NVLink
     def auto_cache_peers(self, dgl_g, embed_names, capability=None, group=None, local_rows=None):

@@ -61,6 +61,30 @@ def test_fused_matches_fetch_then_aggregate(dims, cap, mode):
         assert cs.try_num == n_src and cs.miss_num == int((~flag[ref.layer_parent_nid(0)]).sum())
 
 
+@pytest.mark.parametrize("cap", [600, 10 ** 9])
+@pytest.mark.parametrize("hot_mb,hint", [("0.12", "1"), ("0", "1"), ("40", "0")])
+def test_fused_l2_reuse_hint_does_not_change_results(cap, hot_mb, hint, monkeypatch):
+    """pg_cache_set_hot tags the row pointers of the top-out-degree rows (bit 0) and the row-fetch kernels mask the tag
+    off: a budget of 50 rows mixes tagged and untagged pointers in one block; results equal the oracle either way."""
+    from pagraph_b200 import ops
+    monkeypatch.setenv("PG_CACHE_HOT_MB", hot_mb)
+    monkeypatch.setenv("PG_AGG_L2HINT", hint)
+    dims = {"features": 600, "norm": 1}
+    cs, nf, ref, host, nid_map, _ = _setup(dims, cap=cap)
+    n_hot = int(cs._hot.sum().item())
+    assert n_hot == int(float(hot_mb) * 1e6 // (601 * 4)) or n_hot == min(cs.node_num, cs.cached_num if not cs.full_cached else cs.node_num)
+    ip, cols, base = ref.block(0)
+    src = host["features"][nid_map[ref.layer_parent_nid(0)]]
+    bi, bc, bb, n_dst, n_src = nf.block_csr(0)
+    for mode in ("mean", "sum"):
+        got = ops.cache_aggregate(cs, "features", nf.layer_parent_nid_dev(0), bi, bc, bb, n_src, n_dst, mode)
+        _close(got.cpu().numpy(), oracle.aggregate(ip, cols, base, src, mode))
+    got = ops.cache_aggregate(cs, "features", nf.layer_parent_nid_dev(0), bi, bc, bb, n_src, n_dst, "mean", dropout_p=0.2, seed=4)
+    keep = oracle.dropout_keep_mask(4, len(src), 600, 0.2)
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(0.2))
+    _close(got.cpu().numpy(), oracle.aggregate(ip, cols, base, np.where(keep, src * scale, np.float32(0)), "mean"))
+
+
 @pytest.mark.parametrize("dim,p", [(600, 0.2), (602, 0.5), (64, 0.2)])
 def test_fused_dropout_mask_contract(dim, p):
     """Same mask for every edge of a source node, keyed by (seed, node, column): equals dropout-then-aggregate."""

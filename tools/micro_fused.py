@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--sweep", default="2:200,3:200,2:120,4:200,1:200", help="depth:smem_kb[:warps],...")
     ap.add_argument("--modes", default="hbm20,vtx20")
     ap.add_argument("--quick", action="store_true", help="only the fused_only sweep")
+    ap.add_argument("--hot-sweep", default="", help="hbm20 only: L2 reuse-hint budgets in MB (PG_CACHE_HOT_MB), e.g. 0,20,40,80; "
+                                                    "'off' = no eviction priorities at all (PG_AGG_L2HINT=0)")
     a = ap.parse_args()
     sys.argv = [sys.argv[0]]
     args = bench.parse_args()
@@ -73,6 +75,15 @@ def main():
                                        dropout_p=p, seed=7)
 
         res = {}
+        if a.hot_sweep and mode == "hbm20":
+            for hb in a.hot_sweep.split(","):
+                os.environ["PG_AGG_L2HINT"] = "0" if hb == "off" else "1"
+                os.environ["PG_CACHE_HOT_MB"] = "0" if hb == "off" else hb
+                cs._mark_hot(wl.g, None)
+                timeit(fused_only, nfs[:3])
+                res["fused_only_hot%s_ms" % hb] = [timeit(fused_only, nfs), timeit(fused_only, nfs)]
+            os.environ.pop("PG_AGG_L2HINT"), os.environ.pop("PG_CACHE_HOT_MB")
+            cs._mark_hot(wl.g, None)
         if not a.quick:
             timeit(unfused, nfs[:3])
             res["unfused_fetch+dropout+agg_ms"] = timeit(unfused, nfs)
