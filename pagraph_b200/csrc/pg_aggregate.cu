@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(W * 32) __maxnreg__(NVEC >= 0 ? 96 : 80)
   // ncu source view — then has a whole task period to land instead of both sharing one, which is what lets short tasks
   // (small GROUP, i.e. a small shared-memory footprint that leaves room for the dense stage's CTAs) keep up.
   const uint64_t pol_hot = a.hints ? pg::l2_policy_evict_last() : pg::l2_policy_evict_normal();
-  const uint64_t pol_cold = a.hints ? pg::l2_policy_evict_first() : pol_hot;
+  const uint64_t pol_cold = a.hints == 1 ? pg::l2_policy_evict_first() : pg::l2_policy_evict_normal();
   int qj = 0;                    // fetched task: this lane's source index (lane < qmeta.x)
   int3 qmeta = make_int3(0, 0, 0);   // {rows | last-task-of-its-row << 8, dst row, degree}
   bool qhave = false;

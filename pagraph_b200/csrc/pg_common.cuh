@@ -105,7 +105,8 @@ struct AggRowsArgs {
                                // are then NodeFlow-wide base / capacity / ignored, and the kernel derives the block's
                                // own from the device (apply_extents)
   int hints;                   // 1: source rows are fetched with L2 eviction priorities (hot rows evict_last, the
-                               // read-once stream evict_first); 0: default priority for every row
+                               // read-once stream evict_first); 2: hot rows evict_last, the rest default; 0: default
+                               // priority for every row
 };
 
 // Device-resident block extents: lo[0..2] = NodeFlow layer offsets of the block's source layer, its destination layer

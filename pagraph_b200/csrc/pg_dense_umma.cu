@@ -39,6 +39,8 @@ constexpr int kThreads = 12 * 32;
 constexpr uint32_t kXBytes = kBlockM * kChunk * 4;            // 16 KB
 constexpr uint32_t kWBytes = kN * kChunk * 4;                 // 4 KB
 constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;       // x, w_hi, w_lo = 24 KB
+constexpr uint32_t kEpiPitch = 2 * kN * 4 + 16;               // staging row of the epilogue: 64 floats + 16 bytes of skew
+constexpr uint32_t kEpiBytes = 2 * kBlockM * kEpiPitch;       // out rows + out_drop rows of one tile = 68 KB
 constexpr uint32_t kAccCols = 2 * kN;                         // 2 accumulator stages
 constexpr uint32_t kTmemCols = 512;                           // 64 accumulator + kStages * 64 operand columns (power of 2)
 static_assert(kAccCols + kStages * 2 * kChunk <= kTmemCols, "TMEM budget");
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __shared__ float bias_sh[kN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + kStages * kStageBytes;   // epilogue staging rows behind the ring
   auto full = [&](int s) { return smem_u32(&bars[s]); };
   auto ready = [&](int s) { return smem_u32(&bars[kStages + s]); };
   auto empty = [&](int s) { return smem_u32(&bars[2 * kStages + s]); };
@@ -263,39 +266,52 @@ __global__ void __launch_bounds__(kThreads, 1)
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tempty(a));                                        // the MMA warp may overwrite this accumulator stage
+      // The thread owns one output row, but a row-per-lane 16-byte store is 32 sectors per warp instruction (measured:
+      // ~8 us of LSU time per tile, the last tile's fully exposed). The row is therefore staged in shared memory (272-byte
+      // pitch: conflict-free per quarter warp) and leaves as ONE bulk copy of the whole row per output tensor.
       const int64_t grow = tile * kBlockM + q * 32 + lane;
-      if (grow < n) {
-        float* orow = out + grow * out_stride;
-        float* drow = out_drop ? out_drop + grow * od_stride : nullptr;
-        const uint64_t rk = drow ? pg::drop_rowkey(stepkey, (uint64_t)grow) : 0ull;
-        auto masked = [&](float4 v, int g) {   // dropout of the 4 columns of group g under the drop_hash contract
-          const uint64_t h = pg::drop_mix(rk, colkey_sh[g]);
-          const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
-          v.x = (hl << 16) >= thr_hi ? v.x * drop.scale : 0.f;
-          v.y = hl >= thr_hi ? v.y * drop.scale : 0.f;
-          v.z = (hh << 16) >= thr_hi ? v.z * drop.scale : 0.f;
-          v.w = hh >= thr_hi ? v.w * drop.scale : 0.f;
-          return v;
-        };
+      const uint32_t e_out = epi_base + (uint32_t)(q * 32 + lane) * kEpiPitch, e_drop = e_out + kBlockM * kEpiPitch;
+      const uint32_t row_bytes = (concat ? 2 * kN : kN) * 4;
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's copies have read the staging rows
+      const bool dropping = out_drop != nullptr;
+      const uint64_t rk = dropping ? pg::drop_rowkey(stepkey, (uint64_t)grow) : 0ull;
+      auto masked = [&](float4 v, int g) {   // dropout of the 4 columns of group g under the drop_hash contract
+        const uint64_t h = pg::drop_mix(rk, colkey_sh[g]);
+        const uint32_t hl = (uint32_t)h, hh = (uint32_t)(h >> 32);
+        v.x = (hl << 16) >= thr_hi ? v.x * drop.scale : 0.f;
+        v.y = hl >= thr_hi ? v.y * drop.scale : 0.f;
+        v.z = (hh << 16) >= thr_hi ? v.z * drop.scale : 0.f;
+        v.w = hh >= thr_hi ? v.w * drop.scale : 0.f;
+        return v;
+      };
+      auto sts4 = [](uint32_t addr, float4 v) {
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      };
 #pragma unroll
-        for (int j = 0; j < kN; j += 4) {
-          const float4 z = make_float4(__uint_as_float(r[j]) + bias_sh[j], __uint_as_float(r[j + 1]) + bias_sh[j + 1],
-                                       __uint_as_float(r[j + 2]) + bias_sh[j + 2], __uint_as_float(r[j + 3]) + bias_sh[j + 3]);
-          const float4 p = make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f));
-          if (concat) {
-            *(float4*)(orow + j) = z;
-            *(float4*)(orow + kN + j) = p;
-            if (drow) {
-              *(float4*)(drow + j) = masked(z, j >> 2);
-              *(float4*)(drow + kN + j) = masked(p, (kN + j) >> 2);
-            }
-          } else {
-            *(float4*)(orow + j) = p;
-            if (drow) *(float4*)(drow + j) = masked(p, j >> 2);
+      for (int j = 0; j < kN; j += 4) {
+        const float4 z = make_float4(__uint_as_float(r[j]) + bias_sh[j], __uint_as_float(r[j + 1]) + bias_sh[j + 1],
+                                     __uint_as_float(r[j + 2]) + bias_sh[j + 2], __uint_as_float(r[j + 3]) + bias_sh[j + 3]);
+        const float4 p = make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f));
+        if (concat) {
+          sts4(e_out + j * 4, z);
+          sts4(e_out + (kN + j) * 4, p);
+          if (dropping) {
+            sts4(e_drop + j * 4, masked(z, j >> 2));
+            sts4(e_drop + (kN + j) * 4, masked(p, (kN + j) >> 2));
           }
+        } else {
+          sts4(e_out + j * 4, p);
+          if (dropping) sts4(e_drop + j * 4, masked(p, j >> 2));
         }
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's writes -> visible to its bulk copies
+      if (grow < n) {
+        pg::bulk_s2g(out + grow * out_stride, e_out, row_bytes);
+        if (dropping) pg::bulk_s2g(out_drop + grow * od_stride, e_drop, row_bytes);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // rows are in global memory before the CTA retires
   }
   // ---- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -363,7 +379,7 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
   pm = get_map(d_weight, kN, (uint64_t)K, (uint64_t)K, kN);
   if (!pm) return PG_ERR_INVALID;
   const CUtensorMap tm_w = *pm;
-  const size_t smem = (size_t)kStages * kStageBytes + 1024;
+  const size_t smem = (size_t)kStages * kStageBytes + kEpiBytes + 1024;
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PG_CUDA(cudaFuncSetAttribute(linear_concat_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -738,7 +738,7 @@ pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, i
   a.keep_scale = 1.0f / (1.0f - dropout_p);
   a.drop_seed = dropout_seed; a.drop_step = d_step;
   a.lo = blk->d_layer_offsets;
-  a.hints = env_int("PG_AGG_L2HINT", 1) != 0;
+  a.hints = env_int("PG_AGG_L2HINT", 1);   // 1: hot evict_last / rest evict_first, 2: hot evict_last / rest default, 0: off
   pg::TimedScope timed(PG_T_FUSED, st);
   return pg::launch_agg_rows(a, dev, st);
 }

@@ -77,8 +77,9 @@ def main():
         res = {}
         if a.hot_sweep and mode == "hbm20":
             for hb in a.hot_sweep.split(","):
-                os.environ["PG_AGG_L2HINT"] = "0" if hb == "off" else "1"
-                os.environ["PG_CACHE_HOT_MB"] = "0" if hb == "off" else hb
+                # "off" = no priorities; "N" = N MB hot (evict_last), rest evict_first; "Nn" = rest default priority
+                os.environ["PG_AGG_L2HINT"] = "0" if hb == "off" else ("2" if hb.endswith("n") else "1")
+                os.environ["PG_CACHE_HOT_MB"] = "0" if hb == "off" else hb.rstrip("n")
                 cs._mark_hot(wl.g, None)
                 timeit(fused_only, nfs[:3])
                 res["fused_only_hot%s_ms" % hb] = [timeit(fused_only, nfs), timeit(fused_only, nfs)]
