@@ -236,6 +236,11 @@ pg_status pg_cache_set_peers(pg_cache* c, int field, int world, int rank, const 
  * aligned); pg_aggregate_rows fetches a tagged row with the L2 evict_last priority and the others with evict_first, and
  * masks the bit off. Results are unchanged; NULL switches the hint off. */
 pg_status pg_cache_set_hot(pg_cache* c, const uint8_t* d_hot);
+/* Scheduling knob of the fused path (no reference counterpart): the row-fetching kernel of pg_aggregate_rows / pg_cache_aggregate
+ * runs one CTA per SM and fills the SM's shared memory, so kernels that need more than ~27 KB of it cannot run beside it. A
+ * pipeline that overlaps the input aggregation of the next minibatch with the small latency-bound kernels of the current one
+ * leaves `n` SMs out of that grid for launches made after this call (process-wide; 0 = use every SM, the default). */
+void pg_set_agg_reserve_sms(int n);
 pg_status pg_aggregate_rows(const float* const* d_rowptr, const pg_block* blk, int32_t dim, float* d_dst,
                             int64_t dst_stride, int mode, const float* d_norm, float dropout_p, uint64_t dropout_seed,
                             const int64_t* d_step, int64_t zero_rows_to, void* stream);

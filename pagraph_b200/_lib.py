@@ -74,6 +74,7 @@ SIGNATURES = {
     "pg_cache_set_peers": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp), c_vp,
                                           ctypes.c_int64, ctypes.c_int64, c_vp]),
     "pg_cache_set_hot": (ctypes.c_int, [c_vp, c_vp]),
+    "pg_set_agg_reserve_sms": (None, [ctypes.c_int]),
     "pg_aggregate_rows": (ctypes.c_int, [c_vp, ctypes.POINTER(pg_block), ctypes.c_int32, c_vp, ctypes.c_int64, ctypes.c_int,
                                          c_vp, ctypes.c_float, ctypes.c_uint64, c_vp, ctypes.c_int64, c_vp]),
     "pg_cache_fetch_dyn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(c_vp), c_vp,

@@ -468,7 +468,11 @@ pg_status launch_rows_tma_w(const pg::AggRowsArgs& a, int dev, cudaStream_t st, 
   PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int64_t rows = std::max(a.n_dst, a.zero_rows_to);   // a negative zero_rows_to is bounded by the capacity n_dst
   const int64_t need = std::max<int64_t>(1, (rows + W - 1) / W);
-  const int grid = (int)std::min<int64_t>(need, (int64_t)pg::sm_count(dev));
+  // One CTA fills an SM's shared memory, so nothing that needs more than ~27 KB of it (the classifier head: 93 KB) can
+  // run beside this kernel. A pipeline that wants its small latency-bound kernels to proceed while the input block of the
+  // next minibatch is aggregated leaves a few SMs out of this grid (PG_AGG_RESERVE_SMS / pg_set_agg_reserve_sms).
+  const int sms = std::max(1, pg::sm_count(dev) - pg::agg_reserve_sms());
+  const int grid = (int)std::min<int64_t>(need, (int64_t)sms);
   kern<<<grid, W * 32, smem, st>>>(a, group, depth);
   PG_CHECK_LAUNCH();
   return PG_OK;

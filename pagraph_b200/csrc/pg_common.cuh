@@ -82,6 +82,9 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // ------------------------------------------------------------------ aggregation from per-source row pointers (pg_aggregate.cu)
 // dst[r] = scale_r * sum_{e in [indptr[r], indptr[r+1])} drop(rowptr[cols[e] - col_base][0..dim)), used by the fused
 // cache-lookup + aggregation (pg_cache_aggregate): rowptr[j] points into the HBM cache table or the miss staging buffer.
+// SMs left out of the fused aggregation's grid (0 = none): see launch_rows_tma_w
+int agg_reserve_sms();
+void set_agg_reserve_sms(int n);
 struct AggRowsArgs {
   const int64_t* indptr;
   const int64_t* cols;

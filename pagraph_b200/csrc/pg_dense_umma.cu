@@ -630,9 +630,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(ready(h));
       }
     }
+    // db: the 8 lanes of a warp that share (lane & 3) own the same 8 outputs — fold them with shuffles first (a float
+    // atomicAdd on shared memory is a CAS loop: 1024 of them onto 32 words cost ~12 us of the r2a kernel)
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (dbv[e] != 0.f) atomicAdd(&db_sh[gj0 + e], dbv[e]);
+    for (int e = 0; e < 8; ++e) {
+      float v = dbv[e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4 && v != 0.f) atomicAdd(&db_sh[gj0 + e], v);
+    }
   }
   // ---- epilogue: accumulators -> shared memory (transposed) -> 16-byte vector reductions into dW
   __syncthreads();                                                    // db_sh complete; producers / transform have issued everything
@@ -653,7 +660,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int t = threadIdx.x - 4 * 32;
     const int kvec = K >> 2;
-    for (int i = t; i < kN * kvec; i += 128) {
+    // every CTA adds the same kN x K block: each starts at its own offset so that the CTAs, which finish together, do
+    // not walk the same addresses (= the same L2 slices) in lock step
+    const int total = kN * kvec;
+    const int rounds = (total + 127) / 128;
+    const int r0 = (int)(((uint64_t)blockIdx.x * (uint64_t)rounds) / gridDim.x);
+    for (int rr = 0; rr < rounds; ++rr) {
+      int rnd = r0 + rr;
+      if (rnd >= rounds) rnd -= rounds;
+      const int i = rnd * 128 + t;
+      if (i >= total) continue;
       const int j = i / kvec, c = (i % kvec) << 2;
       const float4 v = *(const float4*)(stage + j * pitch + c);
       atomicAdd((float4*)(dW + (size_t)j * K + c), v);

@@ -1,7 +1,9 @@
 // pg_runtime.cu — error state, pinned host memory, device info, PCIe probe.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <utility>
@@ -34,6 +36,13 @@ int sm_count(int dev) {
   cache[dev] = n;
   return n;
 }
+
+static std::atomic<int> g_agg_reserve{0};
+int agg_reserve_sms() {
+  static const char* env = getenv("PG_AGG_RESERVE_SMS");   // overrides the caller's setting (experiments)
+  return env ? std::max(0, atoi(env)) : g_agg_reserve.load(std::memory_order_relaxed);
+}
+void set_agg_reserve_sms(int n) { g_agg_reserve.store(std::max(0, n), std::memory_order_relaxed); }
 
 void prefer_max_smem(const void* kernel) {
   static std::mutex mu;
@@ -159,6 +168,8 @@ pg_status pg_dropout_keep_mask(uint64_t seed_plus_step, int64_t n_rows, int32_t 
   }
   return PG_OK;
 }
+
+void pg_set_agg_reserve_sms(int n) { pg::set_agg_reserve_sms(n); }
 
 pg_status pg_device_info(int dev, int* sm, size_t* total_mem, size_t* free_mem) {
   pg::DeviceGuard guard(dev);

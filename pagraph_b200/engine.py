@@ -40,6 +40,7 @@ from .ops import _MODES, LinearConcat, LinearCrossEntropy, linear_concat_backwar
 from .parallel import PeerAdam
 
 _RING = 4          # ring slots: compute k | gather k+1 | sampling k+2 .. k+_AHEAD
+_RESERVE_SMS = int(os.environ.get("PG_ENGINE_RESERVE_SMS", "24"))   # SMs the input aggregation leaves to the dense stage's small kernels
 _AHEAD = 1 + max(1, int(os.environ.get("PG_ENGINE_SAMPLERS", "2")))   # sampling runs this many minibatches ahead of compute
 _BUCKET = 4096     # padded-shape granularity of the dense layers
 
@@ -141,6 +142,8 @@ class GCNTrainEngine:
             if self.host_inputs:
                 self.seeds_host = seeds.pin_memory()
                 self.labels_host = labels.cpu()
+                # without duplicate seeds the seed layer IS the batch, in order: its labels are a slice of labels[seeds]
+                self.labels_by_seed_host = None if self.has_dups else self.labels_host[seeds].pin_memory()
             else:
                 self.seeds_dev = seeds.to(self.dev)
                 self.labels_dev = labels.to(self.dev)
@@ -275,9 +278,17 @@ class GCNTrainEngine:
                                       self.stage_rows, _lib.ptr(counts), _lib.ptr(s.ws), st), "pg_cache_resolve")
         m = self.model
         p = m.dropout.p if (m.dropout is not None and m.training) else 0.0
-        _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptr), ctypes.byref(blk), self.F, _lib.ptr(s.agg), s.agg.stride(0),
-                                       _MODES["mean"], None, float(p), self.drop_seed, _lib.ptr(self.load_counter), -_BUCKET,
-                                       st), "pg_aggregate_rows")
+        # The row-fetching kernel fills every SM it runs on (one CTA, ~200 KB of shared memory), so the classifier head of
+        # the PREVIOUS minibatch (93 KB per CTA) could only start when it ends. With the fused dense stage the grid leaves
+        # _RESERVE_SMS SMs free: the 64-wide aggregation, the head and its backward run there beside it (measured at
+        # config 2, minibatches/s: 0 SMs 3287, 16 3586, 24 3633, 32 3619, 48 3422 — profiles/r2e_*).
+        L.pg_set_agg_reserve_sms(_RESERVE_SMS if self._dense_ok else 0)
+        try:
+            _lib.check(L.pg_aggregate_rows(_lib.ptr(s.rowptr), ctypes.byref(blk), self.F, _lib.ptr(s.agg), s.agg.stride(0),
+                                           _MODES["mean"], None, float(p), self.drop_seed, _lib.ptr(self.load_counter),
+                                           -_BUCKET, st), "pg_aggregate_rows")
+        finally:
+            L.pg_set_agg_reserve_sms(0)
         self.load_counter.add_(1)
 
     def _issue_sample(self, k):
@@ -294,16 +305,19 @@ class GCNTrainEngine:
         side.wait_event(s.done)                         # the slot's previous minibatch has been consumed
         with torch.cuda.stream(side):
             if self.host_inputs:                             # this minibatch's inputs: pinned host -> device
-                s.stage_host[:n] = self.seeds_host[lo:lo + n]
                 s.stage_host[self.batch] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
-                s.seeds_key.copy_(s.stage_host, non_blocking=True)
-                batch_seeds = self.seeds_host[lo:lo + n]
-                if self.has_dups:                            # seed-layer order = first occurrences, in order
-                    b = batch_seeds.numpy()
+                if self.labels_by_seed_host is not None:     # seeds and labels straight from the pinned epoch arrays
+                    s.seeds_key[:n].copy_(self.seeds_host[lo:lo + n], non_blocking=True)
+                    s.seeds_key[self.batch:].copy_(s.stage_host[self.batch:], non_blocking=True)
+                    s.labels[:n].copy_(self.labels_by_seed_host[lo:lo + n], non_blocking=True)
+                else:                                        # seed-layer order = first occurrences, in order
+                    s.stage_host[:n] = self.seeds_host[lo:lo + n]
+                    s.seeds_key.copy_(s.stage_host, non_blocking=True)
+                    b = self.seeds_host[lo:lo + n].numpy()
                     first = np.sort(np.unique(b, return_index=True)[1])
                     batch_seeds = torch.from_numpy(b[first])
-                torch.index_select(self.labels_host, 0, batch_seeds, out=s.labels_host[:len(batch_seeds)])
-                s.labels.copy_(s.labels_host, non_blocking=True)
+                    torch.index_select(self.labels_host, 0, batch_seeds, out=s.labels_host[:len(batch_seeds)])
+                    s.labels.copy_(s.labels_host, non_blocking=True)
             else:
                 s.seeds_key[:n].copy_(self.seeds_dev[lo:lo + n], non_blocking=True)
                 s.stage_host[0] = keyword if keyword < 2 ** 63 else keyword - 2 ** 64
@@ -544,7 +558,7 @@ class GCNTrainEngine:
         self._dense_ok = self._dense_fusable()               # decided (and buffers made) outside any stream capture
         if self._dense_ok:
             self._dense_buffers()
-        split = self._dense_ok and not self.serialize and os.environ.get("PG_ENGINE_SPLIT", "0") != "0"
+        split = self._dense_ok and not self.serialize and os.environ.get("PG_ENGINE_SPLIT", "1") != "0"
         if split != self._split:                             # the compute graphs were captured for the other schedule
             torch.cuda.synchronize(self.dev)
             for sl in self.slots:
