@@ -78,6 +78,17 @@ class _Slot:
 
 
 @contextlib.contextmanager
+class _GraphSeq:
+    """CUDA graphs replayed in order on one stream"""
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+
+    def replay(self):
+        for g in self.parts:
+            g.replay()
+
+
 def _capture_guard():
     """No cyclic garbage collection while a stream capture is open: a collected GraphCacheServer / sampler / engine
     would run its destructor (cudaFree, cudaDeviceSynchronize) on the capturing thread and invalidate the capture."""
@@ -265,17 +276,25 @@ class GCNTrainEngine:
         _lib.check(L.pg_sample_keyed(s.sampler, _lib.ptr(s.seeds_key), n_seeds, key, ctypes.byref(nfb), _lib.ptr(s.h_meta),
                                      _lib.ptr(lab_in), _lib.ptr(lab_out), _lib.stream_ptr()), "pg_sample_keyed")
 
-    def _gather_body(self, s):
-        """stage B: resolve + stage the input layer, aggregate block 0; all sized on the device. The frames of layers
-        1..L (which the reference's fetch_data also fills, storage.py:173-187) have no reader in the training step —
-        GCN / GraphSAGE consume the input layer only (gcn_nssc.py:64) — so they are not gathered here."""
+    _GATHER_PARTS = 2    # _gather_body(s, part): 0 = resolve (+ miss fetch), 1 = aggregate; None = both
+
+    def _gather_body(self, s, part=None):
+        """stage B: resolve + stage the input layer (part 0), aggregate block 0 (part 1); all sized on the device. The
+        frames of layers 1..L (which the reference's fetch_data also fills, storage.py:173-187) have no reader in the
+        training step — GCN / GraphSAGE consume the input layer only (gcn_nssc.py:64) — so they are not gathered here.
+        The two parts are separate graphs: the lookup (and, with a partial cache, the PCIe fetch of the missed rows) only
+        needs the sampled minibatch and runs as soon as it exists; the aggregation is what the split schedule orders
+        behind the previous minibatch's NodeUpdate forward."""
         L, c = _lib.lib(), self.cacher
         st = _lib.stream_ptr()
         counts = c._counts if (c.log and not c.full_cached) else None
         blk = _lib.pg_block(_lib.ptr(s.nf["node_mapping"]), _lib.ptr(s.nf["indptr"]), _lib.ptr(s.nf["indices"]), 0,
                             self.cap_n0, s.agg.shape[0], self._meta_ptr(s, 4))
-        _lib.check(L.pg_cache_resolve(c._handle, self.fi, ctypes.byref(blk), _lib.ptr(s.rowptr), _lib.ptr(s.stage),
-                                      self.stage_rows, _lib.ptr(counts), _lib.ptr(s.ws), st), "pg_cache_resolve")
+        if part in (None, 0):
+            _lib.check(L.pg_cache_resolve(c._handle, self.fi, ctypes.byref(blk), _lib.ptr(s.rowptr), _lib.ptr(s.stage),
+                                          self.stage_rows, _lib.ptr(counts), _lib.ptr(s.ws), st), "pg_cache_resolve")
+        if part == 0:
+            return
         m = self.model
         p = m.dropout.p if (m.dropout is not None and m.training) else 0.0
         # The row-fetching kernel fills every SM it runs on (one CTA, ~200 KB of shared memory), so the classifier head of
@@ -348,19 +367,24 @@ class GCNTrainEngine:
         """Enqueue stage B of global minibatch k (after its stage A, and after the event `after` if given)."""
         s = self.slots[k % _RING]
         self.gather.wait_event(s.sampled)
-        if after is not None:
-            self.gather.wait_event(after)
+        parts = tuple(range(self._GATHER_PARTS)) if self._GATHER_PARTS > 1 else (None,)
         with torch.cuda.stream(self.gather):
             self._mark("gather+", k, self.gather)
-            if self.use_graphs:
-                if s.gather_graph is None:
-                    s.gather_graph, s.gather_kernels = self._capture(self.gather, lambda: self._gather_body(s))
-                s.gather_graph.replay()
-                self.launches += s.gather_kernels
-            else:
-                l0 = _lib.launch_count()
-                self._gather_body(s)
-                self.launches += _lib.launch_count() - l0
+            if self.use_graphs and s.gather_graph is None:
+                caught = [self._capture(self.gather, lambda p=p: self._gather_body(s, p) if p is not None else self._gather_body(s))
+                          for p in parts]
+                s.gather_graph, s.gather_kernels = _GraphSeq([g for g, _ in caught]), sum(n for _, n in caught)
+            l0 = _lib.launch_count()
+            for i, p in enumerate(parts):
+                if after is not None and i == len(parts) - 1:        # only the last part (the aggregation) is ordered behind `after`
+                    self.gather.wait_event(after)
+                if self.use_graphs:
+                    s.gather_graph.parts[i].replay()
+                elif p is None:
+                    self._gather_body(s)
+                else:
+                    self._gather_body(s, p)
+            self.launches += s.gather_kernels if self.use_graphs else _lib.launch_count() - l0
             s.loaded.record(self.gather)
             self._mark("gather-", k, self.gather)
         if self.serialize:
@@ -704,6 +728,8 @@ class GCNPreprocessTrainEngine(GCNTrainEngine):
         if not hasattr(self, "_ident"):
             self._ident = torch.arange(self.cap_n0 + 1, dtype=torch.int64, device=dev)  # indptr and cols of the identity block
 
+    _GATHER_PARTS = 1
+
     def _gather_body(self, s):
         L, c = _lib.lib(), self.cacher
         st = _lib.stream_ptr()
@@ -777,6 +803,8 @@ class SageTrainEngine(GCNTrainEngine):
 
     def _fused_spec(self):
         return None
+
+    _GATHER_PARTS = 1
 
     def _gather_body(self, s):
         L, c = _lib.lib(), self.cacher
