@@ -640,10 +640,20 @@ def gather_only(tr, n_batches, hbm_peak, pcie_peak):
     return out
 
 
+_T0 = time.time()
+
+
+def note(msg):
+    """progress on stderr (rank 0): where the time of a run goes, and where a run that hangs stopped"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench %7.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
     """value (device-resident inputs) and e2e (host inputs + loss read back) of one cache mode."""
     res = {}
     for host_inputs in (False, True):
+        note("mode %s, host inputs %s: trainer" % (mode, host_inputs))
         tr = Trainer(wl, mode, host_inputs)
         gate = None
         if not host_inputs and not args.no_parity_gate:
@@ -661,7 +671,9 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
                     err = "parity gate failed on rank 0"
             if err:
                 raise SystemExit(err)
+        note("warm-up")
         tr.run(args.warmup, record=False, read_loss=host_inputs)
+        note("timed region")
         clock = None
         if wl.rank == 0:
             clock = ClockSampler(wl.dev)
@@ -673,6 +685,7 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
         reg = timed_region(tr, args.steps, host_inputs, clock, world)
         if prof:
             torch.cuda.profiler.stop()
+        note("timed region done: %.4f ms/step" % (reg["ms"] / args.steps))
         replicas = replica_check(tr, world)
         if not replicas:
             raise SystemExit("replica check: ranks hold different parameters after %d steps" % args.steps)
@@ -684,6 +697,7 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
             # three-stream pipeline as it runs (avg_ms_in_pipeline: what contention between the stages adds)
             steps_total, misses_total, sizes_total = len(tr.sizes), reg["misses"], tr.sizes
             ksteps = min(args.kernel_steps, args.steps)
+            note("per-kernel passes")
             tr.engine.use_graphs = False
             kreg = timed_region(tr, ksteps, host_inputs, None, world)
             kern_pipe, _, _ = kernel_report(tr, kreg, hbm_peak, pcie_peak)
@@ -713,6 +727,7 @@ def run_mode(wl, mode, args, world, hbm_peak, pcie_peak):
             N, M = sum(lo[-1] for lo, _ in tr.sizes), misses_total
         else:
             kern, N, M = kernel_report(tr, reg, hbm_peak, pcie_peak)
+        note("gather-only pass")
         gather = gather_only(tr, args.gather_batches, hbm_peak, pcie_peak) if not host_inputs else None
         steps = args.steps
         mbps = world * steps / (reg["ms"] * 1e-3)
@@ -1093,6 +1108,11 @@ def main_ours(args):
     _lib.check(_lib.lib().pg_measure_h2d(dev.index, 1 << 30, 5, ctypes.byref(bw)), "pg_measure_h2d")
     pcie_peak = bw.value
     t_setup = time.time()
+    watchdog = int(os.environ.get("PG_BENCH_WATCHDOG", "0"))
+    if watchdog > 0:                       # a hung run leaves the Python stacks of every thread on stderr
+        import faulthandler
+        faulthandler.dump_traceback_later(watchdog, repeat=True, file=sys.stderr)
+    note("workload")
     wl = Workload(args, rank, world, dev)
     modes = args.modes.split(",")
     results = {}
@@ -1102,6 +1122,7 @@ def main_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        note("cpu baseline")
         threads = host_threads()
         indptr, indices = wl.host_graph()
         tables = {f: wl.store.ndata[f] for f in args.fields}
@@ -1115,6 +1136,7 @@ def main_ours(args):
         cpu = {"value": args.cpu_batches / t, "unit": "minibatches/s", "cores": threads, "kind": "port",
                "sample": "%d full minibatches, oracle port, %d threads" % (args.cpu_batches, threads),
                "stage_s": {k: round(v, 3) for k, v in stage.items()}}
+    note("done")
     wl.close()
     if rank != 0:
         return

@@ -424,9 +424,10 @@ constexpr int kDwHalf = 16;                       // rows per TMEM operand stage
 constexpr int kDwFB = 5;                          // feature blocks of 128 (K <= 640)
 constexpr int kDwXStages = 2;                     // x ring (super-chunks)
 constexpr uint32_t kDwBoxBytes = kDwRows * 128 * 4;                    // [32 rows x 128 features] = 16 KB
-constexpr uint32_t kDwXStageBytes = kDwFB * kDwBoxBytes;               // 80 KB
+constexpr uint32_t kDwGBytes = kDwRows * 2 * kN * 4;                   // staged [32 rows x 64] box of grad_out / of y = 8 KB
+constexpr uint32_t kDwXStageBytes = kDwFB * kDwBoxBytes + 2 * kDwGBytes;   // x (80 KB) + grad_out + y rows = 96 KB
 constexpr uint32_t kDwBBytes = kN * kDwRows * 4;                       // one gz^T plane = 4 KB
-constexpr uint32_t kDwSmemBytes = kDwXStages * kDwXStageBytes + 2 * 2 * kDwBBytes;   // 160 KB + 16 KB
+constexpr uint32_t kDwSmemBytes = kDwXStages * kDwXStageBytes + 2 * 2 * kDwBBytes;   // 192 KB + 16 KB
 constexpr uint32_t kDwAccCols = kDwFB * kN;                            // 160
 constexpr uint32_t kDwOpStageCols = kDwFB * 2 * kDwHalf;               // 160
 
@@ -438,16 +439,24 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// Work counters of the dW kernel: {next super-chunk, CTAs that have exited}, one pair per launch slot (launches take the
+// slots round-robin; the last CTA of a launch zeroes its pair again, so a captured launch can be replayed).
+constexpr int kDwCounterSlots = 64;
+__device__ unsigned g_dw_counters[kDwCounterSlots][2];
+
 __global__ void __launch_bounds__(kThreads, 1)
-    linear_concat_dw_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ gout, int64_t g_stride,
-                                 const float* __restrict__ y, int64_t y_stride, int64_t n, int K, int concat, UmmaDrop drop,
-                                 float* __restrict__ dW, float* __restrict__ db) {
+    linear_concat_dw_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+                                 const __grid_constant__ CUtensorMap tm_y, int64_t n, int K, int concat, UmmaDrop drop,
+                                 float* __restrict__ dW, float* __restrict__ db, unsigned* __restrict__ counters) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // xfull[2], xempty[2] (x ring) | ready[2], opfree[2] (TMEM operand stages) | bfree[2] (gz^T buffers) | done
   __shared__ __align__(8) uint64_t bars[2 * kDwXStages + 4 + 2 + 1];
   __shared__ uint32_t tmem_base_sh;
   __shared__ uint64_t colkey_sh[16];
   __shared__ float db_sh[kN];
+  __shared__ int sc_ring[4];            // super-chunk index of iteration it (slot it & 3), -1 = no work left
+  __shared__ volatile int stop_sh;      // the transform warps found the end marker (read by the MMA issuer)
+  __shared__ volatile int iters_sh;     // super-chunks this CTA has accumulated
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + kDwXStages * kDwXStageBytes;     // [buf][plane] gz^T tiles, 1024-byte aligned
@@ -459,6 +468,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t done = smem_u32(&bars[2 * kDwXStages + 6]);
   const int nfb = (K + 127) / 128;
   const int64_t nsc = (n + kDwRows - 1) / kDwRows;                      // super-chunks
+  const int gcols = concat ? 2 * kN : kN;                               // columns of grad_out and of y
+  const uint32_t g_bytes = (uint32_t)(kDwRows * gcols * 4);             // one staged [32 rows x gcols] box
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDwXStages; ++s) {
@@ -471,6 +482,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(bfree(h), 1);
     }
     mbar_init(done, 1);
+    stop_sh = 0;
+    iters_sh = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 16) colkey_sh[threadIdx.x] = pg::drop_colkey((uint32_t)threadIdx.x);
@@ -486,26 +499,41 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_opnd = tmem_base + kDwAccCols;
 
   if (warp == 0) {
-    // ================================================================== TMA producer: x super-chunks
+    // ================================================================== TMA producer: x, grad_out and y rows of a super-chunk
+    // Super-chunks are handed out by an atomic counter, not by a fixed stride: in the training pipeline this kernel
+    // starts on the few SMs the input aggregation of the next minibatch leaves free and gets the rest of the GPU when
+    // that kernel ends — the CTAs that start early simply take more of the work.
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t sc = blockIdx.x; sc < nsc; sc += gridDim.x, ++it) {
+      for (uint32_t it = 0;; ++it) {
         const int s = it % kDwXStages;
         mbar_wait(xempty(s), ((it / kDwXStages) & 1) ^ 1);
-        mbar_expect_tx(xfull(s), (uint32_t)nfb * kDwBoxBytes);
-        for (int fb = 0; fb < nfb; ++fb)
-          tma_load_2d(smem_base + s * kDwXStageBytes + fb * kDwBoxBytes, &tm_x, fb * 128, (int)(sc * kDwRows), xfull(s));
+        const unsigned sc = atomicAdd(&counters[0], 1u);
+        if ((int64_t)sc >= nsc) {
+          sc_ring[it & 3] = -1;
+          mbar_arrive(xfull(s));                                     // end marker: a phase without bytes
+          break;
+        }
+        sc_ring[it & 3] = (int)sc;
+        const uint32_t st = smem_base + s * kDwXStageBytes;
+        mbar_expect_tx(xfull(s), (uint32_t)nfb * kDwBoxBytes + 2 * g_bytes);
+        for (int fb = 0; fb < nfb; ++fb) tma_load_2d(st + fb * kDwBoxBytes, &tm_x, fb * 128, (int)(sc * kDwRows), xfull(s));
+        tma_load_2d(st + kDwFB * kDwBoxBytes, &tm_g, 0, (int)(sc * kDwRows), xfull(s));
+        tma_load_2d(st + kDwFB * kDwBoxBytes + kDwGBytes, &tm_y, 0, (int)(sc * kDwRows), xfull(s));
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t sc = blockIdx.x; sc < nsc; sc += gridDim.x, ++it) {
+      for (uint32_t it = 0;; ++it) {
         const int b = it & 1;
         const uint64_t b_hi = umma_desc_k_sw128(b_base + b * 2 * kDwBBytes), b_lo = umma_desc_k_sw128(b_base + b * 2 * kDwBBytes + kDwBBytes);
+        bool stop = false;
         for (int h = 0; h < 2; ++h) {
           mbar_wait(ready(h), it & 1);                               // x^T half in TMEM, gz^T tile in shared memory
+          if (h == 0 && stop_sh) {                                   // (or: the end marker)
+            stop = true;
+            break;
+          }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int fb = 0; fb < nfb; ++fb) {
             const uint32_t d = tmem_base + fb * kN;
@@ -521,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           umma_commit(opfree(h));                                    // TMEM operand stage h reusable
         }
+        if (stop) break;
         umma_commit(bfree(b));                                       // gz^T buffer b reusable
       }
       umma_commit(done);
@@ -533,36 +562,37 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t thr_hi = drop.thr << 16;
     const int gr = tt >> 2, gj0 = (tt & 3) * 8;                      // gz: row gr of the super-chunk, outputs gj0 .. gj0 + 7
     float dbv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    // raw operands of gz for one (row, 8 outputs): loaded one super-chunk ahead so that the global-load latency is
-    // hidden behind the x^T fill of the current one
-    float4 ga[2], gb[2], gy[2];
-    auto load_g = [&](int64_t sc) {
-      const int64_t r = sc * kDwRows + gr;
-      ga[0] = ga[1] = gb[0] = gb[1] = gy[0] = gy[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (sc < nsc && r < n) {
-        const float* grow = gout + r * g_stride;
-        const float* yrow = y + r * y_stride;
-        ga[0] = __ldg((const float4*)(grow + gj0));
-        ga[1] = __ldg((const float4*)(grow + gj0 + 4));
-        if (concat) {
-          gb[0] = __ldg((const float4*)(grow + kN + gj0));
-          gb[1] = __ldg((const float4*)(grow + kN + gj0 + 4));
-          gy[0] = __ldg((const float4*)(yrow + kN + gj0));
-          gy[1] = __ldg((const float4*)(yrow + kN + gj0 + 4));
-        } else {
-          gy[0] = __ldg((const float4*)(yrow + gj0));
-          gy[1] = __ldg((const float4*)(yrow + gj0 + 4));
-        }
-      }
+    const uint32_t g_off = (uint32_t)(gr * gcols + gj0) * 4u;        // this thread's 8 values inside a staged [32 x gcols] box
+    auto lds4 = [](uint32_t addr) {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+      return v;
     };
-    load_g(blockIdx.x);
     uint32_t it = 0;
-    for (int64_t sc = blockIdx.x; sc < nsc; sc += gridDim.x, ++it) {
+    for (;; ++it) {
       const int s = it % kDwXStages, b = it & 1;
-      // ---- gz of this thread's (row, 8 outputs)
-      const int64_t r = sc * kDwRows + gr;
+      mbar_wait(xfull(s), (it / kDwXStages) & 1);                    // x, grad_out and y rows of the super-chunk are staged
+      const int sc = ((volatile int*)sc_ring)[it & 3];
+      if (sc < 0) break;
+      const uint32_t st = smem_base + s * kDwXStageBytes;
+      // ---- gz of this thread's (row, 8 outputs); rows beyond n were zero-filled by the TMA
+      const int64_t r = (int64_t)sc * kDwRows + gr;
       float gzv[8];
       {
+        const uint32_t gs = st + kDwFB * kDwBoxBytes + g_off, ys = gs + kDwGBytes;
+        float4 ga[2], gb[2], gy[2];
+        ga[0] = lds4(gs);
+        ga[1] = lds4(gs + 16);
+        if (concat) {
+          gb[0] = lds4(gs + kN * 4);
+          gb[1] = lds4(gs + kN * 4 + 16);
+          gy[0] = lds4(ys + kN * 4);
+          gy[1] = lds4(ys + kN * 4 + 16);
+        } else {
+          gb[0] = gb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          gy[0] = lds4(ys);
+          gy[1] = lds4(ys + 16);
+        }
         const uint64_t rk = drop.thr ? pg::drop_rowkey(stepkey, (uint64_t)r) : 0ull;
         auto factor4 = [&](int g, float (&f)[4]) {                   // keep-scale of the 4 columns of group g
           const uint64_t h = pg::drop_mix(rk, colkey_sh[g]);
@@ -592,7 +622,6 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
-      load_g(sc + gridDim.x);                                          // next super-chunk's operands, in flight from here on
       // ---- gz^T tile: output j is a 128-byte row, minibatch row gr the element inside it (SWIZZLE_128B K-major)
       mbar_wait(bfree(b), ((it >> 1) & 1) ^ 1);
       {
@@ -607,8 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       // ---- x^T: feature lane tt of every block, 16 rows per TMEM operand stage
-      mbar_wait(xfull(s), (it / kDwXStages) & 1);
-      const uint32_t sx = smem_base + s * kDwXStageBytes + (uint32_t)tt * 4u;
+      const uint32_t sx = st + (uint32_t)tt * 4u;
       for (int h = 0; h < 2; ++h) {
         mbar_wait(opfree(h), (it & 1) ^ 1);                          // the MMAs of the previous super-chunk's half h are done
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -630,6 +658,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(ready(h));
       }
     }
+    // end marker: tell the MMA issuer (it waits on ready(0) of this iteration) and the epilogue how much was done. As in a
+    // working iteration the arrival is ordered behind the MMAs of the previous super-chunk's half 0 — the issuer has then
+    // consumed ready(0)'s previous phase, so the barrier can never run two phases ahead of the thread that polls it.
+    if (it > 0) mbar_wait(opfree(0), (it & 1) ^ 1);
+    if (tt == 0) {
+      stop_sh = 1;
+      iters_sh = (int)it;
+    }
+    mbar_arrive(ready(0));
     // db: the 8 lanes of a warp that share (lane & 3) own the same 8 outputs — fold them with shuffles first (a float
     // atomicAdd on shared memory is a CAS loop: 1024 of them onto 32 words cost ~12 us of the r2a kernel)
 #pragma unroll
@@ -642,10 +679,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
   // ---- epilogue: accumulators -> shared memory (transposed) -> 16-byte vector reductions into dW
-  __syncthreads();                                                    // db_sh complete; producers / transform have issued everything
-  if (warp >= 4 && warp < 8) {
+  __syncthreads();                                                    // db_sh / iters_sh complete; producers / transform have issued everything
+  // Every CTA waits for the issuer's last commit, also one that got no work: the commit's arrival is asynchronous, and a
+  // CTA that exits before it lands leaves a stray arrive for whatever the next CTA on this SM keeps at that address.
+  if (warp >= 4 && warp < 8) mbar_wait(done, 0);
+  if (warp >= 4 && warp < 8 && iters_sh > 0) {                        // a CTA that got no work has nothing to add
     const int q = warp & 3;
-    mbar_wait(done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* stage = (float*)(smem + (smem_base - smem_u32(smem)));     // [32 outputs][nfb * 128 + 4] floats, reuses the x ring
     const int pitch = nfb * 128 + 4;
@@ -679,6 +718,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  if (threadIdx.x == 0) {                                             // the last CTA to leave re-arms the counters for a replay
+    __threadfence();
+    if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) {
+      counters[0] = 0;
+      counters[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 int make_map_plain(EncodeTiledFn enc, CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t row_stride_floats,
@@ -712,21 +759,31 @@ pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float*
     }
     enc = (EncodeTiledFn)fn;
   }
-  struct MapEntry { const float* base; uint64_t rows, cols, stride; CUtensorMap map; };
-  static MapEntry cache[8];
+  // tensor maps of the most recent (pointer, shape, box) tuples: the training loop calls with the same persistent buffers
+  struct MapEntry { const float* base; uint64_t rows, cols, stride; uint32_t bc, br; CUtensorMap map; };
+  static MapEntry cache[16];
   static int next_slot = 0;
-  const CUtensorMap* pm = nullptr;
-  for (MapEntry& e : cache)
-    if (e.base == d_x && e.rows == (uint64_t)n && e.cols == (uint64_t)K && e.stride == (uint64_t)x_stride) pm = &e.map;
-  if (!pm) {
+  auto get_map = [&](const float* base, uint64_t rows, uint64_t cols, uint64_t stride, uint32_t bc, uint32_t br) -> const CUtensorMap* {
+    for (MapEntry& e : cache)
+      if (e.base == base && e.rows == rows && e.cols == cols && e.stride == stride && e.bc == bc && e.br == br) return &e.map;
     MapEntry& e = cache[next_slot];
-    next_slot = (next_slot + 1) % 8;
+    next_slot = (next_slot + 1) % 16;
     e.base = nullptr;
-    if (make_map_plain(enc, &e.map, d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, 128, kDwRows)) return PG_ERR_INVALID;
-    e.base = d_x; e.rows = (uint64_t)n; e.cols = (uint64_t)K; e.stride = (uint64_t)x_stride;
-    pm = &e.map;
-  }
+    if (make_map_plain(enc, &e.map, base, rows, cols, stride, bc, br)) return nullptr;
+    e.base = base; e.rows = rows; e.cols = cols; e.stride = stride; e.bc = bc; e.br = br;
+    return &e.map;
+  };
+  // each map is copied out before the next lookup (an insertion may recycle the slot a previous lookup returned)
+  const uint32_t gcols = concat ? 2 * kN : kN;
+  const CUtensorMap* pm = get_map(d_x, (uint64_t)n, (uint64_t)K, (uint64_t)x_stride, 128, kDwRows);
+  if (!pm) return PG_ERR_INVALID;
   const CUtensorMap tm_x = *pm;
+  pm = get_map(d_gout, (uint64_t)n, gcols, (uint64_t)g_stride, gcols, kDwRows);
+  if (!pm) return PG_ERR_INVALID;
+  const CUtensorMap tm_g = *pm;
+  pm = get_map(d_y, (uint64_t)n, gcols, (uint64_t)y_stride, gcols, kDwRows);
+  if (!pm) return PG_ERR_INVALID;
+  const CUtensorMap tm_y = *pm;
   const size_t smem = (size_t)kDwSmemBytes + 1024;
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -741,7 +798,11 @@ pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float*
   drop.step = d_step;
   const int64_t nsc = (n + kDwRows - 1) / kDwRows;
   const int grid = (int)std::min<int64_t>(nsc, (int64_t)pg::sm_count(dev));
-  linear_concat_dw_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, d_gout, g_stride, d_y, y_stride, n, K, concat, drop, d_gw, d_gb);
+  static unsigned* counters = nullptr;
+  static int launch_seq = 0;
+  if (!counters) PG_CUDA(cudaGetSymbolAddress((void**)&counters, g_dw_counters));
+  unsigned* ctr = counters + 2 * (launch_seq++ % kDwCounterSlots);   // zero at rest: the previous user's last CTA re-armed it
+  linear_concat_dw_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_g, tm_y, n, K, concat, drop, d_gw, d_gb, ctr);
   PG_CHECK_LAUNCH();
   return PG_OK;
 }

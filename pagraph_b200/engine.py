@@ -77,7 +77,6 @@ class _Slot:
     pass
 
 
-@contextlib.contextmanager
 class _GraphSeq:
     """CUDA graphs replayed in order on one stream"""
 
@@ -89,6 +88,7 @@ class _GraphSeq:
             g.replay()
 
 
+@contextlib.contextmanager
 def _capture_guard():
     """No cyclic garbage collection while a stream capture is open: a collected GraphCacheServer / sampler / engine
     would run its destructor (cudaFree, cudaDeviceSynchronize) on the capturing thread and invalidate the capture."""
