@@ -305,13 +305,19 @@ pg_status pg_block_linear_cross_entropy(const int64_t* d_indptr_base, const int6
  *   pg_allreduce_adam: d_grad is replaced by the rank-averaged gradient; d_param / d_exp_avg / d_exp_avg_sq are updated in
  *     place with torch.optim.Adam's formulas (no amsgrad). d_step: the optimizer's step count for THIS step (float, on
  *     the device, already incremented); d_step_id: a step number >= 1 on the device that is equal on all ranks and grows
- *     by one per call (it is the flag value peers wait for). world == 1 degenerates to the optimizer step. */
+ *     by one per call (it is the flag value peers wait for). world == 1 degenerates to the optimizer step.
+ *   pg_allreduce_adam_next: the same step, but *d_step and *d_step_id hold the counts BEFORE it: the kernel works with
+ *     count + 1 and leaves the incremented counts behind (the last CTA to finish writes them), which takes the two
+ *     one-element increment kernels of `optimizer.step()` off the critical path of a captured training step. */
 pg_status pg_peer_group_create(int world, int rank, int64_t n, int dev, pg_peer_group** out, unsigned char* handle_out);
 pg_status pg_peer_group_connect(pg_peer_group* g, const unsigned char* handles);
 void pg_peer_group_destroy(pg_peer_group* g);
 pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
                             const float* d_step, const int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
                             float weight_decay, void* stream);
+pg_status pg_allreduce_adam_next(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                                 float* d_step, int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, void* stream);
 
 /* ---------------------------------------------------------------- offline partitioner (host code, host pointers)
  * The streaming "dg" assignment of PaGraph/partition/dg.py:59-103, same assignments bit for bit (see pg_partition.cu).

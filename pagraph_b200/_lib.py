@@ -110,6 +110,8 @@ SIGNATURES = {
     "pg_peer_group_destroy": (None, [c_vp]),
     "pg_allreduce_adam": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_float,
                                          ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp]),
+    "pg_allreduce_adam_next": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_float,
+                                              ctypes.c_float, ctypes.c_float, ctypes.c_float, c_vp]),
     "pg_partition_dg": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                        c_vp, c_vp]),
     "pg_measure_h2d": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int,

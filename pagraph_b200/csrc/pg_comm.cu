@@ -39,7 +39,7 @@ struct AdamArgs {
   float* grad;
   float* exp_avg;
   float* exp_avg_sq;
-  const float* step;       // optimizer step count (already incremented for this step), device scalar
+  float* step;             // optimizer step count, device scalar (already incremented for this step unless `advance`)
   float lr, beta1, beta2, eps, weight_decay;
 };
 
@@ -63,13 +63,17 @@ __device__ __forceinline__ void adam_one(const AdamArgs& ad, int64_t i, float g,
   ad.param[i] = p - step_size * m / (sqrtf(v) / bc2_sqrt + ad.eps);
 }
 
-__global__ void __launch_bounds__(kCommThreads) allreduce_adam_kernel(PeerArgs pa, AdamArgs ad, const int64_t* step_id_ptr) {
-  const unsigned long long step_id = (unsigned long long)*step_id_ptr;
+// advance != 0: the two step counters hold the counts BEFORE this step; the kernel works with count + 1 and the last CTA to
+// finish (ticket) writes the new counts back — every CTA has read them by then. Saves the two one-element increment
+// kernels that would otherwise sit in front of this one on the critical path of the training step.
+__global__ void __launch_bounds__(kCommThreads) allreduce_adam_kernel(PeerArgs pa, AdamArgs ad, int64_t* step_id_ptr, int advance,
+                                                                      unsigned* ticket) {
+  const unsigned long long step_id = (unsigned long long)*step_id_ptr + (advance ? 1ull : 0ull);
   const uint32_t flag = (uint32_t)step_id;
   const int parity = (int)(step_id & 1);
   const int W = pa.world, me = pa.rank;
   const int64_t lines = pa.n_pad / 2;                      // one line = two gradient floats
-  const float step = *ad.step;
+  const float step = *ad.step + (advance ? 1.0f : 0.0f);
   const float bc1 = 1.0f - powf(ad.beta1, step), bc2 = 1.0f - powf(ad.beta2, step);
   const float step_size = ad.lr / bc1, bc2_sqrt = sqrtf(bc2), inv_w = 1.0f / (float)W;
   const int64_t nth = (int64_t)gridDim.x * kCommThreads;
@@ -122,6 +126,14 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_adam_kernel(PeerArgs p
       if (i + 1 < pa.n) adam_one(ad, i + 1, s1, step_size, bc2_sqrt);
     }
   }
+  if (advance) {
+    __syncthreads();                                       // every thread of the CTA has read the counters
+    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0;                                         // re-armed for the next launch (stream-ordered behind this one)
+      *step_id_ptr = (int64_t)step_id;
+      *ad.step = step;
+    }
+  }
 }
 
 }  // namespace
@@ -132,6 +144,7 @@ struct pg_peer_group {
   void* local = nullptr;                 // my region (cudaMalloc)
   void* opened[PG_MAX_RANKS] = {nullptr};
   size_t region_bytes = 0;
+  unsigned* ticket = nullptr;            // CTA ticket of the counter-advancing launch (zero at rest)
 };
 
 static size_t region_bytes_for(int world, int64_t n_pad) { return (size_t)2 * world * (n_pad / 2) * sizeof(uint4); }
@@ -159,6 +172,8 @@ pg_status pg_peer_group_create(int world, int rank, int64_t n, int dev, pg_peer_
     return PG_ERR_NOMEM;
   }
   PG_CUDA(cudaMemset(g->local, 0, g->region_bytes));
+  PG_CUDA(cudaMalloc((void**)&g->ticket, 256));
+  PG_CUDA(cudaMemset(g->ticket, 0, 256));
   g->args.recv[rank] = (uint4*)g->local;
   cudaIpcMemHandle_t h;
   memset(&h, 0, sizeof(h));
@@ -191,6 +206,7 @@ void pg_peer_group_destroy(pg_peer_group* g) {
   for (int p = 0; p < PG_MAX_RANKS; ++p)
     if (g->opened[p]) cudaIpcCloseMemHandle(g->opened[p]);
   cudaFree(g->local);
+  cudaFree(g->ticket);
   cudaGetLastError();
   delete g;
 }
@@ -239,9 +255,9 @@ pg_status pg_peer_free(void* d_ptr, int dev) {
   return PG_OK;
 }
 
-pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
-                            const float* d_step, const int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
-                            float weight_decay, void* stream) {
+static pg_status allreduce_adam_launch(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                                       float* d_step, int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
+                                       float weight_decay, int advance, void* stream) {
   PG_REQUIRE(g && d_param && d_grad && d_exp_avg && d_exp_avg_sq && d_step && d_step_id, "pg_allreduce_adam: null argument");
   for (int p = 0; p < g->args.world; ++p)
     PG_REQUIRE(g->args.recv[p] != nullptr, "pg_allreduce_adam: peer group is not connected");
@@ -249,9 +265,23 @@ pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, flo
   AdamArgs ad{d_param, d_grad, d_exp_avg, d_exp_avg_sq, d_step, lr, beta1, beta2, eps, weight_decay};
   pg::TimedScope timed(PG_T_OPT, (cudaStream_t)stream);
   pg::prefer_max_smem_k(allreduce_adam_kernel);
-  allreduce_adam_kernel<<<g->ctas, kCommThreads, 0, (cudaStream_t)stream>>>(g->args, ad, d_step_id);
+  allreduce_adam_kernel<<<g->ctas, kCommThreads, 0, (cudaStream_t)stream>>>(g->args, ad, d_step_id, advance, g->ticket);
   PG_CHECK_LAUNCH();
   return PG_OK;
+}
+
+pg_status pg_allreduce_adam(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                            const float* d_step, const int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, void* stream) {
+  return allreduce_adam_launch(g, d_param, d_grad, d_exp_avg, d_exp_avg_sq, (float*)d_step, (int64_t*)d_step_id, lr, beta1, beta2,
+                               eps, weight_decay, 0, stream);
+}
+
+pg_status pg_allreduce_adam_next(pg_peer_group* g, float* d_param, float* d_grad, float* d_exp_avg, float* d_exp_avg_sq,
+                                 float* d_step, int64_t* d_step_id, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, void* stream) {
+  return allreduce_adam_launch(g, d_param, d_grad, d_exp_avg, d_exp_avg_sq, d_step, d_step_id, lr, beta1, beta2, eps, weight_decay,
+                               1, stream);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "pg_common.cuh"
 
@@ -39,10 +40,11 @@ constexpr int kThreads = 12 * 32;
 constexpr uint32_t kXBytes = kBlockM * kChunk * 4;            // 16 KB
 constexpr uint32_t kWBytes = kN * kChunk * 4;                 // 4 KB
 constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;       // x, w_hi, w_lo = 24 KB
-constexpr uint32_t kEpiPitch = 2 * kN * 4 + 16;               // staging row of the epilogue: 64 floats + 16 bytes of skew
-constexpr uint32_t kEpiBytes = 2 * kBlockM * kEpiPitch;       // out rows + out_drop rows of one tile = 68 KB
-constexpr uint32_t kAccCols = 2 * kN;                         // 2 accumulator stages
-constexpr uint32_t kTmemCols = 512;                           // 64 accumulator + kStages * 64 operand columns (power of 2)
+constexpr uint32_t kEpiBoxBytes = kBlockM * kN * 4;            // one [128 rows x 32 floats] store box (SWIZZLE_128B) = 16 KB
+constexpr uint32_t kEpiBytes = 4 * kEpiBoxBytes;              // z / relu z halves of out and of out_drop = 64 KB
+constexpr uint32_t kAccStage = 2 * kN;                        // accumulator stage: [x_hi W_hi + x_lo W_hi | x_hi W_lo]
+constexpr uint32_t kAccCols = 2 * kAccStage;                  // 2 accumulator stages
+constexpr uint32_t kTmemCols = 512;                           // 128 accumulator + kStages * 64 operand columns (power of 2)
 static_assert(kAccCols + kStages * 2 * kChunk <= kTmemCols, "TMEM budget");
 
 using pg::smem_u32;
@@ -68,6 +70,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
 // K-major SWIZZLE_128B operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart, tile base 1024-byte aligned):
 // cute::UMMA::SmemDescriptor with version 1, layout_type 2, LBO 1, SBO 64 (both in 16-byte units)
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
@@ -80,15 +86,20 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 // cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), K-major both, N >> 3 at 17, M >> 4 at 24
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+constexpr uint32_t kIdesc = umma_idesc(kN);            // N = 32
+constexpr uint32_t kIdesc2 = umma_idesc(2 * kN);       // N = 64: B = [hi plane ; lo plane], two products per instruction
 
 // D[tmem] (+)= A[tmem] * B[smem]^T
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate,
+                                             uint32_t idesc = kIdesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives when all prior MMAs of this thread are done
@@ -127,8 +138,8 @@ struct UmmaDrop {
 
 __global__ void __launch_bounds__(kThreads, 1)
     linear_concat_fwd_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                                  const float* __restrict__ bias, int64_t n, int K, int concat, float* __restrict__ out,
-                                  int64_t out_stride, float* __restrict__ out_drop, int64_t od_stride, UmmaDrop drop) {
+                                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_drop,
+                                  const float* __restrict__ bias, int64_t n, int K, int concat, int dropping, UmmaDrop drop) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[3 * kStages + 4];   // full[s], ready[s], empty[s], tmem_full[2], tmem_empty[2]
   __shared__ uint32_t tmem_base_sh;
@@ -191,20 +202,23 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int a = tl & 1;
         mbar_wait(tempty(a), ((tl >> 1) & 1) ^ 1);                   // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem_base + a * kN;
+        const uint32_t d = tmem_base + a * kAccStage;
         for (int c = 0; c < nchunks; ++c, ++it) {
           const int s = it % kStages;
           mbar_wait(ready(s), (it / kStages) & 1);                   // x_hi / x_lo in TMEM, W_lo in shared memory
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_base + s * kStageBytes;
           const uint32_t a_hi = tmem_opnd + s * 2 * kChunk, a_lo = a_hi + kChunk;
-          const uint64_t b_hi = umma_desc_k_sw128(st + kXBytes), b_lo = umma_desc_k_sw128(st + kXBytes + kWBytes);
+          // An MMA with the A operand in tensor memory is paced by that operand's read (4 KB per instruction: ~64 clk in the
+          // r2l profile, whatever N is), so the two products of x_hi go out as ONE instruction with N = 64 — its B tile is
+          // the W_hi box and the W_lo plane behind it, 64 rows of 128 bytes — into columns [x W_hi | x W_lo] of the stage;
+          // x_lo W_hi follows with N = 32 into the first 32. The epilogue adds the two halves.
+          const uint64_t b_hi = umma_desc_k_sw128(st + kXBytes);
 #pragma unroll
           for (int k = 0; k < kChunk / kUmmaK; ++k) {
             const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
-            umma_tf32_ts(d, a_lo + k * kUmmaK, b_hi + adv, (c | k) != 0);   // small terms first
-            umma_tf32_ts(d, a_hi + k * kUmmaK, b_lo + adv, 1);
-            umma_tf32_ts(d, a_hi + k * kUmmaK, b_hi + adv, 1);
+            umma_tf32_ts(d, a_hi + k * kUmmaK, b_hi + adv, (c | k) != 0, kIdesc2);
+            umma_tf32_ts(d, a_lo + k * kUmmaK, b_hi + adv, 1, kIdesc);
           }
           umma_commit(empty(s));                                     // ring slot + TMEM operand stage reusable
         }
@@ -261,19 +275,25 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int a = tl & 1;
       mbar_wait(tfull(a), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * kN, r);
+      uint32_t r[32], r2[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStage, r);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccStage + kN, r2);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tempty(a));                                        // the MMA warp may overwrite this accumulator stage
-      // The thread owns one output row, but a row-per-lane 16-byte store is 32 sectors per warp instruction (measured:
-      // ~8 us of LSU time per tile, the last tile's fully exposed). The row is therefore staged in shared memory (272-byte
-      // pitch: conflict-free per quarter warp) and leaves as ONE bulk copy of the whole row per output tensor.
-      const int64_t grow = tile * kBlockM + q * 32 + lane;
-      const uint32_t e_out = epi_base + (uint32_t)(q * 32 + lane) * kEpiPitch, e_drop = e_out + kBlockM * kEpiPitch;
-      const uint32_t row_bytes = (concat ? 2 * kN : kN) * 4;
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's copies have read the staging rows
-      const bool dropping = out_drop != nullptr;
+#pragma unroll
+      for (int j = 0; j < kN; ++j) r[j] = __float_as_uint(__uint_as_float(r2[j]) + __uint_as_float(r[j]));   // small term first
+      // The thread owns one output row, but a row-per-lane 16-byte store is 32 sectors per warp instruction, and one bulk
+      // copy per row is issued lane by lane (a uniform-datapath instruction: 64 serialised UBLKCP per warp and tile — in
+      // the r2l profile the epilogue, not the main loop, bounded the kernel: 8.5 us per tile against 5 us of streaming).
+      // The tile is therefore staged as [128 rows x 32 floats] boxes in the SWIZZLE_128B layout (16-byte unit u of row r at
+      // unit u ^ (r & 7): conflict-free for row-per-lane stores) and leaves as ONE tensor store per box, issued by one
+      // thread; rows beyond n are clipped by the tensor map.
+      const int trow = q * 32 + lane;
+      const uint32_t e_row = epi_base + (uint32_t)trow * 128u, sw = (uint32_t)(trow & 7);
+      const int64_t grow = tile * kBlockM + trow;
+      if (threadIdx.x == 4 * 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile's stores have read the boxes
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint64_t rk = dropping ? pg::drop_rowkey(stepkey, (uint64_t)grow) : 0ull;
       auto masked = [&](float4 v, int g) {   // dropout of the 4 columns of group g under the drop_hash contract
         const uint64_t h = pg::drop_mix(rk, colkey_sh[g]);
@@ -287,31 +307,39 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto sts4 = [](uint32_t addr, float4 v) {
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
       };
+      // boxes: 0 = first 32 columns of out, 1 = its relu half (concat), 2 / 3 = the same of out_drop
 #pragma unroll
       for (int j = 0; j < kN; j += 4) {
         const float4 z = make_float4(__uint_as_float(r[j]) + bias_sh[j], __uint_as_float(r[j + 1]) + bias_sh[j + 1],
                                      __uint_as_float(r[j + 2]) + bias_sh[j + 2], __uint_as_float(r[j + 3]) + bias_sh[j + 3]);
         const float4 p = make_float4(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f));
+        const uint32_t e = e_row + ((((uint32_t)j >> 2) ^ sw) << 4);
         if (concat) {
-          sts4(e_out + j * 4, z);
-          sts4(e_out + (kN + j) * 4, p);
+          sts4(e, z);
+          sts4(e + kEpiBoxBytes, p);
           if (dropping) {
-            sts4(e_drop + j * 4, masked(z, j >> 2));
-            sts4(e_drop + (kN + j) * 4, masked(p, (kN + j) >> 2));
+            sts4(e + 2 * kEpiBoxBytes, masked(z, j >> 2));
+            sts4(e + 3 * kEpiBoxBytes, masked(p, (kN + j) >> 2));
           }
         } else {
-          sts4(e_out + j * 4, p);
-          if (dropping) sts4(e_drop + j * 4, masked(p, j >> 2));
+          sts4(e, p);
+          if (dropping) sts4(e + 2 * kEpiBoxBytes, masked(p, j >> 2));
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's writes -> visible to its bulk copies
-      if (grow < n) {
-        pg::bulk_s2g(out + grow * out_stride, e_out, row_bytes);
-        if (dropping) pg::bulk_s2g(out_drop + grow * od_stride, e_drop, row_bytes);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's writes -> visible to the tensor stores
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 4 * 32) {
+        const int r0 = (int)(tile * kBlockM);
+        tma_store_2d(&tm_out, 0, r0, epi_base);
+        if (concat) tma_store_2d(&tm_out, kN, r0, epi_base + kEpiBoxBytes);
+        if (dropping) {
+          tma_store_2d(&tm_drop, 0, r0, epi_base + 2 * kEpiBoxBytes);
+          if (concat) tma_store_2d(&tm_drop, kN, r0, epi_base + 3 * kEpiBoxBytes);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // rows are in global memory before the CTA retires
+    if (threadIdx.x == 4 * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
   }
   // ---- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -358,7 +386,7 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
   // tensor maps of the most recent (pointer, shape) pairs: the training loop calls with the same persistent buffers
   // every step, so the driver encode (a few microseconds of host time each) is paid once
   struct MapEntry { const float* base; uint64_t rows, cols, stride; uint32_t box; CUtensorMap map; };
-  static MapEntry cache[8];
+  static MapEntry cache[32];
   static int next_slot = 0;
   static const bool no_cache = getenv("PG_UMMA_NOCACHE") != nullptr;
   auto get_map = [&](const float* base, uint64_t rows, uint64_t cols, uint64_t stride, uint32_t box) -> const CUtensorMap* {
@@ -366,7 +394,7 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
       for (MapEntry& e : cache)
       if (e.base == base && e.rows == rows && e.cols == cols && e.stride == stride && e.box == box) return &e.map;
     MapEntry& e = cache[next_slot];
-    next_slot = (next_slot + 1) % 8;
+    next_slot = (next_slot + 1) % 32;
     e.base = nullptr;
     if (make_map(enc, &e.map, base, rows, cols, stride, box)) return nullptr;
     e.base = base; e.rows = rows; e.cols = cols; e.stride = stride; e.box = box;
@@ -379,6 +407,17 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
   pm = get_map(d_weight, kN, (uint64_t)K, (uint64_t)K, kN);
   if (!pm) return PG_ERR_INVALID;
   const CUtensorMap tm_w = *pm;
+  // store maps: [128 rows x 32 floats] boxes of out / out_drop (rows beyond n are clipped)
+  const uint64_t ocols = concat ? 2 * kN : kN;
+  pm = get_map(d_out, (uint64_t)n, ocols, (uint64_t)out_stride, kBlockM);
+  if (!pm) return PG_ERR_INVALID;
+  const CUtensorMap tm_out = *pm;
+  CUtensorMap tm_drop = tm_out;
+  if (d_out_drop) {
+    pm = get_map(d_out_drop, (uint64_t)n, ocols, (uint64_t)od_stride, kBlockM);
+    if (!pm) return PG_ERR_INVALID;
+    tm_drop = *pm;
+  }
   const size_t smem = (size_t)kStages * kStageBytes + kEpiBytes + 1024;
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -393,8 +432,8 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
   drop.scale = drop.thr ? 1.0f / (1.0f - dropout_p) : 1.0f;
   drop.seed = dropout_seed;
   drop.step = d_step;
-  linear_concat_fwd_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_w, d_bias, n, K, concat, d_out, out_stride,
-                                                             d_out_drop, od_stride, drop);
+  linear_concat_fwd_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_w, tm_out, tm_drop, d_bias, n, K, concat,
+                                                             d_out_drop != nullptr, drop);
   PG_CHECK_LAUNCH();
   return PG_OK;
 }
@@ -413,14 +452,18 @@ pg_status linear_concat_fwd_umma(const float* d_x, int64_t x_stride, const float
 //     consecutive words, conflict-free — so the transposition costs nothing; x_hi / x_lo go to TMEM with tcgen05.st.
 //   * B = gz^T is built by the same threads straight into the canonical K-major SWIZZLE_128B layout ([32 outputs] rows of
 //     128 bytes = 32 rows of the minibatch), hi and lo planes.
-//   * 3xTF32 as in the forward (A_lo B_hi + A_hi B_lo + A_hi B_hi), fp32 accumulators in TMEM: ceil(K/128) x 32 columns.
-// One CTA per SM walks 32-row super-chunks (stride gridDim); at the end the accumulators go through shared memory and
-// are added to dW with 16-byte vector reductions (red.global.add.v4.f32), db with scalar ones.
-// TMEM: 160 accumulator columns + 2 operand stages x (5 blocks x 2 planes x 16 rows) = 480 of 512.
+//   * 3xTF32 as in the forward (A_lo B_hi + A_hi B_lo + A_hi B_hi), fp32 accumulators in TMEM. An instruction with its A
+//     operand in tensor memory is paced by that operand's read, so A_hi meets both B planes in ONE N = 64 instruction
+//     (accumulator columns [A_hi B_hi | A_hi B_lo]) and A_lo B_hi follows with N = 32: ceil(K/128) x 64 columns.
+// One CTA per SM takes 32-row super-chunks from an atomic counter; at the end every thread of the epilogue warps adds the
+// 32 outputs of its feature to dW with scalar reductions (a warp covers 32 consecutive floats of a dW row: one 128-byte
+// packet per instruction), db likewise.
+// TMEM: 320 accumulator columns + 2 operand stages x (5 blocks x 2 planes x 8 rows) = 480 of 512.
 namespace {
 
 constexpr int kDwRows = 32;                       // rows per super-chunk (one 128-byte swizzle row of gz^T)
-constexpr int kDwHalf = 16;                       // rows per TMEM operand stage
+constexpr int kDwHalf = 8;                        // rows per TMEM operand stage (one k-step)
+constexpr int kDwParts = 4;                       // operand stages per super-chunk (kDwRows / kDwHalf), two in flight
 constexpr int kDwFB = 5;                          // feature blocks of 128 (K <= 640)
 constexpr int kDwXStages = 2;                     // x ring (super-chunks)
 constexpr uint32_t kDwBoxBytes = kDwRows * 128 * 4;                    // [32 rows x 128 features] = 16 KB
@@ -428,15 +471,14 @@ constexpr uint32_t kDwGBytes = kDwRows * 2 * kN * 4;                   // staged
 constexpr uint32_t kDwXStageBytes = kDwFB * kDwBoxBytes + 2 * kDwGBytes;   // x (80 KB) + grad_out + y rows = 96 KB
 constexpr uint32_t kDwBBytes = kN * kDwRows * 4;                       // one gz^T plane = 4 KB
 constexpr uint32_t kDwSmemBytes = kDwXStages * kDwXStageBytes + 2 * 2 * kDwBBytes;   // 192 KB + 16 KB
-constexpr uint32_t kDwAccCols = kDwFB * kN;                            // 160
-constexpr uint32_t kDwOpStageCols = kDwFB * 2 * kDwHalf;               // 160
+constexpr uint32_t kDwAccCols = kDwFB * 2 * kN;                        // 320: per feature block [x gz_hi | x_hi gz_lo]
+constexpr uint32_t kDwOpStageCols = kDwFB * 2 * kDwHalf;               // 80
+static_assert(kDwAccCols + 2 * kDwOpStageCols <= 512, "TMEM budget of the dW kernel");
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 
 // Work counters of the dW kernel: {next super-chunk, CTAs that have exited}, one pair per launch slot (launches take the
@@ -447,7 +489,7 @@ __device__ unsigned g_dw_counters[kDwCounterSlots][2];
 __global__ void __launch_bounds__(kThreads, 1)
     linear_concat_dw_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                                  const __grid_constant__ CUtensorMap tm_y, int64_t n, int K, int concat, UmmaDrop drop,
-                                 float* __restrict__ dW, float* __restrict__ db, unsigned* __restrict__ counters) {
+                                 float* __restrict__ dW, float* __restrict__ db, unsigned* __restrict__ counters, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // xfull[2], xempty[2] (x ring) | ready[2], opfree[2] (TMEM operand stages) | bfree[2] (gz^T buffers) | done
   __shared__ __align__(8) uint64_t bars[2 * kDwXStages + 4 + 2 + 1];
@@ -526,28 +568,29 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       for (uint32_t it = 0;; ++it) {
         const int b = it & 1;
-        const uint64_t b_hi = umma_desc_k_sw128(b_base + b * 2 * kDwBBytes), b_lo = umma_desc_k_sw128(b_base + b * 2 * kDwBBytes + kDwBBytes);
+        // B tile of the N = 64 instruction: the gz_hi^T plane and the gz_lo^T plane behind it (64 rows of 128 bytes)
+        const uint64_t b_hi = umma_desc_k_sw128(b_base + b * 2 * kDwBBytes);
         bool stop = false;
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(ready(h), it & 1);                               // x^T half in TMEM, gz^T tile in shared memory
-          if (h == 0 && stop_sh) {                                   // (or: the end marker)
+        for (int part = 0; part < kDwParts; ++part) {
+          const int stg = part & 1;
+          const uint32_t use = 2 * it + (uint32_t)(part >> 1);       // how often this operand stage has been filled before
+          mbar_wait(ready(stg), use & 1);                            // 8 rows of x^T in TMEM, gz^T tile in shared memory
+          if (part == 0 && stop_sh) {                                // (or: the end marker)
             stop = true;
             break;
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t adv = (uint64_t)((part * kDwHalf * 4) >> 4);   // rows part*8 .. inside the 128-byte row
+          const uint32_t acc = (it | (uint32_t)part) != 0;
           for (int fb = 0; fb < nfb; ++fb) {
-            const uint32_t d = tmem_base + fb * kN;
-            const uint32_t a_hi = tmem_opnd + h * kDwOpStageCols + fb * 2 * kDwHalf, a_lo = a_hi + kDwHalf;
-#pragma unroll
-            for (int ks = 0; ks < kDwHalf / kUmmaK; ++ks) {
-              const uint64_t adv = (uint64_t)(((h * kDwHalf + ks * kUmmaK) * 4) >> 4);   // rows h*16 + ks*8 .. inside the 128-byte row
-              const uint32_t acc = (it | (uint32_t)h | (uint32_t)ks) != 0;
-              umma_tf32_ts(d, a_lo + ks * kUmmaK, b_hi + adv, acc);
-              umma_tf32_ts(d, a_hi + ks * kUmmaK, b_lo + adv, 1);
-              umma_tf32_ts(d, a_hi + ks * kUmmaK, b_hi + adv, 1);
-            }
+            // as in the forward: the A operand's read paces the instruction, so x_hi meets [gz_hi ; gz_lo] in ONE N = 64
+            // instruction (columns [x_hi gz_hi | x_hi gz_lo] of the block's accumulator) and x_lo gz_hi follows with N = 32
+            const uint32_t d = tmem_base + fb * 2 * kN;
+            const uint32_t a_hi = tmem_opnd + stg * kDwOpStageCols + fb * 2 * kDwHalf, a_lo = a_hi + kDwHalf;
+            umma_tf32_ts(d, a_hi, b_hi + adv, acc, kIdesc2);
+            umma_tf32_ts(d, a_lo, b_hi + adv, 1, kIdesc);
           }
-          umma_commit(opfree(h));                                    // TMEM operand stage h reusable
+          umma_commit(opfree(stg));                                  // TMEM operand stage reusable
         }
         if (stop) break;
         umma_commit(bfree(b));                                       // gz^T buffer b reusable
@@ -635,33 +678,35 @@ __global__ void __launch_bounds__(kThreads, 1)
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(bl + off), "r"(tf32_lo(bits)) : "memory");
         }
       }
-      // ---- x^T: feature lane tt of every block, 16 rows per TMEM operand stage
+      // ---- x^T: feature lane tt of every block, 8 rows (one k-step) per TMEM operand stage
       const uint32_t sx = st + (uint32_t)tt * 4u;
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(opfree(h), (it & 1) ^ 1);                          // the MMAs of the previous super-chunk's half h are done
+      for (int part = 0; part < kDwParts; ++part) {
+        const int stg = part & 1;
+        const uint32_t use = 2 * it + (uint32_t)(part >> 1);
+        mbar_wait(opfree(stg), (use & 1) ^ 1);                       // the MMAs of this stage's previous fill are done
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int fb = 0; fb < nfb; ++fb) {
-          uint32_t hi[16], lo[16];
+          uint32_t hi[kDwHalf], lo[kDwHalf];
 #pragma unroll
           for (int rr = 0; rr < kDwHalf; ++rr)
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hi[rr]) : "r"(sx + fb * kDwBoxBytes + (uint32_t)(h * kDwHalf + rr) * 512u));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hi[rr]) : "r"(sx + fb * kDwBoxBytes + (uint32_t)(part * kDwHalf + rr) * 512u));
 #pragma unroll
           for (int rr = 0; rr < kDwHalf; ++rr) lo[rr] = tf32_lo(hi[rr]);
-          const uint32_t ta = tmem_opnd + ((uint32_t)(q * 32) << 16) + h * kDwOpStageCols + fb * 2 * kDwHalf;
-          tmem_st16(ta, hi);
-          tmem_st16(ta + kDwHalf, lo);
+          const uint32_t ta = tmem_opnd + ((uint32_t)(q * 32) << 16) + stg * kDwOpStageCols + fb * 2 * kDwHalf;
+          tmem_st8(ta, hi);
+          tmem_st8(ta + kDwHalf, lo);
         }
-        if (h == 1) mbar_arrive(xempty(s));                          // every load of this stage has been consumed (lo[])
+        if (part == kDwParts - 1) mbar_arrive(xempty(s));            // every load of this stage has been consumed (lo[])
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the gz^T stores -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(ready(h));
+        mbar_arrive(ready(stg));
       }
     }
     // end marker: tell the MMA issuer (it waits on ready(0) of this iteration) and the epilogue how much was done. As in a
     // working iteration the arrival is ordered behind the MMAs of the previous super-chunk's half 0 — the issuer has then
     // consumed ready(0)'s previous phase, so the barrier can never run two phases ahead of the thread that polls it.
-    if (it > 0) mbar_wait(opfree(0), (it & 1) ^ 1);
+    if (it > 0) mbar_wait(opfree(0), 1);                             // use 2 * it of stage 0: its previous fill's phase is odd
     if (tt == 0) {
       stop_sh = 1;
       iters_sh = (int)it;
@@ -678,41 +723,35 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (lane < 4 && v != 0.f) atomicAdd(&db_sh[gj0 + e], v);
     }
   }
-  // ---- epilogue: accumulators -> shared memory (transposed) -> 16-byte vector reductions into dW
+  // ---- epilogue: accumulators -> reductions into dW
   __syncthreads();                                                    // db_sh / iters_sh complete; producers / transform have issued everything
   // Every CTA waits for the issuer's last commit, also one that got no work: the commit's arrival is asynchronous, and a
   // CTA that exits before it lands leaves a stray arrive for whatever the next CTA on this SM keeps at that address.
   if (warp >= 4 && warp < 8) mbar_wait(done, 0);
-  if (warp >= 4 && warp < 8 && iters_sh > 0) {                        // a CTA that got no work has nothing to add
+  // Every CTA adds its kN x K block to dW straight from the accumulators: the thread that owns feature f (its TMEM lane)
+  // adds the 32 outputs of f, so a warp's reduction covers 32 consecutive floats of one dW row — one 128-byte packet for
+  // the L2 atomic units, the same number of packets as 16-byte vector reductions would make. (r2q/r2r timing experiments:
+  // of the 8 us this epilogue used to take, the atomics were 2; staging the block in shared memory for vector reductions,
+  // the index arithmetic and the second pass over it were 6 — and summing the blocks of a cluster through distributed
+  // shared memory first, 4x fewer atomics, made the kernel slower, not faster.)
+  if (warp >= 4 && warp < 8 && iters_sh > 0 && !(dbg & 2)) {          // a CTA that got no work has nothing to add
     const int q = warp & 3;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* stage = (float*)(smem + (smem_base - smem_u32(smem)));     // [32 outputs][nfb * 128 + 4] floats, reuses the x ring
-    const int pitch = nfb * 128 + 4;
-    for (int fb = 0; fb < nfb; ++fb) {
-      uint32_t rg[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + fb * kN, rg);
+    // blocks are visited from a CTA-dependent start so that the CTAs, which finish together, spread over dW
+    for (int i = 0; i < nfb; ++i) {
+      const int fb = (i + (int)(blockIdx.x % (unsigned)nfb)) % nfb;
+      uint32_t rg[32], rg2[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + fb * 2 * kN, rg);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + fb * 2 * kN + kN, rg2);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int f = fb * 128 + q * 32 + lane;
+      if (f < K && !(dbg & 1)) {
+        float* col = dW + f;
 #pragma unroll
-      for (int j = 0; j < kN; ++j) stage[j * pitch + f] = __uint_as_float(rg[j]);   // lanes -> consecutive words
+        for (int j = 0; j < kN; ++j) atomicAdd(col + (size_t)j * K, __uint_as_float(rg2[j]) + __uint_as_float(rg[j]));   // small term first
+      }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int t = threadIdx.x - 4 * 32;
-    const int kvec = K >> 2;
-    // every CTA adds the same kN x K block: each starts at its own offset so that the CTAs, which finish together, do
-    // not walk the same addresses (= the same L2 slices) in lock step
-    const int total = kN * kvec;
-    const int rounds = (total + 127) / 128;
-    const int r0 = (int)(((uint64_t)blockIdx.x * (uint64_t)rounds) / gridDim.x);
-    for (int rr = 0; rr < rounds; ++rr) {
-      int rnd = r0 + rr;
-      if (rnd >= rounds) rnd -= rounds;
-      const int i = rnd * 128 + t;
-      if (i >= total) continue;
-      const int j = i / kvec, c = (i % kvec) << 2;
-      const float4 v = *(const float4*)(stage + j * pitch + c);
-      atomicAdd((float4*)(dW + (size_t)j * K + c), v);
-    }
     if (db && t < kN) atomicAdd(db + t, db_sh[t]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -785,12 +824,6 @@ pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float*
   if (!pm) return PG_ERR_INVALID;
   const CUtensorMap tm_y = *pm;
   const size_t smem = (size_t)kDwSmemBytes + 1024;
-  static bool attr_set[64] = {false};
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
   UmmaDrop drop;
   drop.thr = dropout_p > 0.f ? (uint32_t)(dropout_p * 65536.0f + 0.5f) : 0u;
   drop.scale = drop.thr ? 1.0f / (1.0f - dropout_p) : 1.0f;
@@ -802,7 +835,14 @@ pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float*
   static int launch_seq = 0;
   if (!counters) PG_CUDA(cudaGetSymbolAddress((void**)&counters, g_dw_counters));
   unsigned* ctr = counters + 2 * (launch_seq++ % kDwCounterSlots);   // zero at rest: the previous user's last CTA re-armed it
-  linear_concat_dw_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_g, tm_y, n, K, concat, drop, d_gw, d_gb, ctr);
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(cudaFuncSetAttribute(linear_concat_dw_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  static const int dbg = getenv("PG_DW_DEBUG") ? atoi(getenv("PG_DW_DEBUG")) : 0;   // timing experiments only (wrong results)
+  linear_concat_dw_umma_kernel<<<grid, kThreads, smem, st>>>(tm_x, tm_g, tm_y, n, K, concat, drop, d_gw, d_gb, ctr, dbg);
   PG_CHECK_LAUNCH();
   return PG_OK;
 }

@@ -432,8 +432,7 @@ class GCNTrainEngine:
             self.opt.zero_grad(set_to_none=False)
         loss.backward()
         if self.fused_opt is not None:                       # gradient all-reduce + Adam: one kernel over NVLink peer memory
-            self.step_counter.add_(1)
-            self.fused_opt.step(self.step_counter)
+            self.fused_opt.step(self.step_counter, advance=True)   # ... which also advances both step counters
         else:
             if self.sync is not None:
                 self.sync()
@@ -524,8 +523,7 @@ class GCNTrainEngine:
         linear_concat_backward(x, ghd, out, True, w0.grad, b0.grad if b0 is not None else None, p, self.drop_seed_hidden,
                                self.step_counter)
         if self.fused_opt is not None:                       # gradient all-reduce + Adam: one kernel over NVLink peer memory
-            self.step_counter.add_(1)
-            self.fused_opt.step(self.step_counter)
+            self.fused_opt.step(self.step_counter, advance=True)   # ... which also advances both step counters
         else:
             if self.sync is not None:
                 self.sync()

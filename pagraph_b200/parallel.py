@@ -152,17 +152,21 @@ class PeerAdam:
         elif err is not None:
             raise err
 
-    def step(self, step_id):
-        """step_id: int64 CUDA scalar tensor, >= 1, equal on all ranks, +1 per call."""
+    def step(self, step_id, advance=False):
+        """step_id: int64 CUDA scalar tensor, equal on all ranks. advance=False: the caller has already incremented it for
+        this step (>= 1, +1 per call). advance=True: it holds the number of steps taken so far and the kernel increments
+        it — and the optimizer's own `step` — itself (pg_allreduce_adam_next: two one-element kernels fewer per step)."""
         _lib = self._lib
         g = self.opt.param_groups[0]
-        self.state["step"].add_(1)
+        if not advance:
+            self.state["step"].add_(1)
+        fn, name = ((_lib.lib().pg_allreduce_adam_next, "pg_allreduce_adam_next") if advance else
+                    (_lib.lib().pg_allreduce_adam, "pg_allreduce_adam"))
         with torch.cuda.device(self.flat.device):
-            _lib.check(_lib.lib().pg_allreduce_adam(self._handle, _lib.ptr(self.flat), _lib.ptr(self.sync.flat_grad),
-                                                    _lib.ptr(self.state["exp_avg"]), _lib.ptr(self.state["exp_avg_sq"]),
-                                                    _lib.ptr(self.state["step"]), _lib.ptr(step_id), float(g["lr"]),
-                                                    float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                                                    float(g["weight_decay"]), _lib.stream_ptr()), "pg_allreduce_adam")
+            _lib.check(fn(self._handle, _lib.ptr(self.flat), _lib.ptr(self.sync.flat_grad), _lib.ptr(self.state["exp_avg"]),
+                          _lib.ptr(self.state["exp_avg_sq"]), _lib.ptr(self.state["step"]), _lib.ptr(step_id), float(g["lr"]),
+                          float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                          _lib.stream_ptr()), name)
 
     def close(self):
         if self._handle is not None:

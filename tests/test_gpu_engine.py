@@ -164,8 +164,10 @@ def test_engine_dropout_trains_and_graph_replays_rekey():
     eng.close()
 
 
-def test_peer_adam_single_rank_matches_torch_adam():
-    """pg_allreduce_adam with world == 1 is torch.optim.Adam (capturable math) on the flat bucket."""
+@pytest.mark.parametrize("advance", [False, True])
+def test_peer_adam_single_rank_matches_torch_adam(advance):
+    """pg_allreduce_adam with world == 1 is torch.optim.Adam (capturable math) on the flat bucket; pg_allreduce_adam_next
+    (advance) is the same step with both step counters incremented by the kernel itself."""
     import torch
     from pagraph_b200.parallel import FlatGradAllReduce, PeerAdam
     torch.manual_seed(0)
@@ -183,9 +185,13 @@ def test_peer_adam_single_rank_matches_torch_adam():
         for m in (a, b):
             m.zero_grad(set_to_none=False) if m is b else sync.zero_grad()
             m(x).square().mean().backward()
-        step.add_(1)
-        fused.step(step)
+        if advance:
+            fused.step(step, advance=True)
+        else:
+            step.add_(1)
+            fused.step(step)
         opt_b.step()
+        assert int(step.item()) == it + 1
     for pa, pb in zip(a.parameters(), b.parameters()):
         torch.testing.assert_close(pa, pb, rtol=1e-4, atol=1e-6)
     assert float(opt_a.state[sync.flat_parameters()[0]]["step"]) == 6.0
@@ -213,8 +219,7 @@ def _two_rank_worker(rank, world, port, out):
         def body():
             sync.zero_grad()
             model(static_x).square().mean().backward()
-            step.add_(1)
-            fused.step(step)
+            fused.step(step, advance=True)         # the counter-advancing launch, as the engine issues it
         if it < 3:
             body()
         else:
