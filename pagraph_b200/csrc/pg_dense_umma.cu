@@ -546,10 +546,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     // starts on the few SMs the input aggregation of the next minibatch leaves free and gets the rest of the GPU when
     // that kernel ends — the CTAs that start early simply take more of the work.
     if (lane == 0) {
-      for (uint32_t it = 0;; ++it) {
+      unsigned sc = atomicAdd(&counters[0], 1u);                     // claimed one super-chunk ahead: the round trip of the
+      for (uint32_t it = 0;; ++it) {                                 // atomic hides behind the wait for a free stage
         const int s = it % kDwXStages;
         mbar_wait(xempty(s), ((it / kDwXStages) & 1) ^ 1);
-        const unsigned sc = atomicAdd(&counters[0], 1u);
         if ((int64_t)sc >= nsc) {
           sc_ring[it & 3] = -1;
           mbar_arrive(xfull(s));                                     // end marker: a phase without bytes
@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int fb = 0; fb < nfb; ++fb) tma_load_2d(st + fb * kDwBoxBytes, &tm_x, fb * 128, (int)(sc * kDwRows), xfull(s));
         tma_load_2d(st + kDwFB * kDwBoxBytes, &tm_g, 0, (int)(sc * kDwRows), xfull(s));
         tma_load_2d(st + kDwFB * kDwBoxBytes + kDwGBytes, &tm_y, 0, (int)(sc * kDwRows), xfull(s));
+        sc = atomicAdd(&counters[0], 1u);
       }
     }
   } else if (warp == 1) {
@@ -757,8 +758,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
-  if (threadIdx.x == 0) {                                             // the last CTA to leave re-arms the counters for a replay
-    __threadfence();
+  // The last CTA to leave re-arms the counters for a replay. This thread's own claims on counters[0] have all returned
+  // their values, i.e. they have been performed, before it counts itself out: no fence is needed in between.
+  if (threadIdx.x == 0) {
     if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) {
       counters[0] = 0;
       counters[1] = 0;

@@ -39,13 +39,14 @@ def test_sass_is_sm_100a_with_bulk_copies():
 
 def test_sass_has_the_tcgen05_forward():
     """The first NodeUpdate's forward is a tcgen05 kernel (pg_dense_umma.cu): tensor-core MMAs issued from tensor memory
-    (UTCHMMA), TMEM stores / loads (STTM / LDTM), 2-D TMA tile loads (UTMALDG) and tcgen05.commit (UTCBAR)."""
+    (UTCHMMA), TMEM stores / loads (STTM / LDTM), 2-D TMA tile loads and stores (UTMALDG / UTMASTG) and tcgen05.commit
+    (UTCBAR)."""
     import subprocess
     path = pg_build.build()
     out = subprocess.run(["cuobjdump", "-sass", "-fun", "linear_concat_fwd_umma_kernel", path], capture_output=True, text=True).stdout
     if "Function" not in out:      # older cuobjdump: no mangled-substring match, scan the whole library
         out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "STTM", "LDTM", "UTMALDG", "UTCBAR"):
+    for mnemonic in ("UTCHMMA", "STTM", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR"):
         assert mnemonic in out, mnemonic
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmark of the dense-stage kernels at bench.py scale (config 2: n_1 = 36 864 padded rows, F = 600, hidden 32,
 6000 seeds, 60 classes) on synthetic inputs — no graph, no cache: seconds to set up, so it is also the cheap target for
-`ncu --set full`. Inputs rotate over buffers larger than L2. CUDA events, median.
+`ncu --set full`. Inputs rotate over buffers larger than L2. CUDA events around CUDA-graph replays, median.
     python tools/micro_dense.py [--iters 30] [--fwd-variants 0,1,5] [--only fwd|bwd|head]
 """
 import argparse
@@ -13,20 +13,28 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 
-def med(fn, iters):
+def med(fn, iters, reps=6):
+    """median GPU time of one call, in us. The calls are replayed from a CUDA graph (`reps` per replay, inputs rotating):
+    issued one by one from Python, a 25 us kernel is followed by an idle GPU and the event pair times the host."""
     for _ in range(3):
         fn(0)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        for r in range(reps):
+            fn(r)
+    g.replay()
     torch.cuda.synchronize()
     evs = []
     for i in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn(i)
+        g.replay()
         b.record()
         evs.append((a, b))
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in evs)
-    return ts[len(ts) // 2] * 1e3   # us
+    return ts[len(ts) // 2] * 1e3 / reps   # us
 
 
 def main():
