@@ -973,6 +973,14 @@ def _r(x, nd=5):
     return round(x, nd - 1 - int(floor(log10(abs(x)))))
 
 
+def dominant_kernel(kernels):
+    """The HBM-bound kernel class with the largest serialised time per launch: the roofline record's subject. Only
+    single-kernel classes qualify (`sample` is a chain of seven), and the all-reduce does not — its duration is the
+    wait for the slowest rank of the step, not bytes moved."""
+    hbm_k = {k: x for k, x in kernels.items() if x["bound"] == "hbm" and "sample" not in k and "allreduce" not in k}
+    return max(hbm_k, key=lambda k: hbm_k[k]["avg_ms"])
+
+
 def compact_line(d):
     """The LAST stdout line: < 1150 bytes (the driver keeps a 1500-byte tail), every string <= 120 chars, one JSON object the driver parses. `d` is the full
     detail record (written to gpurun_out/bench_detail_n{N}.json); only the contract keys and the headline split go here."""
@@ -1143,10 +1151,8 @@ def main_ours(args):
     head = results[modes[0]]
     v, e = head["value"], head["e2e"]
     # dominant HBM-bound kernel of the headline mode
-    hbm_k = {k: x for k, x in v["kernels"].items() if x["bound"] == "hbm"}
-    # single-kernel classes only; the all-reduce's duration is the wait for the slowest rank, not bytes moved
-    top = max(hbm_k, key=lambda k: hbm_k[k]["avg_ms"] * (0 if ("sample" in k or "allreduce" in k) else 1))
-    tk = hbm_k[top]
+    top = dominant_kernel(v["kernels"])
+    tk = v["kernels"][top]
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

@@ -89,3 +89,12 @@ def test_compact_line_without_optional_parts():
     c["clocks"] = None
     d = json.loads(bench.compact_line(c))
     assert d["cpu_baseline"] is None and "vtx20" not in d and d["clocks"]["reasons"] == []
+
+
+def test_dominant_kernel_skips_the_sampler_chain_and_the_all_reduce():
+    k = {"sample(all kernels of one pg_sample)": {"bound": "hbm", "avg_ms": 0.26},
+         "allreduce+adam(allreduce_adam_kernel)": {"bound": "hbm", "avg_ms": 0.20},
+         "gather_miss(rows_bulk_kernel)": {"bound": "pcie", "avg_ms": 3.0},
+         "cache_aggregate_blocks0..1(agg_rows_tma_kernel,D=600)": {"bound": "hbm", "avg_ms": 0.0975},
+         "gather_hit(rows_ldg_kernel)": {"bound": "hbm", "avg_ms": 0.0247}}
+    assert bench.dominant_kernel(k).startswith("cache_aggregate")
