@@ -15,12 +15,15 @@
 //               from TMEM, not from shared memory: an SS-mode M = 128 tf32 MMA would fetch 4 KB of A per instruction and
 //               run at the shared-memory port's 128 B/clk (~32 clk) instead of the tensor core's 16 clk; it also splits
 //               the chunk's W box in place next to it (W_lo plane)
-//   warp 1      MMA issuer (one thread): 4 k-steps x 3 terms of tcgen05.mma.cta_group::1.kind::tf32 (M 128, N 32, K 8) per
-//               chunk, A from TMEM, B = W_hi / W_lo from shared memory; tcgen05.commit releases the ring slot
-//   warps 4-7   epilogue, one output row per thread: tcgen05.ld of the 32 accumulator columns, + bias, relu, concat,
-//               dropout mask (pg_common.cuh drop_hash contract), 16-byte stores; double-buffered accumulators
-// Roofline: the kernel streams x once (HBM floor 13.5 us at config 2); tensor time per tile 19 x 12 x 16 clk = 1.9 us,
-// shared-memory traffic per chunk ~56 KB (TMA fill 20 KB, transform read 20 KB + W_lo 4 KB, B operand 12 KB) = 440 clk.
+//   warp 1      MMA issuer (one thread): per chunk 4 k-steps x 2 instructions of tcgen05.mma.cta_group::1.kind::tf32 (M 128,
+//               K 8), A from TMEM, B from shared memory: x_hi against [W_hi ; W_lo] with N = 64 (two of the three products
+//               in one instruction — an instruction with its A operand in TMEM is paced by that operand's read, not by N)
+//               and x_lo against W_hi with N = 32; tcgen05.commit releases the ring slot
+//   warps 4-7   epilogue, one output row per thread: tcgen05.ld of the 64 accumulator columns, the two halves summed,
+//               + bias, relu, concat, dropout mask (pg_common.cuh drop_hash contract); the tile is staged as [128 x 32]
+//               SWIZZLE_128B boxes and stored with one TMA tensor store per box; double-buffered accumulators
+// Measured (ncu, profiles/r2_dense_kernel_timing.md): 6.9 us fixed + 8.8 us per wave of 148 tiles — 0.79 of the measured HBM
+// peak while streaming; 24.4 us at config 2 (HBM floor 13.5 us).
 #include <cuda.h>
 
 #include <algorithm>
