@@ -42,6 +42,7 @@ def lib():
             build()
         _lib = ctypes.CDLL(_SO)
         _lib.pgo_sample.restype = ctypes.c_void_p
+        _lib.pgo_sample_stdlib.restype = ctypes.c_void_p
         _lib.pgo_draw.restype = ctypes.c_uint64
         _lib.pgo_sample_batches.restype = ctypes.c_int64
         _lib.pgo_fetch.restype = ctypes.c_int64
@@ -118,6 +119,20 @@ def sample(indptr, indices, eids, seeds, fanouts, seed=0, epoch=0, batch=0):
     L.pgo_nf_copy(h, *[_p(a, _i64p) for a in out])
     L.pgo_nf_free(h)
     return OracleNodeFlow(*out)
+
+
+def sample_stdlib(indptr, indices, eids, seeds, fanouts, seed=1):
+    """The same minibatch drawn the way a single DGL-0.4.1 sampling thread draws it: one std::default_random_engine
+    (libstdc++ minstd_rand0) seeded with `seed`, consumed sequentially, layers expanded in discovery order (SURVEY §8c,
+    Appendix A.3). Not comparable draw by draw with `sample` (a different generator); used to cross-check its structure."""
+    L = lib()
+    indptr, indices, seeds = _c64(indptr), _c64(indices), _c64(seeds)
+    eids = _c64(eids) if eids is not None else None
+    fan = _c64(fanouts)
+    h = L.pgo_sample_stdlib(_p(indptr, _i64p), _p(indices, _i64p), _p(eids, _i64p), ctypes.c_int64(len(indptr) - 1),
+                            _p(seeds, _i64p), ctypes.c_int64(len(seeds)), ctypes.c_int(len(fan)), _p(fan, _i64p),
+                            ctypes.c_uint64(seed))
+    return _nf_from_handle(h)
 
 
 def sample_batches(indptr, indices, eids, seeds, batch_size, first_batch, n_batches, fanouts,

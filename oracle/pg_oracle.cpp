@@ -14,6 +14,10 @@
 //     by construction because the NodeFlow is then a pure function of (graph, seeds).
 //   * DGL draws from an unseeded thread-local std::default_random_engine, so the reference is
 //     not reproducible with itself; oracle and GPU share the counter-based generator below.
+//     pgo_sample_stdlib draws the same minibatch from DGL's own generator (libstdc++ minstd_rand0 +
+//     uniform_int_distribution, one sequential stream, discovery-order expansion) given a seed: it
+//     cannot be compared draw by draw with the counter-based mode, but it shares GetUniformSample's
+//     structure and ConstructNodeFlow with it and must agree exactly wherever no draw is made.
 //   * gather (PaGraph/storage/storage.py:157-216) is pinned by golden vectors produced by the
 //     real reference module (tests/golden/make_golden.py).
 //   * aggregation (dgl block_compute copy_src + sum/mean, call sites PaGraph/model/gcn_nssc.py:71-74)
@@ -29,6 +33,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <random>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -103,7 +108,38 @@ struct NodeFlow {
   std::vector<int64_t> node_mapping, layer_offsets, indptr, indices, edge_mapping, flow_offsets;
 };
 
-// SURVEY.md Appendix A.3 SampleSubgraph + A.4 ConstructNodeFlow.
+// SURVEY.md Appendix A.4 ConstructNodeFlow. layer[h]: vertices of sampling layer h (0 = seeds, in seed order; h >= 1 ascending);
+// nb_src / nb_eid / nb_off[h]: sampled sources, edge ids and row offsets of hop h, rows in the NodeFlow order of layer[h-1].
+NodeFlow* construct_nodeflow(const std::vector<std::vector<int64_t>>& layer, const std::vector<std::vector<int64_t>>& nb_src,
+                             const std::vector<std::vector<int64_t>>& nb_eid, const std::vector<std::vector<int64_t>>& nb_off,
+                             int L) {
+  NodeFlow* nf = new NodeFlow;
+  nf->num_layers = L + 1;
+  nf->layer_offsets.push_back(0);
+  for (int j = 0; j <= L; ++j) {
+    const std::vector<int64_t>& lay = layer[L - j];
+    nf->node_mapping.insert(nf->node_mapping.end(), lay.begin(), lay.end());
+    nf->layer_offsets.push_back((int64_t)nf->node_mapping.size());
+  }
+  nf->indptr.assign(nf->layer_offsets[1] + 1, 0);  // layer-0 rows are empty
+  nf->flow_offsets.push_back(0);
+  for (int j = 1; j <= L; ++j) {
+    const int h = L - j + 1;                       // hop whose expansion feeds NodeFlow layer j
+    const std::vector<int64_t>& srcs = layer[h];   // NodeFlow layer j-1 (sorted)
+    const int64_t col_base = nf->layer_offsets[j - 1];
+    const int64_t e_base = (int64_t)nf->indices.size();
+    for (size_t e = 0; e < nb_src[h].size(); ++e) {
+      const int64_t rank = std::lower_bound(srcs.begin(), srcs.end(), nb_src[h][e]) - srcs.begin();
+      nf->indices.push_back(col_base + rank);
+      nf->edge_mapping.push_back(nb_eid[h][e]);
+    }
+    for (size_t r = 1; r < nb_off[h].size(); ++r) nf->indptr.push_back(e_base + nb_off[h][r]);
+    nf->flow_offsets.push_back((int64_t)nf->indices.size());
+  }
+  return nf;
+}
+
+// SURVEY.md Appendix A.3 SampleSubgraph (counter-based generator of the RNG contract above).
 NodeFlow* sample_one(const int64_t* indptr, const int64_t* indices, const int64_t* eids, int64_t V,
                      const int64_t* seeds, int64_t n_seeds, int num_hops, const int64_t* fanouts,
                      uint64_t seed, int64_t epoch, int64_t batch) {
@@ -140,30 +176,77 @@ NodeFlow* sample_one(const int64_t* indptr, const int64_t* indices, const int64_
     std::sort(layer[h].begin(), layer[h].end());
   }
   (void)V;
-  NodeFlow* nf = new NodeFlow;
-  nf->num_layers = L + 1;
-  nf->layer_offsets.push_back(0);
-  for (int j = 0; j <= L; ++j) {
-    const std::vector<int64_t>& lay = layer[L - j];
-    nf->node_mapping.insert(nf->node_mapping.end(), lay.begin(), lay.end());
-    nf->layer_offsets.push_back((int64_t)nf->node_mapping.size());
+  return construct_nodeflow(layer, nb_src, nb_eid, nb_off, L);
+}
+
+// DGL's own random stream: ONE std::default_random_engine — libstdc++'s minstd_rand0 —
+// consumed sequentially through std::uniform_int_distribution<size_t>(0, deg - 1), the previous layer expanded in
+// DISCOVERY order (the order in which its vertices were first seen), layers sorted only when the NodeFlow is built.
+// DGL seeds the engine from std::random_device unless dgl.random.seed is called, which PaGraph never does, so the
+// reference is not reproducible with itself; with an explicit seed this mode reproduces what a single sampling thread
+// of DGL 0.4.1 built against libstdc++ would draw. It shares GetUniformSample's structure and ConstructNodeFlow with
+// the counter-based mode above and exists to cross-check them (tests/test_oracle.py): RNG-free cases must agree
+// exactly, random cases must satisfy the same invariants and the same inclusion frequencies.
+NodeFlow* sample_one_stdlib(const int64_t* indptr, const int64_t* indices, const int64_t* eids, int64_t V,
+                            const int64_t* seeds, int64_t n_seeds, int num_hops, const int64_t* fanouts, uint64_t seed) {
+  std::default_random_engine engine((std::default_random_engine::result_type)seed);
+  auto rand_int = [&](int64_t upper) {                        // RandInt(upper): uniform in [0, upper)
+    return (int64_t)std::uniform_int_distribution<size_t>(0, (size_t)upper - 1)(engine);
+  };
+  const int L = num_hops;
+  std::vector<std::vector<int64_t>> disc(L + 1), layer(L + 1);
+  std::vector<std::vector<int64_t>> nb_src(L + 1), nb_eid(L + 1), nb_off(L + 1);
+  {
+    std::unordered_set<int64_t> seen;
+    for (int64_t i = 0; i < n_seeds; ++i)
+      if (seen.insert(seeds[i]).second) disc[0].push_back(seeds[i]);
+    layer[0] = disc[0];
   }
-  nf->indptr.assign(nf->layer_offsets[1] + 1, 0);  // layer-0 rows are empty
-  nf->flow_offsets.push_back(0);
-  for (int j = 1; j <= L; ++j) {
-    const int h = L - j + 1;                       // hop whose expansion feeds NodeFlow layer j
-    const std::vector<int64_t>& srcs = layer[h];   // NodeFlow layer j-1 (sorted)
-    const int64_t col_base = nf->layer_offsets[j - 1];
-    const int64_t e_base = (int64_t)nf->indices.size();
-    for (size_t e = 0; e < nb_src[h].size(); ++e) {
-      const int64_t rank = std::lower_bound(srcs.begin(), srcs.end(), nb_src[h][e]) - srcs.begin();
-      nf->indices.push_back(col_base + rank);
-      nf->edge_mapping.push_back(nb_eid[h][e]);
+  struct Rec { int64_t v, start, cnt; };
+  for (int h = 1; h <= L; ++h) {
+    std::unordered_set<int64_t> seen;
+    std::vector<Rec> recs;
+    std::vector<int64_t> tsrc, teid, pos;
+    const int64_t k = fanouts[h - 1];
+    for (int64_t v : disc[h - 1]) {
+      const int64_t s = indptr[v], deg = indptr[v + 1] - s;
+      pos.clear();
+      if (deg <= k) {
+        for (int64_t p = 0; p < deg; ++p) pos.push_back(p);
+      } else {
+        const bool complement = deg <= 2 * k;
+        const int64_t m = complement ? deg - k : k;
+        std::unordered_set<int64_t> chosen;
+        while ((int64_t)chosen.size() < m) chosen.insert(rand_int(deg));
+        if (!complement) {
+          pos.assign(chosen.begin(), chosen.end());
+          std::sort(pos.begin(), pos.end());
+        } else {
+          for (int64_t p = 0; p < deg; ++p)
+            if (!chosen.count(p)) pos.push_back(p);
+        }
+      }
+      recs.push_back({v, (int64_t)tsrc.size(), (int64_t)pos.size()});
+      for (int64_t p : pos) {
+        const int64_t u = indices[s + p];
+        tsrc.push_back(u);
+        teid.push_back(eids ? eids[s + p] : s + p);
+        if (seen.insert(u).second) disc[h].push_back(u);
+      }
     }
-    for (size_t r = 1; r < nb_off[h].size(); ++r) nf->indptr.push_back(e_base + nb_off[h][r]);
-    nf->flow_offsets.push_back((int64_t)nf->indices.size());
+    // rows of the block follow the NodeFlow order of the expanded layer: seed order for the seeds, ascending id otherwise
+    if (h > 1) std::sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) { return x.v < y.v; });
+    nb_off[h].push_back(0);
+    for (const Rec& r : recs) {
+      nb_src[h].insert(nb_src[h].end(), tsrc.begin() + r.start, tsrc.begin() + r.start + r.cnt);
+      nb_eid[h].insert(nb_eid[h].end(), teid.begin() + r.start, teid.begin() + r.start + r.cnt);
+      nb_off[h].push_back((int64_t)nb_src[h].size());
+    }
+    layer[h] = disc[h];
+    std::sort(layer[h].begin(), layer[h].end());
   }
-  return nf;
+  (void)V;
+  return construct_nodeflow(layer, nb_src, nb_eid, nb_off, L);
 }
 
 }  // namespace
@@ -216,6 +299,12 @@ void* pgo_sample(const int64_t* indptr, const int64_t* indices, const int64_t* e
                  const int64_t* seeds, int64_t n_seeds, int num_hops, const int64_t* fanouts,
                  uint64_t seed, int64_t epoch, int64_t batch) {
   return sample_one(indptr, indices, eids, V, seeds, n_seeds, num_hops, fanouts, seed, epoch, batch);
+}
+
+// The same minibatch drawn from DGL's own generator (std::default_random_engine, sequential; see sample_one_stdlib).
+void* pgo_sample_stdlib(const int64_t* indptr, const int64_t* indices, const int64_t* eids, int64_t V,
+                        const int64_t* seeds, int64_t n_seeds, int num_hops, const int64_t* fanouts, uint64_t seed) {
+  return sample_one_stdlib(indptr, indices, eids, V, seeds, n_seeds, num_hops, fanouts, seed);
 }
 
 // sizes: [num_layers, total_nodes, total_edges]

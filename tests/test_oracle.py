@@ -132,6 +132,65 @@ def test_sampler_uniformity():
         assert np.all(np.abs(p - k / deg) < 5 * np.sqrt(k / deg * (1 - k / deg) / trials))
 
 
+# ------------------------------------------------------------------ sampling: DGL's own generator (libstdc++ minstd_rand0, sequential)
+def test_stdlib_engine_is_minstd_rand0():
+    """std::default_random_engine of libstdc++ is minstd_rand0 (x <- 16807 x mod 2^31 - 1): with a range of 2^31 - 2
+    values uniform_int_distribution passes the engine's output through (minus its minimum, 1), so a vertex of that
+    degree would pick position engine() - 1. Checked on a two-vertex graph small enough to build: deg = 3 > 2k = 2,
+    k = 1 -> one draw; libstdc++ down-scales by rejection with scaling = (2^31 - 2) / 3."""
+    indptr = np.array([0, 3, 3, 3, 3], dtype=np.int64)
+    indices = np.array([1, 2, 3], dtype=np.int64)
+    for seed in (1, 2, 12345):
+        x, rng, scaling = seed, 2 ** 31 - 2, (2 ** 31 - 2) // 3
+        while True:                                   # libstdc++ uniform_int_distribution, urngrange > urange branch
+            x = (16807 * x) % (2 ** 31 - 1)
+            r = x - 1
+            if r < 3 * scaling:
+                break
+        nf = oracle.sample_stdlib(indptr, indices, None, [0], [1], seed=seed)
+        assert nf.layer_parent_nid(0).tolist() == [1 + r // scaling]
+
+
+@pytest.mark.parametrize("fanouts", [[2, 2], [5, 3], [3], [4, 2, 3]])
+def test_stdlib_sampler_structure(fanouts):
+    indptr, indices, eids, _ = random_in_csr(300, 3000, seed=1)
+    seeds = np.random.default_rng(2).choice(300, 40, replace=False)
+    nf = oracle.sample_stdlib(indptr, indices, eids, seeds, fanouts, seed=7)
+    _check_structure(nf, indptr, indices, eids, seeds, fanouts)
+    # sequential stream: the same seed reproduces the minibatch, another seed draws another one
+    same = oracle.sample_stdlib(indptr, indices, eids, seeds, fanouts, seed=7)
+    other = oracle.sample_stdlib(indptr, indices, eids, seeds, fanouts, seed=8)
+    np.testing.assert_array_equal(nf.edge_mapping, same.edge_mapping)
+    assert not np.array_equal(nf.edge_mapping, other.edge_mapping)
+
+
+def test_stdlib_sampler_equals_counter_based_sampler_when_rng_free():
+    """fanout >= max degree (how the reference calls the sampler for partitioning and evaluation): both generators must
+    give the same NodeFlow, array for array — discovery-order expansion and sorted expansion meet in ConstructNodeFlow."""
+    indptr, indices, eids, _ = random_in_csr(200, 1500, seed=4)
+    seeds = np.array([3, 17, 42, 99, 150, 17])
+    a = oracle.sample(indptr, indices, eids, seeds, [200, 200, 200], seed=3, epoch=1, batch=2)
+    b = oracle.sample_stdlib(indptr, indices, eids, seeds, [200, 200, 200], seed=5)
+    for name in ("node_mapping", "layer_offsets", "indptr", "indices", "edge_mapping", "flow_offsets"):
+        np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
+
+
+def test_stdlib_sampler_uniformity_matches_counter_based():
+    """Inclusion frequencies under DGL's generator agree with k / deg (direct and complement branch). One sequential
+    stream over many vertices that share a neighbour list (consecutive small seeds would only show minstd_rand0's
+    first output, which is 16807 * seed)."""
+    deg, trials = 30, 3000
+    indptr = np.concatenate([np.arange(trials + 1) * deg, np.full(deg, trials * deg)]).astype(np.int64)
+    indices = np.tile(np.arange(trials, trials + deg, dtype=np.int64), trials)
+    for k in (4, 20):
+        nf = oracle.sample_stdlib(indptr, indices, None, np.arange(trials), [k], seed=12345)
+        assert nf.flow_offsets[-1] == k * trials
+        src = nf.layer_parent_nid(0)[nf.indices - nf.layer_offsets[0]]
+        p = np.bincount(src - trials, minlength=deg) / trials
+        assert abs(p.mean() - k / deg) < 1e-9
+        assert np.all(np.abs(p - k / deg) < 5 * np.sqrt(k / deg * (1 - k / deg) / trials))
+
+
 def test_sampler_depends_on_epoch_and_batch_only_when_sampling():
     indptr, indices, eids, _ = random_in_csr(300, 6000, seed=5)
     seeds = np.arange(0, 300, 7)
