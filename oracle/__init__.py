@@ -38,8 +38,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()                                   # no-op when the library is newer than its source
         _lib = ctypes.CDLL(_SO)
         _lib.pgo_sample.restype = ctypes.c_void_p
         _lib.pgo_sample_stdlib.restype = ctypes.c_void_p
