@@ -836,9 +836,13 @@ pg_status linear_concat_dw_umma(const float* d_x, int64_t x_stride, const float*
   drop.step = d_step;
   const int64_t nsc = (n + kDwRows - 1) / kDwRows;
   const int grid = (int)std::min<int64_t>(nsc, (int64_t)pg::sm_count(dev));
-  static unsigned* counters = nullptr;
+  static unsigned* counters_of[64] = {nullptr};                      // a __device__ symbol has one instance per device
   static int launch_seq = 0;
-  if (!counters) PG_CUDA(cudaGetSymbolAddress((void**)&counters, g_dw_counters));
+  unsigned* counters = (dev >= 0 && dev < 64) ? counters_of[dev] : nullptr;
+  if (!counters) {                                                   // `dev` is the current device (the caller asked the runtime)
+    PG_CUDA(cudaGetSymbolAddress((void**)&counters, g_dw_counters));
+    if (dev >= 0 && dev < 64) counters_of[dev] = counters;
+  }
   unsigned* ctr = counters + 2 * (launch_seq++ % kDwCounterSlots);   // zero at rest: the previous user's last CTA re-armed it
   static bool attr_set[64] = {false};
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
