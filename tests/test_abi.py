@@ -50,6 +50,18 @@ def test_sass_has_the_tcgen05_forward():
         assert mnemonic in out, mnemonic
 
 
+def test_sass_has_the_tcgen05_backward():
+    """dW / db of the first NodeUpdate is a tcgen05 kernel too: MMAs with x^T in tensor memory (UTCHMMA, STTM), TMA tile
+    loads of x / grad_out / y (UTMALDG), accumulators read back with LDTM and added to dW with global reductions."""
+    import subprocess
+    path = pg_build.build()
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "linear_concat_dw_umma_kernel", path], capture_output=True, text=True).stdout
+    if "Function" not in out:
+        out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "STTM", "LDTM", "UTMALDG", "UTCBAR", "ATOMG.E.ADD.F32"):
+        assert mnemonic in out, mnemonic
+
+
 def test_constants_match_header():
     text = open(os.path.join(ROOT, "include", "pagraph_b200.h")).read()
     assert int(re.search(r"#define PG_MAX_FIELDS (\d+)", text).group(1)) == _lib.PG_MAX_FIELDS
